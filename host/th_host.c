@@ -1,0 +1,304 @@
+/*
+ * th_host.c -- host C above the GPU C ABI: derives the reference's floating-point fields from the
+ * integer results, applies the adapter logic and record filters, and formats the output text.
+ * Compiled with -ffp-contract=off so that every expression rounds like the reference's plain SSE2
+ * doubles ("Host floating point").
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <math.h>
+#include "th_host.h"
+
+#define TH_SLOTS 4096 /* CHUNK_READ_N, src/tidehunter.h:10: tandem_seq_t slots are reused every 4096 reads */
+
+typedef struct { char *s; size_t l, m; } str_t;
+
+struct th_host {
+    th_host_para p;
+    th_gpu_ctx *gpu;
+    char *five_rc, *three_rc; int five_len, three_len;
+    str_t out;
+    str_t qual[TH_SLOTS];     /* persistent quality buffers: qual.l is never reset in the reference */
+    int64_t read_counter;
+    th_gpu_stats stats;
+};
+
+static char g_err[1024];
+const char *th_host_last_error(void) { return g_err; }
+static void set_err(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap); }
+
+void th_host_default_para(th_host_para *p) {
+    memset(p, 0, sizeof(*p));
+    th_gpu_default_params(&p->gpu);
+    p->out_fmt = 1; p->min_len = 30; p->ada_match_rat = 0.8f; p->chunk_reads = 16384;
+}
+
+static void str_reserve(str_t *s, size_t extra) {
+    if (s->l + extra + 1 > s->m) { s->m = (s->l + extra + 1) * 2; s->s = (char *)realloc(s->s, s->m); }
+}
+static void str_write(str_t *s, const char *d, size_t n) { str_reserve(s, n); memcpy(s->s + s->l, d, n); s->l += n; s->s[s->l] = 0; }
+static void str_printf(str_t *s, const char *fmt, ...) {
+    va_list ap; int n;
+    str_reserve(s, 128);
+    va_start(ap, fmt); n = vsnprintf(s->s + s->l, s->m - s->l, fmt, ap); va_end(ap);
+    if ((size_t)n >= s->m - s->l) { str_reserve(s, (size_t)n + 1); va_start(ap, fmt); n = vsnprintf(s->s + s->l, s->m - s->l, fmt, ap); va_end(ap); }
+    s->l += n;
+}
+
+static char *revcomp(const char *s, int l) { /* src/seq.c:89-95 */
+    char *r = (char *)malloc(l + 1); int i;
+    for (i = 0; i < l; ++i) {
+        char c = s[i], o = 'N';
+        switch (c) { case 'A': case 'a': o = 'T'; break; case 'C': case 'c': o = 'G'; break; case 'G': case 'g': o = 'C'; break; case 'T': case 't': o = 'A'; break; default: o = 'N'; }
+        r[l - i - 1] = o;
+    }
+    r[l] = 0;
+    return r;
+}
+
+th_host *th_host_create(const th_host_para *p, int device) {
+    th_host *h = (th_host *)calloc(1, sizeof(th_host));
+    h->p = *p;
+    h->p.gpu.need_cov = (p->out_fmt == 3 || p->out_fmt == 4 || p->min_cov > 0 || p->min_frac > 0.0) ? 1 : 0;
+    if (h->p.chunk_reads <= 0) h->p.chunk_reads = 16384;
+    h->gpu = th_gpu_create(&h->p.gpu, device < 0 ? 0 : device);
+    if (!h->gpu) { set_err("%s", th_gpu_last_error()); free(h); return NULL; }
+    if (p->five_seq && p->three_seq) {
+        h->five_len = (int)strlen(p->five_seq); h->three_len = (int)strlen(p->three_seq);
+        h->p.five_seq = strdup(p->five_seq); h->p.three_seq = strdup(p->three_seq);
+        h->five_rc = revcomp(p->five_seq, h->five_len); h->three_rc = revcomp(p->three_seq, h->three_len);
+    } else { h->p.five_seq = h->p.three_seq = NULL; }
+    return h;
+}
+void th_host_destroy(th_host *h) {
+    int i;
+    if (!h) return;
+    th_gpu_destroy(h->gpu);
+    free(h->five_rc); free(h->three_rc); free((void *)h->p.five_seq); free((void *)h->p.three_seq);
+    for (i = 0; i < TH_SLOTS; ++i) free(h->qual[i].s);
+    free(h->out.s); free(h);
+}
+void th_host_stats(const th_host *h, th_gpu_stats *s) { *s = h->stats; }
+th_gpu_ctx *th_host_gpu(th_host *h) { return h->gpu; }
+
+/* Infix edit distance with threshold (edlib_align_HW, src/edlib_align.c:73-85): edit distance,
+ * first end location, and for it the smallest start reaching that distance (edlib/src/edlib.cpp:141-236).
+ * Plain DP over the adapter (<= ~100 bp) x 2*cons_len; case-insensitive equality. */
+static int infix_ed(const char *q, int ql, const char *t, int tl, int *start, int *end, int k) {
+    int i, j, best = -1, best_end = -1, best_start = -1;
+    int *col;
+    if (ql <= 0 || tl <= 0) return -1;
+    col = (int *)malloc(sizeof(int) * (ql + 1));
+    for (i = 0; i <= ql; ++i) col[i] = i;
+    for (j = 0; j < tl; ++j) {
+        int diag = col[0];
+        col[0] = 0;
+        for (i = 1; i <= ql; ++i) {
+            int up = col[i - 1] + 1, left = col[i] + 1, d = diag + (((q[i - 1] | 0x20) == (t[j] | 0x20)) ? 0 : 1);
+            int v = d < up ? d : up;
+            if (left < v) v = left;
+            diag = col[i]; col[i] = v;
+        }
+        if (best < 0 || col[ql] < best) { best = col[ql]; best_end = j; }
+    }
+    if (best > ql) best = ql;
+    if (k >= 0 && best > k) { free(col); return -1; }
+    for (i = 0; i <= ql; ++i) col[i] = i;
+    for (j = 0; j <= best_end; ++j) {
+        int diag = col[0];
+        col[0] = j + 1;
+        for (i = 1; i <= ql; ++i) {
+            int up = col[i - 1] + 1, left = col[i] + 1, d = diag + (((q[ql - i] | 0x20) == (t[best_end - j] | 0x20)) ? 0 : 1);
+            int v = d < up ? d : up;
+            if (left < v) v = left;
+            diag = col[i]; col[i] = v;
+        }
+        if (col[ql] == best) best_start = best_end - j;
+    }
+    free(col);
+    *start = best_start; *end = best_end;
+    return best;
+}
+
+typedef struct { /* one record of tandem_seq_t */
+    int cons_start, cons_end, cons_len, full_length, pos_n;
+    double copy_num, ave_match;
+    const int32_t *sub_pos;
+    size_t seq_off;          /* into the per-read consensus text */
+} rec_t;
+
+/* one read: turn its tasks into records (seqs_msa tail + write_tandem_cons_seq) and print them */
+static void emit_read(th_host *h, const th_gpu_result *R, int r, const char *name, const char *seq, int len, int64_t global_index) {
+    const th_host_para *p = &h->p;
+    const int with_qual = (p->out_fmt == 3 || p->out_fmt == 4);
+    int t, i, n_rec = 0, m_rec = 0;
+    rec_t *rec = NULL;
+    str_t cons_txt = {0, 0, 0};
+    str_t *qs = &h->qual[global_index % TH_SLOTS];
+    size_t qual_base = qs->l; (void)qual_base;
+    for (t = R->read_task_off[r]; t < R->read_task_off[r + 1]; ++t) {
+        const int p0 = R->task_pos_off[t], pos_n = R->task_pos_off[t + 1] - p0;
+        const int32_t *pos = R->pos + p0;
+        if (p->gpu.only_unit) { /* write_tandem_unit */
+            if (n_rec == m_rec) { m_rec = m_rec ? m_rec * 2 : 4; rec = (rec_t *)realloc(rec, sizeof(rec_t) * m_rec); }
+            memset(&rec[n_rec], 0, sizeof(rec_t)); rec[n_rec].pos_n = pos_n; rec[n_rec].sub_pos = pos; ++n_rec;
+            continue;
+        }
+        if (R->task_status[t] != 0) { fprintf(stderr, "[th_host] read %s: consensus task failed on the GPU (code %d); record dropped\n", name, R->task_status[t]); continue; }
+        {
+            const int c0 = R->task_cons_off[t]; int cons_len = R->task_cons_off[t + 1] - c0;
+            const int n_seqs = R->task_n_seqs[t];
+            const uint8_t *cb = R->cons_base + c0; const int32_t *cov = R->cons_cov + c0;
+            char *cons_seq; uint8_t *cons_qual = NULL;
+            double ave_match = 0, copy_num; int cons_start, cons_end, full_length = 0, skip = 0, min_cov = 0;
+            if (cons_len <= 0) continue; /* the reference would spin here (src/gen_cons.c:206) */
+            /* min-cov filter of abpoa_gen_cons (src/abpoa_cons.c:52-98) */
+            if (p->min_frac > 0.0) min_cov = (int)(n_seqs * p->min_frac); else if (p->min_cov > 0) min_cov = p->min_cov;
+            if (min_cov > 0) {
+                if (n_seqs <= 2) {
+                    int _min_cov = 2, l0 = pos[1] - pos[0], l1 = pos[2] - pos[1];
+                    if (l0 != l1) _min_cov = 1; else for (i = 0; i < l0; ++i) if ((seq[pos[0] + 1 + i] | 0x20) != (seq[pos[1] + 1 + i] | 0x20)) { _min_cov = 1; break; }
+                    if (_min_cov < min_cov) skip = 1;
+                } else for (i = 0; i < cons_len; ++i) if (cov[i] < min_cov) { skip = 1; break; }
+            }
+            if (skip) continue; /* reference: cons_len = 0 -> spins; we drop the record */
+            cons_seq = (char *)malloc((size_t)cons_len * 2 + 2);
+            for (i = 0; i < cons_len; ++i) cons_seq[i] = "ACGTN"[cb[i] > 4 ? 4 : cb[i]];
+            cons_seq[cons_len] = 0;
+            if (with_qual) { /* phred from coverage, src/abpoa_cons.c:100-107; n_seqs <= 2 -> '!' */
+                cons_qual = (uint8_t *)malloc((size_t)cons_len * 2 + 2);
+                for (i = 0; i < cons_len; ++i) {
+                    if (n_seqs <= 2) cons_qual[i] = 33;
+                    else {
+                        double x = 13.8 * (1.25 * cov[i] / n_seqs - 0.25);
+                        double pr = 1 - 1.0 / (1.0 + pow(2.718281828459045, -1 * x));
+                        cons_qual[i] = (uint8_t)(33 + (int)(-10 * log10(pr) + 0.499));
+                    }
+                }
+            }
+            for (i = 0; i < pos_n - 1; ++i) { /* src/gen_cons.c:208-214 */
+                int ulen = pos[i + 1] - pos[i], iden_n = R->iden_n[p0 + i];
+                ave_match += (iden_n * 100 / (ulen + 0.0));
+            }
+            copy_num = n_seqs;
+            cons_start = pos[0] - R->ext[4 * t + 1];
+            copy_num += (R->ext[4 * t + 0] + 1.0) / cons_len;
+            cons_end = pos[pos_n - 1] + R->ext[4 * t + 3] + 1;
+            copy_num += (R->ext[4 * t + 2] + 1.0) / cons_len;
+            if (p->five_seq && p->three_seq && cons_len > h->five_len + h->three_len) { /* src/gen_cons.c:224-291 */
+                char *cons2 = (char *)malloc(((size_t)cons_len << 1) + 1); uint8_t *qual2 = NULL;
+                int tar_start = -1, tar_end = -1, tot_ed = INT32_MAX, _5_ed, _3_ed, _5_start = -1, _5_end = -1, _3_start = -1, _3_end = -1, k;
+                int k5 = (int)(h->five_len * (1 - p->ada_match_rat)), k3 = (int)(h->three_len * (1 - p->ada_match_rat));
+                memcpy(cons2, cons_seq, cons_len); memcpy(cons2 + cons_len, cons_seq, cons_len); cons2[cons_len << 1] = 0;
+                if (cons_qual) { qual2 = (uint8_t *)malloc((size_t)cons_len << 1); memcpy(qual2, cons_qual, cons_len); memcpy(qual2 + cons_len, cons_qual, cons_len); }
+                _5_ed = infix_ed(p->five_seq, h->five_len, cons2, cons_len << 1, &_5_start, &_5_end, k5);
+                if (_5_ed == -1) goto REV;
+                _3_ed = infix_ed(h->three_rc, h->three_len, cons2, cons_len << 1, &_3_start, &_3_end, k3);
+                if (_3_ed == -1) goto REV;
+                if (_3_start <= _5_end) {
+                    if (_3_end + cons_len < cons_len << 1 && _3_start + cons_len > _5_end) { tar_start = _5_end + 1; tar_end = _3_start + cons_len - 1; full_length = 1; tot_ed = _5_ed + _3_ed; }
+                } else { tar_start = _5_end + 1; tar_end = _3_start - 1; tot_ed = _5_ed + _3_ed; full_length = 1; }
+                if (tot_ed == 0) goto WRITE_CONS;
+REV:
+                _5_ed = infix_ed(h->five_rc, h->five_len, cons2, cons_len << 1, &_5_start, &_5_end, k5);
+                if (_5_ed == -1) goto WRITE_CONS;
+                _3_ed = infix_ed(p->three_seq, h->three_len, cons2, cons_len << 1, &_3_start, &_3_end, k3);
+                if (_3_ed == -1) goto WRITE_CONS;
+                if (_5_ed + _3_ed < tot_ed) {
+                    if (_5_start <= _3_end) {
+                        if (_5_end + cons_len < cons_len << 1 && _5_start + cons_len > _3_end) { tar_start = _3_end + 1; tar_end = _5_start + cons_len - 1; full_length = 2; }
+                    } else { tar_start = _3_end + 1; tar_end = _5_start - 1; full_length = 2; }
+                }
+WRITE_CONS:
+                if (tar_start > 0 && tar_end > tar_start) {
+                    memcpy(cons_seq, cons2 + tar_start, tar_end - tar_start + 1);
+                    cons_seq[tar_end - tar_start + 1] = 0;
+                    if (cons_qual) for (k = tar_start; k <= tar_end; ++k) cons_qual[k - tar_start] = qual2[k];
+                    cons_len = tar_end - tar_start + 1;
+                }
+                free(cons2); free(qual2);
+            }
+            if (!p->only_full_length || full_length > 0) { /* write_tandem_cons_seq, src/gen_cons.c:10-62 */
+                int keep = !(cons_len < p->min_len || cons_len > p->gpu.max_p);
+                if (keep && p->only_longest && n_rec == 1) {
+                    if (cons_end - cons_start > rec[0].cons_end - rec[0].cons_start) { n_rec = 0; cons_txt.l = 0; }
+                    else keep = 0;
+                }
+                if (keep) {
+                    if (n_rec == m_rec) { m_rec = m_rec ? m_rec * 2 : 4; rec = (rec_t *)realloc(rec, sizeof(rec_t) * m_rec); }
+                    rec[n_rec].cons_start = cons_start; rec[n_rec].cons_end = cons_end; rec[n_rec].cons_len = cons_len;
+                    rec[n_rec].full_length = full_length; rec[n_rec].pos_n = pos_n; rec[n_rec].sub_pos = pos;
+                    rec[n_rec].copy_num = copy_num; rec[n_rec].ave_match = ave_match / (pos_n - 1);
+                    rec[n_rec].seq_off = cons_txt.l;
+                    str_write(&cons_txt, cons_seq, cons_len);
+                    if (cons_qual) str_write(qs, (const char *)cons_qual, cons_len); /* appended at qual.l, never rewound */
+                    ++n_rec;
+                }
+            }
+            free(cons_seq); free(cons_qual);
+        }
+    }
+    /* mini_tandem_output, src/main.c:214-271 */
+    {
+        str_t *o = &h->out; int ci, j; size_t qoff = 0;
+        for (ci = 0; ci < n_rec; ++ci) {
+            const rec_t *c = rec + ci;
+            if (p->gpu.only_unit) {
+                if (p->out_fmt == 1) {
+                    for (i = 0; i < c->pos_n - 1; ++i) {
+                        str_printf(o, ">%s_rep%d_sub%d\n", name, ci, i);
+                        if (c->sub_pos[i + 1] > c->sub_pos[i]) str_write(o, seq + c->sub_pos[i] + 1, c->sub_pos[i + 1] - c->sub_pos[i]);
+                        str_write(o, "\n", 1);
+                    }
+                } else if (p->out_fmt == 2) { /* the tabular unit output drops the last base (`<` vs `<=`) */
+                    for (i = 0; i < c->pos_n - 1; ++i) {
+                        str_printf(o, "%s\trep%d\tsub%d\t", name, ci, i);
+                        if (c->sub_pos[i + 1] - 1 > c->sub_pos[i]) str_write(o, seq + c->sub_pos[i] + 1, c->sub_pos[i + 1] - 1 - c->sub_pos[i]);
+                        str_write(o, "\n", 1);
+                    }
+                }
+                continue;
+            }
+            if (p->out_fmt == 1 || p->out_fmt == 3)
+                str_printf(o, "%c%s_rep%d_%.1f %d_%d_%d_%d_%.1f_%d_", p->out_fmt == 1 ? '>' : '@', name, ci, c->copy_num, len, c->cons_start + 1, c->cons_end + 1, c->cons_len, c->ave_match, c->full_length);
+            else
+                str_printf(o, "%s\trep%d\t%.1f\t%d\t%d\t%d\t%d\t%.1f\t%d\t", name, ci, c->copy_num, len, c->cons_start + 1, c->cons_end + 1, c->cons_len, c->ave_match, c->full_length);
+            str_printf(o, "%d", c->sub_pos[0] + 2);
+            for (j = 1; j < c->pos_n - 1; ++j) str_printf(o, ",%d", c->sub_pos[j] + 2);
+            str_printf(o, ",%d%c", c->sub_pos[j] + 1, (p->out_fmt == 1 || p->out_fmt == 3) ? '\n' : '\t');
+            str_write(o, cons_txt.s + c->seq_off, c->cons_len);
+            if (p->out_fmt == 3) str_write(o, "\n+\n", 3); else if (p->out_fmt == 4) str_write(o, "\t", 1);
+            if (with_qual) { /* printed from offset 0 of the slot's buffer, whatever it holds (main.c:258-262) */
+                str_write(o, qs->s + qoff, c->cons_len);
+                qoff += c->cons_len;
+            }
+            str_write(o, "\n", 1);
+        }
+    }
+    free(rec); free(cons_txt.s);
+}
+
+const char *th_host_run(th_host *h, int n, const char *const *names, const char *const *seqs, const int32_t *lens, size_t *out_len) {
+    int c0;
+    h->out.l = 0; str_reserve(&h->out, 16); h->out.s[0] = 0;
+    memset(&h->stats, 0, sizeof(h->stats));
+    if (h->p.single_copy && h->p.only_full_length && h->p.five_seq) { set_err("-s (single-copy full-length) is not implemented"); *out_len = 0; return NULL; }
+    for (c0 = 0; c0 < n; c0 += h->p.chunk_reads) {
+        int m = n - c0 < h->p.chunk_reads ? n - c0 : h->p.chunk_reads, r;
+        th_gpu_result R;
+        if (th_gpu_process_chunk(h->gpu, m, seqs + c0, lens + c0, &R)) { set_err("%s", th_gpu_last_error()); *out_len = 0; return NULL; }
+        for (r = 0; r < m; ++r) emit_read(h, &R, r, names[c0 + r], seqs[c0 + r], lens[c0 + r], h->read_counter + r);
+        h->read_counter += m;
+        {
+            th_gpu_stats *a = &h->stats, *b = &R.stats;
+            a->ms_h2d += b->ms_h2d; a->ms_pack += b->ms_pack; a->ms_seed += b->ms_seed; a->ms_chain += b->ms_chain; a->ms_select += b->ms_select;
+            a->ms_partition += b->ms_partition; a->ms_poa += b->ms_poa; a->ms_ksw += b->ms_ksw; a->ms_d2h += b->ms_d2h; a->ms_total += b->ms_total;
+            a->n_bases += b->n_bases; a->n_hits += b->n_hits; a->n_chain_evals += b->n_chain_evals; a->n_poa_cells += b->n_poa_cells; a->n_poa_rows += b->n_poa_rows;
+            a->n_ksw_cells += b->n_ksw_cells; a->n_tasks += b->n_tasks; a->n_launches += b->n_launches; a->h2d_bytes += b->h2d_bytes; a->d2h_bytes += b->d2h_bytes;
+        }
+    }
+    *out_len = h->out.l;
+    return h->out.s;
+}

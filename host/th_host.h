@@ -1,0 +1,55 @@
+/*
+ * th_host.h -- host-side C layer above the GPU C ABI (include/th_gpu.h).
+ *
+ * Mirrors what the reference keeps on the CPU around tidehunter_core: the option structure
+ * (mini_tandem_para, src/tidehunter.h:47-61), the floating-point scalars derived from the integer
+ * alignment results (src/gen_cons.c:204-223, src/abpoa_cons.c:100-107), the adapter / full-length
+ * logic (src/gen_cons.c:224-291), record filtering (src/gen_cons.c:10-16) and the output formats of
+ * mini_tandem_output (src/main.c:214-271), including its quirks.
+ */
+#ifndef TH_HOST_H
+#define TH_HOST_H
+#include <stddef.h>
+#include <stdint.h>
+#include "../include/th_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    th_gpu_params gpu;
+    int out_fmt;            /* -f 1 FASTA, 2 tab, 3 FASTQ, 4 tab+qual */
+    int min_len;            /* -m */
+    int min_cov;            /* -r (integer form) */
+    double min_frac;        /* -r (fraction form) */
+    int only_longest;       /* -l */
+    int only_full_length;   /* -F */
+    int single_copy;        /* -s */
+    float ada_match_rat;    /* -a */
+    const char *five_seq, *three_seq; /* -5 / -3 adapter sequences (already read from their files) or NULL */
+    int chunk_reads;        /* reads per GPU chunk (the reference uses 4096, src/tidehunter.h:10) */
+} th_host_para;
+
+void th_host_default_para(th_host_para *p);
+
+typedef struct th_host th_host;
+
+/* device < 0: use CUDA device 0.  NULL on failure (see th_host_last_error). */
+th_host *th_host_create(const th_host_para *p, int device);
+void th_host_destroy(th_host *h);
+
+/* Process reads [0,n) and append the text the reference would print for them to an internal buffer;
+ * returns a pointer to it (valid until the next call) and its length.  Reads are numbered across
+ * calls so that the FASTQ quality slot-reuse quirk of the reference (src/main.c:266-267) is kept. */
+const char *th_host_run(th_host *h, int n, const char *const *names, const char *const *seqs, const int32_t *lens, size_t *out_len);
+
+/* stats of the last th_host_run (summed over its chunks) */
+void th_host_stats(const th_host *h, th_gpu_stats *s);
+th_gpu_ctx *th_host_gpu(th_host *h);
+const char *th_host_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

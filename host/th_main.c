@@ -1,0 +1,179 @@
+/*
+ * th_main.c -- command line front end with TideHunter's options (src/main.c:16-147, 438-535), running
+ * the per-read hot path on the GPU through host/th_host.c -> include/th_gpu.h.
+ *
+ *   tidehunter-b200 [options] in.fa/fq[.gz] > cons.fa
+ *
+ * Same flags and output formats as the reference; `-t` is accepted and ignored (the GPU replaces the
+ * pthread pool), `--device N` selects the CUDA device, `--chunk N` the reads per GPU chunk.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <getopt.h>
+#include <zlib.h>
+#include <time.h>
+#include "th_host.h"
+
+#define PROG "tidehunter-b200"
+
+static const struct option long_opt[] = {
+    {"kmer-length", 1, NULL, 'k'}, {"window-size", 1, NULL, 'w'}, {"HPC-kmer", 0, NULL, 'H'},
+    {"min-copy", 1, NULL, 'c'}, {"max-diverg", 1, NULL, 'e'}, {"min-period", 1, NULL, 'p'}, {"max-period", 1, NULL, 'P'},
+    {"match", 1, NULL, 'M'}, {"mismatch", 1, NULL, 'X'}, {"gap_open", 1, NULL, 'O'}, {"gap_ext", 1, NULL, 'E'},
+    {"five-prime", 1, NULL, '5'}, {"three-prime", 1, NULL, '3'}, {"ada-match-rat", 1, NULL, 'a'},
+    {"output", 1, NULL, 'o'}, {"min-len", 1, NULL, 'm'}, {"min-cov", 1, NULL, 'r'}, {"unit-seq", 0, NULL, 'u'},
+    {"longest", 0, NULL, 'l'}, {"full-len", 0, NULL, 'F'}, {"single-copy", 0, NULL, 's'}, {"out-fmt", 1, NULL, 'f'},
+    {"thread", 1, NULL, 't'}, {"help", 0, NULL, 'h'}, {"version", 0, NULL, 'v'},
+    {"device", 1, NULL, 1001}, {"chunk", 1, NULL, 1002},
+    {0, 0, 0, 0}};
+
+static long long parse_num(const char *str) { /* th_parse_num, src/main.c:54-64 */
+    char *p; double x = strtod(str, &p);
+    if (*p == 'G' || *p == 'g') x *= 1e9; else if (*p == 'M' || *p == 'm') x *= 1e6; else if (*p == 'K' || *p == 'k') x *= 1e3;
+    return (long long)(x + .499);
+}
+
+static int usage(void) {
+    fprintf(stderr, "\n%s: tandem repeat detection and consensus calling from noisy long reads (B200 GPU path)\n\n", PROG);
+    fprintf(stderr, "Usage:   %s [options] in.fa/fq > cons.fa\n\n", PROG);
+    fprintf(stderr, "Options (identical to TideHunter v1.5.5):\n"
+                    "  -k INT  k-mer length (<=16) [8]        -w INT  minimizer window [1]       -H  HPC k-mers\n"
+                    "  -c INT  min copy number (>=2) [2]      -e FLT  max divergence [0.25]\n"
+                    "  -p INT  min period (>=2) [30]          -P INT  max period [10K]\n"
+                    "  -M/-X INT match/mismatch [2/4]         -O INT(,INT) gap open [4,24]       -E INT(,INT) gap ext [2,1]\n"
+                    "  -5/-3 STR adapter FASTA files          -a FLT  adapter match ratio [0.80]\n"
+                    "  -o STR  output file [stdout]           -m INT  min consensus length [30]  -r FLT|INT min coverage\n"
+                    "  -u unit sequences only   -l longest only   -F full-length only   -s single-copy (not implemented)\n"
+                    "  -f INT  1 FASTA, 2 tabular, 3 FASTQ, 4 tabular+quality [1]\n"
+                    "  -t INT  accepted, ignored              --device INT CUDA device [0]       --chunk INT reads per GPU chunk [16384]\n\n");
+    return 1;
+}
+
+/* ---- FASTA/FASTQ(.gz) reader with kseq semantics (src/kseq.h:174-217): name = up to first whitespace ---- */
+typedef struct { gzFile fp; unsigned char *buf; int beg, end, eof; } stream_t;
+static int st_getc(stream_t *s) {
+    if (s->beg >= s->end) {
+        if (s->eof) return -1;
+        s->beg = 0; s->end = gzread(s->fp, s->buf, 1 << 20);
+        if (s->end <= 0) { s->eof = 1; s->end = 0; return -1; }
+    }
+    return s->buf[s->beg++];
+}
+typedef struct { char *s; size_t l, m; } kstr_t;
+static void ks_push(kstr_t *k, int c) { if (k->l + 2 > k->m) { k->m = k->m ? k->m * 2 : 256; k->s = (char *)realloc(k->s, k->m); } k->s[k->l++] = (char)c; k->s[k->l] = 0; }
+static int last_char = 0;
+static int read_record(stream_t *s, kstr_t *name, kstr_t *seq) {
+    int c;
+    if (last_char == 0) { while ((c = st_getc(s)) != -1 && c != '>' && c != '@') ; if (c == -1) return -1; last_char = c; }
+    name->l = seq->l = 0; ks_push(name, 0); name->l = 0; ks_push(seq, 0); seq->l = 0;
+    while ((c = st_getc(s)) != -1 && c != ' ' && c != '\t' && c != '\n' && c != '\r') ks_push(name, c);
+    if (c == -1) return -1;
+    if (c != '\n') while ((c = st_getc(s)) != -1 && c != '\n') ;
+    while ((c = st_getc(s)) != -1 && c != '>' && c != '+' && c != '@') {
+        if (c == '\n') continue;
+        if (c > 32 && c < 127) ks_push(seq, c); /* kseq keeps isgraph() characters */
+        while ((c = st_getc(s)) != -1 && c != '\n') if (c > 32 && c < 127) ks_push(seq, c);
+    }
+    if (c == '>' || c == '@') last_char = c;
+    if (c != '+') { if (c == -1) last_char = 0; return (int)seq->l; }
+    while ((c = st_getc(s)) != -1 && c != '\n') ; /* skip the rest of '+' line */
+    { size_t ql = 0; while (ql < seq->l && (c = st_getc(s)) != -1) if (c > 32 && c < 127) ++ql; }
+    last_char = 0;
+    return (int)seq->l;
+}
+
+static char *read_first_seq(const char *fn) { /* get_seq_from_fx, src/seq.c */
+    stream_t s; kstr_t name = {0, 0, 0}, seq = {0, 0, 0}; char *r = NULL;
+    memset(&s, 0, sizeof(s));
+    s.fp = gzopen(fn, "r"); if (!s.fp) { fprintf(stderr, "[%s] fail to open %s\n", PROG, fn); exit(1); }
+    s.buf = (unsigned char *)malloc(1 << 20);
+    last_char = 0;
+    if (read_record(&s, &name, &seq) > 0) r = strdup(seq.s);
+    gzclose(s.fp); free(s.buf); free(name.s); free(seq.s); last_char = 0;
+    if (!r) { fprintf(stderr, "[%s] No sequence found in %s.\n", PROG, fn); exit(1); }
+    return r;
+}
+
+int main(int argc, char *argv[]) {
+    th_host_para p; int c, device = 0; const char *out_fn = NULL, *five_fn = NULL, *three_fn = NULL; char *s;
+    th_host_default_para(&p);
+    if (argc < 2) return usage();
+    while ((c = getopt_long(argc, argv, "k:w:m:Hhvc:e:p:P:M:X:E:O:5:3:a:o:ur:qslFf:t:", long_opt, NULL)) >= 0) {
+        switch (c) {
+        case 'k': p.gpu.k = atoi(optarg); break;
+        case 'w': p.gpu.w = atoi(optarg); break;
+        case 'H': p.gpu.hpc = 1; break;
+        case 'c': p.gpu.min_copy = atoi(optarg); break;
+        case 'e': p.gpu.max_div = atof(optarg); break;
+        case 'p': p.gpu.min_p = parse_num(optarg); break;
+        case 'P': p.gpu.max_p = parse_num(optarg); break;
+        case 'M': p.gpu.match = atoi(optarg); break;
+        case 'X': p.gpu.mismatch = atoi(optarg); break;
+        case 'O': p.gpu.gap_open1 = (int)strtol(optarg, &s, 10); if (*s == ',') p.gpu.gap_open2 = (int)strtol(s + 1, &s, 10); break;
+        case 'E': p.gpu.gap_ext1 = (int)strtol(optarg, &s, 10); if (*s == ',') p.gpu.gap_ext2 = (int)strtol(s + 1, &s, 10); break;
+        case '5': five_fn = optarg; break;
+        case '3': three_fn = optarg; break;
+        case 'a': p.ada_match_rat = (float)atof(optarg); break;
+        case 'o': out_fn = optarg; break;
+        case 'm': p.min_len = atoi(optarg); break;
+        case 'r': { double v = atof(optarg); if (v > 0 && v < 1) p.min_frac = v; else p.min_cov = (int)v; break; }
+        case 'u': p.gpu.only_unit = 1; break;
+        case 'l': p.only_longest = 1; break;
+        case 'F': p.only_full_length = 1; break;
+        case 's': p.single_copy = 1; break;
+        case 'f': p.out_fmt = atoi(optarg); break;
+        case 't': break;
+        case 'q': break;
+        case 1001: device = atoi(optarg); break;
+        case 1002: p.chunk_reads = atoi(optarg); break;
+        case 'v': printf("%s (TideHunter v1.5.5 compatible)\n", PROG); return 0;
+        case 'h': default: return usage();
+        }
+    }
+    /* option validation of the reference (src/main.c:505-523) */
+    if (p.gpu.k > 16) { fprintf(stderr, "[main] k-mer length must be no larger than 16\n"); return 1; }
+    if (p.gpu.min_copy < 2) { fprintf(stderr, "[main] min copy number must be >= 2\n"); return 1; }
+    if (p.gpu.min_p < 2) { fprintf(stderr, "[main] min period must be >= 2\n"); return 1; }
+    if (p.out_fmt < 1 || p.out_fmt > 4) { fprintf(stderr, "[main] unknown output format %d\n", p.out_fmt); return 1; }
+    if (p.gpu.only_unit && p.out_fmt > 2) { fprintf(stderr, "[main] -u only works with -f 1/2\n"); return 1; }
+    if (p.only_full_length && !(five_fn && three_fn)) { fprintf(stderr, "[main] -F needs -5 and -3\n"); return 1; }
+    if (optind + 1 > argc) return usage();
+    if (five_fn && three_fn) { p.five_seq = read_first_seq(five_fn); p.three_seq = read_first_seq(three_fn); }
+    {
+        struct timespec t0, t1; FILE *out = out_fn ? fopen(out_fn, "w") : stdout;
+        th_host *h; stream_t st; kstr_t name = {0, 0, 0}, seq = {0, 0, 0};
+        int n = 0, m = 0, i; char **names = NULL, **seqs = NULL; int32_t *lens = NULL; long long tot_reads = 0;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        if (!out) { fprintf(stderr, "[main] cannot open %s\n", out_fn); return 1; }
+        h = th_host_create(&p, device);
+        if (!h) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
+        memset(&st, 0, sizeof(st));
+        st.fp = strcmp(argv[optind], "-") ? gzopen(argv[optind], "r") : gzdopen(0, "r");
+        if (!st.fp) { fprintf(stderr, "[main] fail to open %s\n", argv[optind]); return 1; }
+        st.buf = (unsigned char *)malloc(1 << 20);
+        last_char = 0;
+        while (1) {
+            int l = read_record(&st, &name, &seq);
+            if (l >= 0) {
+                if (n == m) { m = m ? m * 2 : 1024; names = (char **)realloc(names, sizeof(char *) * m); seqs = (char **)realloc(seqs, sizeof(char *) * m); lens = (int32_t *)realloc(lens, sizeof(int32_t) * m); }
+                names[n] = strdup(name.s); seqs[n] = (char *)malloc(seq.l + 1); memcpy(seqs[n], seq.s, seq.l + 1); lens[n] = (int32_t)seq.l; ++n;
+            }
+            if (n == p.chunk_reads || (l < 0 && n > 0)) {
+                size_t ol; const char *txt = th_host_run(h, n, (const char *const *)names, (const char *const *)seqs, lens, &ol);
+                if (!txt) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
+                fwrite(txt, 1, ol, out);
+                tot_reads += n;
+                for (i = 0; i < n; ++i) { free(names[i]); free(seqs[i]); }
+                n = 0;
+            }
+            if (l < 0) break;
+        }
+        gzclose(st.fp); free(st.buf); free(name.s); free(seq.s); free(names); free(seqs); free(lens);
+        th_host_destroy(h);
+        if (out != stdout) fclose(out);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "[main] Real time: %.3f sec; reads: %lld\n", (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec), tot_reads);
+    }
+    return 0;
+}

@@ -1,0 +1,301 @@
+// th_chain.cuh -- period-consistent chaining DP and chain extraction.
+//
+// Replaces src/tandem_chain.c:113-166 (init_dp, get_con_score), :290-356 (main DP) and
+// :21-111, :170-223, :251-255, :358-403 (ranking, greedy extraction, ordering) of the reference.
+//
+// chain_dp_kernel: one warp per read.  Cells are the hits in (end, period) order; with one hit per
+// end (always true for -w 1) the reference's scan "rows downwards, stop rules in order" is a linear
+// scan over earlier hits, evaluated 32 predecessors at a time: a shuffle prefix-max reproduces the
+// running max_score each predecessor would have seen, and ballots pick the first lane that triggers
+// one of the ordered stop rules.  Reads with repeated ends (possible only with minimizer seeds) go to
+// chain_dp_generic_kernel, a literal one-thread restatement.
+#pragma once
+#include "th_common.cuh"
+
+enum { CON_NO = 0, CON_REG = 1, CON_SAME = 2, CON_OVL = 3 };
+
+// get_con_score (tandem_chain.c:151-166).  The reference's double test `cur_p >= pre_p * 1.8` equals
+// 5*cur_p >= 9*pre_p for all int periods: when 9*pre_p/5 is an integer N the correctly rounded product
+// fl(pre_p * 1.8) is exactly N (1.8's representation error is 2.5e-17 relative, below half an ulp),
+// otherwise the exact product is at least 0.2 away from any integer.
+__device__ __forceinline__ int con_score(int cs, int ce, int ps, int pe, int k, int &score) {
+    int cp = ce - cs, pp = pe - ps;
+    if (cs <= ps || 5ll * cp >= 9ll * pp || 5ll * pp >= 9ll * cp) return CON_NO;
+    int de = abs(ce - pe), ds = abs(cs - ps), dpd = abs(cp - pp);
+    int matched = min(de, k) + min(ds, k);
+    uint32_t v = (uint32_t)(de + ds);
+    int lg = v ? 31 - __clz(v) : -1;
+    score = matched - (dpd * dpd / 2 + lg / 2);
+    if (dpd == 0) return matched < 2 * k ? CON_OVL : CON_SAME;
+    return CON_REG;
+}
+
+#define CHAIN_WARPS 4
+__global__ void __launch_bounds__(CHAIN_WARPS * 32)
+chain_dp_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ nhits,
+                const int32_t *__restrict__ hend, const int32_t *__restrict__ hper,
+                int32_t *score, int32_t *from, int32_t *__restrict__ generic_flag,
+                unsigned long long *__restrict__ eval_count) {
+    const int lane = lane_id();
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long evals = 0;
+    for (int r = wid; r < n_reads; r += nw) {
+        const int n = nhits[r];
+        const int64_t off = roff[r];
+        const int32_t *en = hend + off, *pr = hper + off;
+        int32_t *sc = score + off, *fr = from + off;
+        if (n < 2) { if (lane == 0) generic_flag[r] = 0; continue; }
+        // repeated ends? (rows with more than one cell) -> generic kernel
+        int dup = 0;
+        for (int i = lane + 1; i < n; i += 32) dup |= (en[i] == en[i - 1]);
+        dup = __any_sync(TH_FULL, dup);
+        if (lane == 0) generic_flag[r] = dup;
+        if (dup) continue;
+        for (int i = lane; i < n; i += 32) { sc[i] = P.k + min(P.k, pr[i]); fr[i] = -1; } // init_dp
+        __syncwarp();
+        for (int cur = 1; cur < n; ++cur) {
+            const int ce = en[cur], cp = pr[cur], cs = ce - cp;
+            const int init = P.k + min(P.k, cp);
+            int max_score = init, best_pre = -1, iter_in = 0;
+            const int max_h = cp;
+            for (int base = cur - 1; base >= 0; base -= 32) {
+                const int pre = base - lane;
+                const bool valid = pre >= 0;
+                int pe = 0, pp = 1, psc = 0;
+                if (valid) { pe = en[pre]; pp = pr[pre]; psc = sc[pre]; }
+                const bool cstop = !valid || pe < cs;           // stop BEFORE this predecessor
+                int con = 0, cls = CON_NO;
+                if (!cstop) cls = con_score(cs, ce, pe - pp, pe, P.k, con);
+                const int s = cls != CON_NO ? psc + con : INT_MIN;
+                // running max each lane would have seen = max(max_score, s of earlier lanes)
+                int inc = s;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(TH_FULL, inc, d); if (lane >= d) inc = max(inc, o); }
+                int excl = __shfl_up_sync(TH_FULL, inc, 1);
+                excl = lane == 0 ? max_score : max(max_score, excl);
+                const bool imp = cls != CON_NO && s > excl;
+                const unsigned impm = __ballot_sync(TH_FULL, imp);
+                // rows without improvement so far (iter_n), as of this lane
+                const unsigned below = impm & (0xffffffffu >> (31 - lane));
+                const int cnt = below ? lane - (31 - __clz(below)) : iter_in + lane + 1;
+                const bool stop_after = (imp && (cls == CON_SAME || cls == CON_OVL)) || (!imp && cls == CON_OVL) || (!imp && cnt >= max_h);
+                const unsigned cm = __ballot_sync(TH_FULL, cstop), am = __ballot_sync(TH_FULL, stop_after && !cstop);
+                const int first_c = cm ? __ffs(cm) - 1 : 32, first_a = am ? __ffs(am) - 1 : 32;
+                const bool processed = lane < first_c && lane <= first_a;
+                evals += __popc(__ballot_sync(TH_FULL, processed));
+                const int sp = processed ? s : INT_MIN;
+                const int bm = __reduce_max_sync(TH_FULL, sp);
+                if (bm > max_score) {
+                    const unsigned wm = __ballot_sync(TH_FULL, processed && imp && s == bm);
+                    max_score = bm; best_pre = base - (__ffs(wm) - 1);
+                }
+                if (first_c < 32 || first_a < 32) break;
+                iter_in = __shfl_sync(TH_FULL, cnt, 31);
+            }
+            if (lane == 0 && max_score > init) { sc[cur] = max_score; fr[cur] = best_pre; }
+            __syncwarp();
+        }
+    }
+    evals = __shfl_sync(TH_FULL, evals, 0);
+    if (lane == 0 && evals) atomicAdd(eval_count, evals);
+}
+
+// Literal restatement for reads whose hits repeat an end position (ragged DP rows); thread per read.
+__global__ void chain_dp_generic_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ nhits,
+                                        const int32_t *__restrict__ hend, const int32_t *__restrict__ hper,
+                                        int32_t *score, int32_t *from, const int32_t *__restrict__ generic_flag,
+                                        int32_t *rowbeg_scratch) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads || !generic_flag[r]) return;
+    const int n = nhits[r]; const int64_t off = roff[r];
+    const int32_t *en = hend + off, *pr = hper + off; int32_t *sc = score + off, *fr = from + off;
+    int32_t *row_beg = rowbeg_scratch + off; // n+1 entries fit: capacity L >= n+1
+    int tot = 0;
+    for (int i = 0; i < n; ++i) {
+        if (i == 0 || en[i] != en[i - 1]) row_beg[tot++] = i;
+        sc[i] = P.k + min(P.k, pr[i]); fr[i] = -1;
+    }
+    row_beg[tot] = n;
+    for (int ci = 1; ci < tot; ++ci)
+        for (int cur = row_beg[ci]; cur < row_beg[ci + 1]; ++cur) {
+            int max_score = sc[cur], max_pre = -1, max_h = pr[cur], iter_n = 0; bool stop = false;
+            int ce = en[cur], cs = ce - pr[cur];
+            for (int pi = ci - 1; pi >= 0 && !stop; --pi) {
+                bool gt = false;
+                if (en[row_beg[pi]] < cs) break;
+                for (int pre = row_beg[pi]; pre < row_beg[pi + 1]; ++pre) {
+                    int con, cls = con_score(cs, ce, en[pre] - pr[pre], en[pre], P.k, con);
+                    if (cls == CON_NO) continue;
+                    int s = sc[pre] + con;
+                    if (s > max_score) { max_score = s; max_pre = pre; if (cls == CON_SAME || cls == CON_OVL) { stop = true; break; } gt = true; }
+                    else if (cls == CON_OVL) { stop = true; break; }
+                }
+                if (stop) break;
+                if (gt) iter_n = 0; else if (++iter_n >= max_h) break;
+            }
+            if (max_score > sc[cur]) { sc[cur] = max_score; fr[cur] = max_pre; }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ranking: cells with score > 0 ordered by score descending, ties by the reference's listing order
+// (row descending, then period ascending; tandem_chain.c:32-43 + glibc's stable merge-sort qsort).
+// Block per read.  key = score<<40 | last_cell_of_row<<20 | (0xfffff - index_in_row), sorted
+// descending; requires score < 2^24 and hit_n < 2^20 (flagged otherwise).
+// ---------------------------------------------------------------------------------------------
+#define RANK_THREADS 256
+#define RANK_SMEM_CAP 4096
+__global__ void __launch_bounds__(RANK_THREADS)
+rank_kernel(int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ nhits,
+            const int32_t *__restrict__ hend, const int32_t *__restrict__ score,
+            uint64_t *__restrict__ gscratch, int64_t gcap, int32_t *__restrict__ rank, int32_t *__restrict__ nrank,
+            int32_t *__restrict__ read_status) {
+    __shared__ uint64_t sbuf[RANK_SMEM_CAP];
+    __shared__ int s_cnt, s_bad;
+    for (int r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const int n = nhits[r]; const int64_t off = roff[r];
+        if (n < 2) { if (threadIdx.x == 0) nrank[r] = 0; continue; }
+        const int npow = next_pow2(n);
+        uint64_t *buf = npow <= RANK_SMEM_CAP ? sbuf : gscratch + (int64_t)blockIdx.x * gcap;
+        if (threadIdx.x == 0) { s_cnt = 0; s_bad = n >= (1 << 20); }
+        __syncthreads();
+        for (int i = threadIdx.x; i < npow; i += blockDim.x) {
+            uint64_t v = 0;
+            if (i < n && score[off + i] > 0) {
+                int lo = i, hi = i; const int e = hend[off + i];
+                while (lo > 0 && hend[off + lo - 1] == e) --lo;
+                while (hi + 1 < n && hend[off + hi + 1] == e) ++hi;
+                const int sc = score[off + i];
+                if (sc >= (1 << 24)) s_bad = 1;
+                v = ((uint64_t)(uint32_t)sc << 40) | ((uint64_t)(uint32_t)hi << 20) | (uint64_t)(0xfffff - (i - lo));
+                atomicAdd(&s_cnt, 1);
+            }
+            buf[i] = v;
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        block_bitonic_sort<true>(buf, npow);
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint64_t v = buf[i];
+            int hi = (int)((v >> 20) & 0xfffff), lo = hi; const int e = hend[off + hi];
+            while (lo > 0 && hend[off + lo - 1] == e) --lo;
+            rank[off + i] = lo + (0xfffff - (int)(v & 0xfffff));
+        }
+        if (threadIdx.x == 0) { nrank[r] = s_bad ? 0 : cnt; if (s_bad) read_status[r] = TH_ERR_CAP; }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Greedy chain extraction; one thread per read (sequential by nature).  Literal restatement of
+// tandem_chain.c:358-403 on flat cell ids.  Output: post-chains (>= 3 cells, ascending end).
+// Per-read scratch (all at the read's base offset, capacity L):
+//   tracked[L] u8, ch_off/ch_len/ch_score/ch_idx [L/2+1 via half offsets], cells[L]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int row_first(const int32_t *en, int c) { while (c > 0 && en[c - 1] == en[c]) --c; return c; }
+
+__global__ void chain_select_kernel(int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ nhits,
+                                    const int32_t *__restrict__ hend, const int32_t *__restrict__ hper,
+                                    const int32_t *__restrict__ score, const int32_t *__restrict__ from,
+                                    const int32_t *__restrict__ rank, const int32_t *__restrict__ nrank,
+                                    uint8_t *tracked, int32_t *ch_off, int32_t *ch_len, int32_t *ch_score, int32_t *ch_idx,
+                                    int32_t *cells, int32_t *__restrict__ pch_n, int32_t *pch_off, int32_t *pch_len, const int ragged_ok) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int n = nhits[r]; const int64_t off = roff[r], hoff = off / 2;
+    pch_n[r] = 0;
+    if (n < 2) return;
+    const int32_t *en = hend + off, *pr = hper + off, *sc = score + off, *fr = from + off, *rk = rank + off;
+    uint8_t *trk = tracked + off; int32_t *cl = cells + off;
+    int32_t *coff = ch_off + hoff, *clen = ch_len + hoff, *cscore = ch_score + hoff, *cidx = ch_idx + hoff;
+    const int cap = n / 2 + 1, top_N = 1000;
+    for (int i = 0; i < n; ++i) trk[i] = 0;
+    const int score_n = nrank[r];
+    int ch_n = 0, pool = 0; // pool: next free slot in cl[]; the slot of chain ch_n is rewritten until accepted
+    for (int i = 0; i < cap && i < top_N; ++i) cidx[i] = i;
+#define ST(c) (en[c] - pr[c])
+    for (int i = 0; i < score_n && ch_n < top_N && ch_n < cap; ++i) {
+        const int c = rk[i];
+        bool in_chain = false;
+        { // is_in_chain (:170-185); cell_start is taken from the first cell of the row
+            const int cell_start = ST(row_first(en, c)), cell_end = en[c];
+            for (int _i = 0; _i < ch_n; ++_i) {
+                const int ci = cidx[_i];
+                if (clen[ci] <= 0) continue;
+                const int chain_start = ST(cl[coff[ci]]), chain_end = en[cl[coff[ci] + clen[ci] - 1]];
+                if (chain_end < cell_start) break;
+                else if (chain_start > cell_end) continue;
+                else if (cell_end - chain_start >= (chain_end - chain_start) / 2) { in_chain = true; break; }
+            }
+        }
+        if (in_chain) continue;
+        bool accepted = false;
+        if (!trk[c]) { // backtrack_dp (:86-111)
+            int s = sc[c], cur = c, len = 0;
+            while (true) {
+                trk[cur] = 1; cl[pool + len++] = cur;
+                const int p = fr[cur];
+                if (p == -1) break;
+                if (trk[p]) { s -= sc[p]; break; }
+                cur = p;
+            }
+            for (int a = 0, b = len - 1; a < b; ++a, --b) { int t = cl[pool + a]; cl[pool + a] = cl[pool + b]; cl[pool + b] = t; }
+            coff[ch_n] = pool; clen[ch_n] = len; cscore[ch_n] = s;
+            if (len > 1) { // is_overlap_chain (:54-83)
+                bool ovl = false;
+                if (ch_n > 0) {
+                    const int start = ST(cl[pool + len - 1]);
+                    for (int j = ch_n - 1; j >= 0; --j) {
+                        if (clen[j] <= 0) continue;
+                        if (en[cl[coff[j] + clen[j] - 1]] <= start) break;
+                        const int s1 = ST(cl[coff[j]]), e1 = ST(cl[coff[j] + clen[j] - 1]);
+                        const int s2 = ST(cl[pool]), e2 = ST(cl[pool + len - 1]);
+                        const int mn = min(e1 - s1, e2 - s2), ovlp = min(e1, e2) - max(s1, s2);
+                        if (ovlp / (mn + 0.0) >= 0.5) {
+                            if (cscore[j] > s) ovl = true; else clen[j] = 0;
+                            break;
+                        }
+                    }
+                }
+                accepted = !ovl;
+            }
+        }
+        if (accepted) { pool += clen[ch_n]; ++ch_n; }
+        // sort_chain (:188-207) runs after every candidate in the reference; it performs no swap when the live
+        // chain ends are already non-increasing, so that O(ch_n) test replaces the O(ch_n^2) pass; otherwise
+        // the literal pass (incl. its stale `i`) runs.
+        if (ch_n >= 2) {
+            bool sorted = true; int last_end = INT_MAX;
+            for (int _i = 0; _i < ch_n; ++_i) {
+                const int ci = cidx[_i];
+                if (clen[ci] <= 0) continue;
+                const int e = en[cl[coff[ci] + clen[ci] - 1]];
+                if (e > last_end) { sorted = false; break; }
+                last_end = e;
+            }
+            if (!sorted) {
+                for (int _i = 0; _i < ch_n - 1; ++_i) {
+                    const int ii = cidx[_i];
+                    if (clen[ii] <= 0) continue;
+                    int end1 = en[cl[coff[ii] + clen[ii] - 1]];
+                    for (int _j = _i + 1; _j < ch_n; ++_j) {
+                        const int jj = cidx[_j];
+                        if (clen[jj] <= 0) continue;
+                        const int end2 = en[cl[coff[jj] + clen[jj] - 1]];
+                        if (end1 < end2) { cidx[_i] = jj; cidx[_j] = ii; end1 = end2; }
+                    }
+                }
+            }
+        }
+    }
+#undef ST
+    // post-process (:392-399): ascending end, chains with >= 3 cells
+    int pn = 0;
+    for (int i = ch_n - 1; i >= 0; --i) {
+        const int ci = cidx[i];
+        if (clen[ci] - 1 < 2) continue;
+        pch_off[hoff + pn] = coff[ci]; pch_len[hoff + pn] = clen[ci]; ++pn;
+    }
+    pch_n[r] = pn;
+    (void)ragged_ok;
+}

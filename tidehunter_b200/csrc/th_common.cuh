@@ -1,0 +1,58 @@
+// th_common.cuh -- shared device helpers for the TideHunter hot-path kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define TH_WARP 32
+#define TH_FULL 0xffffffffu
+
+// error codes reported per read / per task
+enum { TH_OK = 0, TH_ERR_ARENA = 1, TH_ERR_BAND = 2, TH_ERR_BACKTRACK = 3, TH_ERR_CAP = 4, TH_ERR_LEN = 5 };
+
+struct DevParams {
+    int k, w, hpc, min_copy;
+    uint32_t min_p, max_p;
+    double max_div;
+    int match, mismatch, o1, e1, o2, e2;
+    int pn;          // int16 lanes of the emulated abPOA vector (16)
+    int only_unit;
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ---------------------------------------------------------------------------------------------
+// Block-wide bitonic sort of n (power of two) 64-bit keys; `a` may live in shared or global memory.
+// Every key is distinct in all our uses (position / index in the low bits), so the result is the
+// unique sorted order and any correct sort is bit-exact with the reference's radix sort
+// (src/ksort.h:101-151) and its stable qsort (src/tandem_chain.c:21-43).
+// ---------------------------------------------------------------------------------------------
+template <bool DESC>
+__device__ void block_bitonic_sort(uint64_t *a, int n) {
+    const int half = n >> 1;
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int p = threadIdx.x; p < half; p += blockDim.x) {
+                int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                int x = i | j;
+                bool up = ((i & k) == 0) != DESC;
+                uint64_t ai = a[i], ax = a[x];
+                if ((ai > ax) == up) { a[i] = ax; a[x] = ai; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed signed 16x2 helpers (DPX / video SIMD; all map to single SASS ops on sm_100a)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pk(int lo, int hi) { return ((uint32_t)(uint16_t)lo) | ((uint32_t)(uint16_t)hi << 16); }
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xffff); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16); }

@@ -1,0 +1,141 @@
+// th_ksw.cuh -- warp-systolic affine-gap alignment with ksw2's exact tie-breaking, no traceback matrix.
+//
+// Replaces ksw_extz2_sse (ksw2/ksw2_extz2_sse.c:23-304) + ksw_backtrack (ksw2/ksw2.h:119-151) as used
+// through src/ksw2_align.c:62-173: scoring +1/-2, N = -1, gap 2+1*g, full matrix (w = -1, zdrop = -1).
+//
+// One warp per alignment.  Lane l owns C consecutive query columns of a 32*C-column block and walks
+// down the target rows one step behind lane l-1 (systolic wavefront); H/F of the block's last column
+// are handed to the next lane by shuffle, and to the next column block through a per-warp boundary
+// array in global memory (16 B per target row), so memory is O(tlen) for any size.
+//
+// Instead of storing ksw2's 5-bit direction matrix and walking it backwards, every DP state carries
+// the value its traceback would produce ("payload"): the traceback parent of each (cell, state) is a
+// pure function of the cell's own scores (diag unless E > diag, then F unless F > max; E/F continue
+// iff strictly better than re-opening), so quantities that are sums along the traced path can be
+// pushed forward with the scores.  Payloads:
+//   iden  : number of M columns with equal codes (ksw2_get_xid, src/ksw2_align.c:62-86)
+//   istop : target bases consumed when the path has consumed X = qlen - q_left_ext query bases, i.e.
+//           tlen - ksw2_backtrack_left_end(...) (src/ksw2_align.c:88-115)
+// Extension mode keeps no payload but reproduces the reference's arg-max visiting order
+// (anti-diagonal by anti-diagonal, last cell first, four interleaved lanes, tail; ksw2_extz2_sse.c:224-261).
+#pragma once
+#include "th_common.cuh"
+
+#define KSW_Q 2
+#define KSW_E 1
+enum { KSW_GLOBAL = 0, KSW_GLOBAL_STOP = 1, KSW_EXT = 2 };
+
+// rank of target index t inside anti-diagonal r (lower = visited earlier by the reference)
+__device__ __forceinline__ long long ksw_diag_rank(int t, int r, int ql, int tl) {
+    int st0 = r - ql + 1 > 0 ? r - ql + 1 : 0, en0 = r < tl - 1 ? r : tl - 1;
+    if (t == en0) return 0;
+    int en1 = st0 + (en0 - st0) / 4 * 4;
+    if (t < en1) return 1 + (long long)((t - st0) & 3) * 0x40000000ll + (t - st0) / 4;
+    return 1 + 4 * 0x40000000ll + (t - en1);
+}
+__device__ __forceinline__ bool ksw_ext_better(int z1, int i1, int j1, int z2, int i2, int j2, int ql, int tl) {
+    if (z1 != z2) return z1 > z2;
+    if (i2 < 0) return true;
+    int r1 = i1 + j1, r2 = i2 + j2;
+    if (r1 != r2) return r1 < r2;
+    return ksw_diag_rank(i1, r1, ql, tl) < ksw_diag_rank(i2, r2, ql, tl);
+}
+
+// bnd: 2*tl int4 entries of per-warp scratch.  Results: GLOBAL -> out0 = iden; GLOBAL_STOP -> out0 =
+// iden, out1 = t_left_ext; EXT -> out0 = max_q, out1 = max_t.  All lanes must call; all get the result.
+template <int MODE, int C>
+__device__ void ksw_warp(const uint8_t *q, int ql, const uint8_t *t, int tl, int X,
+                         int4 *bnd, int &out0, int &out1) {
+    const int lane = lane_id();
+    out0 = MODE == KSW_EXT ? -1 : 0; out1 = MODE == KSW_EXT ? -1 : 0;
+    if (ql <= 0 || tl <= 0) return;
+    const int BW = 32 * C;
+    const int nblk = (ql + BW - 1) / BW;
+    int bestz = 0, besti = -1, bestj = -1;
+    int resz = 0, resp = 0;
+    for (int b = 0; b < nblk; ++b) {
+        const int jb = b * BW;
+        const int bw = min(ql - jb, BW), nl = (bw + C - 1) / C;
+        const int j0 = jb + lane * C;
+        const int4 *bin = bnd + (size_t)(b & 1) * tl;
+        int4 *bout = bnd + (size_t)((b + 1) & 1) * tl;
+        int Hp[C], Ea[C], pH[C], pE[C], qb[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = j0 + c;
+            Hp[c] = -(KSW_Q + KSW_E * (j + 1));
+            Ea[c] = Hp[c] - KSW_Q - KSW_E;
+            pH[c] = 0; pE[c] = 0;
+            qb[c] = j < ql ? q[j] : 6; // sentinel: columns past the query end only produce dead values
+        }
+        int hdiag = j0 == 0 ? 0 : -(KSW_Q + KSW_E * j0), phdiag = 0;
+        int oH = 0, oF = 0, oPH = 0, oPF = 0;
+        const int nstep = tl + nl - 1;
+        for (int s = 0; s < nstep; ++s) {
+            const int i = s - lane;
+            int iH = __shfl_up_sync(TH_FULL, oH, 1), iF = __shfl_up_sync(TH_FULL, oF, 1);
+            int iPH = 0, iPF = 0;
+            if (MODE != KSW_EXT) { iPH = __shfl_up_sync(TH_FULL, oPH, 1); iPF = __shfl_up_sync(TH_FULL, oPF, 1); }
+            if (lane == 0) {
+                if (b == 0) { iH = -(KSW_Q + KSW_E * (s + 1)); iF = iH - KSW_Q - KSW_E; iPH = 0; iPF = 0; }
+                else if (s < tl) { int4 v = bin[s]; iH = v.x; iF = v.y; iPH = v.z; iPF = v.w; }
+            }
+            if (i >= 0 && i < tl && lane < nl) {
+                const int tb = t[i];
+                int hd = hdiag, phd = phdiag, F = iF, pF = iPF;
+                hdiag = iH; phdiag = iPH;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int eq = tb == qb[c];
+                    const int sc = ((tb | qb[c]) & 4) ? -KSW_E : (eq ? 1 : -2);
+                    int z = hd + sc, pz = 0;
+                    const int e = Ea[c];
+                    if (MODE != KSW_EXT) {
+                        pz = phd + eq;
+                        if (MODE == KSW_GLOBAL_STOP && j0 + c == X) pz = (pz & 0xffff) | (i << 16);
+                        if (e > z) pz = pE[c];
+                    }
+                    z = max(z, e);
+                    if (MODE != KSW_EXT) { if (F > z) pz = pF; }
+                    z = max(z, F);
+                    const int t1 = z - KSW_Q;
+                    if (MODE != KSW_EXT) {
+                        pE[c] = e > t1 ? pE[c] : pz;
+                        pF = F > t1 ? pF : pz;
+                        if (MODE == KSW_GLOBAL_STOP && j0 + c + 1 == X) pF = (pF & 0xffff) | ((i + 1) << 16);
+                    }
+                    Ea[c] = max(e, t1) - KSW_E;
+                    F = max(F, t1) - KSW_E;
+                    hd = Hp[c]; phd = pH[c];
+                    Hp[c] = z; pH[c] = pz;
+                    if (MODE == KSW_EXT) {
+                        if (z >= bestz && z > 0 && j0 + c < ql) {
+                            if (ksw_ext_better(z, i, j0 + c, bestz, besti, bestj, ql, tl)) { bestz = z; besti = i; bestj = j0 + c; }
+                        }
+                    }
+                }
+                oH = Hp[C - 1]; oF = F; oPH = pH[C - 1]; oPF = pF;
+                if (lane == nl - 1 && b + 1 < nblk) bout[i] = make_int4(oH, oF, oPH, oPF);
+            }
+        }
+        if (b == nblk - 1 && MODE != KSW_EXT) { // cell (tl-1, ql-1) lives in lane nl-1, column (ql-1-jb) % C
+            const int cc = (ql - 1 - jb) - (nl - 1) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) if (c == cc) { resz = Hp[c]; resp = pH[c]; }
+            resz = __shfl_sync(TH_FULL, resz, nl - 1); resp = __shfl_sync(TH_FULL, resp, nl - 1);
+        }
+        __syncwarp();
+    }
+    if (MODE == KSW_EXT) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            int oz = __shfl_xor_sync(TH_FULL, bestz, d), oi = __shfl_xor_sync(TH_FULL, besti, d), oj = __shfl_xor_sync(TH_FULL, bestj, d);
+            if (oi >= 0 && (besti < 0 || ksw_ext_better(oz, oi, oj, bestz, besti, bestj, ql, tl))) { bestz = oz; besti = oi; bestj = oj; }
+        }
+        out0 = bestj; out1 = besti;
+    } else {
+        (void)resz;
+        out0 = MODE == KSW_GLOBAL_STOP ? (resp & 0xffff) : resp;
+        if (MODE == KSW_GLOBAL_STOP) out1 = tl - (int)((unsigned)resp >> 16);
+    }
+}

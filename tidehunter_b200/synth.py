@@ -1,0 +1,70 @@
+"""Seeded synthetic tandem-repeat read generator for the BASELINE.json workloads.
+
+Each read = 50 bp random flank + `copies` copies of a uniform-random unit (rotated by a random
+offset) + 50 bp random flank, passed through a per-base error channel: with probability `err` a
+template base is hit by an error, split 40 % substitution / 30 % insertion (a uniform base is
+inserted before the template base) / 30 % deletion.  The PRNG is numpy's counter-based Philox keyed by
+(seed, shape id), so every rank / test regenerates the same reads without sharing state.
+
+Shapes (BASELINE.json `configs`):
+  r2c2   : unit 1000, 10 copies, err 0.15            (config 2, the bench workload)
+  short  : unit U{50..200}, copies U{20..50}, err 0.10  (config 3)
+  long   : unit U{4000..5000}, copies U{2..4}, err 0.20  (config 4)
+"""
+import numpy as np
+
+SEED = 20260117
+SHAPES = {
+    "r2c2": dict(unit=(1000, 1000), copies=(10, 10), err=0.15, sid=0),
+    "short": dict(unit=(50, 200), copies=(20, 50), err=0.10, sid=1),
+    "long": dict(unit=(4000, 5000), copies=(2, 4), err=0.20, sid=2),
+}
+FLANK = 50
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def gen_reads(shape, n, start=0, seed=SEED, adapters=None):
+    """Return (names, seqs): `n` reads of `shape`, read indices start..start+n-1.
+
+    Read i depends only on (seed, shape, i).  `adapters` = (five, three) splices
+    five + unit + revcomp(three)-style R2C2 structure: the unit itself becomes
+    three_rc... kept simple: unit' = five + unit + three (both as given), so -5/-3 searches succeed.
+    """
+    cfg = SHAPES[shape]
+    names, seqs = [], []
+    for i in range(start, start + n):
+        rng = np.random.Generator(np.random.Philox(key=[seed + cfg["sid"], i]))
+        ulen = int(rng.integers(cfg["unit"][0], cfg["unit"][1] + 1))
+        copies = int(rng.integers(cfg["copies"][0], cfg["copies"][1] + 1))
+        unit = rng.integers(0, 4, ulen, dtype=np.uint8)
+        if adapters is not None:
+            five, three = adapters
+            a5 = np.frombuffer(five.encode(), dtype=np.uint8)
+            a3 = np.frombuffer(three.encode(), dtype=np.uint8)
+            lut = np.zeros(256, dtype=np.uint8)
+            lut[ord("A")], lut[ord("C")], lut[ord("G")], lut[ord("T")] = 0, 1, 2, 3
+            unit = np.concatenate([lut[a5], unit, lut[a3]])
+            ulen = len(unit)
+        rot = int(rng.integers(0, ulen))
+        body = np.tile(unit, copies + 1)[rot:rot + ulen * copies]
+        tmpl = np.concatenate([rng.integers(0, 4, FLANK, dtype=np.uint8), body, rng.integers(0, 4, FLANK, dtype=np.uint8)])
+        u = rng.random(len(tmpl))
+        e = cfg["err"]
+        sub = u < 0.4 * e
+        ins = (u >= 0.4 * e) & (u < 0.7 * e)
+        dele = (u >= 0.7 * e) & (u < e)
+        rb = rng.integers(0, 4, len(tmpl), dtype=np.uint8)   # replacement / inserted bases
+        shift = rng.integers(1, 4, len(tmpl), dtype=np.uint8)
+        base = np.where(sub, (tmpl + shift) & 3, tmpl)
+        cnt = np.where(dele, 0, np.where(ins, 2, 1))
+        out = np.repeat(base, cnt)
+        # first emitted base of an insertion site is the random inserted base
+        pos = np.cumsum(cnt) - cnt
+        out[pos[ins]] = rb[ins]
+        seqs.append(_ACGT[out].tobytes())
+        names.append(("%s%d" % (shape[0], i)).encode())
+    return names, seqs
+
+
+def total_bases(seqs):
+    return int(sum(len(s) for s in seqs))
