@@ -31,7 +31,7 @@ def main():
         sets[tag] = (n, s)
     n, s = O.read_fastx(os.path.join(REF, "test.fq"))
     sets["testfq30"] = (n[:30], s[:30])
-    sets["testfq_all"] = (n, s)  # md5-only cases (inputs not stored)
+    sets["testfq_all"] = (n, s)  # all 100 reads are stored; testfq30 = their first 30 (derived by the tests)
     sets["syn_r2c2"] = synth.gen_reads("r2c2", 20)
     sets["syn_short"] = synth.gen_reads("short", 20)
     sets["syn_long"] = synth.gen_reads("long", 8)
@@ -63,7 +63,7 @@ def main():
 
     out = {"inputs": {}, "cases": [], "adapters": {"five": five, "three": three}}
     for tag, (n, s) in sets.items():
-        if tag.startswith("syn") or tag == "testfq_all":
+        if tag.startswith("syn") or tag == "testfq30":
             continue
         out["inputs"][tag] = {"names": [x.decode() for x in n], "seqs": [x.decode() for x in s]}
     with tempfile.TemporaryDirectory() as td:

@@ -1,0 +1,67 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, exports every symbol
+include/th_gpu.h declares, and fails loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(th_(?:gpu|host)_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_gpu_abi_exports_every_declared_symbol():
+    import tidehunter_b200 as T
+    g = T.gpu_lib()
+    names = _declared("include/th_gpu.h")
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(g, n), n
+
+
+def test_host_layer_exports_every_declared_symbol():
+    import tidehunter_b200 as T
+    h = T.host_lib()
+    for n in _declared("host/th_host.h"):
+        assert hasattr(h, n), n
+
+
+def test_abi_structs_match_header_sizes():
+    import tidehunter_b200 as T
+    # th_gpu_params: 4 x i32, f64, 2 x i64, 6 x i32, 3 x i32 -> 16 + 8 + 16 + 36 (+4 pad) = 80
+    assert C.sizeof(T.GpuParams) == 80
+    assert C.sizeof(T.GpuStats) == 10 * 4 + 10 * 8
+    p = T.GpuParams()
+    T.gpu_lib().th_gpu_default_params(C.byref(p))
+    assert (p.k, p.w, p.min_copy, p.min_p, p.max_p, p.simd_lanes16) == (8, 1, 2, 30, 10000, 16)
+    assert (p.match, p.mismatch, p.gap_open1, p.gap_ext1, p.gap_open2, p.gap_ext2) == (2, 4, 4, 2, 24, 1)
+    assert p.max_div == 0.25
+
+
+def test_no_cpu_fallback():
+    import tidehunter_b200 as T
+    g = T.gpu_lib()
+    if g.th_gpu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError):
+        T.GpuContext()
+    with pytest.raises(RuntimeError):
+        T.TideHunter()
+    assert b"CUDA" in g.th_gpu_last_error()
+
+
+def test_product_never_touches_the_oracle():
+    bad = []
+    for d in ("tidehunter_b200", "host", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, d)):
+            for f in fs:
+                if f.endswith((".py", ".c", ".h", ".cu", ".cuh")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"oracle_py|th_oracle|libth_oracle|oracle/", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad

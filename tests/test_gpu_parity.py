@@ -1,0 +1,173 @@
+"""GPU parity tests: every call goes through the C ABI (include/th_gpu.h) or the host layer above it
+and is compared, bit-exact, with the CPU oracle and with the golden outputs of the unmodified
+reference (tests/golden/golden.json.gz).  Integer work only => equality, no tolerances."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import tidehunter_b200 as T
+    if T.gpu_lib().th_gpu_device_count() <= 0:
+        pytest.fail("no CUDA device: the gpu tests must run on the B200 box")
+    return T
+
+
+def _stage_inputs(golden_inputs):
+    from tidehunter_b200 import synth
+    names, seqs = [], []
+    for tag in ("test_50x4", "test_1000x10", "testfq30"):
+        n, s = golden_inputs(tag)
+        names += n; seqs += s
+    for shape, cnt in (("r2c2", 12), ("short", 12), ("long", 4)):
+        n, s = synth.gen_reads(shape, cnt, start=100)
+        names += n; seqs += s
+    # edge cases: empty, shorter than k, all N, N runs inside a repeat, lower case, no repeat
+    unit = b"ACGGTCATTGCAGTCCGATAGCTTAGGCTAACGTTCAGGATCCATGA"
+    seqs += [b"", b"ACG", b"N" * 300, (unit + b"NNNN") * 8, (unit * 9).lower(), b"ACGTTGCAAGGCTTAACCGGTT"]
+    names += [b"e%d" % i for i in range(6)]
+    return names, seqs
+
+
+STAGE_PARAS = [dict(), dict(k=12, w=5), dict(hpc=1), dict(min_p=2, k=5), dict(k=16), dict(hpc=1, w=4)]
+
+
+@pytest.mark.parametrize("pk", range(len(STAGE_PARAS)))
+def test_stage_parity(T, oracle, golden_inputs, pk):
+    """hits, chain DP cells, chains and par_pos of every read, stage by stage."""
+    kw = STAGE_PARAS[pk]
+    names, seqs = _stage_inputs(golden_inputs)
+    para = oracle.default_para(**kw)
+    ctx = T.GpuContext(only_unit=1, **kw)
+    ctx.process(seqs)
+    bad = {"hits": [], "dp": [], "chains": [], "par": []}
+    for r, s in enumerate(seqs):
+        oh = H.hits(s, para)
+        n, ge, gp = ctx.hits(r, max(len(s), 1))
+        if n != len(oh) or list(zip(ge, gp)) != oh:
+            bad["hits"].append((r, n, len(oh)))
+            continue
+        if len(oh) < 2:
+            continue
+        oc = H.chain(oh, para)
+        n, gs, gf = ctx.chain_dp(r, len(oh))
+        if gs != oc.score or gf != oc.frm:
+            first = next(i for i in range(len(oh)) if gs[i] != oc.score[i] or gf[i] != oc.frm[i])
+            bad["dp"].append((r, first, gs[first], oc.score[first], gf[first], oc.frm[first]))
+            continue
+        gc = ctx.chains(r, len(oh) + 8)
+        if gc != oc.chains:
+            bad["chains"].append((r, len(gc), len(oc.chains)))
+            continue
+        for ci in range(len(oc.chains)):
+            op = H.partition(s, oc, ci, para)
+            gpp = ctx.par_pos(r, ci)
+            if gpp != op:
+                bad["par"].append((r, ci, gpp[:12] if gpp else gpp, op[:12]))
+        oracle.lib().tho_chain_free(oc.raw)
+    ctx.close()
+    assert not any(bad.values()), {k: v[:5] for k, v in bad.items() if v}
+
+
+def test_ksw_global_and_extension(T, oracle):
+    rng = np.random.default_rng(7)
+    pairs = (H.random_pairs(rng, 60, 1, 40) + H.random_pairs(rng, 60, 30, 300, with_n=True) +
+             H.random_pairs(rng, 12, 500, 1300) + H.random_pairs(rng, 3, 2500, 4200, div=0.2))
+    # low complexity / tandem pairs stress the tie-breaking
+    for _ in range(30):
+        u = rng.integers(0, 2, int(rng.integers(1, 5)), dtype=np.uint8)
+        a = np.tile(u, int(rng.integers(3, 40)))[: int(rng.integers(3, 120))]
+        b = np.tile(u, int(rng.integers(3, 40)))[: int(rng.integers(3, 120))]
+        pairs.append((a.tobytes(), b.tobytes()))
+    qs = [p[0] for p in pairs]; ts = [p[1] for p in pairs]
+    ctx = T.GpuContext()
+    g0 = ctx.ksw_batch(0, qs, ts)
+    exp0 = [H.ksw_global(q, t) for q, t in pairs]
+    bad = [(i, len(qs[i]), len(ts[i]), g0[i][0], exp0[i][0]) for i in range(len(pairs)) if g0[i][0] != exp0[i][0]]
+    assert not bad, ("global iden", bad[:8])
+    # boundary projection: ksw2_global_with_cigar + ksw2_backtrack_left_end for several q_left_ext each
+    q1, t1, a1, e1 = [], [], [], []
+    for i, (q, t) in enumerate(pairs):
+        for x in sorted({1, len(q) // 3, len(q) // 2, len(q) - 1, len(q)}):
+            if 0 < x <= len(q):
+                q1.append(q); t1.append(t); a1.append(x)
+                e1.append((exp0[i][0], H.ksw_left_end(exp0[i][1], len(q), len(t), x)))
+    g1 = ctx.ksw_batch(1, q1, t1, a1)
+    bad = [(i, len(q1[i]), len(t1[i]), a1[i], g1[i], e1[i]) for i in range(len(q1)) if tuple(g1[i]) != e1[i]]
+    assert not bad, ("left end", bad[:8])
+    g2 = ctx.ksw_batch(2, qs, ts)
+    e2 = [H.ksw_ext(q, t) for q, t in pairs]
+    bad = [(i, len(qs[i]), len(ts[i]), g2[i], e2[i]) for i in range(len(pairs)) if tuple(g2[i]) != e2[i]]
+    assert not bad, ("extension", bad[:8])
+    ctx.close()
+
+
+def _run_case(T, golden_inputs, c, **extra):
+    names, seqs = golden_inputs(c["input"])
+    th = T.TideHunter(**dict(c["para"], **extra))
+    out = th.run(names, seqs)
+    st = th.stats()
+    th.close()
+    return out, st
+
+
+def test_config1_golden(T, golden, golden_inputs):
+    """BASELINE config 1: test_data/test_1000x10.fa, default options, FASTA -- byte-identical."""
+    c = next(c for c in golden["cases"] if c["input"] == "test_1000x10" and c["args"] == ["-f", "1"])
+    out, st = _run_case(T, golden_inputs, c)
+    assert out.decode() == c["text"]
+    assert hashlib.md5(out).hexdigest() == "6518be7cff7c168de0e4c42465b3a6dd"
+    assert st["n_launches"] > 0 and st["n_poa_cells"] > 0 and st["n_ksw_cells"] > 0
+
+
+def test_all_golden_cases(T, golden, golden_inputs):
+    bad = []
+    for c in golden["cases"]:
+        out, _ = _run_case(T, golden_inputs, c)
+        if hashlib.md5(out).hexdigest() != c["md5"]:
+            exp = c.get("text", "")
+            got = out.decode()
+            gl, el = got.split("\n"), exp.split("\n")
+            first = next((i for i in range(min(len(gl), len(el))) if gl[i] != el[i]), min(len(gl), len(el)))
+            bad.append((c["input"], c["args"], len(gl), len(el), first, gl[first][:160] if first < len(gl) else None, el[first][:160] if first < len(el) else None))
+    assert not bad, bad[:6]
+
+
+def test_chunking_does_not_change_output(T, golden, golden_inputs):
+    c = next(c for c in golden["cases"] if c["input"] == "testfq_all" and c["args"] == ["-f", "4"])
+    out, _ = _run_case(T, golden_inputs, c, chunk_reads=7)
+    assert hashlib.md5(out).hexdigest() == c["md5"]
+
+
+@pytest.mark.parametrize("shape,n", [("r2c2", 96), ("short", 128), ("long", 24)])
+def test_synthetic_vs_oracle(T, oracle, shape, n):
+    from tidehunter_b200 import synth
+    names, seqs = synth.gen_reads(shape, n, start=1000)
+    exp, cnt = oracle.run_batch(names, seqs, oracle.default_para(out_fmt=2), threads=8)
+    th = T.TideHunter(out_fmt=2)
+    out = th.run(names, seqs)
+    st = th.stats()
+    th.close()
+    if out != exp:
+        gl, el = out.decode().split("\n"), exp.decode().split("\n")
+        diff = [(i, gl[i][:150], el[i][:150]) for i in range(min(len(gl), len(el))) if gl[i] != el[i]]
+        pytest.fail("%d/%d lines differ (%d vs %d lines); first: %r" % (len(diff), len(el), len(gl), len(el), diff[:2]))
+    # the GPU's work counters are the roofline numerators: they must equal the oracle's
+    assert st["n_hits"] == cnt["hits"]
+    assert st["n_chain_evals"] == cnt["chain_evals"]
+    assert st["n_poa_cells"] == cnt["poa_cells"]
+
+
+def test_edge_reads(T, oracle):
+    names = [b"e", b"s", b"n", b"u"]
+    seqs = [b"", b"ACGT", b"N" * 500, b"ACGTTGCA" * 4 + b"GATTACAGATTACCA"]
+    th = T.TideHunter()
+    assert th.run(names, seqs) == oracle.run_batch(names, seqs, oracle.default_para())[0]
+    assert th.run([], []) == b""
+    th.close()

@@ -372,12 +372,17 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         for (const PoaTask &T : tasks) {
             if (T.n_seqs <= 2) continue;
             const size_t fixed = poa_fixed_bytes(T.ncap, T.qmax, T.n_seqs);
+            // DP arena of ONE alignment (it is recycled for every unit): rows <= nodes, 5 int16 states per banded cell.
+            // typical: the graph holds <= ~2.5 units worth of nodes and the adaptive band covers ~60 % of the unit
             const int wband = 10 + T.qmax / 100;
-            const size_t typ = std::max<size_t>((size_t)T.ncap * (2 * wband + 128) * 5, (size_t)1 << 20);
+            const size_t rows_typ = std::min<size_t>((size_t)T.ncap, (size_t)T.qmax * 5 / 2 + 64);
+            const size_t width_typ = std::min<size_t>((size_t)T.qmax + 64, (size_t)T.qmax * 3 / 5 + 2 * wband + 64);
+            const size_t typ = std::max<size_t>(rows_typ * width_typ * 10, (size_t)1 << 20);
             const size_t full = (size_t)T.ncap * ((size_t)T.qmax + 64) * 10;
             slab_typ = std::max(slab_typ, fixed + std::min(typ, full) + 4096);
             slab_full = std::max(slab_full, fixed + full + 4096);
         }
+        slab_typ = (slab_typ + 255) & ~(size_t)255; slab_full = (slab_full + 255) & ~(size_t)255; // slabs hold 32-bit and 16x2 accesses
         if (c->d_tasks.ensure(sizeof(PoaTask) * (size_t)nt) || c->d_torder.ensure(4 * (size_t)nt) || c->d_ustart.ensure(4 * ustart.size() + 64) ||
             c->d_ulen.ensure(4 * ulen.size() + 64) || c->d_consb.ensure((size_t)cons_total + 64) || c->d_consc.ensure(4 * (size_t)cons_total + 64) ||
             c->d_consl.ensure(4 * (size_t)nt) || c->d_tstatus.ensure(4 * (size_t)nt)) return -1;

@@ -46,8 +46,9 @@ partition_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, con
             const int p0 = used; int pn_ = 0; bool overflow = false;
 #define PUSH(v) do { if (used < cap) { if (lane == 0) out[used] = (v); ++used; ++pn_; } else overflow = true; } while (0)
             PUSH(est_start); PUSH(est_start + est_period);
-            int ch_i = 0, s = est_start, e = est_start + est_period;
+            int ch_i = 0, s = est_start, e = est_start + est_period, guard = 0;
             while (ch_i < len - 1 && e <= last_start && !overflow) {
+                if (++guard > 4 * L + 64) { overflow = true; break; } // the reference would spin; never seen, but never hang the GPU
                 int s1 = s, e1 = e, i; bool brk = false;
                 for (i = ch_i + 1; i < len; ++i) {
                     const int e2 = en[cc[i]], s2 = e2 - pr[cc[i]];

@@ -494,7 +494,7 @@ __device__ int poa_consensus(PoaWs &w, int node_n, int n_seq, uint8_t *cons, int
     }
     max_out[last_id] = 1;
     int id = max_out[0], l = 0;
-    while (id != 1) { cons[l++] = w.base[id]; id = max_out[id]; }
+    while (id != 1 && l <= node_n) { cons[l++] = w.base[id]; id = max_out[id]; }
     return l;
 }
 

@@ -1,0 +1,34 @@
+"""Read-batch sharding across ranks and the host-side ordered gather.
+
+Reads are independent (the reference's only parallelism is a thread pool over reads, src/main.c:273-291),
+so rank r of W processes the contiguous block shard_range(n, r, W) of every batch on its own GPU and
+there is no data-path collective.  Output order = input order: rank 0 concatenates the ranks' output
+texts in rank order, exactly what mini_tandem_output (src/main.c:214-271) prints for the whole batch.
+The gather runs over a gloo (host) group; NCCL / NVLink are not on the data path.
+"""
+
+
+def shard_range(n, rank, world):
+    """Contiguous, balanced block of [0, n) for `rank`; blocks of consecutive ranks tile [0, n) in order."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def ordered_gather(payload, rank, world, group=None, dst=0):
+    """Gather one bytes payload per rank on `dst`, in rank order.  Returns the list on dst, None elsewhere."""
+    if world == 1:
+        return [payload]
+    import torch.distributed as dist
+    out = [None] * world if rank == dst else None
+    dist.gather_object(payload, out, dst=dst, group=group)
+    return out
+
+
+def run_sharded(th, names, seqs, rank, world, group=None):
+    """Process this rank's block of (names, seqs) with `th` (a tidehunter_b200.TideHunter) and gather the
+    text on rank 0 in input order.  Returns bytes on rank 0, None elsewhere."""
+    lo, hi = shard_range(len(seqs), rank, world)
+    text = th.run(names[lo:hi], seqs[lo:hi])
+    parts = ordered_gather(text, rank, world, group)
+    return b"".join(parts) if parts is not None else None
