@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the TideHunter per-read hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): synthetic ONT R2C2-style reads, 10 kb, 1 kb unit x 10 copies, 15 %
+error, default options (-k 8 -w 1 -p 30 -P 10000 -c 2 -e 0.25, -f 1).  A step = one pass of the whole hot
+path (pack, seeding, chaining, partition, POA consensus, ksw2 identity/extension) over one batch of
+`--reads` reads PER GPU (weak scaling; reads are independent, no data-path collective).
+
+  value : reads/s over all ranks, reads already resident in HBM (th_gpu_upload before the timed
+          region, th_gpu_process_resident per step); host-clock time between synchronised barriers, max
+          over ranks.
+  e2e   : the same metric through the user-facing call (host layer th_host_run over the C ABI) with
+          HOST buffers: pinned staging + H2D, all kernels, D2H of the results, record formatting, and
+          the host-side ordered gather of the output text on rank 0.
+  roofline / kernels : per-stage device time from CUDA events recorded on the library's own stream
+          (th_gpu_stats), algorithmic work counters from the kernels themselves.
+  cpu_baseline : the unmodified reference (oracle/_ref/TideHunter, -t <all cores>) on a bounded
+          sample of the same reads (rank 0, N = 1 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "synthetic ONT R2C2-style reads: 10 kb, 1 kb unit x 10 copies, 15% error (BASELINE.json configs[1])"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(p.get("sm_max_mhz", 1965.0))
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU implementation on the host cores
+# ---------------------------------------------------------------------------------------------------
+def _ref_runner():
+    """Returns (kind, fn(names, seqs, threads) -> seconds).  'reference' = unmodified TideHunter binary
+    built by oracle/Makefile into oracle/_ref/; 'port' = the oracle's C restatement (only if that binary
+    is missing)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    if os.path.exists(O.REF_BIN):
+        def run(names, seqs, threads):
+            with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+                path = os.path.join(td, "sample.fa")
+                O.write_fasta(path, names, seqs)
+                t0 = time.perf_counter()
+                subprocess.run([O.REF_BIN, "-t", str(threads), "-f", "1", path], stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL, check=True)
+                return time.perf_counter() - t0
+        return "reference", run
+
+    def run_port(names, seqs, threads):
+        t0 = time.perf_counter()
+        O.run_batch(names, seqs, O.default_para(out_fmt=1), threads=threads)
+        return time.perf_counter() - t0
+    return "port", run_port
+
+
+def cpu_sample_size(run, threads, target_s):
+    """Calibrate on a few reads, then size the sample for ~target_s seconds of wall time."""
+    from tidehunter_b200 import synth
+    n0 = max(4 * threads, 32)
+    names, seqs = synth.gen_reads("r2c2", n0, start=900000)
+    rate = n0 / max(run(names, seqs, threads), 1e-3)
+    n1 = int(min(max(rate * 1.5, n0), 4096))          # second pass long enough to amortise start-up
+    names, seqs = synth.gen_reads("r2c2", n1, start=900000)
+    rate = n1 / max(run(names, seqs, threads), 1e-3)
+    return int(min(max(rate * target_s, 2 * threads), 16384))
+
+
+def reference_arm(args):
+    """bench.py --impl reference: the reference's own CPU implementation, all host threads, same
+    workload / metric / unit; each step is a bounded sample of the batch."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from tidehunter_b200 import synth
+    cores = os.cpu_count() or 1
+    kind, run = _ref_runner()
+    n = cpu_sample_size(run, cores, 4.0)
+    names, seqs = synth.gen_reads("r2c2", n, start=0)
+    bases = synth.total_bases(seqs)
+    for _ in range(args.warmup):
+        run(names[: max(n // 4, 1)], seqs[: max(n // 4, 1)], cores)
+    times = [run(names, seqs, cores) for _ in range(args.steps)]
+    tot = sum(times)
+    value = n * args.steps / tot
+    line = {
+        "impl": "reference", "metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int16/int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reads_per_step": n, "bases_per_step": bases, "options": "defaults, -f 1"},
+        "gbp_per_s": bases * args.steps / tot / 1e9,
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": kind,
+                         "sample": "%d reads (%d bases) per step, TideHunter -t %d" % (n, bases, cores)},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(5)
+            except Exception:
+                self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(pw)}
+
+
+STAGES = ("pack", "seed", "chain", "select", "partition", "poa", "ksw", "d2h")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=8192, help="reads per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import tidehunter_b200 as T
+    from tidehunter_b200 import synth
+    from tidehunter_b200.shard import ordered_gather
+    if not torch.cuda.is_available() or T.gpu_lib().th_gpu_device_count() <= 0:
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    gloo = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        gloo = dist.new_group(backend="gloo")  # host-side ordered gather only; no data-path collective
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=gloo)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # this rank's batch: read indices [rank*reads, (rank+1)*reads) of the seeded generator
+    n = args.reads
+    names, seqs = synth.gen_reads("r2c2", n, start=rank * n)
+    bases = synth.total_bases(seqs)
+
+    # ---------------- device-resident leg (value) ----------------
+    ctx = T.GpuContext(device=local)
+    ctx.upload(seqs)
+    for _ in range(args.warmup):
+        ctx.process_resident()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    acc = {k: 0.0 for k in STAGES + ("total",)}
+    cnt = {}
+    launches = 0
+    for _ in range(args.steps):
+        r = ctx.process_resident()
+        s = r.stats.as_dict()
+        for k in STAGES + ("total",):
+            acc[k] += s["ms_" + k]
+        launches += s["n_launches"]
+        cnt = s
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    dt = max_over_ranks(dt)
+    n_tasks = cnt["n_tasks"]
+    ctx.close()
+
+    # ---------------- end-to-end leg through the host layer (e2e) ----------------
+    th = T.TideHunter(device=local, out_fmt=1, chunk_reads=n)
+    for _ in range(2):
+        th.run(names, seqs)
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    out_bytes = 0
+    for _ in range(args.steps):
+        text = th.run(names, seqs)
+        parts = ordered_gather(text, rank, world, gloo)
+        if parts is not None:
+            out_bytes = sum(len(p) for p in parts)
+        s = th.stats()
+        h2d += s["h2d_bytes"]; d2h += s["d2h_bytes"]
+    barrier()
+    dt_e2e = max_over_ranks(time.perf_counter() - t0)
+    th.close()
+
+    tot_reads = sum_over_ranks(n) * args.steps
+    tot_bases = sum_over_ranks(bases) * args.steps
+    value = tot_reads / dt
+    e2e = tot_reads / dt_e2e
+
+    # ---------------- roofline for the dominant kernel + per-kernel table ----------------
+    hbm_peak, peak_src, sm_max = load_peaks()
+    per = {k: acc[k] / args.steps for k in STAGES}
+    work = {  # algorithmic units per step on this rank, counted by the kernels themselves
+        "pack": ("bases", cnt["n_bases"]), "seed": ("hits", cnt["n_hits"]), "chain": ("pair_evals", cnt["n_chain_evals"]),
+        "poa": ("cells", cnt["n_poa_cells"]), "ksw": ("cells", cnt["n_ksw_cells"]),
+    }
+    kernels = {}
+    tot_ms = sum(per.values())
+    for k in STAGES:
+        e = {"ms_per_step": round(per[k], 3), "share": round(per[k] / tot_ms, 4) if tot_ms > 0 else None}
+        if k in work and per[k] > 0:
+            e["unit"] = work[k][0]
+            e["g_units_per_s"] = round(work[k][1] / (per[k] * 1e-3) / 1e9, 3)
+        kernels[k] = e
+    dom = max(("poa", "ksw", "chain", "seed", "pack"), key=lambda k: per[k])
+    # algorithmic HBM bytes per unit (DESIGN.md section "kernels"): POA stores 5 int16 states per banded cell and
+    # re-reads them once as a predecessor row (20 B/cell); ksw keeps rows in registers (boundary hand-off only:
+    # 16 B per target row per 512-column block, ~0.03 B/cell); chain reads 12 B per evaluated predecessor (L1/L2 hits);
+    # seeding reads L/4 + L/8 bytes and writes 8 B per hit.
+    bytes_per_unit = {"poa": 20.0, "ksw": 16.0 / 512, "chain": 12.0, "seed": None, "pack": 1.0 + 1.0 + 0.25 + 0.125}
+    if dom == "seed":
+        alg_bytes = cnt["n_bases"] * (0.25 + 0.125) + 8.0 * cnt["n_hits"]
+    else:
+        alg_bytes = work[dom][1] * bytes_per_unit[dom]
+    achieved = alg_bytes / (per[dom] * 1e-3) / 1e9 if per[dom] > 0 else 0.0
+    roofline = {"kernel": {"poa": "poa_kernel", "ksw": "ksw_items_kernel", "chain": "chain_dp_kernel", "seed": "seed_kernel", "pack": "pack_kernel"}[dom],
+                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per[dom],
+                "note": "integer DP kernel: see `kernels` for cell-update rates (GCUPS); the HBM fraction shows it is not bandwidth-bound"}
+
+    line = {
+        "metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16/int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reads_per_gpu_per_step": n, "bases_per_gpu_per_step": bases, "options": "defaults, -f 1",
+                   "l2": "per-step working set (reads + DP arenas, > 1 GB) exceeds the 126 MB L2", "parallelism": "read-sharded x%d, no collective" % world},
+        "gbp_per_s": tot_bases / dt / 1e9,
+        "poa_gcups": kernels["poa"].get("g_units_per_s"), "ksw_gcups": kernels["ksw"].get("g_units_per_s"),
+        "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
+                "ms_per_step": 1e3 * dt_e2e / args.steps, "output_bytes_per_step": out_bytes, "gbp_per_s": tot_bases / dt_e2e / 1e9},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "device_ms_per_step": round(acc["total"] / args.steps, 3), "poa_tasks_per_step": n_tasks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        kind, run = _ref_runner()
+        cores = os.cpu_count() or 1
+        ns = cpu_sample_size(run, cores, 15.0)
+        ns = min(ns, n)
+        t = run(names[:ns], seqs[:ns], cores)
+        line["cpu_baseline"] = {"value": ns / t, "unit": "reads/s", "cores": cores, "kind": kind,
+                                "sample": "first %d reads of the step's batch (%d bases), TideHunter -t %d -f 1, %.1f s" % (ns, synth.total_bases(seqs[:ns]), cores, t)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier(group=gloo)
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

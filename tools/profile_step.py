@@ -1,0 +1,19 @@
+"""One device-resident step of the hot path over N synthetic R2C2 reads: the command ncu wraps.
+usage: python tools/profile_step.py [n_reads] [steps] [shape]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import tidehunter_b200 as T
+from tidehunter_b200 import synth
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+shape = sys.argv[3] if len(sys.argv) > 3 else "r2c2"
+names, seqs = synth.gen_reads(shape, n)
+ctx = T.GpuContext()
+ctx.upload(seqs)
+for _ in range(steps):
+    r = ctx.process_resident()
+print({k: v for k, v in r.stats.as_dict().items()})
+ctx.close()
