@@ -91,6 +91,10 @@ int th_gpu_debug_chain_dp(th_gpu_ctx *ctx, int32_t read, int32_t cap, int32_t *s
 int th_gpu_debug_chains(th_gpu_ctx *ctx, int32_t read, int32_t cap, int32_t *n_chain, int32_t *chain_len, int32_t *cells); /* returns total cells */
 int th_gpu_debug_par_pos(th_gpu_ctx *ctx, int32_t read, int32_t chain, int32_t cap, int32_t *par_pos);  /* returns par_n */
 
+/* Raw device work / cycle counters of the last chunk (profiling aid): [0] chain evals, [1] POA cells, [2] POA rows,
+ * [3] ksw cells, [16..22] POA warp-cycles per phase (setup, rows, backtrack, merge, reorder, consensus, total). */
+int th_gpu_debug_counters(th_gpu_ctx *ctx, int32_t cap, int64_t *out);                                   /* returns entries written */
+
 /* Stand-alone ksw2-style alignments on nt4-coded HOST sequences (tests of the alignment kernels).
  * mode 0: global -> out[0] = iden_n;  mode 1: global + left-end projection with q_left_ext = arg ->
  * out[0] = iden_n, out[1] = t_left_ext;  mode 2: extension -> out[0] = max_q, out[1] = max_t. */

@@ -78,6 +78,7 @@ def _load():
         g.th_gpu_debug_par_pos.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
         g.th_gpu_ksw_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        g.th_gpu_debug_counters.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]
         g.th_gpu_last_error.restype = C.c_char_p
         g.th_gpu_device_count.restype = C.c_int
         h.th_host_default_para.argtypes = [C.POINTER(HostPara)]
@@ -225,6 +226,13 @@ class GpuContext:
         a = (C.c_int32 * cap)()
         n = gpu_lib().th_gpu_debug_par_pos(self._c, read, chain, cap, a)
         return None if n < 0 else list(a[:n])
+
+    def counters(self):
+        a = (C.c_int64 * 32)()
+        n = gpu_lib().th_gpu_debug_counters(self._c, 32, a)
+        if n < 0:
+            raise RuntimeError(self._err())
+        return list(a[:n])
 
     def ksw_batch(self, mode, qs, ts, args=None):
         n = len(qs)

@@ -36,8 +36,9 @@ def _run(cmd):
 def build(force=False, verbose=False):
     cu_src = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "th_gpu.h")]
     if force or _newer(GPU_SO, cu_src):
+        extra = os.environ.get("TH_NVCC_FLAGS", "").split()   # tuning experiments only (e.g. -DPOA_MIN_BLOCKS=6)
         out = _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-                    "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-o", GPU_SO, os.path.join(CSRC, "th_api.cu")])
+                    "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"] + extra + ["-o", GPU_SO, os.path.join(CSRC, "th_api.cu")])
         if verbose:
             print(out)
     host_src = [os.path.join(HOST, "th_host.c"), os.path.join(HOST, "th_host.h"), os.path.join(ROOT, "include", "th_gpu.h"), GPU_SO]

@@ -373,10 +373,11 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
             if (T.n_seqs <= 2) continue;
             const size_t fixed = poa_fixed_bytes(T.ncap, T.qmax, T.n_seqs);
             // DP arena of ONE alignment (it is recycled for every unit): rows <= nodes, 5 int16 states per banded cell.
-            // typical: the graph holds <= ~2.5 units worth of nodes and the adaptive band covers ~60 % of the unit
+            // typical: the graph holds <= ~2.5 units worth of nodes; the adaptive band is 2w+1 columns around the
+            // predecessors' row maxima, rounded to whole vectors (measured mean ~61 columns on 1 kb units)
             const int wband = 10 + T.qmax / 100;
             const size_t rows_typ = std::min<size_t>((size_t)T.ncap, (size_t)T.qmax * 5 / 2 + 64);
-            const size_t width_typ = std::min<size_t>((size_t)T.qmax + 64, (size_t)T.qmax * 3 / 5 + 2 * wband + 64);
+            const size_t width_typ = std::min<size_t>((size_t)T.qmax + 64, (size_t)2 * wband + 256);
             const size_t typ = std::max<size_t>(rows_typ * width_typ * 10, (size_t)1 << 20);
             const size_t full = (size_t)T.ncap * ((size_t)T.qmax + 64) * 10;
             slab_typ = std::max(slab_typ, fixed + std::min(typ, full) + 4096);
@@ -395,13 +396,13 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         size_t free_b = 0, total_b = 0; CK(cudaMemGetInfo(&free_b, &total_b));
         if (slab_typ == 0) slab_typ = 1 << 20;
         size_t budget = (size_t)((double)(free_b + c->d_slabs.cap) * 0.6);
-        int nwarps = (int)std::min<size_t>((size_t)c->n_sm * 16, std::max<size_t>(1, budget / slab_typ));
+        int nwarps = (int)std::min<size_t>((size_t)c->n_sm * POA_MIN_BLOCKS * POA_WARPS, std::max<size_t>(1, budget / slab_typ));
         nwarps = std::min(nwarps, std::max(nt, 1));
         int grid = (nwarps + POA_WARPS - 1) / POA_WARPS;
         if (c->d_slabs.ensure((size_t)grid * POA_WARPS * slab_typ)) return -1;
         poa_kernel<<<grid, POA_WARPS * 32, 0, st>>>(P, nt, c->d_tasks.as<PoaTask>(), c->d_torder.as<int32_t>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(),
                                                  c->d_bseq.as<uint8_t>(), c->d_slabs.as<uint8_t>(), slab_typ, cnt32 + 1, c->d_consb.as<uint8_t>(), c->d_consc.as<int32_t>(),
-                                                 c->d_consl.as<int32_t>(), c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2);
+                                                 c->d_consl.as<int32_t>(), c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2, cnt64 + 16);
         S.n_launches++;
         CK(cudaMemcpyAsync(c->r_task_status.data(), c->d_tstatus.p, 4 * (size_t)nt, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -418,7 +419,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
             CK(cudaMemsetAsync(cnt32 + 1, 0, 4, st));
             poa_kernel<<<rgrid, POA_WARPS * 32, 0, st>>>(P, (int)retry.size(), c->d_tasks.as<PoaTask>(), c->d_torder.as<int32_t>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(),
                                                       c->d_bseq.as<uint8_t>(), c->d_slabs.as<uint8_t>(), slab_full, cnt32 + 1, c->d_consb.as<uint8_t>(), c->d_consc.as<int32_t>(),
-                                                      c->d_consl.as<int32_t>(), c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2);
+                                                      c->d_consl.as<int32_t>(), c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2, cnt64 + 16);
             S.n_launches++;
         }
         CK(cudaEventRecord(c->ev[ei++], st)); // 9
@@ -506,6 +507,15 @@ extern "C" int th_gpu_process_chunk(th_gpu_ctx *c, int32_t n_reads, const char *
 }
 
 // ---- stage probes -----------------------------------------------------------------------------
+extern "C" int th_gpu_debug_counters(th_gpu_ctx *c, int32_t cap, int64_t *out) {
+    CK(cudaSetDevice(c->device));
+    if (!c->d_counters.p) { set_err("no chunk processed yet"); return -1; }
+    int64_t h[32];
+    CK(cudaMemcpy(h, c->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const int m = std::min(cap, 32);
+    for (int i = 0; i < m; ++i) out[i] = h[i];
+    return m;
+}
 extern "C" int th_gpu_debug_hits(th_gpu_ctx *c, int32_t read, int32_t cap, int32_t *end, int32_t *period) {
     CK(cudaSetDevice(c->device));
     if (read < 0 || read >= c->n_reads) { set_err("read out of range"); return -1; }

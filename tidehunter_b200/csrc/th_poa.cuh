@@ -38,44 +38,51 @@ struct PoaTask {
 #define POA_WARPS 4
 #define POA_MAXPRE 32
 #define POA_NEGP 0x80008000u
+#define POA_RING 64       // rows of metadata kept in shared memory per warp (power of two)
 
+// Row descriptor (static per alignment, by row index):  x = first predecessor row (-1: none),
+//   y = np | base << 10 | node << 13,  z = qlen - max_remain term of the band centre,
+//   w = second predecessor row (np == 2) or offset into plist (np > 2).
+// Row metadata (written when the row is computed):  x = arena offset, y = first column, z = last column,
+//   w = max_i + 1 of the row (what the reference scatters into max_pos_left/right of the successors).
 struct PoaWs {
-    int32_t *out_head, *out_tail, *in_head, *in_tail, *aln_n, *aln, *n2i, *remain, *mpl, *mpr, *hs;
-    int32_t *e_to, *e_from, *e_w, *e_no, *e_ni;
+    int4 *rdesc, *rmeta;
+    int32_t *out_head, *out_tail, *in_head, *in_tail, *aln_n, *aln, *n2i, *ri, *hs;
+    int32_t *e_to, *e_from, *e_w, *e_no, *e_ni, *plist;
     int32_t *ord, *ord2, *ev_anchor, *ev_node, *hi_idx;
-    uint32_t *row_off; int32_t *row_bsn, *row_esn;
-    int16_t *qp; uint32_t *cigar; uint8_t *base;
+    int16_t *qp; uint32_t *cigar; int32_t *cigq; uint8_t *base;
     int16_t *arena; uint32_t arena_cap;
-    int32_t qp_stride;
+    int32_t qp_stride, ncap;
 };
 
 __host__ __device__ inline size_t poa_fixed_bytes(int ncap, int qmax, int nseq) {
     size_t ecap = (size_t)ncap + nseq + 2;
     size_t b = 0;
-    b += (size_t)ncap * 4 * (11 + 4 - 1 + 1);        // 11 node arrays (aln counts as 4) = 15 x int32... see carve
-    b += ecap * 4 * 5;
+    b += (size_t)ncap * 16 * 2;                        // rdesc, rmeta
+    b += (size_t)ncap * 4 * (9 + 3);                   // 9 node arrays (aln counts as 4) = 12 x int32
+    b += ecap * 4 * 6;                                 // 5 edge arrays + plist
     b += (size_t)ncap * 4 * 3;                         // ord, ord2, hi_idx
     b += (size_t)(qmax + 2) * 4 * 2;                   // events
-    b += (size_t)ncap * 4 * 3;                         // row meta
-    b += (size_t)5 * (qmax + 1 + 128) * 2;             // profile
-    b += (size_t)(qmax + ncap + 8) * 4;                // cigar
+    b += (size_t)5 * (qmax + 1 + 128) * 2 + 8;         // profile
+    b += (size_t)(qmax + ncap + 8) * 4 * 2;            // cigar, cigq
     b += (size_t)ncap + 64;                            // base
     return (b + 4095) & ~(size_t)4095;
 }
 
 __device__ inline void poa_carve(PoaWs &w, uint8_t *slab, size_t slab_bytes, int ncap, int qmax, int nseq) {
     size_t ecap = (size_t)ncap + nseq + 2;
-    int32_t *p = reinterpret_cast<int32_t *>(slab);
+    w.ncap = ncap;
+    w.rdesc = reinterpret_cast<int4 *>(slab); w.rmeta = w.rdesc + ncap;
+    int32_t *p = reinterpret_cast<int32_t *>(w.rmeta + ncap);
     w.out_head = p; p += ncap; w.out_tail = p; p += ncap; w.in_head = p; p += ncap; w.in_tail = p; p += ncap;
-    w.aln_n = p; p += ncap; w.aln = p; p += 4 * (size_t)ncap; w.n2i = p; p += ncap; w.remain = p; p += ncap;
-    w.mpl = p; p += ncap; w.mpr = p; p += ncap; w.hs = p; p += ncap;
-    w.e_to = p; p += ecap; w.e_from = p; p += ecap; w.e_w = p; p += ecap; w.e_no = p; p += ecap; w.e_ni = p; p += ecap;
+    w.aln_n = p; p += ncap; w.aln = p; p += 4 * (size_t)ncap; w.n2i = p; p += ncap; w.ri = p; p += ncap; w.hs = p; p += ncap;
+    w.e_to = p; p += ecap; w.e_from = p; p += ecap; w.e_w = p; p += ecap; w.e_no = p; p += ecap; w.e_ni = p; p += ecap; w.plist = p; p += ecap;
     w.ord = p; p += ncap; w.ord2 = p; p += ncap; w.hi_idx = p; p += ncap;
     w.ev_anchor = p; p += qmax + 2; w.ev_node = p; p += qmax + 2;
-    w.row_off = reinterpret_cast<uint32_t *>(p); p += ncap; w.row_bsn = p; p += ncap; w.row_esn = p; p += ncap;
     w.qp_stride = (qmax + 1 + 128) & ~1;
     w.qp = reinterpret_cast<int16_t *>(p); p += ((size_t)5 * w.qp_stride * 2 + 3) / 4;
     w.cigar = reinterpret_cast<uint32_t *>(p); p += qmax + ncap + 8;
+    w.cigq = p; p += qmax + ncap + 8;
     w.base = reinterpret_cast<uint8_t *>(p);
     size_t fixed = poa_fixed_bytes(ncap, qmax, nseq);
     w.arena = reinterpret_cast<int16_t *>(slab + fixed);
@@ -86,8 +93,9 @@ __device__ inline void poa_carve(PoaWs &w, uint8_t *slab, size_t slab_bytes, int
 
 __device__ __forceinline__ uint32_t ld32(const int16_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
 __device__ __forceinline__ void st32(int16_t *p, uint32_t v) { *reinterpret_cast<uint32_t *>(p) = v; }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// graph edits (lane 0 only) ------------------------------------------------------------------
+// graph edit used for the final edge into the sink (lane 0 only)
 __device__ inline void g_add_edge(PoaWs &w, int &edge_n, int from, int to, bool check) {
     if (check) {
         for (int e = w.out_head[from]; e >= 0; e = w.e_no[e])
@@ -100,43 +108,59 @@ __device__ inline void g_add_edge(PoaWs &w, int &edge_n, int from, int to, bool 
     if (w.in_tail[to] < 0) w.in_head[to] = e; else w.e_ni[w.in_tail[to]] = e;
     w.in_tail[to] = e;
 }
-__device__ inline int g_new_node(PoaWs &w, int &node_n, uint8_t b) {
-    int v = node_n++;
-    w.base[v] = b; w.out_head[v] = w.out_tail[v] = w.in_head[v] = w.in_tail[v] = -1; w.aln_n[v] = 0;
-    return v;
-}
+
+struct PoaSmem { int4 desc[POA_RING]; int4 meta[POA_RING]; int4 pre[POA_MAXPRE]; };
 
 // one warp aligns sequence `query` to the graph and merges it in.  Returns an error code.
 __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *query, int qlen, int &node_n, int &edge_n,
-                                int *s_pre /* POA_MAXPRE*4 ints of shared scratch for this warp */,
-                                unsigned long long &cells, unsigned long long &rows) {
+                                PoaSmem &sm, unsigned long long &cells, unsigned long long &rows, long long *ph) {
+    long long t_ph = clock64();
+#define PH(k) do { long long t_ = clock64(); ph[k] += t_ - t_ph; t_ph = t_; } while (0)
     const int lane = lane_id();
-    const int n = node_n, pn = P.pn;
+    const int n = node_n, pn = P.pn, lp = P.pn == 16 ? 4 : 3;
     const int o1 = P.o1, e1 = P.e1, o2 = P.o2, e2 = P.e2, oe1 = o1 + e1, oe2 = o2 + e2;
     const int mis = P.mismatch > 0 ? P.mismatch : -P.mismatch, mat = P.match < 0 ? -P.match : P.match;
     { // int16 path only (simd_abpoa_align.c:1610-1621)
         int len = qlen > n ? qlen : n;
         int max_score = max(qlen * mat, len * e1 + o1);
-        if (max_score > 32767 - mis - oe1 - oe2) return TH_ERR_LEN;
+        if (max_score > 32767 - mis - oe1 - oe2 - 64 * max(e1, e2)) return TH_ERR_LEN;
     }
     const int inf_min = max(max(-32768 + mis, -32768 + oe1), -32768 + oe2) + 31 * max(e1, e2);
     const uint32_t INFP = pk(inf_min, inf_min);
     const int wband = 10 + (int)(0.01f * (float)qlen); // wb + (int)(wf*qlen), float (simd_abpoa_align.c:393)
-    // ---- order index, heaviest successor, max_remain --------------------------------------
+    // ---- row descriptors: order index, predecessors by row, heaviest successor ----------------
     for (int i = lane; i < n; i += 32) w.n2i[w.ord[i]] = i;
     __syncwarp();
-    for (int v = lane; v < n; v += 32) { // first out-edge with maximum weight (abpoa_graph.c:216-226)
-        int mw = -1, mt = -1;
-        for (int e = w.out_head[v]; e >= 0; e = w.e_no[e]) if (w.e_w[e] > mw) { mw = w.e_w[e]; mt = w.e_to[e]; }
-        w.hs[v] = mt;
-        w.mpl[v] = n; w.mpr[v] = 0; // reset of abpoa_topological_sort (abpoa_graph.c:267-272)
+    {
+        int pl_base = 0, bad = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            int np = 0, p0 = -1, p1 = -1, hi = 0x7fffffff, v = 0, b = 0;
+            if (i < n) {
+                v = w.ord[i]; b = w.base[v];
+                for (int e = w.in_head[v]; e >= 0; e = w.e_ni[e]) { const int pi = w.n2i[w.e_from[e]]; if (np == 0) p0 = pi; else if (np == 1) p1 = pi; ++np; }
+                int mw = -1, mt = -1; // first out-edge with maximum weight (abpoa_graph.c:216-226)
+                for (int e = w.out_head[v]; e >= 0; e = w.e_no[e]) if (w.e_w[e] > mw) { mw = w.e_w[e]; mt = w.e_to[e]; }
+                if (mt >= 0) hi = w.n2i[mt];
+            }
+            const int cnt = np > 2 ? np : 0;
+            int inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(TH_FULL, inc, d); if (lane >= d) inc += o; }
+            const int off = pl_base + inc - cnt;
+            pl_base += __shfl_sync(TH_FULL, inc, 31);
+            if (i < n) {
+                if (np > 2) { int k = 0; for (int e = w.in_head[v]; e >= 0; e = w.e_ni[e]) w.plist[off + k++] = w.n2i[w.e_from[e]]; }
+                w.hi_idx[i] = hi; bad |= np > 1023;
+                w.rdesc[i] = make_int4(p0, min(np, 1023) | (min(b, 7) << 10) | (v << 13), 0, np > 2 ? off : p1);
+            }
+        }
+        if (__any_sync(TH_FULL, bad)) return TH_ERR_CAP;
     }
     __syncwarp();
-    for (int i = lane; i < n; i += 32) { int h = w.hs[w.ord[i]]; w.hi_idx[i] = h >= 0 ? w.n2i[h] : 0x7fffffff; }
-    __syncwarp();
-    // remain by index, 32 indices at a time from the sink backwards; chains inside a chunk are
+    // max_remain by index, 32 indices at a time from the sink backwards; chains inside a chunk are
     // collapsed by pointer jumping on shuffles (remain[v] = remain[heaviest successor] + 1)
-    int32_t *ri = w.row_bsn; // temporary: remain by index (row_bsn is rewritten by the DP below)
+    int32_t *ri = w.ri;
     for (int cb = ((n - 1) / 32) * 32; cb >= 0; cb -= 32) {
         const int idx = cb + lane;
         int ptr = 0x7fffffff, dist = 0;
@@ -151,7 +175,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         if (idx < n) {
             const int val = (ptr == 0x7fffffff ? 0 : ri[ptr]) + dist;
             ri[idx] = val;
-            w.remain[w.ord[idx]] = val;
+            reinterpret_cast<int32_t *>(w.rdesc + idx)[2] = qlen - val;
         }
         __syncwarp();
     }
@@ -167,18 +191,12 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         }
     }
     // ---- first row (simd_abpoa_align.c:538-555, 591-610) ------------------------------------
-    if (lane == 0) {
-        w.mpl[0] = w.mpr[0] = 0;
-        for (int e = w.out_head[0]; e >= 0; e = w.e_no[e]) { w.mpl[w.e_to[e]] = 1; w.mpr[w.e_to[e]] = 1; }
-    }
-    __syncwarp();
     uint32_t used = 0;
     {
-        const int r = w.remain[0];
-        const int end = min(qlen, max(w.mpr[0], qlen - r) + wband);
-        const int esn = end / pn, width = (esn + 1) * pn;
+        const int end = min(qlen, max(0, qlen - ri[0]) + wband);
+        const int esn = end >> lp, width = (esn + 1) << lp;
         if ((uint64_t)used + 5ull * width > w.arena_cap) return TH_ERR_ARENA;
-        if (lane == 0) { w.row_off[0] = used; w.row_bsn[0] = 0; w.row_esn[0] = esn; }
+        if (lane == 0) { const int4 m = make_int4(0, 0, width - 1, 1); w.rmeta[0] = m; sm.meta[0] = m; } // the source hands 1 to its successors (:549-552)
         int16_t *H = w.arena + used, *E1 = H + width, *E2 = E1 + width, *F1 = E2 + width, *F2 = F1 + width;
         for (int j = lane; j < width; j += 32) {
             int f1 = -o1 - e1 * j, f2 = -o2 - e2 * j;
@@ -189,99 +207,105 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         used += 5u * width; cells += width; rows += 1;
     }
     __syncwarp();
+    PH(0);
     // ---- rows in topological order ----------------------------------------------------------
-    const uint32_t OE1P = pk(oe1, oe1), OE2P = pk(oe2, oe2), E1P = pk(e1, e1), E2P = pk(e2, e2), E12P = pk(e1, e2);
+    // Value bounds that make plain 16-bit adds exact here: every H is >= inf_min - mis (the M term), so
+    // H - oe, E - e and the final F never reach -32768: the reference's saturating subtractions
+    // (_mm256_subs_epi16 in SIMD_SET_F) only ever clip intermediate candidates that lose the max anyway.
+    // F1[j] = max_k<=j (A1[k] - e1 (j-k)) is evaluated as a prefix MAX of G[k] = A1[k] + e1 (k - j0) over the
+    // chunk (no subtraction inside the scan, hence no underflow), F = G - e1 (j - j0).  The int16 range check
+    // above leaves 64 max(e1,e2) of headroom for G.
+    const uint32_t NOE1P = pk(-oe1, -oe1), NOE2P = pk(-oe2, -oe2), NE1P = pk(-e1, -e1), NE2P = pk(-e2, -e2);
+    const uint32_t C1 = pk(e1 * 2 * lane - oe1, e1 * (2 * lane + 1) - oe1), C2 = pk(e2 * 2 * lane - oe2, e2 * (2 * lane + 1) - oe2);
+    const uint32_t NJ1 = pk(-e1 * 2 * lane, -e1 * (2 * lane + 1)), NJ2 = pk(-e2 * 2 * lane, -e2 * (2 * lane + 1));
     const int lam_bits = pn - 1;
+    const uint32_t lamk_lo = (uint32_t)(lam_bits - ((2 * lane) & lam_bits)) << 12, lamk_hi = (uint32_t)(lam_bits - ((2 * lane + 1) & lam_bits)) << 12;
+    const int lane_vec = (2 * lane) >> lp;
+    const int qsn = qlen >> lp;
     for (int i = 1; i < n - 1; ++i) {
-        const int v = w.ord[i];
-        const int r = w.remain[v];
-        const int beg0 = max(0, min(w.mpl[v], qlen - r) - wband), end0 = min(qlen, max(w.mpr[v], qlen - r) + wband);
-        // predecessors (in_id order); every lane walks the same list
-        int np = 0, min_pre_bsn = 0x7fffffff;
-        for (int e = w.in_head[v]; e >= 0; e = w.e_ni[e]) {
-            const int pi = w.n2i[w.e_from[e]];
-            const int pb = w.row_bsn[pi];
-            min_pre_bsn = min(min_pre_bsn, pb);
-            if (np < POA_MAXPRE && lane == 0) { s_pre[np * 4] = (int)w.row_off[pi]; s_pre[np * 4 + 1] = pb * pn; s_pre[np * 4 + 2] = (w.row_esn[pi] + 1) * pn - 1; s_pre[np * 4 + 3] = pi; }
-            ++np;
+        if ((i & 31) == 0 || i == 1) { // descriptors of the next 32 rows
+            const int idx = (i & ~31) + lane;
+            if (idx < n) sm.desc[idx & (POA_RING - 1)] = w.rdesc[idx];
+            __syncwarp();
         }
+        const int4 d = sm.desc[i & (POA_RING - 1)];
+        const int np = d.y & 1023;
         if (np > POA_MAXPRE) return TH_ERR_CAP;
+        // band: what the predecessors' row maxima and max_remain say (abpoa_align.h:34-35, simd_abpoa_align.c:846-854)
+        int mpl = n, mpr = 0, min_pre_beg = 0x7fffffff;
+        for (int p = 0; p < np; ++p) {
+            const int pi = p == 0 ? d.x : (np == 2 ? d.w : w.plist[d.w + p]);
+            const int4 m = (i - pi < POA_RING) ? sm.meta[pi & (POA_RING - 1)] : w.rmeta[pi];
+            mpl = min(mpl, m.w); mpr = max(mpr, m.w); min_pre_beg = min(min_pre_beg, m.y);
+            if (lane == 0) sm.pre[p] = m;
+        }
         __syncwarp();
-        const int bsn = max(beg0 / pn, min_pre_bsn), esn = end0 / pn;
-        if (bsn > esn) return TH_ERR_BAND;
-        const int beg = bsn * pn, dend = (esn + 1) * pn - 1, width = dend - beg + 1;
-        if ((uint64_t)used + 5ull * width > w.arena_cap) return TH_ERR_ARENA;
-        if (lane == 0) { w.row_off[i] = used; w.row_bsn[i] = bsn; w.row_esn[i] = esn; }
-        int16_t *H = w.arena + used, *E1 = H + width, *E2 = E1 + width, *F1 = E2 + width, *F2 = F1 + width;
+        const int beg0 = max(0, min(mpl, d.z) - wband), end0 = min(qlen, max(mpr, d.z) + wband);
+        const int beg = max((beg0 >> lp) << lp, min_pre_beg), esn = end0 >> lp, dend = ((esn + 1) << lp) - 1;
+        if (beg > dend) return TH_ERR_BAND;
+        const int bsn = beg >> lp, width = dend - beg + 1;
+        if (5u * (uint32_t)width > w.arena_cap - used) return TH_ERR_ARENA;
+        int16_t *H = w.arena + used;
+        const uint32_t row_off = used;
         used += 5u * width; cells += width; rows += 1;
-        const int16_t *qrow = w.qp + (int)w.base[v] * w.qp_stride;
-        const bool mask_tail = esn == qlen / pn;
-        uint32_t best = 0, carryH = 0; int carryF1 = 0, carryF2 = 0;
+        const int16_t *qrow = w.qp + ((d.y >> 10) & 7) * w.qp_stride;
+        const int jmax = esn == qsn ? qlen : dend;       // columns past the query end do not compete for the row maximum
+        const int vlast = esn - bsn;                      // the row's last vector is visited first by the reference's arg-max
+        uint32_t best = 0, carryH = 0, carryF = POA_NEGP; // carryF: (F1 - e1, F2 - e2) of the previous chunk's last column
         const int nchunk = (width + 63) >> 6;
         for (int ch = 0; ch < nchunk; ++ch) {
             const int j = beg + (ch << 6) + 2 * lane;
-            const bool in_row = j <= dend;
             uint32_t Mx = INFP, E1x = INFP, E2x = INFP;
             for (int p = 0; p < np; ++p) {
-                const int poff = s_pre[p * 4], pb = s_pre[p * 4 + 1], pe = s_pre[p * 4 + 2], pw = pe - pb + 1;
-                const int16_t *Hp = w.arena + (uint32_t)poff;
+                const int4 pm = sm.pre[p];
+                const int pb = pm.y, pe = pm.z, pw = pe - pb + 1;
+                const int16_t *Hp = w.arena + (uint32_t)pm.x + (j - pb);
                 const bool inb = j >= pb && j <= pe;
-                const uint32_t Xh = inb ? ld32(Hp + (j - pb)) : INFP;
+                uint32_t Xh = INFP;
+                if (inb) { Xh = ld32(Hp); E1x = __vmaxs2(E1x, ld32(Hp + pw)); E2x = __vmaxs2(E2x, ld32(Hp + 2 * pw)); }
                 uint32_t prev = __shfl_up_sync(TH_FULL, Xh, 1);
-                if (lane == 0) { const int jm = j - 1; int pv = (jm >= pb && jm <= pe) ? (int)Hp[jm - pb] : inf_min; prev = (uint32_t)(uint16_t)pv << 16; }
+                if (lane == 0) { const int jm = j - 1; const int pv = (jm >= pb && jm <= pe) ? (int)Hp[-1] : inf_min; prev = (uint32_t)pv << 16; }
                 Mx = __vmaxs2(Mx, __funnelshift_r(prev, Xh, 16));
-                if (inb) { E1x = __vmaxs2(E1x, ld32(Hp + pw + (j - pb))); E2x = __vmaxs2(E2x, ld32(Hp + 2 * pw + (j - pb))); }
             }
             const uint32_t S = ld32(qrow + j);
             const uint32_t Ms = __vadd2(Mx, S);
-            const uint32_t Hme = __vmaxs2(__vmaxs2(Ms, E1x), E2x);
+            const uint32_t Hme = __vimax3_s16x2(Ms, E1x, E2x);
             uint32_t hp = __shfl_up_sync(TH_FULL, Hme, 1);
             if (lane == 0) hp = ch == 0 ? (Ms << 16) : carryH;
             const uint32_t Hsh = __funnelshift_r(hp, Hme, 16);
-            uint32_t A1 = __vsubss2(Hsh, OE1P), A2 = __vsubss2(Hsh, OE2P);
-            if (lane == 0 && ch > 0) {
-                A1 = pk(max(lo16(A1), carryF1 - e1), hi16(A1));
-                A2 = pk(max(lo16(A2), carryF2 - e2), hi16(A2));
-            }
-            A1 = __vmaxs2(A1, (__vsubss2(A1, E1P) << 16) | 0x8000u);
-            A2 = __vmaxs2(A2, (__vsubss2(A2, E2P) << 16) | 0x8000u);
-            uint32_t TT = __byte_perm(A1, A2, 0x7632); // lo = F1 at this lane's odd column, hi = F2
+            uint32_t G1 = __vadd2(Hsh, C1), G2 = __vadd2(Hsh, C2);   // G = (Hme[j-1] - oe) + e (j - j0)
+            if (lane == 0) { G1 = __vmaxs2(G1, (carryF & 0xffffu) | 0x80000000u); G2 = __vmaxs2(G2, (carryF >> 16) | 0x80000000u); }
+            G1 = __vmaxs2(G1, (G1 << 16) | 0x8000u); G2 = __vmaxs2(G2, (G2 << 16) | 0x8000u); // odd column also sees the even one
+            uint32_t TT = __byte_perm(G1, G2, 0x7632); // lo = G1 at this lane's odd column, hi = G2
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(TH_FULL, TT, d);
-                o = __vsubss2(o, pk(2 * d * e1, 2 * d * e2));
-                if (lane >= d) TT = __vmaxs2(TT, o);
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const uint32_t o = __shfl_up_sync(TH_FULL, TT, dd);
+                if (lane >= dd) TT = __vmaxs2(TT, o);
             }
             uint32_t Pv = __shfl_up_sync(TH_FULL, TT, 1);
             if (lane == 0) Pv = POA_NEGP;
-            Pv = __vsubss2(Pv, E12P); // (F1[j-1]-e1, F2[j-1]-e2)
-            uint32_t Fa = __vmaxs2(A1, (Pv & 0xffffu) | 0x80000000u);
-            uint32_t Fb = __vmaxs2(A2, (Pv >> 16) | 0x80000000u);
-            Fa = __vmaxs2(Fa, (__vsubss2(Fa, E1P) << 16) | 0x8000u);
-            Fb = __vmaxs2(Fb, (__vsubss2(Fb, E2P) << 16) | 0x8000u);
-            const uint32_t Hn = __vmaxs2(Hme, __vmaxs2(Fa, Fb));
-            const uint32_t E1o = __vmaxs2(__vsub2(E1x, E1P), __vsub2(Hn, OE1P));
-            const uint32_t E2o = __vmaxs2(__vsub2(E2x, E2P), __vsub2(Hn, OE2P));
-            carryH = __shfl_sync(TH_FULL, Hme, 31) & 0xffff0000u;
-            carryF1 = hi16(__shfl_sync(TH_FULL, Fa, 31)); carryF2 = hi16(__shfl_sync(TH_FULL, Fb, 31));
-            if (in_row) {
-                const int c = j - beg;
-                st32(H + c, Hn); st32(E1 + c, E1o); st32(E2 + c, E2o); st32(F1 + c, Fa); st32(F2 + c, Fb);
+            G1 = __vmaxs2(G1, __byte_perm(Pv, Pv, 0x1010)); G2 = __vmaxs2(G2, __byte_perm(Pv, Pv, 0x3232));
+            const uint32_t Fa = __vadd2(G1, NJ1), Fb = __vadd2(G2, NJ2);
+            const uint32_t Hn = __vimax3_s16x2(Hme, Fa, Fb);
+            const uint32_t E1o = __viaddmax_s16x2(E1x, NE1P, __vadd2(Hn, NOE1P));
+            const uint32_t E2o = __viaddmax_s16x2(E2x, NE2P, __vadd2(Hn, NOE2P));
+            if (ch + 1 < nchunk) {
+                carryH = __shfl_sync(TH_FULL, Hme, 31) & 0xffff0000u;
+                const uint32_t fa = __shfl_sync(TH_FULL, Fa, 31), fb = __shfl_sync(TH_FULL, Fb, 31);
+                carryF = __vadd2(__byte_perm(fa, fb, 0x7632), pk(-e1, -e2)); // G of column j0 - 1 in the next chunk's frame
+            }
+            if (j <= dend) {
+                int16_t *Hc = H + (j - beg);
+                st32(Hc, Hn); st32(Hc + width, E1o); st32(Hc + 2 * width, E2o); st32(Hc + 3 * width, Fa); st32(Hc + 4 * width, Fb);
                 // row arg-max key: value, then lane (j mod pn) ascending, then vector order with end_sn first
-                const int vsn = j / pn, vr = vsn == esn ? 0 : vsn - bsn + 1;
-                const uint32_t tail = (uint32_t)(0xfff - vr);
-                if (!(mask_tail && j > qlen)) {
-                    uint32_t key = ((uint32_t)(lo16(Hn) + 32768) << 16) | ((uint32_t)(lam_bits - (j & lam_bits)) << 12) | tail;
-                    best = max(best, key);
-                }
-                if (!(mask_tail && j + 1 > qlen)) {
-                    uint32_t key = ((uint32_t)(hi16(Hn) + 32768) << 16) | ((uint32_t)(lam_bits - ((j + 1) & lam_bits)) << 12) | tail;
-                    best = max(best, key);
-                }
+                const int rel = lane_vec + (ch << (6 - lp));
+                const uint32_t tail = (uint32_t)(0xfff - (rel == vlast ? 0 : rel + 1));
+                if (j <= jmax) best = max(best, ((Hn << 16) ^ 0x80000000u) | lamk_lo | tail);
+                if (j < jmax) best = max(best, ((Hn & 0xffff0000u) ^ 0x80000000u) | lamk_hi | tail);
             }
         }
         best = __reduce_max_sync(TH_FULL, best);
-        if (lane == 0) { // simd_abpoa_max_in_row + simd_abpoa_ada_max_i
+        { // simd_abpoa_max_in_row + simd_abpoa_ada_max_i: successors pull max_i + 1 from this row's metadata
             const int val = (int)(best >> 16) - 32768;
             int max_i = -1;
             if (best != 0 && val > inf_min) {
@@ -289,146 +313,232 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 const int vsn = vr == 0 ? esn : bsn + vr - 1;
                 max_i = vsn * pn + lam;
             }
-            const int out_i = max_i + 1;
-            for (int e = w.out_head[v]; e >= 0; e = w.e_no[e]) {
-                const int o = w.e_to[e];
-                if (out_i > w.mpr[o]) w.mpr[o] = out_i;
-                if (out_i < w.mpl[o]) w.mpl[o] = out_i;
-            }
+            if (lane == 0) { const int4 m = make_int4((int)row_off, beg, dend, max_i + 1); sm.meta[i & (POA_RING - 1)] = m; w.rmeta[i] = m; }
         }
         __syncwarp();
     }
-    // ---- best end cell, backtrack by value comparison (lane 0) -------------------------------
-    int n_cig = 0, err = TH_OK;
-    if (lane == 0) {
-#define ROWP(idx) (w.arena + w.row_off[idx])
-#define RBEG(idx) (w.row_bsn[idx] * pn)
-#define REND(idx) ((w.row_esn[idx] + 1) * pn - 1)
-#define RW(idx) ((w.row_esn[idx] - w.row_bsn[idx] + 1) * pn)
-        int best_score = inf_min, bi = 0, bj = 0;
-        for (int e = w.in_head[1]; e >= 0; e = w.e_ni[e]) {
-            const int pi = w.n2i[w.e_from[e]];
-            const int end = qlen > REND(pi) ? REND(pi) : qlen;
-            const int s = ROWP(pi)[end - RBEG(pi)];
-            if (s > best_score) { best_score = s; bi = pi; bj = end; }
+    PH(1);
+    // ---- best end cell (simd_abpoa_align.c:976-989): sink's in-neighbours in in_id order, strict > ----
+    int bi = 0, bj = 0;
+    {
+        const int4 ds = w.rdesc[n - 1];
+        const int nps = ds.y & 1023;
+        int best_score = inf_min;
+        for (int p0 = 0; p0 < nps; p0 += 32) {
+            const int p = p0 + lane;
+            int s = -0x7fffffff, pi = 0, end = 0;
+            if (p < nps) {
+                pi = p == 0 ? ds.x : (nps == 2 ? ds.w : w.plist[ds.w + p]);
+                const int4 m = w.rmeta[pi];
+                end = qlen > m.z ? m.z : qlen;
+                s = (w.arena + (uint32_t)m.x)[end - m.y];
+            }
+            const int mx = __reduce_max_sync(TH_FULL, s);
+            if (mx > best_score) {
+                const unsigned bm = __ballot_sync(TH_FULL, s == mx);
+                const int f = __ffs(bm) - 1;
+                best_score = mx; bi = __shfl_sync(TH_FULL, pi, f); bj = __shfl_sync(TH_FULL, end, f);
+            }
         }
+    }
+    // ---- backtrack by value comparison (simd_abpoa_align.c:248-377).  The walk is sequential, but every
+    // step's loads (own row, all predecessors) are issued together by the warp, row metadata comes from a
+    // shared-memory window filled 32 rows at a time, and the DP values of the rows ahead are prefetched into L2.
+    int n_cig = 0, err = TH_OK;
+    {
         enum { M_OP = 1, E1_OP = 2, E2_OP = 4, E_OP = 6, F1_OP = 8, F2_OP = 16, F_OP = 24, ALL_OP = 31 };
         int i = bi, j = bj, cur_op = ALL_OP;
-        uint32_t *cg = w.cigar;
-#define PUSH_I(len_) do { if (n_cig && (cg[n_cig - 1] & 3) == 1) cg[n_cig - 1] += (uint32_t)(len_) << 2; else cg[n_cig++] = ((uint32_t)(len_) << 2) | 1; } while (0)
-        if (bj < qlen) PUSH_I(qlen - bj);
-        while (i > 0 && j > 0 && err == TH_OK) {
-            const int v = w.ord[i];
-            const int16_t *Hi = ROWP(i); const int ib = RBEG(i), iw = RW(i);
-            const int s = (query[j - 1] < 4 && w.base[v] < 4) ? (query[j - 1] == w.base[v] ? mat : -mis) : 0;
-            const int hij = Hi[j - ib];
-            bool hit = false;
+        uint32_t *cg = w.cigar; int32_t *cq = w.cigq;
+        for (int t = lane; t < qlen - bj; t += 32) { cg[t] = 1; cq[t] = qlen - 1 - t; } // unaligned query tail
+        if (bj < qlen) n_cig = qlen - bj;
+        int wlo = n, whi = -1; // rows [wlo, whi] are in the window
+        while (i > 0 && j > 0) {
+            if (i < wlo || (i < wlo + 16 && wlo > 0)) {
+                const int top = i < wlo ? i + 1 : wlo; // load rows [top-32, top)
+                if (i < wlo) whi = i;
+                const int r = top - 32 + lane;
+                if (r >= 0) {
+                    const int4 m = w.rmeta[r];
+                    sm.desc[r & (POA_RING - 1)] = w.rdesc[r]; sm.meta[r & (POA_RING - 1)] = m;
+                    const int rw = m.z - m.y + 1;
+                    int jp = j - (i - r); jp = min(max(jp, m.y), m.z);
+                    const int c0 = max(jp - 12, m.y) - m.y, c1 = min(jp + 12, m.z) - m.y;
+                    const int16_t *Hr = w.arena + (uint32_t)m.x;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) { prefetch_l2(Hr + k * rw + c0); prefetch_l2(Hr + k * rw + c1); }
+                }
+                wlo = max(0, top - 32); whi = min(whi, wlo + POA_RING - 1);
+                __syncwarp();
+            }
+            const int4 d = sm.desc[i & (POA_RING - 1)], mi = sm.meta[i & (POA_RING - 1)];
+            const int np = d.y & 1023, vb = (d.y >> 10) & 7, v = d.y >> 13;
+            const int qb = query[j - 1];
+            const int s = (qb < 4 && vb < 4) ? (qb == vb ? mat : -mis) : 0;
+            const int16_t *Hi = w.arena + (uint32_t)mi.x; const int ib = mi.y, iw = mi.z - mi.y + 1;
+            // own-row values (same address in every lane)
+            const int c = j - ib;
+            const int hij = Hi[c], e1ij = Hi[iw + c], e2ij = Hi[2 * iw + c], f1 = Hi[3 * iw + c], f2 = Hi[4 * iw + c];
+            int hm1 = 0, f1m1 = 0, f2m1 = 0;
+            if (c >= 1) { hm1 = Hi[c - 1]; f1m1 = Hi[3 * iw + c - 1]; f2m1 = Hi[4 * iw + c - 1]; }
+            // predecessor values: lane p holds predecessor p
+            int pi = 0, a = 0, b = 0, x1 = 0, x2 = 0; bool in1 = false, in0 = false;
+            if (lane < np) {
+                pi = lane == 0 ? d.x : (np == 2 ? d.w : w.plist[d.w + lane]);
+                const int4 pm = pi >= wlo ? sm.meta[pi & (POA_RING - 1)] : w.rmeta[pi];
+                const int16_t *Hp = w.arena + (uint32_t)pm.x; const int pb = pm.y, pw = pm.z - pm.y + 1;
+                in1 = j - 1 >= pb && j - 1 <= pm.z; in0 = j >= pb && j <= pm.z;
+                if (in1) a = Hp[j - 1 - pb];
+                if (in0) { b = Hp[j - pb]; x1 = Hp[pw + j - pb]; x2 = Hp[2 * pw + j - pb]; }
+            }
+            if (np > 32) { err = TH_ERR_CAP; break; }
             if (cur_op & M_OP) {
-                for (int e = w.in_head[v]; e >= 0; e = w.e_ni[e]) {
-                    const int pi = w.n2i[w.e_from[e]];
-                    if (j - 1 < RBEG(pi) || j - 1 > REND(pi)) continue;
-                    if ((int)ROWP(pi)[j - 1 - RBEG(pi)] + s == hij) {
-                        cg[n_cig++] = ((uint32_t)v << 2) | 0;
-                        cur_op = ALL_OP; hit = true; i = pi; --j;
-                        break;
-                    }
+                const unsigned mm = __ballot_sync(TH_FULL, in1 && a + s == hij);
+                if (mm) {
+                    const int f = __ffs(mm) - 1;
+                    if (lane == 0) { cg[n_cig] = ((uint32_t)v << 2) | 0; cq[n_cig] = j - 1; }
+                    ++n_cig; cur_op = ALL_OP; i = __shfl_sync(TH_FULL, pi, f); --j;
+                    continue;
                 }
             }
-            if (!hit && (cur_op & E_OP)) {
-                for (int e = w.in_head[v]; e >= 0 && !hit; e = w.e_ni[e]) {
-                    const int pi = w.n2i[w.e_from[e]];
-                    if (j < RBEG(pi) || j > REND(pi)) continue;
-                    const int16_t *Hp = ROWP(pi); const int pc = j - RBEG(pi), pw = RW(pi);
-                    if (cur_op & E1_OP) {
-                        const int pe1 = Hp[pw + pc];
-                        const bool ok = (cur_op & M_OP) ? (hij == pe1) : ((int)Hi[iw + j - ib] == pe1 - e1);
-                        if (ok) {
-                            cur_op = ((int)Hp[pc] - oe1 == pe1) ? (M_OP | F_OP) : E1_OP;
-                            cg[n_cig++] = ((uint32_t)v << 2) | 2; hit = true; i = pi;
-                            break;
-                        }
-                    }
-                    if (cur_op & E2_OP) {
-                        const int pe2 = Hp[2 * pw + pc];
-                        const bool ok = (cur_op & M_OP) ? (hij == pe2) : ((int)Hi[2 * iw + j - ib] == pe2 - e2);
-                        if (ok) {
-                            cur_op = ((int)Hp[pc] - oe2 == pe2) ? (M_OP | F_OP) : E2_OP;
-                            cg[n_cig++] = ((uint32_t)v << 2) | 2; hit = true; i = pi;
-                            break;
-                        }
-                    }
+            if (cur_op & E_OP) {
+                const bool ok1 = (cur_op & E1_OP) && in0 && ((cur_op & M_OP) ? (hij == x1) : (e1ij == x1 - e1));
+                const bool ok2 = (cur_op & E2_OP) && in0 && ((cur_op & M_OP) ? (hij == x2) : (e2ij == x2 - e2));
+                const unsigned em = __ballot_sync(TH_FULL, ok1 || ok2);
+                if (em) {
+                    const int f = __ffs(em) - 1;
+                    int nop;
+                    if (ok1) nop = (b - oe1 == x1) ? (M_OP | F_OP) : E1_OP;
+                    else nop = (b - oe2 == x2) ? (M_OP | F_OP) : E2_OP;
+                    cur_op = __shfl_sync(TH_FULL, nop, f);
+                    if (lane == 0) { cg[n_cig] = ((uint32_t)v << 2) | 2; cq[n_cig] = j - 1; }
+                    ++n_cig; i = __shfl_sync(TH_FULL, pi, f);
+                    continue;
                 }
             }
-            if (!hit && (cur_op & F_OP)) {
-                if (j - 1 < ib) { err = TH_ERR_BACKTRACK; break; }
+            if (cur_op & F_OP) {
+                if (c < 1) { err = TH_ERR_BACKTRACK; break; }
+                bool hit = false;
                 if (cur_op & F1_OP) {
-                    const int f1 = Hi[3 * iw + j - ib];
                     if (!(cur_op & M_OP) || hij == f1) {
-                        if ((int)Hi[j - 1 - ib] - oe1 == f1) { cur_op = M_OP | E_OP; hit = true; }
-                        else if ((int)Hi[3 * iw + j - 1 - ib] - e1 == f1) { cur_op = F1_OP; hit = true; }
+                        if (hm1 - oe1 == f1) { cur_op = M_OP | E_OP; hit = true; }
+                        else if (f1m1 - e1 == f1) { cur_op = F1_OP; hit = true; }
                         else { err = TH_ERR_BACKTRACK; break; }
                     }
                 }
                 if (!hit && (cur_op & F2_OP)) {
-                    const int f2 = Hi[4 * iw + j - ib];
                     if (!(cur_op & M_OP) || hij == f2) {
-                        if ((int)Hi[j - 1 - ib] - oe2 == f2) { cur_op = M_OP | E_OP; hit = true; }
-                        else if ((int)Hi[4 * iw + j - 1 - ib] - e2 == f2) { cur_op = F2_OP; hit = true; }
+                        if (hm1 - oe2 == f2) { cur_op = M_OP | E_OP; hit = true; }
+                        else if (f2m1 - e2 == f2) { cur_op = F2_OP; hit = true; }
                         else { err = TH_ERR_BACKTRACK; break; }
                     }
                 }
-                PUSH_I(1); --j; hit = true;
+                if (lane == 0) { cg[n_cig] = 1; cq[n_cig] = j - 1; }
+                ++n_cig; --j;
+                continue;
             }
-            if (!hit) { err = TH_ERR_BACKTRACK; break; }
+            err = TH_ERR_BACKTRACK; break;
         }
-        if (err == TH_OK && j > 0) PUSH_I(j);
-#undef PUSH_I
+        if (err != TH_OK) return err;
+        for (int t = lane; t < j; t += 32) { cg[n_cig + t] = 1; cq[n_cig + t] = j - 1 - t; } // unaligned query head
+        if (j > 0) n_cig += j;
+        __syncwarp();
     }
-    err = __shfl_sync(TH_FULL, err, 0);
-    if (err != TH_OK) return err;
-    n_cig = __shfl_sync(TH_FULL, n_cig, 0);
-    // ---- merge the alignment into the graph (abpoa_graph.c:1218-1284), lane 0 ---------------
+    PH(2);
+    // ---- merge the alignment into the graph (abpoa_graph.c:1218-1284), 32 path steps at a time ----------
+    // A path visits every node and every aligned group at most once, so all steps touch distinct adjacency lists
+    // and groups; ids of new nodes/edges are creation-ordered prefix sums, exactly what the sequential walk yields.
     int n_ev = 0;
-    if (lane == 0) {
-        int query_id = -1, last_id = 0; bool last_new = false; int pend = 0; // events [pend, n_ev) wait for their anchor
-        for (int c = n_cig - 1; c >= 0; --c) {
-            const uint32_t cv = w.cigar[c]; const int op = cv & 3;
+    {
+        const int node_n0 = node_n;
+        int last_id = 0, last_new = 0, pend_lo = 0; // events [pend_lo, n_ev) wait for the next match column
+        for (int k0 = 0; k0 < n_cig; k0 += 32) {
+            const int k = k0 + lane;
+            int op = 2, v = 0, q = 0;
+            if (k < n_cig) { const uint32_t cv = w.cigar[n_cig - 1 - k]; op = cv & 3; v = (int)(cv >> 2); q = w.cigq[n_cig - 1 - k]; }
+            const bool prod = op != 2;
+            int tgt = -1, isnew = 0, bf = 0, bl = 0, an = 0, al[4] = {0, 0, 0, 0};
+            uint8_t qb = 0;
+            if (prod) qb = query[q];
             if (op == 0) {
-                const int node = (int)(cv >> 2);
-                ++query_id;
-                const uint8_t qb = query[query_id];
-                int bf = w.n2i[node], bl = bf;               // block of the aligned group in the old order
-                for (int a = 0; a < w.aln_n[node]; ++a) { const int x = w.n2i[w.aln[node * 4 + a]]; bf = min(bf, x); bl = max(bl, x); }
-                for (; pend < n_ev; ++pend) w.ev_anchor[pend] = bf;
-                if (w.base[node] != qb) {
-                    int aid = -1;
-                    for (int a = 0; a < w.aln_n[node]; ++a) { const int x = w.aln[node * 4 + a]; if (w.base[x] == qb) { aid = x; break; } }
-                    if (aid != -1) { g_add_edge(w, edge_n, last_id, aid, !last_new); last_id = aid; last_new = false; }
-                    else {
-                        const int x = g_new_node(w, node_n, qb);
-                        g_add_edge(w, edge_n, last_id, x, false); last_id = x; last_new = true;
-                        const int n0 = w.aln_n[node]; // abpoa_add_graph_aligned_node (:1036-1044)
-                        for (int a = 0; a < n0; ++a) { const int y = w.aln[node * 4 + a]; w.aln[y * 4 + w.aln_n[y]++] = x; w.aln[x * 4 + w.aln_n[x]++] = y; }
-                        w.aln[node * 4 + w.aln_n[node]++] = x; w.aln[x * 4 + w.aln_n[x]++] = node;
-                        w.ev_node[n_ev] = x; w.ev_anchor[n_ev] = bl + 1; ++n_ev; pend = n_ev;
-                    }
-                } else { g_add_edge(w, edge_n, last_id, node, !last_new); last_id = node; last_new = false; }
-            } else if (op == 1) {
-                const int len = (int)(cv >> 2);
-                query_id += len;
-                for (int jj = len - 1; jj >= 0; --jj) {
-                    const int x = g_new_node(w, node_n, query[query_id - jj]);
-                    g_add_edge(w, edge_n, last_id, x, false); last_id = x; last_new = true;
-                    w.ev_node[n_ev++] = x;
+                bf = w.n2i[v]; bl = bf; an = w.aln_n[v];
+                int aid = -1;
+                for (int a = 0; a < an; ++a) {
+                    al[a] = w.aln[v * 4 + a];
+                    const int x = w.n2i[al[a]]; bf = min(bf, x); bl = max(bl, x);
+                    if (aid < 0 && w.base[al[a]] == qb) aid = al[a];
+                }
+                if (w.base[v] == qb) tgt = v; else if (aid >= 0) tgt = aid; else isnew = 1;
+            } else if (op == 1) isnew = 1;
+            const unsigned newm = __ballot_sync(TH_FULL, isnew), prodm = __ballot_sync(TH_FULL, prod), mm = __ballot_sync(TH_FULL, op == 0);
+            const unsigned below = (1u << lane) - 1;
+            const int ev = n_ev + __popc(newm & below); // event id == rank of the new node
+            if (isnew) tgt = node_n0 + ev;
+            // previous producing step
+            int from = last_id, from_new = last_new;
+            { const unsigned lower = prodm & below; const int src = lower ? 31 - __clz(lower) : 0;
+              const int pt = __shfl_sync(TH_FULL, tgt, src), pnw = __shfl_sync(TH_FULL, isnew, src);
+              if (lower) { from = pt; from_new = pnw; } }
+            // new nodes first (their adjacency heads must exist before edges are linked)
+            if (isnew) {
+                if (tgt >= w.ncap) err = TH_ERR_CAP;
+                else { w.base[tgt] = qb; w.out_head[tgt] = w.out_tail[tgt] = w.in_head[tgt] = w.in_tail[tgt] = -1; w.aln_n[tgt] = 0; w.ev_node[ev] = tgt; }
+            }
+            if (__any_sync(TH_FULL, err != TH_OK)) return TH_ERR_CAP;
+            if (isnew && op == 0) { // abpoa_add_graph_aligned_node (:1036-1044): all-pairs with the old group
+                if (an >= 4) err = TH_ERR_CAP; // a column holds at most 5 distinct codes (ACGT + N): 4 aligned nodes per node
+                else {
+                    for (int a = 0; a < an; ++a) { const int y = al[a]; w.aln[y * 4 + w.aln_n[y]] = tgt; w.aln_n[y] += 1; w.aln[tgt * 4 + a] = y; }
+                    w.aln[v * 4 + an] = tgt; w.aln_n[v] = an + 1; w.aln[tgt * 4 + an] = v; w.aln_n[tgt] = an + 1;
+                    w.ev_anchor[ev] = bl + 1;
                 }
             }
+            if (__any_sync(TH_FULL, err != TH_OK)) return TH_ERR_CAP;
+            // insertion events take the first index of the next match column's group
+            if (mm) {
+                const int fm = __ffs(mm) - 1, bff = __shfl_sync(TH_FULL, bf, fm);
+                const int hi_ev = n_ev + __popc(newm & ((1u << fm) - 1)); // events created before that step
+                for (int e = pend_lo + lane; e < hi_ev; e += 32) w.ev_anchor[e] = bff;
+            }
+            {
+                const unsigned higher = mm & ~(below | (1u << lane));
+                const int src = higher ? __ffs(higher) - 1 : 0;
+                const int bfn = __shfl_sync(TH_FULL, bf, src);
+                if (op == 1 && higher) w.ev_anchor[ev] = bfn;
+            }
+            { // events after the last match column of this batch stay pending
+                const int lastm = mm ? 31 - __clz(mm) : -1;
+                if (mm) pend_lo = n_ev + __popc(newm & ((2u << lastm) - 1));
+            }
+            __syncwarp();
+            // edges (abpoa_add_graph_edge :1063-1106): weight + 1 on an existing edge, else append to both lists
+            int found = -1;
+            if (prod && !from_new && !isnew)
+                for (int e = w.out_head[from]; e >= 0; e = w.e_no[e]) if (w.e_to[e] == tgt) { found = e; break; }
+            const bool mk = prod && found < 0;
+            const unsigned mkm = __ballot_sync(TH_FULL, mk);
+            if (found >= 0) w.e_w[found] += 1;
+            if (mk) {
+                const int e = edge_n + __popc(mkm & below);
+                w.e_to[e] = tgt; w.e_from[e] = from; w.e_w[e] = 1; w.e_no[e] = -1; w.e_ni[e] = -1;
+                const int ot = w.out_tail[from];
+                if (ot < 0) w.out_head[from] = e; else w.e_no[ot] = e;
+                w.out_tail[from] = e;
+                const int it = w.in_tail[tgt];
+                if (it < 0) w.in_head[tgt] = e; else w.e_ni[it] = e;
+                w.in_tail[tgt] = e;
+            }
+            edge_n += __popc(mkm);
+            n_ev += __popc(newm);
+            if (prodm) { const int src = 31 - __clz(prodm); last_id = __shfl_sync(TH_FULL, tgt, src); last_new = __shfl_sync(TH_FULL, isnew, src); }
+            __syncwarp();
         }
-        g_add_edge(w, edge_n, last_id, 1, !last_new);
-        for (; pend < n_ev; ++pend) w.ev_anchor[pend] = n - 1; // before the sink
+        node_n = node_n0 + n_ev;
+        if (lane == 0) g_add_edge(w, edge_n, last_id, 1, !last_new);
+        edge_n = __shfl_sync(TH_FULL, edge_n, 0);
+        for (int e = pend_lo + lane; e < n_ev; e += 32) w.ev_anchor[e] = n - 1; // before the sink
     }
-    n_ev = __shfl_sync(TH_FULL, n_ev, 0);
-    node_n = __shfl_sync(TH_FULL, node_n, 0); edge_n = __shfl_sync(TH_FULL, edge_n, 0);
     __syncwarp();
+    PH(3);
     // new order: old node at index i moves to i + #(events with anchor <= i); event e lands at anchor_e + e
     for (int i = lane; i < n; i += 32) {
         int lo = 0, hi = n_ev;
@@ -438,12 +548,14 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
     for (int e = lane; e < n_ev; e += 32) w.ord2[w.ev_anchor[e] + e] = w.ev_node[e];
     __syncwarp();
     { int32_t *t = w.ord; w.ord = w.ord2; w.ord2 = t; }
+    PH(4);
+#undef PH
     return TH_OK;
 }
 
 // heaviest-column consensus (abpoa_graph.c:279-359, 604-648, 467-478); lane 0.  Returns cons_len.
 __device__ int poa_consensus(PoaWs &w, int node_n, int n_seq, uint8_t *cons, int32_t *cov) {
-    int32_t *deg = w.n2i, *stk = w.ord2, *rank = w.remain;
+    int32_t *deg = w.n2i, *stk = w.ord2, *rank = w.ri;
     int32_t *rcw = reinterpret_cast<int32_t *>(w.arena); // 5 x msa_l weights, then 5 x msa_l node ids
     for (int i = 0; i < node_n; ++i) { int d = 0; for (int e = w.in_head[i]; e >= 0; e = w.e_ni[e]) ++d; deg[i] = d; }
     int sp = 0, msa_rank = 0;
@@ -499,18 +611,24 @@ __device__ int poa_consensus(PoaWs &w, int node_n, int n_seq, uint8_t *cons, int
 }
 
 // persistent warps pull tasks from an atomic counter
-__global__ void __launch_bounds__(POA_WARPS * 32)
+#ifndef POA_MIN_BLOCKS
+#define POA_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(POA_WARPS * 32, POA_MIN_BLOCKS)
 poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const int32_t *__restrict__ task_order,
            const int32_t *__restrict__ u_start, const int32_t *__restrict__ u_len, const uint8_t *__restrict__ bseq,
            uint8_t *slabs, size_t slab_bytes, int *task_counter,
            uint8_t *__restrict__ cons_base, int32_t *__restrict__ cons_cov, int32_t *__restrict__ cons_len,
-           int32_t *__restrict__ task_status, unsigned long long *__restrict__ stat_cells, unsigned long long *__restrict__ stat_rows) {
-    __shared__ int s_pre[POA_WARPS][POA_MAXPRE * 4];
+           int32_t *__restrict__ task_status, unsigned long long *__restrict__ stat_cells, unsigned long long *__restrict__ stat_rows,
+           unsigned long long *__restrict__ stat_phase) {
+    __shared__ PoaSmem s_mem[POA_WARPS];
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * POA_WARPS + wib;
     uint8_t *slab = slabs + (size_t)gw * slab_bytes;
     unsigned long long cells = 0, rows = 0;
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     while (true) {
+        long long t_task = clock64();
         int ti = 0;
         if (lane == 0) ti = atomicAdd(task_counter, 1);
         ti = __shfl_sync(TH_FULL, ti, 0);
@@ -543,8 +661,9 @@ poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const in
         __syncwarp();
         int node_n = l0 + 2, edge_n = l0 + 1, err = TH_OK;
         for (int s = 1; s < T.n_seqs && err == TH_OK; ++s)
-            err = poa_add_sequence(w, P, rseq + u_start[T.unit_off + s], u_len[T.unit_off + s], node_n, edge_n, s_pre[wib], cells, rows);
+            err = poa_add_sequence(w, P, rseq + u_start[T.unit_off + s], u_len[T.unit_off + s], node_n, edge_n, s_mem[wib], cells, rows, ph);
         int cl = 0;
+        long long t_c0 = clock64();
         if (err == TH_OK) {
             if (lane == 0) { cl = poa_consensus(w, node_n, T.n_seqs, cons, cov); }
             cl = __shfl_sync(TH_FULL, cl, 0);
@@ -552,6 +671,10 @@ poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const in
         }
         if (lane == 0) { cons_len[t] = cl; task_status[t] = err; }
         __syncwarp();
+        { long long t_ = clock64(); ph[5] += t_ - t_c0; ph[6] += t_ - t_task; }
     }
-    if (lane == 0 && cells) { atomicAdd(stat_cells, cells); atomicAdd(stat_rows, rows); }
+    if (lane == 0 && cells) {
+        atomicAdd(stat_cells, cells); atomicAdd(stat_rows, rows);
+        for (int k = 0; k < 7; ++k) atomicAdd(stat_phase + k, (unsigned long long)ph[k]);
+    }
 }

@@ -16,4 +16,9 @@ ctx.upload(seqs)
 for _ in range(steps):
     r = ctx.process_resident()
 print({k: v for k, v in r.stats.as_dict().items()})
+cn = ctx.counters()
+ph = cn[16:23]
+names = ["setup", "rows", "backtrack", "merge", "reorder", "consensus", "total"]
+print("poa phase share of warp-cycles:", {k: round(v / max(ph[6], 1), 4) for k, v in zip(names, ph)})
+print("poa warp-cycles per task: %.0f" % (ph[6] / max(r.stats.n_tasks, 1)))
 ctx.close()
