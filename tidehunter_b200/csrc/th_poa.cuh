@@ -109,13 +109,30 @@ __device__ inline void g_add_edge(PoaWs &w, int &edge_n, int from, int to, bool 
     w.in_tail[to] = e;
 }
 
+// contributions of one predecessor row to columns (j, j+1) of the current row: M from H[p][j-1], H[p][j];
+// E1, E2 from the same columns.  A = arena base, pm = the predecessor's row metadata.  Cells outside the
+// predecessor's band count as inf_min (simd_abpoa_align.c:860-905).
+__device__ __forceinline__ void poa_pred(const int16_t *A, const int4 pm, const int j, const uint32_t INFP,
+                                         uint32_t &Mx, uint32_t &E1x, uint32_t &E2x) {
+    const int pb = pm.y, pw = pm.z - pm.y + 1;
+    const uint32_t idx = (uint32_t)pm.x + (uint32_t)(j - pb);
+    uint32_t Xh = INFP, prev = INFP;
+    if (j >= pb && j <= pm.z) { Xh = ld32(A + idx); E1x = __vmaxs2(E1x, ld32(A + idx + pw)); E2x = __vmaxs2(E2x, ld32(A + idx + 2 * pw)); }
+    if (j > pb && j - 1 <= pm.z) prev = ld32(A + idx - 2); // the pair to the left; only its upper half (column j-1) is used
+    Mx = __vmaxs2(Mx, __funnelshift_r(prev, Xh, 16));
+}
+
 struct PoaSmem { int4 desc[POA_RING]; int4 meta[POA_RING]; int4 pre[POA_MAXPRE]; };
 
 // one warp aligns sequence `query` to the graph and merges it in.  Returns an error code.
 __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *query, int qlen, int &node_n, int &edge_n,
                                 PoaSmem &sm, unsigned long long &cells, unsigned long long &rows, long long *ph) {
+#ifdef POA_PROFILE   // per-phase warp-cycle counters (tools/profile_step.py); cost ~16 registers, off in the product build
     long long t_ph = clock64();
 #define PH(k) do { long long t_ = clock64(); ph[k] += t_ - t_ph; t_ph = t_; } while (0)
+#else
+#define PH(k) do { } while (0)
+#endif
     const int lane = lane_id();
     const int n = node_n, pn = P.pn, lp = P.pn == 16 ? 4 : 3;
     const int o1 = P.o1, e1 = P.e1, o2 = P.o2, e2 = P.e2, oe1 = o1 + e1, oe2 = o2 + e2;
@@ -222,6 +239,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
     const uint32_t lamk_lo = (uint32_t)(lam_bits - ((2 * lane) & lam_bits)) << 12, lamk_hi = (uint32_t)(lam_bits - ((2 * lane + 1) & lam_bits)) << 12;
     const int lane_vec = (2 * lane) >> lp;
     const int qsn = qlen >> lp;
+    const int16_t *A = w.arena;
     for (int i = 1; i < n - 1; ++i) {
         if ((i & 31) == 0 || i == 1) { // descriptors of the next 32 rows
             const int idx = (i & ~31) + lane;
@@ -230,22 +248,24 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         }
         const int4 d = sm.desc[i & (POA_RING - 1)];
         const int np = d.y & 1023;
-        if (np > POA_MAXPRE) return TH_ERR_CAP;
+        if ((unsigned)(np - 1) >= POA_MAXPRE) return TH_ERR_CAP;
         // band: what the predecessors' row maxima and max_remain say (abpoa_align.h:34-35, simd_abpoa_align.c:846-854)
-        int mpl = n, mpr = 0, min_pre_beg = 0x7fffffff;
-        for (int p = 0; p < np; ++p) {
-            const int pi = p == 0 ? d.x : (np == 2 ? d.w : w.plist[d.w + p]);
-            const int4 m = (i - pi < POA_RING) ? sm.meta[pi & (POA_RING - 1)] : w.rmeta[pi];
-            mpl = min(mpl, m.w); mpr = max(mpr, m.w); min_pre_beg = min(min_pre_beg, m.y);
-            if (lane == 0) sm.pre[p] = m;
+        const int4 pm0 = (i - d.x < POA_RING) ? sm.meta[d.x & (POA_RING - 1)] : w.rmeta[d.x];
+        int mpl = min(n, pm0.w), mpr = max(0, pm0.w), min_pre_beg = pm0.y;
+        if (np > 1) {
+            for (int p = 1; p < np; ++p) {
+                const int pi = np == 2 ? d.w : w.plist[d.w + p];
+                const int4 m = (i - pi < POA_RING) ? sm.meta[pi & (POA_RING - 1)] : w.rmeta[pi];
+                mpl = min(mpl, m.w); mpr = max(mpr, m.w); min_pre_beg = min(min_pre_beg, m.y);
+                if (lane == 0) sm.pre[p] = m;
+            }
+            __syncwarp();
         }
-        __syncwarp();
         const int beg0 = max(0, min(mpl, d.z) - wband), end0 = min(qlen, max(mpr, d.z) + wband);
         const int beg = max((beg0 >> lp) << lp, min_pre_beg), esn = end0 >> lp, dend = ((esn + 1) << lp) - 1;
         if (beg > dend) return TH_ERR_BAND;
         const int bsn = beg >> lp, width = dend - beg + 1;
         if (5u * (uint32_t)width > w.arena_cap - used) return TH_ERR_ARENA;
-        int16_t *H = w.arena + used;
         const uint32_t row_off = used;
         used += 5u * width; cells += width; rows += 1;
         const int16_t *qrow = w.qp + ((d.y >> 10) & 7) * w.qp_stride;
@@ -256,17 +276,8 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         for (int ch = 0; ch < nchunk; ++ch) {
             const int j = beg + (ch << 6) + 2 * lane;
             uint32_t Mx = INFP, E1x = INFP, E2x = INFP;
-            for (int p = 0; p < np; ++p) {
-                const int4 pm = sm.pre[p];
-                const int pb = pm.y, pe = pm.z, pw = pe - pb + 1;
-                const int16_t *Hp = w.arena + (uint32_t)pm.x + (j - pb);
-                const bool inb = j >= pb && j <= pe;
-                uint32_t Xh = INFP;
-                if (inb) { Xh = ld32(Hp); E1x = __vmaxs2(E1x, ld32(Hp + pw)); E2x = __vmaxs2(E2x, ld32(Hp + 2 * pw)); }
-                uint32_t prev = __shfl_up_sync(TH_FULL, Xh, 1);
-                if (lane == 0) { const int jm = j - 1; const int pv = (jm >= pb && jm <= pe) ? (int)Hp[-1] : inf_min; prev = (uint32_t)pv << 16; }
-                Mx = __vmaxs2(Mx, __funnelshift_r(prev, Xh, 16));
-            }
+            poa_pred(A, pm0, j, INFP, Mx, E1x, E2x);
+            for (int p = 1; p < np; ++p) poa_pred(A, sm.pre[p], j, INFP, Mx, E1x, E2x);
             const uint32_t S = ld32(qrow + j);
             const uint32_t Ms = __vadd2(Mx, S);
             const uint32_t Hme = __vimax3_s16x2(Ms, E1x, E2x);
@@ -278,10 +289,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
             G1 = __vmaxs2(G1, (G1 << 16) | 0x8000u); G2 = __vmaxs2(G2, (G2 << 16) | 0x8000u); // odd column also sees the even one
             uint32_t TT = __byte_perm(G1, G2, 0x7632); // lo = G1 at this lane's odd column, hi = G2
 #pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-                const uint32_t o = __shfl_up_sync(TH_FULL, TT, dd);
-                if (lane >= dd) TT = __vmaxs2(TT, o);
-            }
+            for (int dd = 1; dd < 32; dd <<= 1) TT = __vmaxs2(TT, __shfl_up_sync(TH_FULL, TT, dd)); // lanes < dd get their own value back
             uint32_t Pv = __shfl_up_sync(TH_FULL, TT, 1);
             if (lane == 0) Pv = POA_NEGP;
             G1 = __vmaxs2(G1, __byte_perm(Pv, Pv, 0x1010)); G2 = __vmaxs2(G2, __byte_perm(Pv, Pv, 0x3232));
@@ -295,7 +303,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 carryF = __vadd2(__byte_perm(fa, fb, 0x7632), pk(-e1, -e2)); // G of column j0 - 1 in the next chunk's frame
             }
             if (j <= dend) {
-                int16_t *Hc = H + (j - beg);
+                int16_t *Hc = w.arena + (row_off + (uint32_t)(j - beg));
                 st32(Hc, Hn); st32(Hc + width, E1o); st32(Hc + 2 * width, E2o); st32(Hc + 3 * width, Fa); st32(Hc + 4 * width, Fb);
                 // row arg-max key: value, then lane (j mod pn) ascending, then vector order with end_sn first
                 const int rel = lane_vec + (ch << (6 - lp));
@@ -374,21 +382,23 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
             const int np = d.y & 1023, vb = (d.y >> 10) & 7, v = d.y >> 13;
             const int qb = query[j - 1];
             const int s = (qb < 4 && vb < 4) ? (qb == vb ? mat : -mis) : 0;
-            const int16_t *Hi = w.arena + (uint32_t)mi.x; const int ib = mi.y, iw = mi.z - mi.y + 1;
+            const int ib = mi.y, iw = mi.z - mi.y + 1;
             // own-row values (same address in every lane)
             const int c = j - ib;
-            const int hij = Hi[c], e1ij = Hi[iw + c], e2ij = Hi[2 * iw + c], f1 = Hi[3 * iw + c], f2 = Hi[4 * iw + c];
+            const uint32_t ci = (uint32_t)mi.x + (uint32_t)c;
+            const int hij = A[ci], e1ij = A[ci + iw], e2ij = A[ci + 2 * iw], f1 = A[ci + 3 * iw], f2 = A[ci + 4 * iw];
             int hm1 = 0, f1m1 = 0, f2m1 = 0;
-            if (c >= 1) { hm1 = Hi[c - 1]; f1m1 = Hi[3 * iw + c - 1]; f2m1 = Hi[4 * iw + c - 1]; }
+            if (c >= 1) { hm1 = A[ci - 1]; f1m1 = A[ci + 3 * iw - 1]; f2m1 = A[ci + 4 * iw - 1]; }
             // predecessor values: lane p holds predecessor p
             int pi = 0, a = 0, b = 0, x1 = 0, x2 = 0; bool in1 = false, in0 = false;
             if (lane < np) {
                 pi = lane == 0 ? d.x : (np == 2 ? d.w : w.plist[d.w + lane]);
                 const int4 pm = pi >= wlo ? sm.meta[pi & (POA_RING - 1)] : w.rmeta[pi];
-                const int16_t *Hp = w.arena + (uint32_t)pm.x; const int pb = pm.y, pw = pm.z - pm.y + 1;
+                const int pb = pm.y, pw = pm.z - pm.y + 1;
+                const uint32_t pci = (uint32_t)pm.x + (uint32_t)(j - pb);
                 in1 = j - 1 >= pb && j - 1 <= pm.z; in0 = j >= pb && j <= pm.z;
-                if (in1) a = Hp[j - 1 - pb];
-                if (in0) { b = Hp[j - pb]; x1 = Hp[pw + j - pb]; x2 = Hp[2 * pw + j - pb]; }
+                if (in1) a = A[pci - 1];
+                if (in0) { b = A[pci]; x1 = A[pci + pw]; x2 = A[pci + 2 * pw]; }
             }
             if (np > 32) { err = TH_ERR_CAP; break; }
             if (cur_op & M_OP) {
@@ -553,38 +563,51 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
     return TH_OK;
 }
 
-// heaviest-column consensus (abpoa_graph.c:279-359, 604-648, 467-478); lane 0.  Returns cons_len.
+// heaviest-column consensus (abpoa_graph.c:279-359, 604-648, 467-478).  All lanes call; returns cons_len.
+// The DFS that assigns MSA ranks is order dependent (stack discipline, abpoa_graph.c:279-339) and stays on lane 0;
+// in-degrees, column weights and the column vote are data parallel.
 __device__ int poa_consensus(PoaWs &w, int node_n, int n_seq, uint8_t *cons, int32_t *cov) {
+    const int lane = lane_id();
     int32_t *deg = w.n2i, *stk = w.ord2, *rank = w.ri;
     int32_t *rcw = reinterpret_cast<int32_t *>(w.arena); // 5 x msa_l weights, then 5 x msa_l node ids
-    for (int i = 0; i < node_n; ++i) { int d = 0; for (int e = w.in_head[i]; e >= 0; e = w.e_ni[e]) ++d; deg[i] = d; }
-    int sp = 0, msa_rank = 0;
-    stk[sp++] = 0; rank[0] = -1;
-    while (sp > 0) {
-        const int cur = stk[--sp];
-        if (rank[cur] < 0) {
-            rank[cur] = msa_rank;
-            for (int a = 0; a < w.aln_n[cur]; ++a) rank[w.aln[cur * 4 + a]] = msa_rank;
-            ++msa_rank;
-        }
-        if (cur == 1) break;
-        for (int e = w.out_head[cur]; e >= 0; e = w.e_no[e]) {
-            const int o = w.e_to[e];
-            if (--deg[o] == 0) {
-                bool ok = true;
-                for (int a = 0; a < w.aln_n[o]; ++a) if (deg[w.aln[o * 4 + a]] != 0) { ok = false; break; }
-                if (!ok) continue;
-                stk[sp++] = o; rank[o] = -1;
-                for (int a = 0; a < w.aln_n[o]; ++a) { const int x = w.aln[o * 4 + a]; stk[sp++] = x; rank[x] = -1; }
+    for (int i = lane; i < node_n; i += 32) { int d = 0; for (int e = w.in_head[i]; e >= 0; e = w.e_ni[e]) ++d; deg[i] = d; }
+    __syncwarp();
+    int msa_l = 0;
+    if (lane == 0) {
+        int sp = 0, msa_rank = 0;
+        stk[sp++] = 0; rank[0] = -1;
+        while (sp > 0) {
+            const int cur = stk[--sp];
+            if (rank[cur] < 0) {
+                rank[cur] = msa_rank;
+                for (int a = 0; a < w.aln_n[cur]; ++a) rank[w.aln[cur * 4 + a]] = msa_rank;
+                ++msa_rank;
+            }
+            if (cur == 1) break;
+            for (int e = w.out_head[cur]; e >= 0; e = w.e_no[e]) {
+                const int o = w.e_to[e];
+                if (--deg[o] == 0) {
+                    bool ok = true;
+                    const int an = w.aln_n[o];
+                    for (int a = 0; a < an; ++a) if (deg[w.aln[o * 4 + a]] != 0) { ok = false; break; }
+                    if (!ok) continue;
+                    stk[sp++] = o; rank[o] = -1;
+                    for (int a = 0; a < an; ++a) { const int x = w.aln[o * 4 + a]; stk[sp++] = x; rank[x] = -1; }
+                }
             }
         }
+        msa_l = rank[1] - 1;
     }
-    const int msa_l = rank[1] - 1;
+    msa_l = __shfl_sync(TH_FULL, msa_l, 0);
+    __syncwarp();
     if (msa_l <= 0) return 0;
     if ((uint64_t)msa_l * 10 * 2 > w.arena_cap) return -1;
     int32_t *nodeid = rcw + 5 * (size_t)msa_l;
-    for (int i = 0; i < 5 * msa_l; ++i) { rcw[i] = 0; nodeid[i] = 0; }
-    for (int i = 2; i < node_n; ++i) { // abpoa_set_row_column_weight; popcount(read_ids) == sum of out weights
+    for (int i = lane; i < 5 * msa_l; i += 32) { rcw[i] = 0; nodeid[i] = 0; }
+    __syncwarp();
+    // abpoa_set_row_column_weight; popcount(read_ids) == sum of out weights.  A column is one aligned group and a
+    // group holds one node per base, so every (column, base) slot has a single writer.
+    for (int i = 2 + lane; i < node_n; i += 32) {
         int rk = rank[i];
         for (int a = 0; a < w.aln_n[i]; ++a) rk = max(rk, rank[w.aln[i * 4 + a]]);
         int wsum = 0;
@@ -593,21 +616,20 @@ __device__ int poa_consensus(PoaWs &w, int node_n, int n_seq, uint8_t *cons, int
         rcw[(rk - 1) * 5 + b] += wsum;
         nodeid[(rk - 1) * 5 + b] = i;
     }
-    int last_id = 0, cons_i = 0;
-    int32_t *max_out = w.hs;
-    for (int i = 0; i < msa_l; ++i) {
-        int max_w = 0, max_base = 5, gap_w = n_seq;
-        for (int b = 0; b < 4; ++b) { const int x = rcw[i * 5 + b]; if (x > max_w) { max_base = b; max_w = x; } gap_w -= x; }
-        if (max_w >= gap_w) {
-            const int cur = nodeid[i * 5 + max_base];
-            max_out[last_id] = cur; last_id = cur;
-            cov[cons_i++] = max_w;
+    __syncwarp();
+    int cons_i = 0;
+    for (int c0 = 0; c0 < msa_l; c0 += 32) { // abpoa_heaviest_column_consensus (:604-629): first heaviest base, kept iff max_w >= gap weight
+        const int c = c0 + lane;
+        int max_w = 0, max_base = 5, gap_w = n_seq; bool sel = false;
+        if (c < msa_l) {
+            for (int b = 0; b < 4; ++b) { const int x = rcw[c * 5 + b]; if (x > max_w) { max_base = b; max_w = x; } gap_w -= x; }
+            sel = max_w >= gap_w && max_base < 5;
         }
+        const unsigned m = __ballot_sync(TH_FULL, sel);
+        if (sel) { const int pos = cons_i + __popc(m & ((1u << lane) - 1)); cons[pos] = w.base[nodeid[c * 5 + max_base]]; cov[pos] = max_w; }
+        cons_i += __popc(m);
     }
-    max_out[last_id] = 1;
-    int id = max_out[0], l = 0;
-    while (id != 1 && l <= node_n) { cons[l++] = w.base[id]; id = max_out[id]; }
-    return l;
+    return cons_i;
 }
 
 // persistent warps pull tasks from an atomic counter
@@ -626,9 +648,15 @@ poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const in
     const int gw = blockIdx.x * POA_WARPS + wib;
     uint8_t *slab = slabs + (size_t)gw * slab_bytes;
     unsigned long long cells = 0, rows = 0;
+#ifdef POA_PROFILE
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#else
+    long long *ph = nullptr;
+#endif
     while (true) {
+#ifdef POA_PROFILE
         long long t_task = clock64();
+#endif
         int ti = 0;
         if (lane == 0) ti = atomicAdd(task_counter, 1);
         ti = __shfl_sync(TH_FULL, ti, 0);
@@ -663,18 +691,23 @@ poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const in
         for (int s = 1; s < T.n_seqs && err == TH_OK; ++s)
             err = poa_add_sequence(w, P, rseq + u_start[T.unit_off + s], u_len[T.unit_off + s], node_n, edge_n, s_mem[wib], cells, rows, ph);
         int cl = 0;
+#ifdef POA_PROFILE
         long long t_c0 = clock64();
+#endif
         if (err == TH_OK) {
-            if (lane == 0) { cl = poa_consensus(w, node_n, T.n_seqs, cons, cov); }
-            cl = __shfl_sync(TH_FULL, cl, 0);
+            cl = poa_consensus(w, node_n, T.n_seqs, cons, cov);
             if (cl < 0) { err = TH_ERR_ARENA; cl = 0; }
         }
         if (lane == 0) { cons_len[t] = cl; task_status[t] = err; }
         __syncwarp();
+#ifdef POA_PROFILE
         { long long t_ = clock64(); ph[5] += t_ - t_c0; ph[6] += t_ - t_task; }
+#endif
     }
     if (lane == 0 && cells) {
         atomicAdd(stat_cells, cells); atomicAdd(stat_rows, rows);
+#ifdef POA_PROFILE
         for (int k = 0; k < 7; ++k) atomicAdd(stat_phase + k, (unsigned long long)ph[k]);
+#endif
     }
 }
