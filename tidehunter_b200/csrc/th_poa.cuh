@@ -109,16 +109,23 @@ __device__ inline void g_add_edge(PoaWs &w, int &edge_n, int from, int to, bool 
     w.in_tail[to] = e;
 }
 
+// DP arena layout.  A row of W columns (W a multiple of pn) that starts at int16 offset `off` owns 5 W int16:
+//   W/2 records of 16 bytes, record q = columns (beg + 2q, beg + 2q + 1) as four s16x2 words {H, E1, E2, F1},
+//   followed by W/2 words of F2 pairs.  One 16-byte access moves everything the next rows need from a column
+//   pair, and a backtrack step touches one or two sectors per row instead of five.
+__device__ __forceinline__ const uint4 *poa_recs(const uint32_t *A32, int off) { return reinterpret_cast<const uint4 *>(A32 + (off >> 1)); }
+__device__ __forceinline__ int s16_at(uint32_t word, int odd) { return odd ? hi16(word) : lo16(word); }
+
 // contributions of one predecessor row to columns (j, j+1) of the current row: M from H[p][j-1], H[p][j];
-// E1, E2 from the same columns.  A = arena base, pm = the predecessor's row metadata.  Cells outside the
-// predecessor's band count as inf_min (simd_abpoa_align.c:860-905).
-__device__ __forceinline__ void poa_pred(const int16_t *A, const int4 pm, const int j, const uint32_t INFP,
+// E1, E2 from the same columns.  pm = the predecessor's row metadata.  Cells outside the predecessor's band
+// count as inf_min (simd_abpoa_align.c:860-905).
+__device__ __forceinline__ void poa_pred(const uint32_t *A32, const int4 pm, const int j, const uint32_t INFP,
                                          uint32_t &Mx, uint32_t &E1x, uint32_t &E2x) {
-    const int pb = pm.y, pw = pm.z - pm.y + 1;
-    const uint32_t idx = (uint32_t)pm.x + (uint32_t)(j - pb);
+    const int pb = pm.y;
+    const uint32_t wi = (uint32_t)(pm.x >> 1) + 2u * (uint32_t)(j - pb); // word index of record (j - pb) / 2
     uint32_t Xh = INFP, prev = INFP;
-    if (j >= pb && j <= pm.z) { Xh = ld32(A + idx); E1x = __vmaxs2(E1x, ld32(A + idx + pw)); E2x = __vmaxs2(E2x, ld32(A + idx + 2 * pw)); }
-    if (j > pb && j - 1 <= pm.z) prev = ld32(A + idx - 2); // the pair to the left; only its upper half (column j-1) is used
+    if (j >= pb && j <= pm.z) { const uint4 r = *reinterpret_cast<const uint4 *>(A32 + wi); Xh = r.x; E1x = __vmaxs2(E1x, r.y); E2x = __vmaxs2(E2x, r.z); }
+    if (j > pb && j - 1 <= pm.z) prev = A32[wi - 4]; // H of the pair to the left; only its upper half (column j-1) is used
     Mx = __vmaxs2(Mx, __funnelshift_r(prev, Xh, 16));
 }
 
@@ -214,12 +221,19 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         const int esn = end >> lp, width = (esn + 1) << lp;
         if ((uint64_t)used + 5ull * width > w.arena_cap) return TH_ERR_ARENA;
         if (lane == 0) { const int4 m = make_int4(0, 0, width - 1, 1); w.rmeta[0] = m; sm.meta[0] = m; } // the source hands 1 to its successors (:549-552)
-        int16_t *H = w.arena + used, *E1 = H + width, *E2 = E1 + width, *F1 = E2 + width, *F2 = F1 + width;
-        for (int j = lane; j < width; j += 32) {
-            int f1 = -o1 - e1 * j, f2 = -o2 - e2 * j;
-            H[j] = (int16_t)(j == 0 ? 0 : max((int)(int16_t)f1, (int)(int16_t)f2));
-            E1[j] = (int16_t)(j == 0 ? -oe1 : inf_min); E2[j] = (int16_t)(j == 0 ? -oe2 : inf_min);
-            F1[j] = (int16_t)(j == 0 ? inf_min : f1); F2[j] = (int16_t)(j == 0 ? inf_min : f2);
+        uint4 *R = reinterpret_cast<uint4 *>(w.arena); uint32_t *F2w = reinterpret_cast<uint32_t *>(w.arena) + 2 * width;
+        for (int q = lane; q < width / 2; q += 32) {
+            uint32_t hh = 0, ee1 = 0, ee2 = 0, ff1 = 0, ff2 = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * q + h;
+                const int f1 = -o1 - e1 * j, f2 = -o2 - e2 * j;
+                const int vh = j == 0 ? 0 : max((int)(int16_t)f1, (int)(int16_t)f2);
+                const int v1 = j == 0 ? -oe1 : inf_min, v2 = j == 0 ? -oe2 : inf_min, vf1 = j == 0 ? inf_min : f1, vf2 = j == 0 ? inf_min : f2;
+                hh |= (uint32_t)(uint16_t)vh << (16 * h); ee1 |= (uint32_t)(uint16_t)v1 << (16 * h); ee2 |= (uint32_t)(uint16_t)v2 << (16 * h);
+                ff1 |= (uint32_t)(uint16_t)vf1 << (16 * h); ff2 |= (uint32_t)(uint16_t)vf2 << (16 * h);
+            }
+            R[q] = make_uint4(hh, ee1, ee2, ff1); F2w[q] = ff2;
         }
         used += 5u * width; cells += width; rows += 1;
     }
@@ -239,7 +253,8 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
     const uint32_t lamk_lo = (uint32_t)(lam_bits - ((2 * lane) & lam_bits)) << 12, lamk_hi = (uint32_t)(lam_bits - ((2 * lane + 1) & lam_bits)) << 12;
     const int lane_vec = (2 * lane) >> lp;
     const int qsn = qlen >> lp;
-    const int16_t *A = w.arena;
+    const uint32_t *A32 = reinterpret_cast<const uint32_t *>(w.arena);
+    uint32_t *A32w = reinterpret_cast<uint32_t *>(w.arena);
     for (int i = 1; i < n - 1; ++i) {
         if ((i & 31) == 0 || i == 1) { // descriptors of the next 32 rows
             const int idx = (i & ~31) + lane;
@@ -276,8 +291,8 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         for (int ch = 0; ch < nchunk; ++ch) {
             const int j = beg + (ch << 6) + 2 * lane;
             uint32_t Mx = INFP, E1x = INFP, E2x = INFP;
-            poa_pred(A, pm0, j, INFP, Mx, E1x, E2x);
-            for (int p = 1; p < np; ++p) poa_pred(A, sm.pre[p], j, INFP, Mx, E1x, E2x);
+            poa_pred(A32, pm0, j, INFP, Mx, E1x, E2x);
+            for (int p = 1; p < np; ++p) poa_pred(A32, sm.pre[p], j, INFP, Mx, E1x, E2x);
             const uint32_t S = ld32(qrow + j);
             const uint32_t Ms = __vadd2(Mx, S);
             const uint32_t Hme = __vimax3_s16x2(Ms, E1x, E2x);
@@ -303,8 +318,9 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 carryF = __vadd2(__byte_perm(fa, fb, 0x7632), pk(-e1, -e2)); // G of column j0 - 1 in the next chunk's frame
             }
             if (j <= dend) {
-                int16_t *Hc = w.arena + (row_off + (uint32_t)(j - beg));
-                st32(Hc, Hn); st32(Hc + width, E1o); st32(Hc + 2 * width, E2o); st32(Hc + 3 * width, Fa); st32(Hc + 4 * width, Fb);
+                const uint32_t wi = (row_off >> 1) + 2u * (uint32_t)(j - beg);
+                *reinterpret_cast<uint4 *>(A32w + wi) = make_uint4(Hn, E1o, E2o, Fa);
+                A32w[(row_off >> 1) + 2u * (uint32_t)width + ((uint32_t)(j - beg) >> 1)] = Fb;
                 // row arg-max key: value, then lane (j mod pn) ascending, then vector order with end_sn first
                 const int rel = lane_vec + (ch << (6 - lp));
                 const uint32_t tail = (uint32_t)(0xfff - (rel == vlast ? 0 : rel + 1));
@@ -339,7 +355,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 pi = p == 0 ? ds.x : (nps == 2 ? ds.w : w.plist[ds.w + p]);
                 const int4 m = w.rmeta[pi];
                 end = qlen > m.z ? m.z : qlen;
-                s = (w.arena + (uint32_t)m.x)[end - m.y];
+                s = s16_at(A32[(m.x >> 1) + 4 * ((end - m.y) >> 1)], (end - m.y) & 1);
             }
             const int mx = __reduce_max_sync(TH_FULL, s);
             if (mx > best_score) {
@@ -370,10 +386,9 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                     sm.desc[r & (POA_RING - 1)] = w.rdesc[r]; sm.meta[r & (POA_RING - 1)] = m;
                     const int rw = m.z - m.y + 1;
                     int jp = j - (i - r); jp = min(max(jp, m.y), m.z);
-                    const int c0 = max(jp - 12, m.y) - m.y, c1 = min(jp + 12, m.z) - m.y;
-                    const int16_t *Hr = w.arena + (uint32_t)m.x;
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) { prefetch_l2(Hr + k * rw + c0); prefetch_l2(Hr + k * rw + c1); }
+                    const int c0 = max(jp - 8, m.y) - m.y, c1 = min(jp + 8, m.z) - m.y;
+                    const uint32_t *Rr = A32 + (m.x >> 1);
+                    prefetch_l2(Rr + 4 * (c0 >> 1)); prefetch_l2(Rr + 4 * (c1 >> 1)); prefetch_l2(Rr + 2 * rw + ((jp - m.y) >> 1));
                 }
                 wlo = max(0, top - 32); whi = min(whi, wlo + POA_RING - 1);
                 __syncwarp();
@@ -383,22 +398,28 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
             const int qb = query[j - 1];
             const int s = (qb < 4 && vb < 4) ? (qb == vb ? mat : -mis) : 0;
             const int ib = mi.y, iw = mi.z - mi.y + 1;
-            // own-row values (same address in every lane)
-            const int c = j - ib;
-            const uint32_t ci = (uint32_t)mi.x + (uint32_t)c;
-            const int hij = A[ci], e1ij = A[ci + iw], e2ij = A[ci + 2 * iw], f1 = A[ci + 3 * iw], f2 = A[ci + 4 * iw];
-            int hm1 = 0, f1m1 = 0, f2m1 = 0;
-            if (c >= 1) { hm1 = A[ci - 1]; f1m1 = A[ci + 3 * iw - 1]; f2m1 = A[ci + 4 * iw - 1]; }
+            // own-row values (same address in every lane): the record of column j and the one to its left
+            const int c = j - ib, q = c >> 1, odd = c & 1;
+            const uint32_t rb = (uint32_t)(mi.x >> 1);
+            const uint4 r0 = *reinterpret_cast<const uint4 *>(A32 + rb + 4 * q);
+            const uint32_t g0 = A32[rb + 2 * iw + q];
+            uint4 r1 = r0; uint32_t g1 = g0;
+            if (!odd && c >= 2) { r1 = *reinterpret_cast<const uint4 *>(A32 + rb + 4 * (q - 1)); g1 = A32[rb + 2 * iw + q - 1]; }
+            const int hij = s16_at(r0.x, odd), e1ij = s16_at(r0.y, odd), e2ij = s16_at(r0.z, odd), f1 = s16_at(r0.w, odd), f2 = s16_at(g0, odd);
+            const int hm1 = s16_at(r1.x, !odd), f1m1 = s16_at(r1.w, !odd), f2m1 = s16_at(g1, !odd); // column j-1 (used only when c >= 1)
             // predecessor values: lane p holds predecessor p
             int pi = 0, a = 0, b = 0, x1 = 0, x2 = 0; bool in1 = false, in0 = false;
             if (lane < np) {
                 pi = lane == 0 ? d.x : (np == 2 ? d.w : w.plist[d.w + lane]);
                 const int4 pm = pi >= wlo ? sm.meta[pi & (POA_RING - 1)] : w.rmeta[pi];
-                const int pb = pm.y, pw = pm.z - pm.y + 1;
-                const uint32_t pci = (uint32_t)pm.x + (uint32_t)(j - pb);
-                in1 = j - 1 >= pb && j - 1 <= pm.z; in0 = j >= pb && j <= pm.z;
-                if (in1) a = A[pci - 1];
-                if (in0) { b = A[pci]; x1 = A[pci + pw]; x2 = A[pci + 2 * pw]; }
+                const int cp = j - pm.y, podd = cp & 1;
+                const uint32_t pbw = (uint32_t)(pm.x >> 1) + 4 * (cp >> 1);
+                in1 = cp >= 1 && j - 1 <= pm.z; in0 = cp >= 0 && j <= pm.z;
+                uint4 rp = make_uint4(0, 0, 0, 0); uint32_t aw = 0;
+                if (in0) rp = *reinterpret_cast<const uint4 *>(A32 + pbw);
+                if (in1 && !podd) aw = A32[pbw - 4];
+                b = s16_at(rp.x, podd); x1 = s16_at(rp.y, podd); x2 = s16_at(rp.z, podd);
+                a = podd ? lo16(rp.x) : hi16(aw);
             }
             if (np > 32) { err = TH_ERR_CAP; break; }
             if (cur_op & M_OP) {
@@ -634,7 +655,7 @@ __device__ int poa_consensus(PoaWs &w, int node_n, int n_seq, uint8_t *cons, int
 
 // persistent warps pull tasks from an atomic counter
 #ifndef POA_MIN_BLOCKS
-#define POA_MIN_BLOCKS 4
+#define POA_MIN_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(POA_WARPS * 32, POA_MIN_BLOCKS)
 poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const int32_t *__restrict__ task_order,
