@@ -257,8 +257,12 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     // ---- chain DP ----
     {
         const int grid = std::min((n + CHAIN_WARPS - 1) / CHAIN_WARPS, c->n_sm * 8);
-        chain_dp_kernel<<<grid, CHAIN_WARPS * 32, 0, st>>>(P, n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(),
-                                                        c->d_score.as<int32_t>(), c->d_from.as<int32_t>(), c->d_gflag.as<int32_t>(), cnt64 + 0);
+        if (P.max_p < (1u << 27)) // hit periods are <= max_p (src/tandem_hit.c:204): the 1.8x gate fits 32-bit products
+            chain_dp_kernel<true><<<grid, CHAIN_WARPS * 32, 0, st>>>(P, n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(),
+                                                                  c->d_score.as<int32_t>(), c->d_from.as<int32_t>(), c->d_gflag.as<int32_t>(), cnt64 + 0);
+        else
+            chain_dp_kernel<false><<<grid, CHAIN_WARPS * 32, 0, st>>>(P, n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(),
+                                                                   c->d_score.as<int32_t>(), c->d_from.as<int32_t>(), c->d_gflag.as<int32_t>(), cnt64 + 0);
         S.n_launches++;
         if (P.w > 1) { // repeated ends can only come from minimizer seeds
             chain_dp_generic_kernel<<<(n + 63) / 64, 64, 0, st>>>(P, n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(),
@@ -274,7 +278,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         if (c->d_scratch2.ensure((size_t)grid * gcap * 8)) return -1;
         rank_kernel<<<grid, RANK_THREADS, 0, st>>>(n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_score.as<int32_t>(), c->d_scratch2.as<uint64_t>(), gcap,
                                                   c->d_rank.as<int32_t>(), c->d_nrank.as<int32_t>(), c->d_rstatus.as<int32_t>());
-        chain_select_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(), c->d_score.as<int32_t>(),
+        chain_select_kernel<<<(n + SELECT_WARPS - 1) / SELECT_WARPS, SELECT_WARPS * 32, 0, st>>>(n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(), c->d_score.as<int32_t>(),
                                                          c->d_from.as<int32_t>(), c->d_rank.as<int32_t>(), c->d_nrank.as<int32_t>(), c->d_tracked.as<uint8_t>(),
                                                          c->d_choff.as<int32_t>(), c->d_chlen.as<int32_t>(), c->d_chscore.as<int32_t>(), c->d_chidx.as<int32_t>(),
                                                          c->d_cells.as<int32_t>(), c->d_pchn.as<int32_t>(), c->d_pchoff.as<int32_t>(), c->d_pchlen.as<int32_t>(), 1);

@@ -18,9 +18,12 @@ enum { CON_NO = 0, CON_REG = 1, CON_SAME = 2, CON_OVL = 3 };
 // 5*cur_p >= 9*pre_p for all int periods: when 9*pre_p/5 is an integer N the correctly rounded product
 // fl(pre_p * 1.8) is exactly N (1.8's representation error is 2.5e-17 relative, below half an ulp),
 // otherwise the exact product is at least 0.2 away from any integer.
+// SMALL: all periods < 2^27 (max_p bounds them), so the products fit 32 bits.
+template <bool SMALL = false>
 __device__ __forceinline__ int con_score(int cs, int ce, int ps, int pe, int k, int &score) {
     int cp = ce - cs, pp = pe - ps;
-    if (cs <= ps || 5ll * cp >= 9ll * pp || 5ll * pp >= 9ll * cp) return CON_NO;
+    if (SMALL) { if (cs <= ps || 5 * cp >= 9 * pp || 5 * pp >= 9 * cp) return CON_NO; }
+    else if (cs <= ps || 5ll * cp >= 9ll * pp || 5ll * pp >= 9ll * cp) return CON_NO;
     int de = abs(ce - pe), ds = abs(cs - ps), dpd = abs(cp - pp);
     int matched = min(de, k) + min(ds, k);
     uint32_t v = (uint32_t)(de + ds);
@@ -31,6 +34,7 @@ __device__ __forceinline__ int con_score(int cs, int ce, int ps, int pe, int k, 
 }
 
 #define CHAIN_WARPS 4
+template <bool SMALL>
 __global__ void __launch_bounds__(CHAIN_WARPS * 32)
 chain_dp_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ nhits,
                 const int32_t *__restrict__ hend, const int32_t *__restrict__ hper,
@@ -65,29 +69,41 @@ chain_dp_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, cons
                 if (valid) { pe = en[pre]; pp = pr[pre]; psc = sc[pre]; }
                 const bool cstop = !valid || pe < cs;           // stop BEFORE this predecessor
                 int con = 0, cls = CON_NO;
-                if (!cstop) cls = con_score(cs, ce, pe - pp, pe, P.k, con);
+                if (!cstop) cls = con_score<SMALL>(cs, ce, pe - pp, pe, P.k, con);
                 const int s = cls != CON_NO ? psc + con : INT_MIN;
-                // running max each lane would have seen = max(max_score, s of earlier lanes)
-                int inc = s;
+                const unsigned cm = __ballot_sync(TH_FULL, cstop);
+                const int first_c = cm ? __ffs(cm) - 1 : 32;
+                int first_a, cnt;
+                if (__reduce_max_sync(TH_FULL, s) <= max_score) {
+                    // no predecessor of this batch can improve (the usual case once the best one, a near one, is
+                    // found): only the non-improving stop rules apply, no running maximum is needed
+                    cnt = iter_in + lane + 1;
+                    const unsigned am = __ballot_sync(TH_FULL, !cstop && (cls == CON_OVL || cnt >= max_h));
+                    first_a = am ? __ffs(am) - 1 : 32;
+                    evals += min(first_c, first_a + 1);
+                } else {
+                    // running max each lane would have seen = max(max_score, s of earlier lanes)
+                    int inc = s;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(TH_FULL, inc, d); if (lane >= d) inc = max(inc, o); }
-                int excl = __shfl_up_sync(TH_FULL, inc, 1);
-                excl = lane == 0 ? max_score : max(max_score, excl);
-                const bool imp = cls != CON_NO && s > excl;
-                const unsigned impm = __ballot_sync(TH_FULL, imp);
-                // rows without improvement so far (iter_n), as of this lane
-                const unsigned below = impm & (0xffffffffu >> (31 - lane));
-                const int cnt = below ? lane - (31 - __clz(below)) : iter_in + lane + 1;
-                const bool stop_after = (imp && (cls == CON_SAME || cls == CON_OVL)) || (!imp && cls == CON_OVL) || (!imp && cnt >= max_h);
-                const unsigned cm = __ballot_sync(TH_FULL, cstop), am = __ballot_sync(TH_FULL, stop_after && !cstop);
-                const int first_c = cm ? __ffs(cm) - 1 : 32, first_a = am ? __ffs(am) - 1 : 32;
-                const bool processed = lane < first_c && lane <= first_a;
-                evals += __popc(__ballot_sync(TH_FULL, processed));
-                const int sp = processed ? s : INT_MIN;
-                const int bm = __reduce_max_sync(TH_FULL, sp);
-                if (bm > max_score) {
-                    const unsigned wm = __ballot_sync(TH_FULL, processed && imp && s == bm);
-                    max_score = bm; best_pre = base - (__ffs(wm) - 1);
+                    for (int d = 1; d < 32; d <<= 1) inc = max(inc, __shfl_up_sync(TH_FULL, inc, d)); // lanes < d get their own value
+                    int excl = __shfl_up_sync(TH_FULL, inc, 1);
+                    excl = lane == 0 ? max_score : max(max_score, excl);
+                    const bool imp = cls != CON_NO && s > excl;
+                    const unsigned impm = __ballot_sync(TH_FULL, imp);
+                    // rows without improvement so far (iter_n), as of this lane
+                    const unsigned below = impm & (0xffffffffu >> (31 - lane));
+                    cnt = below ? lane - (31 - __clz(below)) : iter_in + lane + 1;
+                    const bool stop_after = (imp && (cls == CON_SAME || cls == CON_OVL)) || (!imp && cls == CON_OVL) || (!imp && cnt >= max_h);
+                    const unsigned am = __ballot_sync(TH_FULL, stop_after && !cstop);
+                    first_a = am ? __ffs(am) - 1 : 32;
+                    const bool processed = lane < first_c && lane <= first_a;
+                    evals += min(first_c, first_a + 1);
+                    const int sp = processed ? s : INT_MIN;
+                    const int bm = __reduce_max_sync(TH_FULL, sp);
+                    if (bm > max_score) {
+                        const unsigned wm = __ballot_sync(TH_FULL, processed && imp && s == bm);
+                        max_score = bm; best_pre = base - (__ffs(wm) - 1);
+                    }
                 }
                 if (first_c < 32 || first_a < 32) break;
                 iter_in = __shfl_sync(TH_FULL, cnt, 31);
@@ -187,115 +203,147 @@ rank_kernel(int n_reads, const int64_t *__restrict__ roff, const int32_t *__rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// Greedy chain extraction; one thread per read (sequential by nature).  Literal restatement of
-// tandem_chain.c:358-403 on flat cell ids.  Output: post-chains (>= 3 cells, ascending end).
-// Per-read scratch (all at the read's base offset, capacity L):
+// Greedy chain extraction; one warp per read.  Restatement of tandem_chain.c:358-403 on flat cell ids.
+// The walk over ranked candidates is sequential in the reference, but a candidate only changes state when it
+// is NOT inside an existing chain (is_in_chain, :170-185), and most are: 32 candidates are screened at a time
+// against the current chain set; the first survivor is processed exactly as the reference does (lane 0), and
+// the candidates behind it are screened again because the chain set may have changed.
+// Output: post-chains (>= 3 cells, ascending end).  Per-read scratch (all at the read's base offset, capacity L):
 //   tracked[L] u8, ch_off/ch_len/ch_score/ch_idx [L/2+1 via half offsets], cells[L]
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int row_first(const int32_t *en, int c) { while (c > 0 && en[c - 1] == en[c]) --c; return c; }
 
-__global__ void chain_select_kernel(int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ nhits,
-                                    const int32_t *__restrict__ hend, const int32_t *__restrict__ hper,
-                                    const int32_t *__restrict__ score, const int32_t *__restrict__ from,
-                                    const int32_t *__restrict__ rank, const int32_t *__restrict__ nrank,
-                                    uint8_t *tracked, int32_t *ch_off, int32_t *ch_len, int32_t *ch_score, int32_t *ch_idx,
-                                    int32_t *cells, int32_t *__restrict__ pch_n, int32_t *pch_off, int32_t *pch_len, const int ragged_ok) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
+#define SELECT_WARPS 4
+__global__ void __launch_bounds__(SELECT_WARPS * 32)
+chain_select_kernel(int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ nhits,
+                    const int32_t *__restrict__ hend, const int32_t *__restrict__ hper,
+                    const int32_t *__restrict__ score, const int32_t *__restrict__ from,
+                    const int32_t *__restrict__ rank, const int32_t *__restrict__ nrank,
+                    uint8_t *tracked, int32_t *ch_off, int32_t *ch_len, int32_t *ch_score, int32_t *ch_idx,
+                    int32_t *cells, int32_t *__restrict__ pch_n, int32_t *pch_off, int32_t *pch_len, const int ragged_ok) {
+    const int lane = lane_id();
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n_reads) return;
     const int n = nhits[r]; const int64_t off = roff[r], hoff = off / 2;
-    pch_n[r] = 0;
-    if (n < 2) return;
+    if (n < 2) { if (lane == 0) pch_n[r] = 0; return; }
     const int32_t *en = hend + off, *pr = hper + off, *sc = score + off, *fr = from + off, *rk = rank + off;
     uint8_t *trk = tracked + off; int32_t *cl = cells + off;
     int32_t *coff = ch_off + hoff, *clen = ch_len + hoff, *cscore = ch_score + hoff, *cidx = ch_idx + hoff;
     const int cap = n / 2 + 1, top_N = 1000;
-    for (int i = 0; i < n; ++i) trk[i] = 0;
+    for (int i = lane; i < n; i += 32) trk[i] = 0;
+    for (int i = lane; i < cap && i < top_N; i += 32) cidx[i] = i;
+    __syncwarp();
     const int score_n = nrank[r];
     int ch_n = 0, pool = 0; // pool: next free slot in cl[]; the slot of chain ch_n is rewritten until accepted
-    for (int i = 0; i < cap && i < top_N; ++i) cidx[i] = i;
+    bool need_sort_check = false;
 #define ST(c) (en[c] - pr[c])
-    for (int i = 0; i < score_n && ch_n < top_N && ch_n < cap; ++i) {
-        const int c = rk[i];
-        bool in_chain = false;
-        { // is_in_chain (:170-185); cell_start is taken from the first cell of the row
-            const int cell_start = ST(row_first(en, c)), cell_end = en[c];
-            for (int _i = 0; _i < ch_n; ++_i) {
-                const int ci = cidx[_i];
-                if (clen[ci] <= 0) continue;
-                const int chain_start = ST(cl[coff[ci]]), chain_end = en[cl[coff[ci] + clen[ci] - 1]];
-                if (chain_end < cell_start) break;
-                else if (chain_start > cell_end) continue;
-                else if (cell_end - chain_start >= (chain_end - chain_start) / 2) { in_chain = true; break; }
+    for (int b0 = 0; b0 < score_n && ch_n < top_N && ch_n < cap; b0 += 32) {
+        const int ci = b0 + lane;
+        const bool valid = ci < score_n;
+        int c = 0, cell_start = 0, cell_end = 0;
+        if (valid) { c = rk[ci]; cell_start = ST(row_first(en, c)); cell_end = en[c]; }
+        unsigned remaining = __ballot_sync(TH_FULL, valid), surv = 0;
+        bool rescreen = true;
+        while (remaining && ch_n < top_N && ch_n < cap) {
+            bool in_chain = false;
+            if (rescreen && ((remaining >> lane) & 1)) { // is_in_chain (:170-185); cell_start is taken from the first cell of the row
+                for (int _i = 0; _i < ch_n; ++_i) {
+                    const int k = cidx[_i];
+                    const int kl = clen[k];
+                    if (kl <= 0) continue;
+                    const int ko = coff[k];
+                    const int c1 = cl[ko], c2 = cl[ko + kl - 1];
+                    const int chain_start = ST(c1), chain_end = en[c2];
+                    if (chain_end < cell_start) break;
+                    else if (chain_start > cell_end) continue;
+                    else if (cell_end - chain_start >= (chain_end - chain_start) / 2) { in_chain = true; break; }
+                }
             }
-        }
-        if (in_chain) continue;
-        bool accepted = false;
-        if (!trk[c]) { // backtrack_dp (:86-111)
-            int s = sc[c], cur = c, len = 0;
-            while (true) {
-                trk[cur] = 1; cl[pool + len++] = cur;
-                const int p = fr[cur];
-                if (p == -1) break;
-                if (trk[p]) { s -= sc[p]; break; }
-                cur = p;
-            }
-            for (int a = 0, b = len - 1; a < b; ++a, --b) { int t = cl[pool + a]; cl[pool + a] = cl[pool + b]; cl[pool + b] = t; }
-            coff[ch_n] = pool; clen[ch_n] = len; cscore[ch_n] = s;
-            if (len > 1) { // is_overlap_chain (:54-83)
-                bool ovl = false;
-                if (ch_n > 0) {
-                    const int start = ST(cl[pool + len - 1]);
-                    for (int j = ch_n - 1; j >= 0; --j) {
-                        if (clen[j] <= 0) continue;
-                        if (en[cl[coff[j] + clen[j] - 1]] <= start) break;
-                        const int s1 = ST(cl[coff[j]]), e1 = ST(cl[coff[j] + clen[j] - 1]);
-                        const int s2 = ST(cl[pool]), e2 = ST(cl[pool + len - 1]);
-                        const int mn = min(e1 - s1, e2 - s2), ovlp = min(e1, e2) - max(s1, s2);
-                        if (ovlp / (mn + 0.0) >= 0.5) {
-                            if (cscore[j] > s) ovl = true; else clen[j] = 0;
-                            break;
+            if (rescreen) surv = __ballot_sync(TH_FULL, ((remaining >> lane) & 1) && !in_chain);
+            surv &= remaining;
+            if (!surv) break;
+            const int f = __ffs(surv) - 1;
+            const int cc = __shfl_sync(TH_FULL, c, f);
+            int resc = 0;
+            if (lane == 0) {
+                bool accepted = false, changed = false;
+                if (!trk[cc]) { // backtrack_dp (:86-111)
+                    int s = sc[cc], cur = cc, len = 0;
+                    while (true) {
+                        trk[cur] = 1; cl[pool + len++] = cur;
+                        const int p = fr[cur];
+                        if (p == -1) break;
+                        if (trk[p]) { s -= sc[p]; break; }
+                        cur = p;
+                    }
+                    for (int a = 0, b = len - 1; a < b; ++a, --b) { int t = cl[pool + a]; cl[pool + a] = cl[pool + b]; cl[pool + b] = t; }
+                    coff[ch_n] = pool; clen[ch_n] = len; cscore[ch_n] = s;
+                    if (len > 1) { // is_overlap_chain (:54-83)
+                        bool ovl = false;
+                        if (ch_n > 0) {
+                            const int start = ST(cl[pool + len - 1]);
+                            for (int j = ch_n - 1; j >= 0; --j) {
+                                if (clen[j] <= 0) continue;
+                                if (en[cl[coff[j] + clen[j] - 1]] <= start) break;
+                                const int s1 = ST(cl[coff[j]]), e1 = ST(cl[coff[j] + clen[j] - 1]);
+                                const int s2 = ST(cl[pool]), e2 = ST(cl[pool + len - 1]);
+                                const int mn = min(e1 - s1, e2 - s2), ovlp = min(e1, e2) - max(s1, s2);
+                                if (ovlp / (mn + 0.0) >= 0.5) {
+                                    if (cscore[j] > s) ovl = true; else { clen[j] = 0; changed = true; }
+                                    break;
+                                }
+                            }
+                        }
+                        accepted = !ovl;
+                    }
+                }
+                if (accepted) { pool += clen[ch_n]; ++ch_n; changed = true; }
+                if (changed) need_sort_check = true;
+                // sort_chain (:188-207) runs after every candidate in the reference; it performs no swap when the live
+                // chain ends are already non-increasing, so that O(ch_n) test replaces the O(ch_n^2) pass, and the test
+                // itself is skipped while the chain set is unchanged since the last time it found them ordered.
+                if (ch_n >= 2 && need_sort_check) {
+                    bool sorted = true; int last_end = INT_MAX;
+                    for (int _i = 0; _i < ch_n; ++_i) {
+                        const int k = cidx[_i];
+                        if (clen[k] <= 0) continue;
+                        const int e = en[cl[coff[k] + clen[k] - 1]];
+                        if (e > last_end) { sorted = false; break; }
+                        last_end = e;
+                    }
+                    if (sorted) need_sort_check = false;
+                    else { changed = true; // the literal pass (incl. its stale `i`); may leave the list unsorted, so check again next time
+                        for (int _i = 0; _i < ch_n - 1; ++_i) {
+                            const int ii = cidx[_i];
+                            if (clen[ii] <= 0) continue;
+                            int end1 = en[cl[coff[ii] + clen[ii] - 1]];
+                            for (int _j = _i + 1; _j < ch_n; ++_j) {
+                                const int jj = cidx[_j];
+                                if (clen[jj] <= 0) continue;
+                                const int end2 = en[cl[coff[jj] + clen[jj] - 1]];
+                                if (end1 < end2) { cidx[_i] = jj; cidx[_j] = ii; end1 = end2; }
+                            }
                         }
                     }
                 }
-                accepted = !ovl;
+                resc = changed;
             }
-        }
-        if (accepted) { pool += clen[ch_n]; ++ch_n; }
-        // sort_chain (:188-207) runs after every candidate in the reference; it performs no swap when the live
-        // chain ends are already non-increasing, so that O(ch_n) test replaces the O(ch_n^2) pass; otherwise
-        // the literal pass (incl. its stale `i`) runs.
-        if (ch_n >= 2) {
-            bool sorted = true; int last_end = INT_MAX;
-            for (int _i = 0; _i < ch_n; ++_i) {
-                const int ci = cidx[_i];
-                if (clen[ci] <= 0) continue;
-                const int e = en[cl[coff[ci] + clen[ci] - 1]];
-                if (e > last_end) { sorted = false; break; }
-                last_end = e;
-            }
-            if (!sorted) {
-                for (int _i = 0; _i < ch_n - 1; ++_i) {
-                    const int ii = cidx[_i];
-                    if (clen[ii] <= 0) continue;
-                    int end1 = en[cl[coff[ii] + clen[ii] - 1]];
-                    for (int _j = _i + 1; _j < ch_n; ++_j) {
-                        const int jj = cidx[_j];
-                        if (clen[jj] <= 0) continue;
-                        const int end2 = en[cl[coff[jj] + clen[jj] - 1]];
-                        if (end1 < end2) { cidx[_i] = jj; cidx[_j] = ii; end1 = end2; }
-                    }
-                }
-            }
+            ch_n = __shfl_sync(TH_FULL, ch_n, 0);
+            rescreen = __shfl_sync(TH_FULL, resc, 0) != 0; // an unchanged chain set keeps the screening of the lanes behind f valid
+            __syncwarp();
+            remaining &= ~((2u << f) - 1u);
         }
     }
 #undef ST
     // post-process (:392-399): ascending end, chains with >= 3 cells
-    int pn = 0;
-    for (int i = ch_n - 1; i >= 0; --i) {
-        const int ci = cidx[i];
-        if (clen[ci] - 1 < 2) continue;
-        pch_off[hoff + pn] = coff[ci]; pch_len[hoff + pn] = clen[ci]; ++pn;
+    if (lane == 0) {
+        int pn = 0;
+        for (int i = ch_n - 1; i >= 0; --i) {
+            const int k = cidx[i];
+            if (clen[k] - 1 < 2) continue;
+            pch_off[hoff + pn] = coff[k]; pch_len[hoff + pn] = clen[k]; ++pn;
+        }
+        pch_n[r] = pn;
     }
-    pch_n[r] = pn;
     (void)ragged_ok;
 }

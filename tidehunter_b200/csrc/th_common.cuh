@@ -27,8 +27,8 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 // unique sorted order and any correct sort is bit-exact with the reference's radix sort
 // (src/ksort.h:101-151) and its stable qsort (src/tandem_chain.c:21-43).
 // ---------------------------------------------------------------------------------------------
-template <bool DESC>
-__device__ void block_bitonic_sort(uint64_t *a, int n) {
+template <bool DESC, class K = uint64_t>
+__device__ void block_bitonic_sort(K *a, int n) {
     const int half = n >> 1;
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -36,7 +36,7 @@ __device__ void block_bitonic_sort(uint64_t *a, int n) {
                 int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
                 int x = i | j;
                 bool up = ((i & k) == 0) != DESC;
-                uint64_t ai = a[i], ax = a[x];
+                K ai = a[i], ax = a[x];
                 if ((ai > ax) == up) { a[i] = ax; a[x] = ai; }
             }
             __syncthreads();

@@ -124,6 +124,9 @@ __device__ int seeds_minimizer(const uint8_t *bseq, int len, int k, int w, int h
 
 // One block per read (grid-stride).  gscratch: 2 * gcap uint64 per block (sort buffer for long reads +
 // hit staging).  Output: hend/hper at the read's base offset, nhits[r].
+// Fast path (default options, reads up to 32 k bases): seeds are 32-bit words (key << bits(L) | pos), hits are
+// (end << bits(L) | period); both sorts and the hit staging stay in shared memory.  Same total order as the
+// reference's 64-bit words (key major, position minor / end major, period minor), so any correct sort is exact.
 __global__ void __launch_bounds__(SEED_THREADS, 1)
 seed_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ rlen,
             const uint8_t *__restrict__ bseq, const uint64_t *__restrict__ pack2, const uint32_t *__restrict__ nmask,
@@ -138,12 +141,83 @@ seed_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const in
         const int64_t off = roff[r];
         if (L < P.k || L - P.w <= 0) { if (threadIdx.x == 0) nhits[r] = 0; continue; }
         const int npow = next_pow2(L);
-        uint64_t *buf = npow <= SEED_SMEM_CAP ? sbuf : gbuf;
+        const int bitsL = 32 - __clz(npow - 1 > 0 ? npow - 1 : 1);
         const uint64_t *pw = pack2 + off / 32; const uint32_t *nm = nmask + off / 32;
+        if (P.w <= 1 && !P.hpc && 2 * P.k + bitsL < 32 && 2 * bitsL < 32 && npow <= SEED_SMEM_CAP) {
+            uint32_t *buf = reinterpret_cast<uint32_t *>(sbuf), *hbuf = buf + npow; // 2 x npow x 4 B <= 128 KB
+            const uint32_t posmask = (1u << bitsL) - 1;
+            if (threadIdx.x == 0) s_cnt = 0;
+            __syncthreads();
+            // rolling 2-bit k-mer, 32 positions per thread, k-1 bases of warm-up (tandem_hit.c:37-56)
+            for (int t = threadIdx.x; t * 32 < npow; t += blockDim.x) {
+                const int base0 = t * 32;
+                if (base0 >= L) { for (int p = base0; p < base0 + 32 && p < npow; ++p) buf[p] = 0xffffffffu; continue; }
+                uint32_t key = 0; int l = 0, cnt = 0;
+                int start = base0 - (P.k - 1); if (start < 0) start = 0;
+                const int stop = base0 + 32 < L ? base0 + 32 : L;
+                const uint64_t w0 = pw[start >> 5], w1 = pw[base0 >> 5];
+                const uint32_t m0 = nm[start >> 5], m1 = nm[base0 >> 5];
+                for (int p = start; p < stop; ++p) {
+                    const bool cur = p >= base0;
+                    const uint64_t wd = cur ? w1 : w0; const uint32_t md = cur ? m1 : m0;
+                    uint32_t v = 0xffffffffu;
+                    if ((md >> (p & 31)) & 1) { key = 0; l = 0; }
+                    else {
+                        key = ((key << 2) | (uint32_t)((wd >> (2 * (p & 31))) & 3)) & kmask;
+                        if (++l >= P.k) { v = key << bitsL | (uint32_t)p; if (cur) ++cnt; }
+                    }
+                    if (cur) buf[p] = v;
+                }
+                for (int p = stop; p < base0 + 32 && p < npow; ++p) buf[p] = 0xffffffffu;
+                if (cnt) atomicAdd(&s_cnt, cnt);
+            }
+            __syncthreads();
+            const int n_seed = s_cnt;
+            __syncthreads();
+            if (n_seed == 0) { if (threadIdx.x == 0) nhits[r] = 0; continue; }
+            block_bitonic_sort<false, uint32_t>(buf, npow);
+            // nearest earlier occurrence of the same key at distance >= min_p (tandem_hit.c:186-214); hits are compacted
+            if (threadIdx.x == 0) s_cnt = 0;
+            __syncthreads();
+            for (int j0 = 0; j0 < n_seed; j0 += blockDim.x) {
+                const int j = j0 + threadIdx.x;
+                uint32_t v = 0xffffffffu;
+                if (j < n_seed) {
+                    const uint32_t cur = buf[j], key = cur >> bitsL, pos = cur & posmask; uint32_t d = 0; bool found = false;
+                    for (int kk = j - 1; kk >= 0; --kk) {
+                        const uint32_t o = buf[kk];
+                        if ((o >> bitsL) != key) break;
+                        d = pos - (o & posmask);
+                        if (d >= P.min_p) { found = true; break; }
+                    }
+                    if (found && d <= P.max_p) v = pos << bitsL | d;
+                }
+                const unsigned m = __ballot_sync(TH_FULL, v != 0xffffffffu);
+                int wbase = 0;
+                if ((threadIdx.x & 31) == 0 && m) wbase = atomicAdd(&s_cnt, __popc(m));
+                wbase = __shfl_sync(TH_FULL, wbase, 0);
+                if (v != 0xffffffffu) hbuf[wbase + __popc(m & ((1u << (threadIdx.x & 31)) - 1))] = v;
+            }
+            __syncthreads();
+            const int n_hit = s_cnt;
+            const int hpow = next_pow2(n_hit);
+            for (int j = n_hit + threadIdx.x; j < hpow; j += blockDim.x) hbuf[j] = 0xffffffffu;
+            __syncthreads();
+            if (n_hit > 1) block_bitonic_sort<false, uint32_t>(hbuf, hpow);
+            for (int j = threadIdx.x; j < n_hit; j += blockDim.x) {
+                const uint32_t v = hbuf[j];
+                hend[off + j] = (int32_t)(v >> bitsL);
+                hper[off + j] = (int32_t)(v & posmask);
+            }
+            if (threadIdx.x == 0) nhits[r] = n_hit;
+            __syncthreads();
+            continue;
+        }
+        // ---- general path: 64-bit words, any option ----
+        uint64_t *buf = npow <= SEED_SMEM_CAP ? sbuf : gbuf;
         if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
         if (P.w <= 1 && !P.hpc) {
-            // rolling 2-bit k-mer, 32 positions per thread, k-1 bases of warm-up (tandem_hit.c:37-56)
             for (int t = threadIdx.x; t * 32 < npow; t += blockDim.x) {
                 int base0 = t * 32;
                 if (base0 >= L) { for (int p = base0; p < base0 + 32 && p < npow; ++p) buf[p] = SEED_INVALID; continue; }
@@ -179,10 +253,11 @@ seed_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const in
         __syncthreads();
         if (n_seed == 0) { if (threadIdx.x == 0) nhits[r] = 0; continue; }
         block_bitonic_sort<false>(buf, npow);
-        // nearest earlier occurrence of the same key at distance >= min_p (tandem_hit.c:186-214)
+        // nearest earlier occurrence of the same key at distance >= min_p (tandem_hit.c:186-214); hits are compacted
         if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
-        for (int j = threadIdx.x; j < npow; j += blockDim.x) {
+        for (int j0 = 0; j0 < n_seed; j0 += blockDim.x) {
+            const int j = j0 + threadIdx.x;
             uint64_t v = SEED_INVALID;
             if (j < n_seed) {
                 uint64_t cur = buf[j]; uint32_t key = (uint32_t)(cur >> 32), pos = (uint32_t)cur, d = 0; bool found = false;
@@ -192,17 +267,24 @@ seed_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const in
                     d = pos - (uint32_t)o;
                     if (d >= P.min_p) { found = true; break; }
                 }
-                if (found && d <= P.max_p) { v = (uint64_t)pos << 32 | d; atomicAdd(&s_cnt, 1); }
+                if (found && d <= P.max_p) v = (uint64_t)pos << 32 | d;
             }
-            gtmp[j] = v;
+            const unsigned m = __ballot_sync(TH_FULL, v != SEED_INVALID);
+            int wbase = 0;
+            if ((threadIdx.x & 31) == 0 && m) wbase = atomicAdd(&s_cnt, __popc(m));
+            wbase = __shfl_sync(TH_FULL, wbase, 0);
+            if (v != SEED_INVALID) gtmp[wbase + __popc(m & ((1u << (threadIdx.x & 31)) - 1))] = v;
         }
         __syncthreads();
         const int n_hit = s_cnt;
-        for (int j = threadIdx.x; j < npow; j += blockDim.x) buf[j] = gtmp[j];
+        const int hpow = next_pow2(n_hit);
+        uint64_t *hb = hpow <= SEED_SMEM_CAP ? sbuf : gtmp; // the seeds are no longer needed
+        if (hb != gtmp) for (int j = threadIdx.x; j < n_hit; j += blockDim.x) hb[j] = gtmp[j];
+        for (int j = n_hit + threadIdx.x; j < hpow; j += blockDim.x) hb[j] = SEED_INVALID;
         __syncthreads();
-        if (n_hit > 0) block_bitonic_sort<false>(buf, npow);
+        if (n_hit > 1) block_bitonic_sort<false>(hb, hpow);
         for (int j = threadIdx.x; j < n_hit; j += blockDim.x) {
-            uint64_t v = buf[j];
+            uint64_t v = hb[j];
             hend[off + j] = (int32_t)(v >> 32);
             hper[off + j] = (int32_t)(uint32_t)v;
         }
