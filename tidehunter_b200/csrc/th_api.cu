@@ -77,7 +77,7 @@ struct th_gpu_ctx {
     DBuf d_par, d_paroff, d_parn, d_rstatus, d_scratch, d_scratch2, d_bnd, d_rev, d_counters;
     DBuf d_parstream, d_parused, d_pardoff;
     DBuf d_tasks, d_torder, d_ustart, d_ulen, d_slabs, d_consb, d_consc, d_consl, d_tstatus, d_items, d_iden, d_ext;
-    DBuf d_gsrc, d_gdst, d_glen, d_dense_b, d_dense_c;
+    DBuf d_gsrc, d_gdst, d_glen, d_dense_b, d_dense_c, d_redo;
     HBuf h_tmp, h_tmp2, h_consb, h_consc;
     // host result storage
     std::vector<int32_t> r_read_task_off, r_task_pos_off, r_pos, r_task_n_seqs, r_task_cons_off, r_cons_cov, r_iden, r_ext, r_task_status;
@@ -128,7 +128,7 @@ extern "C" void th_gpu_destroy(th_gpu_ctx *c) {
                   &c->d_gflag, &c->d_rank, &c->d_nrank, &c->d_tracked, &c->d_choff, &c->d_chlen, &c->d_chscore, &c->d_chidx, &c->d_cells, &c->d_pchn, &c->d_pchoff,
                   &c->d_pchlen, &c->d_par, &c->d_paroff, &c->d_parn, &c->d_rstatus, &c->d_scratch, &c->d_scratch2, &c->d_bnd, &c->d_rev, &c->d_counters,
                   &c->d_parstream, &c->d_parused, &c->d_pardoff, &c->d_tasks, &c->d_torder, &c->d_ustart, &c->d_ulen, &c->d_slabs, &c->d_consb, &c->d_consc,
-                  &c->d_consl, &c->d_tstatus, &c->d_items, &c->d_iden, &c->d_ext, &c->d_gsrc, &c->d_gdst, &c->d_glen, &c->d_dense_b, &c->d_dense_c};
+                  &c->d_consl, &c->d_tstatus, &c->d_items, &c->d_iden, &c->d_ext, &c->d_gsrc, &c->d_gdst, &c->d_glen, &c->d_dense_b, &c->d_dense_c, &c->d_redo};
     for (DBuf *b : ds) b->release();
     HBuf *hs[] = {&c->h_ascii, &c->h_tmp, &c->h_tmp2, &c->h_consb, &c->h_consc};
     for (HBuf *b : hs) b->release();
@@ -320,7 +320,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     S.d2h_bytes += 4 * tot_stream + 8 * (int64_t)n;
     // ---- host: split runs into tasks exactly as seqs_msa (src/gen_cons.c:191-200) ----
     std::vector<PoaTask> tasks; std::vector<int32_t> ustart, ulen; std::vector<KswItem> items;
-    std::vector<int32_t> item_task_unit; // for iden placement
+    int pending_single = -1; // index of an unpaired single-unit item
     int64_t cons_total = 0;
     const int min_copy = c->params.min_copy;
     for (int r = 0; r < n; ++r) {
@@ -351,10 +351,21 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
                     for (int q = i; q < j; ++q) c->r_pos.push_back(par[q]);
                     c->r_task_pos_off.push_back((int32_t)c->r_pos.size());
                     c->r_task_n_seqs.push_back(nseq);
-                    if (!P.only_unit) {
-                        for (int q = i; q < j - 1; ++q) { KswItem it = {0, t, par[q] + 1, par[q + 1] - par[q], c->h_roff[r]}; items.push_back(it); }
-                        KswItem le = {1, t, par[i] + 1, 0, c->h_roff[r]}; items.push_back(le);
-                        KswItem re = {2, t, par[j - 1] + 1, L - par[j - 1] - 1, c->h_roff[r]}; items.push_back(re);
+                    if (!P.only_unit) { // post-consensus alignments of seqs_msa (src/gen_cons.c:208-223); units go two per warp
+                        const int p0 = (int)c->r_pos.size() - (j - i);
+                        for (int q = i; q < j - 1; q += 2) {
+                            KswItem it; memset(&it, 0, sizeof(it));
+                            it.task = t; it.seq_off = c->h_roff[r]; it.out = p0 + (q - i);
+                            it.a = par[q] + 1; it.b = par[q + 1] - par[q];
+                            if (q + 1 < j - 1) { it.kind = 3; it.a2 = par[q + 1] + 1; it.b2 = par[q + 2] - par[q + 1]; items.push_back(it); }
+                            else if (pending_single >= 0) { // pair the left-over unit with the previous task's left-over
+                                KswItem &o = items[pending_single];
+                                o.kind = 4; o.task2 = t; o.a2 = it.a; o.b2 = it.b; o.out2 = it.out; o.seq_off2 = it.seq_off;
+                                pending_single = -1;
+                            } else { it.kind = 0; pending_single = (int)items.size(); items.push_back(it); }
+                        }
+                        KswItem le; memset(&le, 0, sizeof(le)); le.kind = 1; le.task = t; le.a = par[i] + 1; le.seq_off = c->h_roff[r]; le.out = 4 * t; items.push_back(le);
+                        KswItem re; memset(&re, 0, sizeof(re)); re.kind = 2; re.task = t; re.a = par[j - 1] + 1; re.b = L - par[j - 1] - 1; re.seq_off = c->h_roff[r]; re.out = 4 * t + 2; items.push_back(re);
                     }
                 }
                 i = j + 1;
@@ -432,25 +443,47 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         {
             std::vector<int32_t> coff(nt);
             for (int t = 0; t < nt; ++t) coff[t] = tasks[t].cons_off;
-            if (c->d_items.ensure(sizeof(KswItem) * (size_t)ni) || c->d_iden.ensure(4 * (size_t)ni) || c->d_ext.ensure(8 * (size_t)ni) || c->d_glen.ensure(4 * (size_t)nt)) return -1;
+            // pairs, singles, extensions: one kernel each (own register budgets)
+            std::stable_sort(items.begin(), items.end(), [](const KswItem &x, const KswItem &y) {
+                auto grp = [](int k) { return k >= 3 ? 0 : (k == 0 ? 1 : 2); };
+                return grp(x.kind) < grp(y.kind); });
+            int n_pairs = 0, n_singles = 0, n_exts = 0;
+            for (const KswItem &it : items) { if (it.kind >= 3) ++n_pairs; else if (it.kind == 0) ++n_singles; else ++n_exts; }
+            if (c->d_items.ensure(sizeof(KswItem) * (size_t)ni + 64) || c->d_iden.ensure(4 * c->r_pos.size() + 64) || c->d_ext.ensure(16 * (size_t)nt + 64) || c->d_glen.ensure(4 * (size_t)nt)) return -1;
             CK(cudaMemcpyAsync(c->d_items.p, items.data(), sizeof(KswItem) * (size_t)ni, cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(c->d_iden.p, 0, 4 * c->r_pos.size() + 64, st));
             CK(cudaMemcpyAsync(c->d_glen.p, coff.data(), 4 * (size_t)nt, cudaMemcpyHostToDevice, st));
-            const int kw = std::min(ni, c->n_sm * 16);
-            const int kgrid = (kw + KSW_WARPS - 1) / KSW_WARPS;
             const int64_t rev_stride = 2 * (int64_t)(c->max_len + 64);
-            if (c->d_bnd.ensure((size_t)kgrid * KSW_WARPS * bnd_stride * sizeof(int4)) || c->d_rev.ensure((size_t)kgrid * KSW_WARPS * rev_stride)) return -1;
-            ksw_items_kernel<<<kgrid, KSW_WARPS * 32, 0, st>>>(ni, c->d_items.as<KswItem>(), c->d_bseq.as<uint8_t>(), c->d_consb.as<uint8_t>(), c->d_glen.as<int32_t>(),
-                                                             c->d_consl.as<int32_t>(), c->d_rev.as<uint8_t>(), rev_stride, c->d_bnd.as<int4>(), bnd_stride, cnt32 + 2,
-                                                             c->d_iden.as<int32_t>(), c->d_ext.as<int32_t>(), cnt64 + 3);
+            const KswItem *d_pairs = c->d_items.as<KswItem>(), *d_singles = d_pairs + n_pairs, *d_exts = d_singles + n_singles;
+            auto grid_for = [&](int n_work, int min_blocks) { const int kw = std::min(std::max(n_work, 1), c->n_sm * min_blocks * KSW_WARPS); return (kw + KSW_WARPS - 1) / KSW_WARPS; };
+            const int g_pair = grid_for(n_pairs, KSW_PAIR_MIN_BLOCKS), g_single = grid_for(n_singles + 64, KSW_MIN_BLOCKS), g_ext = grid_for(n_exts, KSW_MIN_BLOCKS);
+            const int g_max = std::max(g_pair, std::max(g_single, g_ext));
+            if (c->d_bnd.ensure((size_t)g_max * KSW_WARPS * bnd_stride * sizeof(int4)) || c->d_rev.ensure((size_t)g_ext * KSW_WARPS * rev_stride) ||
+                c->d_redo.ensure(4 * (size_t)n_pairs + 64)) return -1;
+            if (n_pairs > 0) {
+                ksw_pair_kernel<<<g_pair, KSW_WARPS * 32, 0, st>>>(n_pairs, d_pairs, c->d_bseq.as<uint8_t>(), c->d_consb.as<uint8_t>(), c->d_glen.as<int32_t>(),
+                                                                 c->d_consl.as<int32_t>(), c->d_bnd.as<int4>(), bnd_stride, cnt32 + 2, c->d_redo.as<int32_t>(), cnt32 + 5,
+                                                                 c->d_iden.as<int32_t>(), cnt64 + 3);
+                S.n_launches++;
+            }
+            ksw_single_kernel<<<g_single, KSW_WARPS * 32, 0, st>>>(n_singles, d_singles, d_pairs, c->d_redo.as<int32_t>(), cnt32 + 5, c->d_bseq.as<uint8_t>(),
+                                                                 c->d_consb.as<uint8_t>(), c->d_glen.as<int32_t>(), c->d_consl.as<int32_t>(), c->d_bnd.as<int4>(), bnd_stride,
+                                                                 cnt32 + 3, c->d_iden.as<int32_t>(), cnt64 + 3);
             S.n_launches++;
+            if (n_exts > 0) {
+                ksw_ext_kernel<<<g_ext, KSW_WARPS * 32, 0, st>>>(n_exts, d_exts, c->d_bseq.as<uint8_t>(), c->d_consb.as<uint8_t>(), c->d_glen.as<int32_t>(),
+                                                               c->d_consl.as<int32_t>(), c->d_rev.as<uint8_t>(), rev_stride, c->d_bnd.as<int4>(), bnd_stride, cnt32 + 4,
+                                                               c->d_ext.as<int32_t>(), cnt64 + 3);
+                S.n_launches++;
+            }
         }
         CK(cudaEventRecord(c->ev[ei++], st)); // 10
         // ---- results to the host ----
-        std::vector<int32_t> cl(nt), iden_h(ni), ext_h(2 * (size_t)ni);
+        std::vector<int32_t> cl(nt);
         CK(cudaMemcpyAsync(cl.data(), c->d_consl.p, 4 * (size_t)nt, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(c->r_task_status.data(), c->d_tstatus.p, 4 * (size_t)nt, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(iden_h.data(), c->d_iden.p, 4 * (size_t)ni, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ext_h.data(), c->d_ext.p, 8 * (size_t)ni, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->r_iden.data(), c->d_iden.p, 4 * c->r_pos.size(), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->r_ext.data(), c->d_ext.p, 16 * (size_t)nt, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         std::vector<int64_t> gs(nt), gd(nt);
         int64_t tot = 0;
@@ -472,15 +505,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         }
         CK(cudaEventRecord(c->ev[ei++], st)); // 11
         CK(cudaStreamSynchronize(st));
-        S.d2h_bytes += 4ll * nt * 2 + 12ll * ni + tot * (c->params.need_cov ? 5 : 1);
-        // scatter item results
-        { size_t it = 0;
-          for (int t = 0; t < nt; ++t) {
-              const int p0 = c->r_task_pos_off[t], pn = c->r_task_pos_off[t + 1] - p0;
-              for (int q = 0; q < pn - 1; ++q) c->r_iden[p0 + q] = iden_h[it++];
-              c->r_ext[4 * t + 0] = ext_h[2 * it]; c->r_ext[4 * t + 1] = ext_h[2 * it + 1]; ++it;
-              c->r_ext[4 * t + 2] = ext_h[2 * it]; c->r_ext[4 * t + 3] = ext_h[2 * it + 1]; ++it;
-          } }
+        S.d2h_bytes += 4ll * nt * 2 + 4ll * (int64_t)c->r_pos.size() + 16ll * nt + tot * (c->params.need_cov ? 5 : 1);
         S.ms_poa = ev_ms(c, 8, 9); S.ms_ksw = ev_ms(c, 9, 10); S.ms_d2h = ev_ms(c, 10, 11);
     } else {
         CK(cudaEventRecord(c->ev[ei++], st)); CK(cudaEventRecord(c->ev[ei++], st)); CK(cudaEventRecord(c->ev[ei++], st));

@@ -139,3 +139,99 @@ __device__ void ksw_warp(const uint8_t *q, int ql, const uint8_t *t, int tl, int
         if (MODE == KSW_GLOBAL_STOP) out1 = tl - (int)((unsigned)resp >> 16);
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Two global alignments in one warp (usually against the same target): alignment A in the low, B in the high 16 bits of
+// every DP word (scores and identity payloads fit int16 for sequences up to KSW2_MAXLEN), so one VIMNMX.S16x2
+// (with its per-half "which operand won" predicates steering the payload selects) updates two cells.  Same
+// recurrences, boundary values and tie-breaking as ksw_warp<KSW_GLOBAL>; sequences must not contain N (the
+// caller checks and falls back), because the score is computed as 1 - 3 * min(q ^ t, 1).
+// ---------------------------------------------------------------------------------------------
+#define KSW2_MAXLEN 8000
+__device__ __forceinline__ uint32_t ksw_sel2(uint32_t a, uint32_t b, bool ph, bool pl) { // (ph ? a : b).hi, (pl ? a : b).lo
+    uint32_t r = b;
+    if (pl) r = __byte_perm(r, a, 0x3254);
+    if (ph) r = __byte_perm(r, a, 0x7610);
+    return r;
+}
+__device__ __forceinline__ uint32_t pk2(int v) { return ((uint32_t)(uint16_t)v) * 0x10001u; }
+
+template <int C>
+__device__ void ksw_warp_global2(const uint8_t *qa, int qla, const uint8_t *ta, int tla, const uint8_t *qb_, int qlb, const uint8_t *tb_, int tlb,
+                                 int4 *bnd, int &idenA, int &idenB) {
+    const int lane = lane_id();
+    idenA = 0; idenB = 0;
+    if (qla <= 0 || tla <= 0) { qla = 0; tla = 0; }
+    if (qlb <= 0 || tlb <= 0) { qlb = 0; tlb = 0; }
+    const int ql = max(qla, qlb), tl = max(tla, tlb);
+    if (ql <= 0 || tl <= 0) return;
+    uint32_t capA = 0, capB = 0; // payload of cell (tl_x - 1, ql_x - 1), captured when its row is computed
+    const int BW = 32 * C;
+    const int nblk = (ql + BW - 1) / BW;
+    const int blkA = qla > 0 ? (qla - 1) / BW : -1, blkB = qlb > 0 ? (qlb - 1) / BW : -1;
+    const uint32_t ONE2 = 0x00010001u, NQ2 = pk2(-KSW_Q), NE2 = pk2(-KSW_E);
+    for (int b = 0; b < nblk; ++b) {
+        const int jb = b * BW;
+        const int bw = min(ql - jb, BW), nl = (bw + C - 1) / C;
+        const int j0 = jb + lane * C;
+        const int4 *bin = bnd + (size_t)(b & 1) * tl;
+        int4 *bout = bnd + (size_t)((b + 1) & 1) * tl;
+        uint32_t Hp[C], Ea[C], pH[C], pE[C], qq[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = j0 + c;
+            const int h0 = -(KSW_Q + KSW_E * (j + 1));
+            Hp[c] = pk2(h0); Ea[c] = pk2(h0 - KSW_Q - KSW_E);
+            pH[c] = 0; pE[c] = 0;
+            const uint32_t a = j < qla ? qa[j] : 8u, bb = j < qlb ? qb_[j] : 8u; // 8 never equals a target code
+            qq[c] = a | bb << 16;
+        }
+        uint32_t hdiag = j0 == 0 ? 0u : pk2(-(KSW_Q + KSW_E * j0)), phdiag = 0;
+        uint32_t oH = 0, oF = 0, oPH = 0, oPF = 0;
+        const int nstep = tl + nl - 1;
+        for (int s = 0; s < nstep; ++s) {
+            const int i = s - lane;
+            uint32_t iH = __shfl_up_sync(TH_FULL, oH, 1), iF = __shfl_up_sync(TH_FULL, oF, 1);
+            uint32_t iPH = __shfl_up_sync(TH_FULL, oPH, 1), iPF = __shfl_up_sync(TH_FULL, oPF, 1);
+            if (lane == 0) {
+                if (b == 0) { const int h0 = -(KSW_Q + KSW_E * (s + 1)); iH = pk2(h0); iF = pk2(h0 - KSW_Q - KSW_E); iPH = 0; iPF = 0; }
+                else if (s < tl) { const int4 v = bin[s]; iH = (uint32_t)v.x; iF = (uint32_t)v.y; iPH = (uint32_t)v.z; iPF = (uint32_t)v.w; }
+            }
+            if (i >= 0 && i < tl && lane < nl) {
+                const uint32_t tb2 = (i < tla ? (uint32_t)ta[i] : 9u) | (i < tlb ? (uint32_t)tb_[i] : 9u) << 16; // 9: past the end, never equal
+                uint32_t hd = hdiag, phd = phdiag, F = iF, pF = iPF;
+                hdiag = iH; phdiag = iPH;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const uint32_t mm = __vminu2(qq[c] ^ tb2, ONE2);           // 0 = equal, 1 = different, per half
+                    uint32_t z = __vadd2(hd, __vadd2(ONE2, mm * 0xFFFDu));       // + (1 - 3 mm)
+                    uint32_t pz = __vadd2(phd, mm ^ ONE2);
+                    const uint32_t e = Ea[c];
+                    bool gh, gl;
+                    z = __vibmax_s16x2(z, e, &gh, &gl); pz = ksw_sel2(pz, pE[c], gh, gl);   // E wins only if strictly greater
+                    z = __vibmax_s16x2(z, F, &gh, &gl); pz = ksw_sel2(pz, pF, gh, gl);      // then F, again strictly
+                    const uint32_t t1 = __vadd2(z, NQ2);
+                    uint32_t m = __vibmax_s16x2(t1, e, &gh, &gl); pE[c] = ksw_sel2(pz, pE[c], gh, gl); Ea[c] = __vadd2(m, NE2);
+                    m = __vibmax_s16x2(t1, F, &gh, &gl); pF = ksw_sel2(pz, pF, gh, gl); F = __vadd2(m, NE2);
+                    hd = Hp[c]; phd = pH[c];
+                    Hp[c] = z; pH[c] = pz;
+                }
+                oH = Hp[C - 1]; oF = F; oPH = pH[C - 1]; oPF = pF;
+                if (lane == nl - 1 && b + 1 < nblk) bout[i] = make_int4((int)oH, (int)oF, (int)oPH, (int)oPF);
+                if (i == tla - 1 && b == blkA) {
+                    const int cc = (qla - 1 - jb) - lane * C;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) if (c == cc) capA = pH[c];
+                }
+                if (i == tlb - 1 && b == blkB) {
+                    const int cc = (qlb - 1 - jb) - lane * C;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) if (c == cc) capB = pH[c];
+                }
+            }
+        }
+        if (b == blkA) idenA = (int)(__shfl_sync(TH_FULL, capA, (qla - 1 - jb) / C) & 0xffffu);
+        if (b == blkB) idenB = (int)(__shfl_sync(TH_FULL, capB, (qlb - 1 - jb) / C) >> 16);
+        __syncwarp();
+    }
+}

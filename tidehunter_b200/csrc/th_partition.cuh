@@ -77,17 +77,106 @@ partition_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, con
     if (lane == 0 && ncell) atomicAdd(stat_cells, ncell);
 }
 
-// item = {kind, task, a, b}: kind 0: global identity of unit (qoff=a,len=b) vs consensus;
-// kind 1: left extension (target = reversed read prefix of length a); kind 2: right extension (target from a, length b)
-struct KswItem { int32_t kind, task, a, b; int64_t seq_off; };
+// item kinds: 0: global identity of unit (offset a, length b) vs consensus -> out_iden[out];
+// 3: two units (a, b) and (a2, b2) against the same consensus, packed 16x2 -> out_iden[out], out_iden[out + 1];
+// 4: two units of different tasks/reads, unit 2 = (seq_off2 + a2, b2) vs the consensus of task2 -> out_iden[out], out_iden[out2];
+// 1: left extension (target = reversed read prefix of length a) -> out_ext[out .. out+1];
+// 2: right extension (target from a, length b) -> out_ext[out .. out+1]
+struct KswItem { int32_t kind, task, a, b, a2, b2, out, task2, out2, pad; int64_t seq_off, seq_off2; };
+
+__device__ __forceinline__ bool warp_has_n(const uint8_t *s, int l) {
+    const int lane = lane_id();
+    bool f = false;
+    for (int i = lane; i < l; i += 32) f |= s[i] >= 4;
+    return __any_sync(TH_FULL, f);
+}
 
 #define KSW_WARPS 4
-__global__ void __launch_bounds__(KSW_WARPS * 32)
-ksw_items_kernel(int n_items, const KswItem *__restrict__ items, const uint8_t *__restrict__ bseq,
-                 const uint8_t *__restrict__ cons_base, const int32_t *__restrict__ cons_off, const int32_t *__restrict__ cons_len,
-                 uint8_t *rev_all, int64_t rev_stride, int4 *bnd_all, int64_t bnd_stride, int *counter,
-                 int32_t *__restrict__ out_iden /* per item */, int32_t *__restrict__ out_ext /* 2 per item */,
-                 unsigned long long *__restrict__ stat_cells) {
+#ifndef KSW_PAIR_MIN_BLOCKS
+#define KSW_PAIR_MIN_BLOCKS 4
+#endif
+#ifndef KSW2_C
+#define KSW2_C 16
+#endif
+#define KSW_MIN_BLOCKS 4
+
+// Post-consensus alignments of seqs_msa (src/gen_cons.c:208-223) run as three kernels with their own register
+// budgets, persistent warps on atomic work counters:
+//   ksw_pair_kernel   kinds 3/4: two unit-vs-consensus global alignments per warp (packed 16x2); pairs that do not
+//                     qualify (N bases, > KSW2_MAXLEN) are appended to a redo list
+//   ksw_single_kernel kind 0 and the redo list: one global alignment per warp, 32-bit
+//   ksw_ext_kernel    kinds 1/2: boundary extensions (score-only, arg-max in the reference's visiting order)
+__global__ void __launch_bounds__(KSW_WARPS * 32, KSW_PAIR_MIN_BLOCKS)
+ksw_pair_kernel(int n_items, const KswItem *__restrict__ items, const uint8_t *__restrict__ bseq,
+                const uint8_t *__restrict__ cons_base, const int32_t *__restrict__ cons_off, const int32_t *__restrict__ cons_len,
+                int4 *bnd_all, int64_t bnd_stride, int *counter, int32_t *__restrict__ redo_list, int *redo_count,
+                int32_t *__restrict__ out_iden, unsigned long long *__restrict__ stat_cells) {
+    const int lane = lane_id();
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int4 *bnd = bnd_all + (int64_t)gw * bnd_stride;
+    unsigned long long ncell = 0;
+    while (true) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(counter, 1);
+        it = __shfl_sync(TH_FULL, it, 0);
+        if (it >= n_items) break;
+        const KswItem I = items[it];
+        const int t2 = I.kind == 4 ? I.task2 : I.task;
+        const int cl = cons_len[I.task], cl2 = cons_len[t2];
+        const uint8_t *cons = cons_base + cons_off[I.task], *cons2 = cons_base + cons_off[t2];
+        const uint8_t *qa = bseq + I.seq_off + I.a, *qb = bseq + (I.kind == 4 ? I.seq_off2 : I.seq_off) + I.a2;
+        const int out2 = I.kind == 4 ? I.out2 : I.out + 1;
+        if (cl <= 0 && cl2 <= 0) { if (lane == 0) { out_iden[I.out] = 0; out_iden[out2] = 0; } continue; }
+        bool ok = cl > 0 && cl2 > 0 && max(max(I.b, I.b2), max(cl, cl2)) <= KSW2_MAXLEN;
+        ok = ok && !warp_has_n(qa, I.b) && !warp_has_n(qb, I.b2) && !warp_has_n(cons, cl) && (cons2 == cons || !warp_has_n(cons2, cl2));
+        if (!ok) { if (lane == 0) redo_list[atomicAdd(redo_count, 1)] = it; continue; }
+        int o0 = 0, o1 = 0;
+        ksw_warp_global2<KSW2_C>(qa, I.b, cons, cl, qb, I.b2, cons2, cl2, bnd, o0, o1);
+        ncell += (unsigned long long)I.b * cl + (unsigned long long)I.b2 * cl2;
+        if (lane == 0) { out_iden[I.out] = o0; out_iden[out2] = o1; }
+    }
+    if (lane == 0 && ncell) atomicAdd(stat_cells, ncell);
+}
+
+__global__ void __launch_bounds__(KSW_WARPS * 32, KSW_MIN_BLOCKS)
+ksw_single_kernel(int n_single, const KswItem *__restrict__ singles, const KswItem *__restrict__ pairs,
+                  const int32_t *__restrict__ redo_list, const int *__restrict__ redo_count, const uint8_t *__restrict__ bseq,
+                  const uint8_t *__restrict__ cons_base, const int32_t *__restrict__ cons_off, const int32_t *__restrict__ cons_len,
+                  int4 *bnd_all, int64_t bnd_stride, int *counter, int32_t *__restrict__ out_iden, unsigned long long *__restrict__ stat_cells) {
+    const int lane = lane_id();
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int4 *bnd = bnd_all + (int64_t)gw * bnd_stride;
+    unsigned long long ncell = 0;
+    const int n_work = n_single + 2 * *redo_count; // each redo pair is two alignments
+    while (true) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(counter, 1);
+        it = __shfl_sync(TH_FULL, it, 0);
+        if (it >= n_work) break;
+        int task, a, b, out; int64_t so;
+        if (it < n_single) { const KswItem I = singles[it]; task = I.task; a = I.a; b = I.b; out = I.out; so = I.seq_off; }
+        else {
+            const KswItem I = pairs[redo_list[(it - n_single) >> 1]];
+            if (((it - n_single) & 1) == 0) { task = I.task; a = I.a; b = I.b; out = I.out; so = I.seq_off; }
+            else if (I.kind == 4) { task = I.task2; a = I.a2; b = I.b2; out = I.out2; so = I.seq_off2; }
+            else { task = I.task; a = I.a2; b = I.b2; out = I.out + 1; so = I.seq_off; }
+        }
+        const int cl = cons_len[task];
+        int o0 = 0, o1 = 0;
+        if (cl > 0) { // ksw2_global(query = unit, target = consensus), src/gen_cons.c:211
+            ksw_warp<KSW_GLOBAL, 16>(bseq + so + a, b, cons_base + cons_off[task], cl, 0, bnd, o0, o1);
+            ncell += (unsigned long long)b * cl;
+        }
+        if (lane == 0) out_iden[out] = o0;
+    }
+    if (lane == 0 && ncell) atomicAdd(stat_cells, ncell);
+}
+
+__global__ void __launch_bounds__(KSW_WARPS * 32, KSW_MIN_BLOCKS)
+ksw_ext_kernel(int n_items, const KswItem *__restrict__ items, const uint8_t *__restrict__ bseq,
+               const uint8_t *__restrict__ cons_base, const int32_t *__restrict__ cons_off, const int32_t *__restrict__ cons_len,
+               uint8_t *rev_all, int64_t rev_stride, int4 *bnd_all, int64_t bnd_stride, int *counter,
+               int32_t *__restrict__ out_ext, unsigned long long *__restrict__ stat_cells) {
     const int lane = lane_id();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int4 *bnd = bnd_all + (int64_t)gw * bnd_stride;
@@ -101,27 +190,23 @@ ksw_items_kernel(int n_items, const KswItem *__restrict__ items, const uint8_t *
         const KswItem I = items[it];
         const int cl = cons_len[I.task];
         const uint8_t *cons = cons_base + cons_off[I.task];
-        int o0 = 0, o1 = 0;
-        if (cl <= 0) { if (lane == 0) { out_iden[it] = 0; out_ext[2 * it] = -1; out_ext[2 * it + 1] = -1; } continue; }
-        if (I.kind == 0) { // ksw2_global(query = unit, target = consensus), src/gen_cons.c:211
-            ksw_warp<KSW_GLOBAL, 16>(bseq + I.seq_off + I.a, I.b, cons, cl, 0, bnd, o0, o1);
-            ncell += (unsigned long long)I.b * cl;
-            if (lane == 0) out_iden[it] = o0;
-        } else if (I.kind == 1) { // ksw2_left_ext: both sequences reversed (src/ksw2_align.c:161-173)
-            const int tl = I.a; const uint8_t *rs = bseq + I.seq_off;
-            uint8_t *rq = rev, *rt = rev + ((cl + 15) & ~15);
-            for (int i = lane; i < cl; i += 32) rq[i] = cons[cl - 1 - i];
-            for (int i = lane; i < tl; i += 32) rt[i] = rs[tl - 1 - i];
-            __syncwarp();
-            ksw_warp<KSW_EXT, 16>(rq, cl, rt, tl, 0, bnd, o0, o1);
-            ncell += (unsigned long long)cl * tl;
-            if (lane == 0) { out_ext[2 * it] = o0; out_ext[2 * it + 1] = o1; }
-            __syncwarp();
-        } else {
-            ksw_warp<KSW_EXT, 16>(cons, cl, bseq + I.seq_off + I.a, I.b, 0, bnd, o0, o1);
-            ncell += (unsigned long long)cl * I.b;
-            if (lane == 0) { out_ext[2 * it] = o0; out_ext[2 * it + 1] = o1; }
+        int o0 = -1, o1 = -1;
+        if (cl > 0) {
+            if (I.kind == 1) { // ksw2_left_ext: both sequences reversed (src/ksw2_align.c:161-173)
+                const int tl = I.a; const uint8_t *rs = bseq + I.seq_off;
+                uint8_t *rq = rev, *rt = rev + ((cl + 15) & ~15);
+                for (int i = lane; i < cl; i += 32) rq[i] = cons[cl - 1 - i];
+                for (int i = lane; i < tl; i += 32) rt[i] = rs[tl - 1 - i];
+                __syncwarp();
+                ksw_warp<KSW_EXT, 16>(rq, cl, rt, tl, 0, bnd, o0, o1);
+                ncell += (unsigned long long)cl * tl;
+                __syncwarp();
+            } else { // ksw2_right_ext (src/ksw2_align.c:153-159)
+                ksw_warp<KSW_EXT, 16>(cons, cl, bseq + I.seq_off + I.a, I.b, 0, bnd, o0, o1);
+                ncell += (unsigned long long)cl * I.b;
+            }
         }
+        if (lane == 0) { out_ext[I.out] = o0; out_ext[I.out + 1] = o1; }
     }
     if (lane == 0 && ncell) atomicAdd(stat_cells, ncell);
 }
