@@ -84,6 +84,8 @@ __device__ void ksw_warp(const uint8_t *q, int ql, const uint8_t *t, int tl, int
                 const int tb = t[i];
                 int hd = hdiag, phd = phdiag, F = iF, pF = iPF;
                 hdiag = iH; phdiag = iPH;
+                int rowk = INT_MIN;
+                const int vcols = ql - j0; // columns past the query end hold dead values
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const int eq = tb == qb[c];
@@ -108,10 +110,15 @@ __device__ void ksw_warp(const uint8_t *q, int ql, const uint8_t *t, int tl, int
                     F = max(F, t1) - KSW_E;
                     hd = Hp[c]; phd = pH[c];
                     Hp[c] = z; pH[c] = pz;
-                    if (MODE == KSW_EXT) {
-                        if (z >= bestz && z > 0 && j0 + c < ql) {
-                            if (ksw_ext_better(z, i, j0 + c, bestz, besti, bestj, ql, tl)) { bestz = z; besti = i; bestj = j0 + c; }
-                        }
+                    if (MODE == KSW_EXT) { // row maximum of this lane's columns, first column on ties (smaller j = earlier anti-diagonal)
+                        if (c < vcols) rowk = max(rowk, z * 32 + (31 - c));
+                    }
+                }
+                if (MODE == KSW_EXT) {
+                    const int zr = rowk >> 5; // arithmetic shift: floor, exact because 0 <= 31 - c < 32
+                    if (zr > 0 && zr >= bestz) {
+                        const int jr = j0 + 31 - (rowk & 31);
+                        if (ksw_ext_better(zr, i, jr, bestz, besti, bestj, ql, tl)) { bestz = zr; besti = i; bestj = jr; }
                     }
                 }
                 oH = Hp[C - 1]; oF = F; oPH = pH[C - 1]; oPF = pF;
