@@ -63,6 +63,7 @@ struct HBuf { // growable pinned host buffer
 
 struct th_gpu_ctx {
     int device = 0, n_sm = 148;
+    double share = 1.0; // fraction of the SM slots the persistent grids of this context claim (TH_GPU_SHARE; several contexts can then co-run)
     th_gpu_params params;
     DevParams dp;
     cudaStream_t stream = nullptr;
@@ -109,6 +110,7 @@ extern "C" th_gpu_ctx *th_gpu_create(const th_gpu_params *p, int device) {
     c->device = device; c->params = *p;
     cudaDeviceProp prop; CKP(cudaGetDeviceProperties(&prop, device));
     c->n_sm = prop.multiProcessorCount;
+    if (const char *e = getenv("TH_GPU_SHARE")) { const double v = atof(e); if (v > 0.05 && v <= 1.0) c->share = v; }
     DevParams &d = c->dp;
     d.k = p->k; d.w = p->w; d.hpc = p->hpc; d.min_copy = p->min_copy; d.min_p = (uint32_t)p->min_p; d.max_p = (uint32_t)p->max_p;
     d.max_div = p->max_div; d.match = p->match; d.mismatch = p->mismatch; d.o1 = p->gap_open1; d.e1 = p->gap_ext1; d.o2 = p->gap_open2; d.e2 = p->gap_ext2;
@@ -256,7 +258,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     CK(cudaEventRecord(c->ev[ei++], st)); // 4
     // ---- chain DP ----
     {
-        const int grid = std::min((n + CHAIN_WARPS - 1) / CHAIN_WARPS, c->n_sm * 8);
+        const int grid = std::min((n + CHAIN_WARPS - 1) / CHAIN_WARPS, std::max(1, (int)(c->n_sm * 8 * c->share)));
         if (P.max_p < (1u << 27)) // hit periods are <= max_p (src/tandem_hit.c:204): the 1.8x gate fits 32-bit products
             chain_dp_kernel<true><<<grid, CHAIN_WARPS * 32, 0, st>>>(P, n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(),
                                                                   c->d_score.as<int32_t>(), c->d_from.as<int32_t>(), c->d_gflag.as<int32_t>(), cnt64 + 0);
@@ -286,7 +288,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     }
     CK(cudaEventRecord(c->ev[ei++], st)); // 6
     // ---- partition ----
-    const int n_pwarps = std::min(n, c->n_sm * 16);
+    const int n_pwarps = std::min(n, std::max(4, (int)(c->n_sm * 16 * c->share)));
     const int64_t bnd_stride = 2 * (int64_t)(c->max_len + 64);
     {
         if (c->d_bnd.ensure((size_t)n_pwarps * bnd_stride * sizeof(int4))) return -1;
@@ -411,7 +413,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         size_t free_b = 0, total_b = 0; CK(cudaMemGetInfo(&free_b, &total_b));
         if (slab_typ == 0) slab_typ = 1 << 20;
         size_t budget = (size_t)((double)(free_b + c->d_slabs.cap) * 0.6);
-        int nwarps = (int)std::min<size_t>((size_t)c->n_sm * POA_MIN_BLOCKS * POA_WARPS, std::max<size_t>(1, budget / slab_typ));
+        int nwarps = (int)std::min<size_t>((size_t)(c->n_sm * POA_MIN_BLOCKS * POA_WARPS * c->share), std::max<size_t>(1, budget / slab_typ));
         nwarps = std::min(nwarps, std::max(nt, 1));
         int grid = (nwarps + POA_WARPS - 1) / POA_WARPS;
         if (c->d_slabs.ensure((size_t)grid * POA_WARPS * slab_typ)) return -1;
@@ -455,7 +457,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
             CK(cudaMemcpyAsync(c->d_glen.p, coff.data(), 4 * (size_t)nt, cudaMemcpyHostToDevice, st));
             const int64_t rev_stride = 2 * (int64_t)(c->max_len + 64);
             const KswItem *d_pairs = c->d_items.as<KswItem>(), *d_singles = d_pairs + n_pairs, *d_exts = d_singles + n_singles;
-            auto grid_for = [&](int n_work, int min_blocks) { const int kw = std::min(std::max(n_work, 1), c->n_sm * min_blocks * KSW_WARPS); return (kw + KSW_WARPS - 1) / KSW_WARPS; };
+            auto grid_for = [&](int n_work, int min_blocks) { const int kw = std::min(std::max(n_work, 1), std::max(4, (int)(c->n_sm * min_blocks * KSW_WARPS * c->share))); return (kw + KSW_WARPS - 1) / KSW_WARPS; };
             const int g_pair = grid_for(n_pairs, KSW_PAIR_MIN_BLOCKS), g_single = grid_for(n_singles + 64, KSW_MIN_BLOCKS), g_ext = grid_for(n_exts, KSW_MIN_BLOCKS);
             const int g_max = std::max(g_pair, std::max(g_single, g_ext));
             if (c->d_bnd.ensure((size_t)g_max * KSW_WARPS * bnd_stride * sizeof(int4)) || c->d_rev.ensure((size_t)g_ext * KSW_WARPS * rev_stride) ||

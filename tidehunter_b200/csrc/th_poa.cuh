@@ -129,7 +129,18 @@ __device__ __forceinline__ void poa_pred(const uint32_t *A32, const int4 pm, con
     Mx = __vmaxs2(Mx, __funnelshift_r(prev, Xh, 16));
 }
 
-struct PoaSmem { int4 desc[POA_RING]; int4 meta[POA_RING]; int4 pre[POA_MAXPRE]; };
+struct PoaSmem { int4 desc[POA_RING]; int4 meta[POA_RING]; int4 pre[POA_MAXPRE]; uint4 last[32]; };
+
+// same contributions when the predecessor is the row this warp computed last and it fits one 64-column chunk: its
+// {H, E1, E2} pairs are still in shared memory (lane l holds columns last_beg + 2l, +1), no trip to L2
+__device__ __forceinline__ void poa_pred_last(const uint4 *last, const int4 pm, const int j, const uint32_t INFP,
+                                              uint32_t &Mx, uint32_t &E1x, uint32_t &E2x) {
+    const int pb = pm.y, l2 = (j - pb) >> 1;
+    uint32_t Xh = INFP, prev = INFP;
+    if (j >= pb && j <= pm.z) { const uint4 r = last[l2]; Xh = r.x; E1x = __vmaxs2(E1x, r.y); E2x = __vmaxs2(E2x, r.z); }
+    if (j > pb && j - 1 <= pm.z) prev = last[l2 - 1].x;
+    Mx = __vmaxs2(Mx, __funnelshift_r(prev, Xh, 16));
+}
 
 // one warp aligns sequence `query` to the graph and merges it in.  Returns an error code.
 __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *query, int qlen, int &node_n, int &edge_n,
@@ -255,6 +266,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
     const int qsn = qlen >> lp;
     const uint32_t *A32 = reinterpret_cast<const uint32_t *>(w.arena);
     uint32_t *A32w = reinterpret_cast<uint32_t *>(w.arena);
+    uint32_t last_off = 0xffffffffu; // arena offset of the row whose values sit in sm.last
     for (int i = 1; i < n - 1; ++i) {
         if ((i & 31) == 0 || i == 1) { // descriptors of the next 32 rows
             const int idx = (i & ~31) + lane;
@@ -291,8 +303,13 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         for (int ch = 0; ch < nchunk; ++ch) {
             const int j = beg + (ch << 6) + 2 * lane;
             uint32_t Mx = INFP, E1x = INFP, E2x = INFP;
-            poa_pred(A32, pm0, j, INFP, Mx, E1x, E2x);
-            for (int p = 1; p < np; ++p) poa_pred(A32, sm.pre[p], j, INFP, Mx, E1x, E2x);
+            if ((uint32_t)pm0.x == last_off) poa_pred_last(sm.last, pm0, j, INFP, Mx, E1x, E2x);
+            else poa_pred(A32, pm0, j, INFP, Mx, E1x, E2x);
+            for (int p = 1; p < np; ++p) {
+                const int4 pm = sm.pre[p];
+                if ((uint32_t)pm.x == last_off) poa_pred_last(sm.last, pm, j, INFP, Mx, E1x, E2x);
+                else poa_pred(A32, pm, j, INFP, Mx, E1x, E2x);
+            }
             const uint32_t S = ld32(qrow + j);
             const uint32_t Ms = __vadd2(Mx, S);
             const uint32_t Hme = __vimax3_s16x2(Ms, E1x, E2x);
@@ -317,6 +334,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 const uint32_t fa = __shfl_sync(TH_FULL, Fa, 31), fb = __shfl_sync(TH_FULL, Fb, 31);
                 carryF = __vadd2(__byte_perm(fa, fb, 0x7632), pk(-e1, -e2)); // G of column j0 - 1 in the next chunk's frame
             }
+            if (nchunk == 1) sm.last[lane] = make_uint4(Hn, E1o, E2o, 0); // every reader of the old contents is past the scan's shuffles
             if (j <= dend) {
                 const uint32_t wi = (row_off >> 1) + 2u * (uint32_t)(j - beg);
                 *reinterpret_cast<uint4 *>(A32w + wi) = make_uint4(Hn, E1o, E2o, Fa);
@@ -339,6 +357,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
             }
             if (lane == 0) { const int4 m = make_int4((int)row_off, beg, dend, max_i + 1); sm.meta[i & (POA_RING - 1)] = m; w.rmeta[i] = m; }
         }
+        last_off = nchunk == 1 ? row_off : 0xffffffffu;
         __syncwarp();
     }
     PH(1);
@@ -377,7 +396,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         if (bj < qlen) n_cig = qlen - bj;
         int wlo = n, whi = -1; // rows [wlo, whi] are in the window
         while (i > 0 && j > 0) {
-            if (i < wlo || (i < wlo + 16 && wlo > 0)) {
+            if (i < wlo || (i < wlo + 32 && wlo > 0)) {
                 const int top = i < wlo ? i + 1 : wlo; // load rows [top-32, top)
                 if (i < wlo) whi = i;
                 const int r = top - 32 + lane;
@@ -392,6 +411,34 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 }
                 wlo = max(0, top - 32); whi = min(whi, wlo + POA_RING - 1);
                 __syncwarp();
+            }
+            if (cur_op == ALL_OP) {
+                // Diagonal run: lane l tests the walker's position after l match steps, (i - l, j - l), provided rows
+                // i .. i-l each have the single predecessor row - 1 (then a match there is what the step below would
+                // pick first, :262-276).  The leading lanes that hold are emitted at once.
+                const int r = i - lane, jj = j - lane;
+                bool good = false; int vr = 0;
+                if (r >= 1 && jj >= 1 && r - 1 >= wlo) {
+                    const int4 dr = sm.desc[r & (POA_RING - 1)];
+                    if ((dr.y & 1023) == 1 && dr.x == r - 1) {
+                        const int4 mr = sm.meta[r & (POA_RING - 1)], mp = sm.meta[(r - 1) & (POA_RING - 1)];
+                        const int c = jj - mr.y, cp = jj - 1 - mp.y;
+                        if (c >= 0 && jj <= mr.z && cp >= 0 && jj - 1 <= mp.z) {
+                            const int hij = s16_at(A32[(mr.x >> 1) + 4 * (c >> 1)], c & 1);
+                            const int a = s16_at(A32[(mp.x >> 1) + 4 * (cp >> 1)], cp & 1);
+                            const int qb = query[jj - 1], vb = (dr.y >> 10) & 7;
+                            const int s = (qb < 4 && vb < 4) ? (qb == vb ? mat : -mis) : 0;
+                            good = a + s == hij; vr = dr.y >> 13;
+                        }
+                    }
+                }
+                const unsigned gm = __ballot_sync(TH_FULL, good);
+                const int run = gm == 0xffffffffu ? 32 : __ffs(~gm) - 1;
+                if (run > 0) {
+                    if (lane < run) { cg[n_cig + lane] = ((uint32_t)vr << 2) | 0; cq[n_cig + lane] = jj - 1; }
+                    n_cig += run; i -= run; j -= run;
+                    continue;
+                }
             }
             const int4 d = sm.desc[i & (POA_RING - 1)], mi = sm.meta[i & (POA_RING - 1)];
             const int np = d.y & 1023, vb = (d.y >> 10) & 7, v = d.y >> 13;
