@@ -155,6 +155,7 @@ __device__ void ksw_warp(const uint8_t *q, int ql, const uint8_t *t, int tl, int
 // caller checks and falls back), because the score is computed as 1 - 3 * min(q ^ t, 1).
 // ---------------------------------------------------------------------------------------------
 #define KSW2_MAXLEN 8000
+#define KSW2_BIAS 16400   // > 2 * KSW2_MAXLEN + gap costs, and BIAS + KSW2_MAXLEN < 32768
 __device__ __forceinline__ uint32_t ksw_sel2(uint32_t a, uint32_t b, bool ph, bool pl) { // (ph ? a : b).hi, (pl ? a : b).lo
     uint32_t r = b;
     if (pl) r = __byte_perm(r, a, 0x3254);
@@ -176,7 +177,10 @@ __device__ void ksw_warp_global2(const uint8_t *qa, int qla, const uint8_t *ta, 
     const int BW = 32 * C;
     const int nblk = (ql + BW - 1) / BW;
     const int blkA = qla > 0 ? (qla - 1) / BW : -1, blkB = qlb > 0 ? (qlb - 1) / BW : -1;
-    const uint32_t ONE2 = 0x00010001u, NQ2 = pk2(-KSW_Q), NE2 = pk2(-KSW_E);
+    // Scores are kept biased by +KSW2_BIAS per half, so every half stays in [1, 32767]: adding small per-half
+    // deltas with ordinary 32-bit integer arithmetic can then neither borrow nor carry across the halves, and the
+    // compiler is free to put those adds on the FMA pipe (IMAD) while the 16x2 max ops take the ALU pipe.
+    const uint32_t ONE2 = 0x00010001u, Q2 = (uint32_t)KSW_Q * 0x10001u, E2 = (uint32_t)KSW_E * 0x10001u;
     for (int b = 0; b < nblk; ++b) {
         const int jb = b * BW;
         const int bw = min(ql - jb, BW), nl = (bw + C - 1) / C;
@@ -187,13 +191,13 @@ __device__ void ksw_warp_global2(const uint8_t *qa, int qla, const uint8_t *ta, 
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = j0 + c;
-            const int h0 = -(KSW_Q + KSW_E * (j + 1));
+            const int h0 = KSW2_BIAS - (KSW_Q + KSW_E * (j + 1));
             Hp[c] = pk2(h0); Ea[c] = pk2(h0 - KSW_Q - KSW_E);
             pH[c] = 0; pE[c] = 0;
             const uint32_t a = j < qla ? qa[j] : 8u, bb = j < qlb ? qb_[j] : 8u; // 8 never equals a target code
             qq[c] = a | bb << 16;
         }
-        uint32_t hdiag = j0 == 0 ? 0u : pk2(-(KSW_Q + KSW_E * j0)), phdiag = 0;
+        uint32_t hdiag = j0 == 0 ? pk2(KSW2_BIAS) : pk2(KSW2_BIAS - (KSW_Q + KSW_E * j0)), phdiag = 0;
         uint32_t oH = 0, oF = 0, oPH = 0, oPF = 0;
         const int nstep = tl + nl - 1;
         for (int s = 0; s < nstep; ++s) {
@@ -201,7 +205,7 @@ __device__ void ksw_warp_global2(const uint8_t *qa, int qla, const uint8_t *ta, 
             uint32_t iH = __shfl_up_sync(TH_FULL, oH, 1), iF = __shfl_up_sync(TH_FULL, oF, 1);
             uint32_t iPH = __shfl_up_sync(TH_FULL, oPH, 1), iPF = __shfl_up_sync(TH_FULL, oPF, 1);
             if (lane == 0) {
-                if (b == 0) { const int h0 = -(KSW_Q + KSW_E * (s + 1)); iH = pk2(h0); iF = pk2(h0 - KSW_Q - KSW_E); iPH = 0; iPF = 0; }
+                if (b == 0) { const int h0 = KSW2_BIAS - (KSW_Q + KSW_E * (s + 1)); iH = pk2(h0); iF = pk2(h0 - KSW_Q - KSW_E); iPH = 0; iPF = 0; }
                 else if (s < tl) { const int4 v = bin[s]; iH = (uint32_t)v.x; iF = (uint32_t)v.y; iPH = (uint32_t)v.z; iPF = (uint32_t)v.w; }
             }
             if (i >= 0 && i < tl && lane < nl) {
@@ -211,15 +215,15 @@ __device__ void ksw_warp_global2(const uint8_t *qa, int qla, const uint8_t *ta, 
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const uint32_t mm = __vminu2(qq[c] ^ tb2, ONE2);           // 0 = equal, 1 = different, per half
-                    uint32_t z = __vadd2(hd, __vadd2(ONE2, mm * 0xFFFDu));       // + (1 - 3 mm)
-                    uint32_t pz = __vadd2(phd, mm ^ ONE2);
+                    uint32_t z = hd + ONE2 - 3u * mm;                          // + (1 - 3 mm) per half
+                    uint32_t pz = phd + ONE2 - mm;                             // identity count + (1 - mm)
                     const uint32_t e = Ea[c];
                     bool gh, gl;
                     z = __vibmax_s16x2(z, e, &gh, &gl); pz = ksw_sel2(pz, pE[c], gh, gl);   // E wins only if strictly greater
                     z = __vibmax_s16x2(z, F, &gh, &gl); pz = ksw_sel2(pz, pF, gh, gl);      // then F, again strictly
-                    const uint32_t t1 = __vadd2(z, NQ2);
-                    uint32_t m = __vibmax_s16x2(t1, e, &gh, &gl); pE[c] = ksw_sel2(pz, pE[c], gh, gl); Ea[c] = __vadd2(m, NE2);
-                    m = __vibmax_s16x2(t1, F, &gh, &gl); pF = ksw_sel2(pz, pF, gh, gl); F = __vadd2(m, NE2);
+                    const uint32_t t1 = z - Q2;
+                    uint32_t m = __vibmax_s16x2(t1, e, &gh, &gl); pE[c] = ksw_sel2(pz, pE[c], gh, gl); Ea[c] = m - E2;
+                    m = __vibmax_s16x2(t1, F, &gh, &gl); pF = ksw_sel2(pz, pF, gh, gl); F = m - E2;
                     hd = Hp[c]; phd = pH[c];
                     Hp[c] = z; pH[c] = pz;
                 }

@@ -625,7 +625,8 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
     }
     for (int e = lane; e < n_ev; e += 32) w.ord2[w.ev_anchor[e] + e] = w.ev_node[e];
     __syncwarp();
-    { int32_t *t = w.ord; w.ord = w.ord2; w.ord2 = t; }
+    if (lane == 0) { int32_t *t = w.ord; w.ord = w.ord2; w.ord2 = t; }
+    __syncwarp();
     PH(4);
 #undef PH
     return TH_OK;
@@ -712,6 +713,7 @@ poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const in
            int32_t *__restrict__ task_status, unsigned long long *__restrict__ stat_cells, unsigned long long *__restrict__ stat_rows,
            unsigned long long *__restrict__ stat_phase) {
     __shared__ PoaSmem s_mem[POA_WARPS];
+    __shared__ PoaWs s_ws[POA_WARPS]; // workspace pointers live in shared memory: one LDS instead of re-deriving them under register pressure
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * POA_WARPS + wib;
     uint8_t *slab = slabs + (size_t)gw * slab_bytes;
@@ -741,8 +743,10 @@ poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const in
             continue;
         }
         if (poa_fixed_bytes(T.ncap, T.qmax, T.n_seqs) + 4096 > slab_bytes) { if (lane == 0) { cons_len[t] = 0; task_status[t] = TH_ERR_ARENA; } continue; }
-        PoaWs w;
-        poa_carve(w, slab, slab_bytes, T.ncap, T.qmax, T.n_seqs);
+        PoaWs &w = s_ws[wib];
+        __syncwarp();
+        if (lane == 0) poa_carve(w, slab, slab_bytes, T.ncap, T.qmax, T.n_seqs);
+        __syncwarp();
         // first sequence: a chain of new nodes (abpoa_graph.c:1108-1124)
         const int l0 = u_len[T.unit_off]; const uint8_t *s0 = rseq + u_start[T.unit_off];
         for (int i = lane; i < l0 + 2; i += 32) { w.out_head[i] = w.out_tail[i] = w.in_head[i] = w.in_tail[i] = -1; w.aln_n[i] = 0; }
