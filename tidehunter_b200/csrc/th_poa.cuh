@@ -267,22 +267,25 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
     const uint32_t *A32 = reinterpret_cast<const uint32_t *>(w.arena);
     uint32_t *A32w = reinterpret_cast<uint32_t *>(w.arena);
     uint32_t last_off = 0xffffffffu; // arena offset of the row whose values sit in sm.last
+    const int16_t *const qp = w.qp; const int qps = w.qp_stride;
+    int4 *const rmeta_g = w.rmeta; const int4 *const rdesc_g = w.rdesc; const int32_t *const plist_g = w.plist;
+    const uint32_t arena_cap = w.arena_cap;
     for (int i = 1; i < n - 1; ++i) {
         if ((i & 31) == 0 || i == 1) { // descriptors of the next 32 rows
             const int idx = (i & ~31) + lane;
-            if (idx < n) sm.desc[idx & (POA_RING - 1)] = w.rdesc[idx];
+            if (idx < n) sm.desc[idx & (POA_RING - 1)] = rdesc_g[idx];
             __syncwarp();
         }
         const int4 d = sm.desc[i & (POA_RING - 1)];
         const int np = d.y & 1023;
         if ((unsigned)(np - 1) >= POA_MAXPRE) return TH_ERR_CAP;
         // band: what the predecessors' row maxima and max_remain say (abpoa_align.h:34-35, simd_abpoa_align.c:846-854)
-        const int4 pm0 = (i - d.x < POA_RING) ? sm.meta[d.x & (POA_RING - 1)] : w.rmeta[d.x];
+        const int4 pm0 = (i - d.x < POA_RING) ? sm.meta[d.x & (POA_RING - 1)] : rmeta_g[d.x];
         int mpl = min(n, pm0.w), mpr = max(0, pm0.w), min_pre_beg = pm0.y;
         if (np > 1) {
             for (int p = 1; p < np; ++p) {
-                const int pi = np == 2 ? d.w : w.plist[d.w + p];
-                const int4 m = (i - pi < POA_RING) ? sm.meta[pi & (POA_RING - 1)] : w.rmeta[pi];
+                const int pi = np == 2 ? d.w : plist_g[d.w + p];
+                const int4 m = (i - pi < POA_RING) ? sm.meta[pi & (POA_RING - 1)] : rmeta_g[pi];
                 mpl = min(mpl, m.w); mpr = max(mpr, m.w); min_pre_beg = min(min_pre_beg, m.y);
                 if (lane == 0) sm.pre[p] = m;
             }
@@ -292,10 +295,10 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         const int beg = max((beg0 >> lp) << lp, min_pre_beg), esn = end0 >> lp, dend = ((esn + 1) << lp) - 1;
         if (beg > dend) return TH_ERR_BAND;
         const int bsn = beg >> lp, width = dend - beg + 1;
-        if (5u * (uint32_t)width > w.arena_cap - used) return TH_ERR_ARENA;
+        if (5u * (uint32_t)width > arena_cap - used) return TH_ERR_ARENA;
         const uint32_t row_off = used;
         used += 5u * width; cells += width; rows += 1;
-        const int16_t *qrow = w.qp + ((d.y >> 10) & 7) * w.qp_stride;
+        const int16_t *qrow = qp + ((d.y >> 10) & 7) * qps;
         const int jmax = esn == qsn ? qlen : dend;       // columns past the query end do not compete for the row maximum
         const int vlast = esn - bsn;                      // the row's last vector is visited first by the reference's arg-max
         uint32_t best = 0, carryH = 0, carryF = POA_NEGP; // carryF: (F1 - e1, F2 - e2) of the previous chunk's last column
@@ -355,7 +358,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 const int vsn = vr == 0 ? esn : bsn + vr - 1;
                 max_i = vsn * pn + lam;
             }
-            if (lane == 0) { const int4 m = make_int4((int)row_off, beg, dend, max_i + 1); sm.meta[i & (POA_RING - 1)] = m; w.rmeta[i] = m; }
+            if (lane == 0) { const int4 m = make_int4((int)row_off, beg, dend, max_i + 1); sm.meta[i & (POA_RING - 1)] = m; rmeta_g[i] = m; }
         }
         last_off = nchunk == 1 ? row_off : 0xffffffffu;
         __syncwarp();
@@ -412,64 +415,28 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 wlo = max(0, top - 32); whi = min(whi, wlo + POA_RING - 1);
                 __syncwarp();
             }
-            if (cur_op == ALL_OP) {
-                // Diagonal run: lane l tests the walker's position after l match steps, (i - l, j - l), provided rows
-                // i .. i-l each have the single predecessor row - 1 (then a match there is what the step below would
-                // pick first, :262-276).  The leading lanes that hold are emitted at once.
-                const int r = i - lane, jj = j - lane;
-                bool good = false; int vr = 0;
-                if (r >= 1 && jj >= 1 && r - 1 >= wlo) {
-                    const int4 dr = sm.desc[r & (POA_RING - 1)];
-                    if ((dr.y & 1023) == 1 && dr.x == r - 1) {
-                        const int4 mr = sm.meta[r & (POA_RING - 1)], mp = sm.meta[(r - 1) & (POA_RING - 1)];
-                        const int c = jj - mr.y, cp = jj - 1 - mp.y;
-                        if (c >= 0 && jj <= mr.z && cp >= 0 && jj - 1 <= mp.z) {
-                            const int hij = s16_at(A32[(mr.x >> 1) + 4 * (c >> 1)], c & 1);
-                            const int a = s16_at(A32[(mp.x >> 1) + 4 * (cp >> 1)], cp & 1);
-                            const int qb = query[jj - 1], vb = (dr.y >> 10) & 7;
-                            const int s = (qb < 4 && vb < 4) ? (qb == vb ? mat : -mis) : 0;
-                            good = a + s == hij; vr = dr.y >> 13;
-                        }
-                    }
-                }
-                const unsigned gm = __ballot_sync(TH_FULL, good);
-                const int run = gm == 0xffffffffu ? 32 : __ffs(~gm) - 1;
-                if (run > 0) {
-                    if (lane < run) { cg[n_cig + lane] = ((uint32_t)vr << 2) | 0; cq[n_cig + lane] = jj - 1; }
-                    n_cig += run; i -= run; j -= run;
-                    continue;
-                }
-            }
             const int4 d = sm.desc[i & (POA_RING - 1)], mi = sm.meta[i & (POA_RING - 1)];
             const int np = d.y & 1023, vb = (d.y >> 10) & 7, v = d.y >> 13;
+            if (np > 32) { err = TH_ERR_CAP; break; }
             const int qb = query[j - 1];
             const int s = (qb < 4 && vb < 4) ? (qb == vb ? mat : -mis) : 0;
             const int ib = mi.y, iw = mi.z - mi.y + 1;
-            // own-row values (same address in every lane): the record of column j and the one to its left
             const int c = j - ib, q = c >> 1, odd = c & 1;
             const uint32_t rb = (uint32_t)(mi.x >> 1);
-            const uint4 r0 = *reinterpret_cast<const uint4 *>(A32 + rb + 4 * q);
-            const uint32_t g0 = A32[rb + 2 * iw + q];
-            uint4 r1 = r0; uint32_t g1 = g0;
-            if (!odd && c >= 2) { r1 = *reinterpret_cast<const uint4 *>(A32 + rb + 4 * (q - 1)); g1 = A32[rb + 2 * iw + q - 1]; }
-            const int hij = s16_at(r0.x, odd), e1ij = s16_at(r0.y, odd), e2ij = s16_at(r0.z, odd), f1 = s16_at(r0.w, odd), f2 = s16_at(g0, odd);
-            const int hm1 = s16_at(r1.x, !odd), f1m1 = s16_at(r1.w, !odd), f2m1 = s16_at(g1, !odd); // column j-1 (used only when c >= 1)
-            // predecessor values: lane p holds predecessor p
-            int pi = 0, a = 0, b = 0, x1 = 0, x2 = 0; bool in1 = false, in0 = false;
+            // lane p holds predecessor p.  Most steps are matches: test those first, with the two loads they need.
+            int pi = 0; bool in1 = false, in0 = false, podd = false; uint32_t pbw = 0;
             if (lane < np) {
                 pi = lane == 0 ? d.x : (np == 2 ? d.w : w.plist[d.w + lane]);
                 const int4 pm = pi >= wlo ? sm.meta[pi & (POA_RING - 1)] : w.rmeta[pi];
-                const int cp = j - pm.y, podd = cp & 1;
-                const uint32_t pbw = (uint32_t)(pm.x >> 1) + 4 * (cp >> 1);
+                const int cp = j - pm.y;
+                podd = cp & 1; pbw = (uint32_t)(pm.x >> 1) + 4 * (cp >> 1);
                 in1 = cp >= 1 && j - 1 <= pm.z; in0 = cp >= 0 && j <= pm.z;
-                uint4 rp = make_uint4(0, 0, 0, 0); uint32_t aw = 0;
-                if (in0) rp = *reinterpret_cast<const uint4 *>(A32 + pbw);
-                if (in1 && !podd) aw = A32[pbw - 4];
-                b = s16_at(rp.x, podd); x1 = s16_at(rp.y, podd); x2 = s16_at(rp.z, podd);
-                a = podd ? lo16(rp.x) : hi16(aw);
             }
-            if (np > 32) { err = TH_ERR_CAP; break; }
+            const int hij = s16_at(A32[rb + 4 * q], odd);
             if (cur_op & M_OP) {
+                uint32_t hpw = 0; // the H word that holds column j-1 of the predecessor
+                if (in1) hpw = A32[podd ? pbw : pbw - 4];
+                const int a = podd ? lo16(hpw) : hi16(hpw);
                 const unsigned mm = __ballot_sync(TH_FULL, in1 && a + s == hij);
                 if (mm) {
                     const int f = __ffs(mm) - 1;
@@ -478,6 +445,15 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                     continue;
                 }
             }
+            // not a match: the other states of this cell, of the cell to its left, and of the predecessors at column j
+            const uint4 r0 = *reinterpret_cast<const uint4 *>(A32 + rb + 4 * q);
+            const uint32_t g0 = A32[rb + 2 * iw + q];
+            uint4 r1 = r0; uint32_t g1 = g0;
+            if (!odd && c >= 2) { r1 = *reinterpret_cast<const uint4 *>(A32 + rb + 4 * (q - 1)); g1 = A32[rb + 2 * iw + q - 1]; }
+            const int e1ij = s16_at(r0.y, odd), e2ij = s16_at(r0.z, odd), f1 = s16_at(r0.w, odd), f2 = s16_at(g0, odd);
+            const int hm1 = s16_at(r1.x, !odd), f1m1 = s16_at(r1.w, !odd), f2m1 = s16_at(g1, !odd); // column j-1 (used only when c >= 1)
+            int b = 0, x1 = 0, x2 = 0;
+            if (in0) { const uint4 rp = *reinterpret_cast<const uint4 *>(A32 + pbw); b = s16_at(rp.x, podd); x1 = s16_at(rp.y, podd); x2 = s16_at(rp.z, podd); }
             if (cur_op & E_OP) {
                 const bool ok1 = (cur_op & E1_OP) && in0 && ((cur_op & M_OP) ? (hij == x1) : (e1ij == x1 - e1));
                 const bool ok2 = (cur_op & E2_OP) && in0 && ((cur_op & M_OP) ? (hij == x2) : (e2ij == x2 - e2));
