@@ -32,6 +32,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# DRAM bytes per banded POA cell from the ncu --set full capture in profiles/ (dram__bytes_read.sum + dram__bytes_write.sum
+# of poa_kernel over its cell count): r1 capture at 8192 reads = (57.67 + 67.70) GB / 5.686 G cells
+NCU_POA_TRAFFIC_PER_CELL = 22.05
+
 WORKLOAD = "synthetic ONT R2C2-style reads: 10 kb, 1 kb unit x 10 copies, 15% error (BASELINE.json configs[1])"
 
 
@@ -172,7 +176,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=8192, help="reads per GPU per step")
+    ap.add_argument("--reads", type=int, default=32768, help="reads per GPU per step")
+    ap.add_argument("--lanes", type=int, default=4, help="GPU contexts (streams) the step's reads are dealt to")
+    ap.add_argument("--chunk", type=int, default=4096, help="reads per chunk of the end-to-end leg (th_host_run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -217,37 +223,67 @@ def main():
 
     # this rank's batch: read indices [rank*reads, (rank+1)*reads) of the seeded generator
     n = args.reads
+    L = max(1, args.lanes)
     names, seqs = synth.gen_reads("r2c2", n, start=rank * n)
     bases = synth.total_bases(seqs)
 
     # ---------------- device-resident leg (value) ----------------
-    ctx = T.GpuContext(device=local)
-    ctx.upload(seqs)
-    for _ in range(args.warmup):
-        ctx.process_resident()
+    # The batch is dealt to L contexts ("lanes": own stream, own buffers) in contiguous blocks; one host thread per
+    # lane drives its context, so the lanes' kernels overlap on the GPU exactly as they do under th_host_run.
+    import threading
+    per_lane = (n + L - 1) // L
+    ctxs = [T.GpuContext(device=local) for _ in range(L)]
+    for k, c in enumerate(ctxs):
+        c.upload(seqs[k * per_lane:(k + 1) * per_lane])
+
+    def run_lanes(steps, collect=None):
+        def work(k):
+            for _ in range(steps):
+                r = ctxs[k].process_resident()
+                if collect is not None:
+                    collect[k].append(r.stats.as_dict())
+        th = [threading.Thread(target=work, args=(k,)) for k in range(L)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    run_lanes(args.warmup)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     t0 = time.perf_counter()
-    acc = {k: 0.0 for k in STAGES + ("total",)}
-    cnt = {}
-    launches = 0
-    for _ in range(args.steps):
-        r = ctx.process_resident()
-        s = r.stats.as_dict()
-        for k in STAGES + ("total",):
-            acc[k] += s["ms_" + k]
-        launches += s["n_launches"]
-        cnt = s
+    lane_stats = [[] for _ in range(L)]
+    run_lanes(args.steps, lane_stats)
     barrier()
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
     dt = max_over_ranks(dt)
+    acc = {k: 0.0 for k in STAGES + ("total",)}
+    cnt = {}
+    launches = 0
+    for k in range(L):
+        for s in lane_stats[k]:
+            for st in STAGES + ("total",):
+                acc[st] += s["ms_" + st]
+            launches += s["n_launches"]
+    for key in ("n_bases", "n_hits", "n_chain_evals", "n_poa_cells", "n_poa_rows", "n_ksw_cells", "n_tasks"):
+        cnt[key] = sum(lane_stats[k][-1][key] for k in range(L))   # per step, all lanes
     n_tasks = cnt["n_tasks"]
-    ctx.close()
+    # one lane alone (serial stages, nothing co-running): the per-kernel times comparable with the ncu launch list
+    serial = {k: 0.0 for k in STAGES}
+    serial_cnt = {}
+    if L > 1:
+        for _ in range(2):
+            s = ctxs[0].process_resident().stats.as_dict()
+            for st in STAGES:
+                serial[st] += s["ms_" + st] / 2
+            serial_cnt = s
+    for c in ctxs:
+        c.close()
 
     # ---------------- end-to-end leg through the host layer (e2e) ----------------
-    th = T.TideHunter(device=local, out_fmt=1, chunk_reads=n)
+    th = T.TideHunter(device=local, out_fmt=1, chunk_reads=args.chunk, lanes=L)
     for _ in range(2):
         th.run(names, seqs)
     barrier()
@@ -270,49 +306,70 @@ def main():
     value = tot_reads / dt
     e2e = tot_reads / dt_e2e
 
-    # ---------------- roofline for the dominant kernel + per-kernel table ----------------
+    # ---------------- roofline for the dominant kernel + per-kernel tables ----------------
+    # `kernels`: one lane alone (each kernel has the whole GPU; comparable with the ncu launch list in profiles/).
+    # `kernels_overlapped`: the same CUDA-event brackets inside the timed region, where the lanes' kernels share the SMs;
+    # times are per launch (one launch of each kernel per lane per step), so they include the co-running slowdown.
     hbm_peak, peak_src, sm_max = load_peaks()
-    per = {k: acc[k] / args.steps for k in STAGES}
-    work = {  # algorithmic units per step on this rank, counted by the kernels themselves
-        "pack": ("bases", cnt["n_bases"]), "seed": ("hits", cnt["n_hits"]), "chain": ("pair_evals", cnt["n_chain_evals"]),
-        "poa": ("cells", cnt["n_poa_cells"]), "ksw": ("cells", cnt["n_ksw_cells"]),
-    }
-    kernels = {}
-    tot_ms = sum(per.values())
-    for k in STAGES:
-        e = {"ms_per_step": round(per[k], 3), "share": round(per[k] / tot_ms, 4) if tot_ms > 0 else None}
-        if k in work and per[k] > 0:
-            e["unit"] = work[k][0]
-            e["g_units_per_s"] = round(work[k][1] / (per[k] * 1e-3) / 1e9, 3)
-        kernels[k] = e
-    dom = max(("poa", "ksw", "chain", "seed", "pack"), key=lambda k: per[k])
+    unit_name = {"pack": "bases", "seed": "hits", "chain": "pair_evals", "poa": "cells", "ksw": "cells"}
+    key_of = {"pack": "n_bases", "seed": "n_hits", "chain": "n_chain_evals", "poa": "n_poa_cells", "ksw": "n_ksw_cells"}
+
+    def table(ms_per_launch, counts):
+        out = {}
+        tot = sum(ms_per_launch.values())
+        for k in STAGES:
+            e = {"ms_per_launch": round(ms_per_launch[k], 3), "share": round(ms_per_launch[k] / tot, 4) if tot > 0 else None}
+            if k in key_of and ms_per_launch[k] > 0:
+                e["unit"] = unit_name[k]
+                e["g_units_per_s"] = round(counts[key_of[k]] / (ms_per_launch[k] * 1e-3) / 1e9, 3)
+            out[k] = e
+        return out
+
+    over_ms = {k: acc[k] / (args.steps * L) for k in STAGES}
+    over_cnt = {key: cnt[key] / L for key in key_of.values()}
+    kernels_over = table(over_ms, over_cnt)
+    if L > 1:
+        kernels = table(serial, serial_cnt)
+        ser_ms, ser_cnt = serial, serial_cnt
+    else:
+        kernels, ser_ms, ser_cnt = kernels_over, over_ms, over_cnt
+    dom = max(("poa", "ksw", "chain", "seed", "pack"), key=lambda k: ser_ms[k])
     # algorithmic HBM bytes per unit (DESIGN.md section "kernels"): POA stores 5 int16 states per banded cell and
     # re-reads them once as a predecessor row (20 B/cell); ksw keeps rows in registers (boundary hand-off only:
     # 16 B per target row per 512-column block, ~0.03 B/cell); chain reads 12 B per evaluated predecessor (L1/L2 hits);
     # seeding reads L/4 + L/8 bytes and writes 8 B per hit.
     bytes_per_unit = {"poa": 20.0, "ksw": 16.0 / 512, "chain": 12.0, "seed": None, "pack": 1.0 + 1.0 + 0.25 + 0.125}
-    if dom == "seed":
-        alg_bytes = cnt["n_bases"] * (0.25 + 0.125) + 8.0 * cnt["n_hits"]
-    else:
-        alg_bytes = work[dom][1] * bytes_per_unit[dom]
-    achieved = alg_bytes / (per[dom] * 1e-3) / 1e9 if per[dom] > 0 else 0.0
-    roofline = {"kernel": {"poa": "poa_kernel", "ksw": "ksw_items_kernel", "chain": "chain_dp_kernel", "seed": "seed_kernel", "pack": "pack_kernel"}[dom],
-                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per[dom],
-                "note": "integer DP kernel: see `kernels` for cell-update rates (GCUPS); the HBM fraction shows it is not bandwidth-bound"}
+
+    def alg_bytes_of(counts):
+        if dom == "seed":
+            return counts["n_bases"] * (0.25 + 0.125) + 8.0 * counts["n_hits"]
+        return counts[key_of[dom]] * bytes_per_unit[dom]
+
+    alg_bytes = alg_bytes_of(ser_cnt)
+    achieved = alg_bytes / (ser_ms[dom] * 1e-3) / 1e9 if ser_ms[dom] > 0 else 0.0
+    achieved_over = alg_bytes_of(over_cnt) / (over_ms[dom] * 1e-3) / 1e9 if over_ms[dom] > 0 else 0.0
+    traffic = {"poa": NCU_POA_TRAFFIC_PER_CELL}.get(dom)
+    roofline = {"kernel": {"poa": "poa_kernel", "ksw": "ksw_pair_kernel+ksw_ext_kernel", "chain": "chain_dp_kernel", "seed": "seed_kernel", "pack": "pack_kernel"}[dom],
+                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": (traffic * ser_cnt[key_of[dom]] / 1e9) if traffic else None, "traffic_unit": "GB per launch (ncu dram bytes per cell x cells of this launch)",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ser_ms[dom],
+                "measured": "CUDA events on the library's stream around the kernel, one lane alone (after the timed region)" if L > 1 else "CUDA events on the library's stream inside the timed region",
+                "in_timed_region": {"ms_per_launch": over_ms[dom], "achieved": achieved_over, "frac": achieved_over / hbm_peak, "lanes_co_running": L},
+                "note": "integer DP kernel, latency/issue bound: see `kernels` for cell-update rates (GCUPS); the HBM fraction shows it is not bandwidth-bound"}
 
     line = {
         "metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int16/int32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "reads_per_gpu_per_step": n, "bases_per_gpu_per_step": bases, "options": "defaults, -f 1",
-                   "l2": "per-step working set (reads + DP arenas, > 1 GB) exceeds the 126 MB L2", "parallelism": "read-sharded x%d, no collective" % world},
+                   "l2": "per-step working set (reads + DP arenas, > 1 GB) exceeds the 126 MB L2", "parallelism": "read-sharded x%d, no collective" % world,
+                   "lanes_per_gpu": L, "e2e_chunk_reads": args.chunk},
         "gbp_per_s": tot_bases / dt / 1e9,
         "poa_gcups": kernels["poa"].get("g_units_per_s"), "ksw_gcups": kernels["ksw"].get("g_units_per_s"),
         "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                 "ms_per_step": 1e3 * dt_e2e / args.steps, "output_bytes_per_step": out_bytes, "gbp_per_s": tot_bases / dt_e2e / 1e9},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
-        "device_ms_per_step": round(acc["total"] / args.steps, 3), "poa_tasks_per_step": n_tasks,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "kernels_overlapped": kernels_over,
+        "lane_ms_per_step": round(acc["total"] / (args.steps * L), 3), "poa_tasks_per_step": n_tasks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         kind, run = _ref_runner()

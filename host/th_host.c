@@ -9,15 +9,19 @@
 #include <string.h>
 #include <stdarg.h>
 #include <math.h>
+#include <pthread.h>
+#include <time.h>
 #include "th_host.h"
 
 #define TH_SLOTS 4096 /* CHUNK_READ_N, src/tidehunter.h:10: tandem_seq_t slots are reused every 4096 reads */
+#define TH_MAX_LANES 8
 
 typedef struct { char *s; size_t l, m; } str_t;
 
 struct th_host {
     th_host_para p;
-    th_gpu_ctx *gpu;
+    th_gpu_ctx *gpu;                        /* = lane[0] */
+    th_gpu_ctx *lane[TH_MAX_LANES]; int n_lanes;
     char *five_rc, *three_rc; int five_len, three_len;
     str_t out;
     str_t qual[TH_SLOTS];     /* persistent quality buffers: qual.l is never reset in the reference */
@@ -32,7 +36,7 @@ static void set_err(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnpr
 void th_host_default_para(th_host_para *p) {
     memset(p, 0, sizeof(*p));
     th_gpu_default_params(&p->gpu);
-    p->out_fmt = 1; p->min_len = 30; p->ada_match_rat = 0.8f; p->chunk_reads = 16384;
+    p->out_fmt = 1; p->min_len = 30; p->ada_match_rat = 0.8f; p->chunk_reads = 8192;
 }
 
 static void str_reserve(str_t *s, size_t extra) {
@@ -62,9 +66,15 @@ th_host *th_host_create(const th_host_para *p, int device) {
     th_host *h = (th_host *)calloc(1, sizeof(th_host));
     h->p = *p;
     h->p.gpu.need_cov = (p->out_fmt == 3 || p->out_fmt == 4 || p->min_cov > 0 || p->min_frac > 0.0) ? 1 : 0;
-    if (h->p.chunk_reads <= 0) h->p.chunk_reads = 16384;
-    h->gpu = th_gpu_create(&h->p.gpu, device < 0 ? 0 : device);
-    if (!h->gpu) { set_err("%s", th_gpu_last_error()); free(h); return NULL; }
+    if (h->p.chunk_reads <= 0) h->p.chunk_reads = 8192;
+    if (h->p.lanes <= 0) { const char *e = getenv("TH_HOST_LANES"); h->p.lanes = e ? atoi(e) : 3; }
+    if (h->p.lanes < 1) h->p.lanes = 1;
+    if (h->p.lanes > TH_MAX_LANES) h->p.lanes = TH_MAX_LANES;
+    for (h->n_lanes = 0; h->n_lanes < h->p.lanes; ++h->n_lanes) {
+        h->lane[h->n_lanes] = th_gpu_create(&h->p.gpu, device < 0 ? 0 : device);
+        if (!h->lane[h->n_lanes]) { int i; set_err("%s", th_gpu_last_error()); for (i = 0; i < h->n_lanes; ++i) th_gpu_destroy(h->lane[i]); free(h); return NULL; }
+    }
+    h->gpu = h->lane[0];
     if (p->five_seq && p->three_seq) {
         h->five_len = (int)strlen(p->five_seq); h->three_len = (int)strlen(p->three_seq);
         h->p.five_seq = strdup(p->five_seq); h->p.three_seq = strdup(p->three_seq);
@@ -75,7 +85,7 @@ th_host *th_host_create(const th_host_para *p, int device) {
 void th_host_destroy(th_host *h) {
     int i;
     if (!h) return;
-    th_gpu_destroy(h->gpu);
+    for (i = 0; i < h->n_lanes; ++i) th_gpu_destroy(h->lane[i]);
     free(h->five_rc); free(h->three_rc); free((void *)h->p.five_seq); free((void *)h->p.three_seq);
     for (i = 0; i < TH_SLOTS; ++i) free(h->qual[i].s);
     free(h->out.s); free(h);
@@ -280,24 +290,98 @@ WRITE_CONS:
     free(rec); free(cons_txt.s);
 }
 
+static void add_stats(th_gpu_stats *a, const th_gpu_stats *b) {
+    a->ms_h2d += b->ms_h2d; a->ms_pack += b->ms_pack; a->ms_seed += b->ms_seed; a->ms_chain += b->ms_chain; a->ms_select += b->ms_select;
+    a->ms_partition += b->ms_partition; a->ms_poa += b->ms_poa; a->ms_ksw += b->ms_ksw; a->ms_d2h += b->ms_d2h; a->ms_total += b->ms_total;
+    a->n_bases += b->n_bases; a->n_hits += b->n_hits; a->n_chain_evals += b->n_chain_evals; a->n_poa_cells += b->n_poa_cells; a->n_poa_rows += b->n_poa_rows;
+    a->n_ksw_cells += b->n_ksw_cells; a->n_tasks += b->n_tasks; a->n_launches += b->n_launches; a->h2d_bytes += b->h2d_bytes; a->d2h_bytes += b->d2h_bytes;
+}
+
+/* One th_host_run in flight: chunk c belongs to lane c % n_lanes.  A lane thread runs its chunks through the GPU one
+ * after the other; the caller's thread formats the chunks strictly in input order (the FASTQ slot quirk and the output
+ * order are sequential), and a lane only starts its next chunk once its previous result has been formatted, because
+ * the result arrays belong to the context. */
+enum { CH_PENDING = 0, CH_READY = 1, CH_EMITTED = 2, CH_FAILED = 3 };
+typedef struct {
+    th_host *h; int n, n_chunks; const char *const *seqs; const int32_t *lens;
+    pthread_mutex_t mu; pthread_cond_t cv;
+    int *state; th_gpu_result *res; int abort; char err[512];
+} run_job;
+typedef struct { run_job *job; int lane; double t_gpu, t_wait; } lane_arg;
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+static void *lane_main(void *arg_) {
+    lane_arg *a = (lane_arg *)arg_; run_job *J = a->job; th_host *h = J->h; int c;
+    for (c = a->lane; c < J->n_chunks; c += h->n_lanes) {
+        const int c0 = c * h->p.chunk_reads, m = J->n - c0 < h->p.chunk_reads ? J->n - c0 : h->p.chunk_reads;
+        int rc, stop;
+        pthread_mutex_lock(&J->mu); stop = J->abort; pthread_mutex_unlock(&J->mu);
+        if (stop) break;
+        { const double t0 = now_s();
+          rc = th_gpu_process_chunk(h->lane[a->lane], m, J->seqs + c0, J->lens + c0, &J->res[c]);
+          a->t_gpu += now_s() - t0; }
+        { const double t0 = now_s();
+        pthread_mutex_lock(&J->mu);
+        if (rc) { J->state[c] = CH_FAILED; J->abort = 1; snprintf(J->err, sizeof(J->err), "%s", th_gpu_last_error()); }
+        else J->state[c] = CH_READY;
+        pthread_cond_broadcast(&J->cv);
+        while (J->state[c] == CH_READY && !J->abort) pthread_cond_wait(&J->cv, &J->mu);
+        stop = J->abort;
+        pthread_mutex_unlock(&J->mu);
+        a->t_wait += now_s() - t0; }
+        if (stop) break;
+    }
+    return NULL;
+}
+
 const char *th_host_run(th_host *h, int n, const char *const *names, const char *const *seqs, const int32_t *lens, size_t *out_len) {
-    int c0;
+    int c, r, n_chunks = (n + h->p.chunk_reads - 1) / h->p.chunk_reads;
     h->out.l = 0; str_reserve(&h->out, 16); h->out.s[0] = 0;
     memset(&h->stats, 0, sizeof(h->stats));
     if (h->p.single_copy && h->p.only_full_length && h->p.five_seq) { set_err("-s (single-copy full-length) is not implemented"); *out_len = 0; return NULL; }
-    for (c0 = 0; c0 < n; c0 += h->p.chunk_reads) {
-        int m = n - c0 < h->p.chunk_reads ? n - c0 : h->p.chunk_reads, r;
-        th_gpu_result R;
-        if (th_gpu_process_chunk(h->gpu, m, seqs + c0, lens + c0, &R)) { set_err("%s", th_gpu_last_error()); *out_len = 0; return NULL; }
-        for (r = 0; r < m; ++r) emit_read(h, &R, r, names[c0 + r], seqs[c0 + r], lens[c0 + r], h->read_counter + r);
-        h->read_counter += m;
-        {
-            th_gpu_stats *a = &h->stats, *b = &R.stats;
-            a->ms_h2d += b->ms_h2d; a->ms_pack += b->ms_pack; a->ms_seed += b->ms_seed; a->ms_chain += b->ms_chain; a->ms_select += b->ms_select;
-            a->ms_partition += b->ms_partition; a->ms_poa += b->ms_poa; a->ms_ksw += b->ms_ksw; a->ms_d2h += b->ms_d2h; a->ms_total += b->ms_total;
-            a->n_bases += b->n_bases; a->n_hits += b->n_hits; a->n_chain_evals += b->n_chain_evals; a->n_poa_cells += b->n_poa_cells; a->n_poa_rows += b->n_poa_rows;
-            a->n_ksw_cells += b->n_ksw_cells; a->n_tasks += b->n_tasks; a->n_launches += b->n_launches; a->h2d_bytes += b->h2d_bytes; a->d2h_bytes += b->d2h_bytes;
+    if (n_chunks <= 1 || h->n_lanes == 1) {
+        for (c = 0; c < n_chunks; ++c) {
+            const int c0 = c * h->p.chunk_reads, m = n - c0 < h->p.chunk_reads ? n - c0 : h->p.chunk_reads;
+            th_gpu_result R;
+            if (th_gpu_process_chunk(h->gpu, m, seqs + c0, lens + c0, &R)) { set_err("%s", th_gpu_last_error()); *out_len = 0; return NULL; }
+            for (r = 0; r < m; ++r) emit_read(h, &R, r, names[c0 + r], seqs[c0 + r], lens[c0 + r], h->read_counter + r);
+            h->read_counter += m;
+            add_stats(&h->stats, &R.stats);
         }
+    } else {
+        run_job J; pthread_t th[TH_MAX_LANES]; lane_arg la[TH_MAX_LANES]; int n_thr = h->n_lanes < n_chunks ? h->n_lanes : n_chunks, failed = 0;
+        memset(&J, 0, sizeof(J));
+        J.h = h; J.n = n; J.n_chunks = n_chunks; J.seqs = seqs; J.lens = lens;
+        J.state = (int *)calloc(n_chunks, sizeof(int)); J.res = (th_gpu_result *)calloc(n_chunks, sizeof(th_gpu_result));
+        pthread_mutex_init(&J.mu, NULL); pthread_cond_init(&J.cv, NULL);
+        const double t_run0 = now_s(); double t_emit = 0, t_mwait = 0;
+        for (c = 0; c < n_thr; ++c) { la[c].job = &J; la[c].lane = c; la[c].t_gpu = la[c].t_wait = 0; pthread_create(&th[c], NULL, lane_main, &la[c]); }
+        for (c = 0; c < n_chunks && !failed; ++c) {
+            const int c0 = c * h->p.chunk_reads, m = n - c0 < h->p.chunk_reads ? n - c0 : h->p.chunk_reads;
+            double t0 = now_s();
+            pthread_mutex_lock(&J.mu);
+            while (J.state[c] == CH_PENDING && !J.abort) pthread_cond_wait(&J.cv, &J.mu);
+            failed = J.state[c] != CH_READY;
+            pthread_mutex_unlock(&J.mu);
+            t_mwait += now_s() - t0;
+            if (failed) break;
+            t0 = now_s();
+            for (r = 0; r < m; ++r) emit_read(h, &J.res[c], r, names[c0 + r], seqs[c0 + r], lens[c0 + r], h->read_counter + r);
+            t_emit += now_s() - t0;
+            h->read_counter += m;
+            add_stats(&h->stats, &J.res[c].stats);
+            pthread_mutex_lock(&J.mu); J.state[c] = CH_EMITTED; pthread_cond_broadcast(&J.cv); pthread_mutex_unlock(&J.mu);
+        }
+        if (failed) { pthread_mutex_lock(&J.mu); J.abort = 1; pthread_cond_broadcast(&J.cv); pthread_mutex_unlock(&J.mu); }
+        for (c = 0; c < n_thr; ++c) pthread_join(th[c], NULL);
+        if (getenv("TH_HOST_TIMING")) {
+            fprintf(stderr, "[th_host_run] %d reads, %d chunks, %d lanes: %.1f ms; formatting %.1f ms, waiting for chunks %.1f ms;", n, n_chunks, n_thr, 1e3 * (now_s() - t_run0), 1e3 * t_emit, 1e3 * t_mwait);
+            for (c = 0; c < n_thr; ++c) fprintf(stderr, " lane%d gpu %.1f wait %.1f;", c, 1e3 * la[c].t_gpu, 1e3 * la[c].t_wait);
+            fprintf(stderr, "\n");
+        }
+        pthread_mutex_destroy(&J.mu); pthread_cond_destroy(&J.cv);
+        if (failed) { set_err("%s", J.err[0] ? J.err : "a GPU lane failed"); free(J.state); free(J.res); *out_len = 0; return NULL; }
+        free(J.state); free(J.res);
     }
     *out_len = h->out.l;
     return h->out.s;

@@ -29,6 +29,9 @@ typedef struct {
     float ada_match_rat;    /* -a */
     const char *five_seq, *three_seq; /* -5 / -3 adapter sequences (already read from their files) or NULL */
     int chunk_reads;        /* reads per GPU chunk (the reference uses 4096, src/tidehunter.h:10) */
+    int lanes;              /* GPU contexts (own stream + buffers) the chunks of one th_host_run rotate over; chunk c+1 is
+                               uploaded and processed while chunk c is formatted, and their kernels fill each other's
+                               tails.  <= 0: default (TH_HOST_LANES or 3); 1 = strictly serial */
 } th_host_para;
 
 void th_host_default_para(th_host_para *p);

@@ -5,7 +5,8 @@
  *   tidehunter-b200 [options] in.fa/fq[.gz] > cons.fa
  *
  * Same flags and output formats as the reference; `-t` is accepted and ignored (the GPU replaces the
- * pthread pool), `--device N` selects the CUDA device, `--chunk N` the reads per GPU chunk.
+ * pthread pool), `--device N` selects the CUDA device, `--chunk N` the reads per GPU chunk,
+ * `--lanes N` the GPU contexts the chunks rotate over (pipelining).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -25,7 +26,7 @@ static const struct option long_opt[] = {
     {"output", 1, NULL, 'o'}, {"min-len", 1, NULL, 'm'}, {"min-cov", 1, NULL, 'r'}, {"unit-seq", 0, NULL, 'u'},
     {"longest", 0, NULL, 'l'}, {"full-len", 0, NULL, 'F'}, {"single-copy", 0, NULL, 's'}, {"out-fmt", 1, NULL, 'f'},
     {"thread", 1, NULL, 't'}, {"help", 0, NULL, 'h'}, {"version", 0, NULL, 'v'},
-    {"device", 1, NULL, 1001}, {"chunk", 1, NULL, 1002},
+    {"device", 1, NULL, 1001}, {"chunk", 1, NULL, 1002}, {"lanes", 1, NULL, 1003},
     {0, 0, 0, 0}};
 
 static long long parse_num(const char *str) { /* th_parse_num, src/main.c:54-64 */
@@ -46,7 +47,7 @@ static int usage(void) {
                     "  -o STR  output file [stdout]           -m INT  min consensus length [30]  -r FLT|INT min coverage\n"
                     "  -u unit sequences only   -l longest only   -F full-length only   -s single-copy (not implemented)\n"
                     "  -f INT  1 FASTA, 2 tabular, 3 FASTQ, 4 tabular+quality [1]\n"
-                    "  -t INT  accepted, ignored              --device INT CUDA device [0]       --chunk INT reads per GPU chunk [16384]\n\n");
+                    "  -t INT  accepted, ignored              --device INT CUDA device [0]       --chunk INT reads per GPU chunk [8192]\n          --lanes INT GPU contexts the chunks rotate over [3]\n\n");
     return 1;
 }
 
@@ -127,6 +128,7 @@ int main(int argc, char *argv[]) {
         case 'q': break;
         case 1001: device = atoi(optarg); break;
         case 1002: p.chunk_reads = atoi(optarg); break;
+        case 1003: p.lanes = atoi(optarg); break;
         case 'v': printf("%s (TideHunter v1.5.5 compatible)\n", PROG); return 0;
         case 'h': default: return usage();
         }
@@ -143,11 +145,13 @@ int main(int argc, char *argv[]) {
     {
         struct timespec t0, t1; FILE *out = out_fn ? fopen(out_fn, "w") : stdout;
         th_host *h; stream_t st; kstr_t name = {0, 0, 0}, seq = {0, 0, 0};
-        int n = 0, m = 0, i; char **names = NULL, **seqs = NULL; int32_t *lens = NULL; long long tot_reads = 0;
+        int n = 0, m = 0, i, batch_reads; char **names = NULL, **seqs = NULL; int32_t *lens = NULL; long long tot_reads = 0;
         clock_gettime(CLOCK_MONOTONIC, &t0);
         if (!out) { fprintf(stderr, "[main] cannot open %s\n", out_fn); return 1; }
         h = th_host_create(&p, device);
         if (!h) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
+        /* one th_host_run covers several chunks so that its GPU lanes overlap (host/th_host.h) */
+        batch_reads = p.chunk_reads * (p.lanes > 0 ? p.lanes : 3) * 2;
         memset(&st, 0, sizeof(st));
         st.fp = strcmp(argv[optind], "-") ? gzopen(argv[optind], "r") : gzdopen(0, "r");
         if (!st.fp) { fprintf(stderr, "[main] fail to open %s\n", argv[optind]); return 1; }
@@ -159,7 +163,7 @@ int main(int argc, char *argv[]) {
                 if (n == m) { m = m ? m * 2 : 1024; names = (char **)realloc(names, sizeof(char *) * m); seqs = (char **)realloc(seqs, sizeof(char *) * m); lens = (int32_t *)realloc(lens, sizeof(int32_t) * m); }
                 names[n] = strdup(name.s); seqs[n] = (char *)malloc(seq.l + 1); memcpy(seqs[n], seq.s, seq.l + 1); lens[n] = (int32_t)seq.l; ++n;
             }
-            if (n == p.chunk_reads || (l < 0 && n > 0)) {
+            if (n == batch_reads || (l < 0 && n > 0)) {
                 size_t ol; const char *txt = th_host_run(h, n, (const char *const *)names, (const char *const *)seqs, lens, &ol);
                 if (!txt) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
                 fwrite(txt, 1, ol, out);

@@ -139,10 +139,14 @@ def test_all_golden_cases(T, golden, golden_inputs):
     assert not bad, bad[:6]
 
 
-def test_chunking_does_not_change_output(T, golden, golden_inputs):
+@pytest.mark.parametrize("lanes", [1, 2, 4])
+def test_chunking_does_not_change_output(T, golden, golden_inputs, lanes):
+    """Chunks rotate over `lanes` GPU contexts on their own host threads (host/th_host.c); the text, including the
+    FASTQ quality slot quirk that depends on the global read order, must not depend on chunk size or lane count."""
     c = next(c for c in golden["cases"] if c["input"] == "testfq_all" and c["args"] == ["-f", "4"])
-    out, _ = _run_case(T, golden_inputs, c, chunk_reads=7)
+    out, st = _run_case(T, golden_inputs, c, chunk_reads=7, lanes=lanes)
     assert hashlib.md5(out).hexdigest() == c["md5"]
+    assert st["n_launches"] >= 10 * ((len(golden_inputs(c["input"])[0]) + 6) // 7)
 
 
 @pytest.mark.parametrize("shape,n", [("r2c2", 96), ("short", 128), ("long", 24)])

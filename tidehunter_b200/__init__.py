@@ -48,7 +48,7 @@ class HostPara(C.Structure):
     _fields_ = [
         ("gpu", GpuParams), ("out_fmt", C.c_int), ("min_len", C.c_int), ("min_cov", C.c_int), ("min_frac", C.c_double),
         ("only_longest", C.c_int), ("only_full_length", C.c_int), ("single_copy", C.c_int), ("ada_match_rat", C.c_float),
-        ("five_seq", C.c_char_p), ("three_seq", C.c_char_p), ("chunk_reads", C.c_int),
+        ("five_seq", C.c_char_p), ("three_seq", C.c_char_p), ("chunk_reads", C.c_int), ("lanes", C.c_int),
     ]
 
 

@@ -44,10 +44,10 @@ def build(force=False, verbose=False):
     host_src = [os.path.join(HOST, "th_host.c"), os.path.join(HOST, "th_host.h"), os.path.join(ROOT, "include", "th_gpu.h"), GPU_SO]
     if force or _newer(HOST_SO, host_src):
         _run(["gcc", "-std=gnu99", "-O2", "-fPIC", "-ffp-contract=off", "-Wall", "-shared", "-o", HOST_SO,
-              os.path.join(HOST, "th_host.c"), "-L" + PKG, "-lth_gpu", "-Wl,-rpath,$ORIGIN", "-lm"])
+              os.path.join(HOST, "th_host.c"), "-L" + PKG, "-lth_gpu", "-Wl,-rpath,$ORIGIN", "-lm", "-lpthread"])
     if force or _newer(CLI, [os.path.join(HOST, "th_main.c"), HOST_SO]):
         _run(["gcc", "-std=gnu99", "-O2", "-ffp-contract=off", "-Wall", "-o", CLI, os.path.join(HOST, "th_main.c"),
-              "-L" + PKG, "-lth_host", "-lth_gpu", "-Wl,-rpath,$ORIGIN/../tidehunter_b200", "-lz", "-lm"])
+              "-L" + PKG, "-lth_host", "-lth_gpu", "-Wl,-rpath,$ORIGIN/../tidehunter_b200", "-lz", "-lm", "-lpthread"])
     return GPU_SO, HOST_SO, CLI
 
 
