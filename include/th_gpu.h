@@ -85,6 +85,13 @@ int th_gpu_process_chunk(th_gpu_ctx *ctx, int32_t n_reads, const char *const *se
 int th_gpu_upload(th_gpu_ctx *ctx, int32_t n_reads, const char *const *seq, const int32_t *seq_len);
 int th_gpu_process_resident(th_gpu_ctx *ctx, th_gpu_result *out);
 
+/* Device-side step brackets: th_gpu_mark records CUDA event `slot` (0..3) on the context's stream;
+ * th_gpu_mark_elapsed returns the device time from mark (a, slot_a) to mark (b, slot_b) of two contexts
+ * on the same GPU (negative when b's mark was reached first).  bench.py times a step that spans
+ * several contexts as max(end marks) - min(start marks). */
+int th_gpu_mark(th_gpu_ctx *ctx, int32_t slot);
+int th_gpu_mark_elapsed(th_gpu_ctx *a, int32_t slot_a, th_gpu_ctx *b, int32_t slot_b, float *ms);
+
 /* Stage probes used by the parity tests (results are written to caller-allocated host arrays). */
 int th_gpu_debug_hits(th_gpu_ctx *ctx, int32_t read, int32_t cap, int32_t *end, int32_t *period);      /* returns hit_n */
 int th_gpu_debug_chain_dp(th_gpu_ctx *ctx, int32_t read, int32_t cap, int32_t *score, int32_t *from);   /* returns hit_n */

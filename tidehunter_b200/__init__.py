@@ -78,6 +78,8 @@ def _load():
         g.th_gpu_debug_par_pos.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
         g.th_gpu_ksw_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        g.th_gpu_mark.argtypes = [C.c_void_p, C.c_int32]
+        g.th_gpu_mark_elapsed.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_float)]
         g.th_gpu_debug_counters.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]
         g.th_gpu_last_error.restype = C.c_char_p
         g.th_gpu_device_count.restype = C.c_int
@@ -203,6 +205,17 @@ class GpuContext:
         if gpu_lib().th_gpu_process_resident(self._c, C.byref(r)):
             raise RuntimeError(self._err())
         return r
+
+    def mark(self, slot):
+        if gpu_lib().th_gpu_mark(self._c, slot):
+            raise RuntimeError(self._err())
+
+    def elapsed_ms(self, slot, other, other_slot):
+        """device time from this context's mark `slot` to `other`'s mark `other_slot`"""
+        ms = C.c_float(0)
+        if gpu_lib().th_gpu_mark_elapsed(self._c, slot, other._c, other_slot, C.byref(ms)):
+            raise RuntimeError(self._err())
+        return ms.value
 
     def hits(self, read, cap):
         e = (C.c_int32 * cap)(); p = (C.c_int32 * cap)()

@@ -68,6 +68,7 @@ struct th_gpu_ctx {
     DevParams dp;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[16];
+    cudaEvent_t mark[4]; // th_gpu_mark: step brackets for callers that time several contexts together
     // resident chunk
     int n_reads = 0; int64_t bpad = 0; int max_len = 0;
     std::vector<int64_t> h_roff; std::vector<int32_t> h_rlen;
@@ -117,6 +118,7 @@ extern "C" th_gpu_ctx *th_gpu_create(const th_gpu_params *p, int device) {
     d.pn = p->simd_lanes16; d.only_unit = p->only_unit;
     CKP(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) CKP(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 4; ++i) CKP(cudaEventCreate(&c->mark[i]));
     CKP(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_CAP * 8));
     memset(&c->stats, 0, sizeof(c->stats));
     return c;
@@ -135,6 +137,7 @@ extern "C" void th_gpu_destroy(th_gpu_ctx *c) {
     HBuf *hs[] = {&c->h_ascii, &c->h_tmp, &c->h_tmp2, &c->h_consb, &c->h_consc};
     for (HBuf *b : hs) b->release();
     for (int i = 0; i < 16; ++i) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(c->mark[i]);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -535,6 +538,21 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
 extern "C" int th_gpu_process_chunk(th_gpu_ctx *c, int32_t n_reads, const char *const *seq, const int32_t *seq_len, th_gpu_result *out) {
     if (th_gpu_upload(c, n_reads, seq, seq_len)) return -1;
     return th_gpu_process_resident(c, out);
+}
+
+// ---- device-side step brackets ------------------------------------------------------------------
+extern "C" int th_gpu_mark(th_gpu_ctx *c, int32_t slot) {
+    if (slot < 0 || slot >= 4) { set_err("mark slot out of range"); return -1; }
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->mark[slot], c->stream));
+    return 0;
+}
+extern "C" int th_gpu_mark_elapsed(th_gpu_ctx *a, int32_t slot_a, th_gpu_ctx *b, int32_t slot_b, float *ms) {
+    if (slot_a < 0 || slot_a >= 4 || slot_b < 0 || slot_b >= 4 || a->device != b->device) { set_err("bad marks"); return -1; }
+    CK(cudaSetDevice(a->device));
+    CK(cudaEventSynchronize(a->mark[slot_a])); CK(cudaEventSynchronize(b->mark[slot_b]));
+    CK(cudaEventElapsedTime(ms, a->mark[slot_a], b->mark[slot_b]));
+    return 0;
 }
 
 // ---- stage probes -----------------------------------------------------------------------------

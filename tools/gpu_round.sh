@@ -7,6 +7,6 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python tools/profile_step.py 2048 2 > gpurun_out/launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'poa_kernel|ksw_items|chain_dp|seed_kernel' -c 8 \
-    -o gpurun_out/prof_full -f python tools/profile_step.py 1024 1 > gpurun_out/prof_full.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'poa_kernel|ksw_pair|ksw_ext|chain_dp_kernel|seed_kernel|chain_select|rank_kernel' -c 7 \
+    -o gpurun_out/prof_full -f python tools/profile_step.py 2048 1 > gpurun_out/prof_full.log 2>&1
 ls -la gpurun_out
