@@ -132,6 +132,36 @@ static int infix_ed(const char *q, int ql, const char *t, int tl, int *start, in
     return best;
 }
 
+/* -s: collect_ed_res (src/gen_cons.c:89-110) -- the best infix hit of an adapter in the read and one more on each side */
+typedef struct { int ed, start, end; } ed_res_t;
+static int collect_ed_res(float ada_match_rat, const char *q, int qlen, const char *seq, int seq_len, ed_res_t *res) {
+    int n = 0, ed, start = 0, end = 0, k = (int)(qlen * (1 - ada_match_rat));
+    ed = infix_ed(q, qlen, seq, seq_len, &start, &end, k);
+    if (ed != -1) {
+        res[0].ed = ed; res[0].start = start; res[0].end = end; n++;
+        if (res[0].start >= qlen) {
+            ed = infix_ed(q, qlen, seq, res[0].start, &start, &end, k);
+            if (ed != -1) { res[n].ed = ed; res[n].start = start; res[n].end = end; n++; }
+        }
+        if (res[0].end <= seq_len - qlen) {
+            ed = infix_ed(q, qlen, seq + res[0].end, seq_len - res[0].end, &start, &end, k);
+            if (ed != -1) { res[n].ed = ed; res[n].start = res[0].end + start; res[n].end = res[0].end + end; n++; }
+        }
+    }
+    return n;
+}
+/* get_full_len_seq (src/gen_cons.c:112-126): adapter pair with the smallest total distance and >= min_len between them */
+static int full_len_pair(int min_len, int left_n, const ed_res_t *left, int right_n, const ed_res_t *right, int *tar_start, int *tar_end) {
+    int tot_ed = INT32_MAX, i, j;
+    for (i = 0; i < left_n; ++i)
+        for (j = 0; j < right_n; ++j)
+            if (right[j].start - left[i].end - 1 >= min_len && tot_ed > left[i].ed + right[j].ed) {
+                tot_ed = left[i].ed + right[j].ed;
+                *tar_start = left[i].end + 1; *tar_end = right[j].start - 1;
+            }
+    return tot_ed;
+}
+
 typedef struct { /* one record of tandem_seq_t */
     int cons_start, cons_end, cons_len, full_length, pos_n;
     double copy_num, ave_match;
@@ -144,6 +174,7 @@ static void emit_read(th_host *h, const th_gpu_result *R, int r, const char *nam
     const th_host_para *p = &h->p;
     const int with_qual = (p->out_fmt == 3 || p->out_fmt == 4);
     int t, i, n_rec = 0, m_rec = 0;
+    int32_t sc_pos[2] = {0, 0};
     rec_t *rec = NULL;
     str_t cons_txt = {0, 0, 0};
     str_t *qs = &h->qual[global_index % TH_SLOTS];
@@ -250,6 +281,44 @@ WRITE_CONS:
             free(cons_seq); free(cons_qual);
         }
     }
+    /* single_copy_full_len_seq, src/gen_cons.c:128-171 (tidehunter_core runs it after the chains, src/tidehunter.c:49-51) */
+    if (p->single_copy == 1 && p->only_full_length && p->five_seq && p->three_seq && len >= p->gpu.k) {
+        ed_res_t e5[3], e3[3]; int n5, n3, tar_start = -1, tar_end = -1, tot_ed, full_length = 0, cons_len = 0;
+        n5 = collect_ed_res(p->ada_match_rat, p->five_seq, h->five_len, seq, len, e5);
+        n3 = collect_ed_res(p->ada_match_rat, h->three_rc, h->three_len, seq, len, e3);
+        tot_ed = full_len_pair(p->min_len, n5, e5, n3, e3, &tar_start, &tar_end);
+        if (tot_ed != INT32_MAX) { sc_pos[0] = tar_start; sc_pos[1] = tar_end; cons_len = tar_end - tar_start + 1; full_length = 1; }
+        if (tot_ed > 0) { /* reverse strand */
+            n5 = collect_ed_res(p->ada_match_rat, h->five_rc, h->five_len, seq, len, e5);
+            n3 = collect_ed_res(p->ada_match_rat, p->three_seq, h->three_len, seq, len, e3);
+            if (full_len_pair(p->min_len, n3, e3, n5, e5, &tar_start, &tar_end) < tot_ed) {
+                sc_pos[0] = tar_start; sc_pos[1] = tar_end; cons_len = tar_end - tar_start + 1; full_length = 2;
+            }
+        }
+        if (full_length > 0) {
+            int keep = 1;
+            if (!p->gpu.only_unit) {
+                keep = !(cons_len < p->min_len || cons_len > p->gpu.max_p);
+                if (keep && p->only_longest && n_rec == 1) {
+                    if (sc_pos[1] - sc_pos[0] > rec[0].cons_end - rec[0].cons_start) { n_rec = 0; cons_txt.l = 0; }
+                    else keep = 0;
+                }
+            }
+            if (keep) {
+                if (n_rec == m_rec) { m_rec = m_rec ? m_rec * 2 : 4; rec = (rec_t *)realloc(rec, sizeof(rec_t) * m_rec); }
+                memset(&rec[n_rec], 0, sizeof(rec_t));
+                rec[n_rec].pos_n = 2; rec[n_rec].sub_pos = sc_pos;
+                if (!p->gpu.only_unit) {
+                    rec[n_rec].cons_start = sc_pos[0]; rec[n_rec].cons_end = sc_pos[1]; rec[n_rec].cons_len = cons_len;
+                    rec[n_rec].full_length = full_length; rec[n_rec].copy_num = 1.0; rec[n_rec].ave_match = 100.0;
+                    rec[n_rec].seq_off = cons_txt.l;
+                    str_write(&cons_txt, seq + sc_pos[0], cons_len);   /* the read's own characters, case kept */
+                    if (with_qual) { str_reserve(qs, cons_len); memset(qs->s + qs->l, 33, cons_len); qs->l += cons_len; qs->s[qs->l] = 0; }
+                }
+                ++n_rec;
+            }
+        }
+    }
     /* mini_tandem_output, src/main.c:214-271 */
     {
         str_t *o = &h->out; int ci, j; size_t qoff = 0;
@@ -338,7 +407,6 @@ const char *th_host_run(th_host *h, int n, const char *const *names, const char 
     int c, r, n_chunks = (n + h->p.chunk_reads - 1) / h->p.chunk_reads;
     h->out.l = 0; str_reserve(&h->out, 16); h->out.s[0] = 0;
     memset(&h->stats, 0, sizeof(h->stats));
-    if (h->p.single_copy && h->p.only_full_length && h->p.five_seq) { set_err("-s (single-copy full-length) is not implemented"); *out_len = 0; return NULL; }
     if (n_chunks <= 1 || h->n_lanes == 1) {
         for (c = 0; c < n_chunks; ++c) {
             const int c0 = c * h->p.chunk_reads, m = n - c0 < h->p.chunk_reads ? n - c0 : h->p.chunk_reads;

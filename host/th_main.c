@@ -45,7 +45,7 @@ static int usage(void) {
                     "  -M/-X INT match/mismatch [2/4]         -O INT(,INT) gap open [4,24]       -E INT(,INT) gap ext [2,1]\n"
                     "  -5/-3 STR adapter FASTA files          -a FLT  adapter match ratio [0.80]\n"
                     "  -o STR  output file [stdout]           -m INT  min consensus length [30]  -r FLT|INT min coverage\n"
-                    "  -u unit sequences only   -l longest only   -F full-length only   -s single-copy (not implemented)\n"
+                    "  -u unit sequences only   -l longest only   -F full-length only   -s single-copy full-length (with -F -5 -3)\n"
                     "  -f INT  1 FASTA, 2 tabular, 3 FASTQ, 4 tabular+quality [1]\n"
                     "  -t INT  accepted, ignored              --device INT CUDA device [0]       --chunk INT reads per GPU chunk [8192]\n          --lanes INT GPU contexts the chunks rotate over [3]\n\n");
     return 1;

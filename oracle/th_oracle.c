@@ -594,6 +594,63 @@ WRITE_CONS:
     free(cons_seq); free(cons_bseq); free(cons_qual);
 }
 
+/* ------------------------------------------------------------------ -s: single-copy full-length reads
+ * collect_ed_res src/gen_cons.c:89-110: best infix hit of the adapter, then one more on each side of it */
+typedef struct { int ed, start, end; } ed_res_t;
+static int collect_ed_res(const tho_para_t *p, const char *q, int qlen, const char *seq, int seq_len, ed_res_t *res) {
+    int n = 0, ed, start = 0, end = 0, k = (int)(qlen * (1 - p->ada_match_rat));
+    ed = edlib_hw(q, qlen, seq, seq_len, &start, &end, k);
+    if (ed != -1) {
+        res[0].ed = ed; res[0].start = start; res[0].end = end; n++;
+        if (res[0].start >= qlen) {
+            ed = edlib_hw(q, qlen, seq, res[0].start, &start, &end, k);
+            if (ed != -1) { res[n].ed = ed; res[n].start = start; res[n].end = end; n++; }
+        }
+        if (res[0].end <= seq_len - qlen) {
+            ed = edlib_hw(q, qlen, seq + res[0].end, seq_len - res[0].end, &start, &end, k);
+            if (ed != -1) { res[n].ed = ed; res[n].start = res[0].end + start; res[n].end = res[0].end + end; n++; }
+        }
+    }
+    return n;
+}
+/* get_full_len_seq src/gen_cons.c:112-126 */
+static int get_full_len_seq(const tho_para_t *p, int left_n, const ed_res_t *left, int right_n, const ed_res_t *right, int *tar_start, int *tar_end) {
+    int tot_ed = INT32_MAX, i, j;
+    for (i = 0; i < left_n; ++i)
+        for (j = 0; j < right_n; ++j)
+            if (right[j].start - left[i].end - 1 >= p->min_len && tot_ed > left[i].ed + right[j].ed) {
+                tot_ed = left[i].ed + right[j].ed;
+                *tar_start = left[i].end + 1; *tar_end = right[j].start - 1;
+            }
+    return tot_ed;
+}
+/* single_copy_full_len_seq src/gen_cons.c:128-171 */
+static void single_copy_full_len(int seq_len, const char *seq, tho_read_t *r, const tho_para_t *p, const char *five_rc, const char *three_rc) {
+    int cons_len = 0, full_length = 0, tar_start = -1, tar_end = -1, tot_ed, _5_n, _3_n, par_pos[2];
+    int five_len = (int)strlen(p->five_seq), three_len = (int)strlen(p->three_seq);
+    ed_res_t _5[3], _3[3];
+    _5_n = collect_ed_res(p, p->five_seq, five_len, seq, seq_len, _5);
+    _3_n = collect_ed_res(p, three_rc, three_len, seq, seq_len, _3);
+    tot_ed = get_full_len_seq(p, _5_n, _5, _3_n, _3, &tar_start, &tar_end);
+    if (tot_ed != INT32_MAX) { par_pos[0] = tar_start; par_pos[1] = tar_end; cons_len = tar_end - tar_start + 1; full_length = 1; }
+    if (tot_ed > 0) {
+        _5_n = collect_ed_res(p, five_rc, five_len, seq, seq_len, _5);
+        _3_n = collect_ed_res(p, p->three_seq, three_len, seq, seq_len, _3);
+        if (get_full_len_seq(p, _3_n, _3, _5_n, _5, &tar_start, &tar_end) < tot_ed) {
+            par_pos[0] = tar_start; par_pos[1] = tar_end; cons_len = tar_end - tar_start + 1; full_length = 2;
+        }
+    }
+    if (full_length > 0) {
+        if (p->only_unit) write_unit(r, par_pos, 2);
+        else {
+            uint8_t *cons_qual = NULL; int i;
+            if (p->out_fmt == 3 || p->out_fmt == 4) { cons_qual = (uint8_t *)malloc(cons_len > 0 ? cons_len : 1); for (i = 0; i < cons_len; ++i) cons_qual[i] = 33; }
+            write_cons(r, p, seq + par_pos[0], cons_qual, cons_len, par_pos[0], par_pos[1], 1.0, 100.0, full_length, par_pos, 2, NULL);
+            free(cons_qual);
+        }
+    }
+}
+
 /* src/tidehunter.c:23-60 */
 void tho_process_read(const char *seq, int len, const tho_para_t *p, tho_read_t *r) {
     if (len < p->k) return;
@@ -612,9 +669,8 @@ void tho_process_read(const char *seq, int len, const tho_para_t *p, tho_read_t 
         if (par_n >= p->min_copy + 1) seqs_msa(len, bseq, par_n, par_pos, r, p, five_rc, three_rc);
         free(par_pos);
     }
-    if (p->single_copy == 1 && p->only_full_length && p->five_seq && p->three_seq) {
-        fprintf(stderr, "[tho] -s single-copy mode is not restated\n"); exit(1);
-    }
+    if (p->single_copy == 1 && p->only_full_length && p->five_seq && p->three_seq)
+        single_copy_full_len(len, seq, r, p, five_rc, three_rc);
     free(five_rc); free(three_rc);
     if (hit_n >= 2) tho_chain_free(&ch);
     free(bseq);

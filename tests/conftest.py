@@ -46,6 +46,8 @@ def golden_inputs(golden):
             v = synth.gen_reads("long", 8)
         elif tag == "syn_adapter":
             v = synth.gen_reads("r2c2", 12, adapters=(five, three))
+        elif tag == "syn_single":
+            v = synth.gen_single_copy(24, (five, three))
         else:
             raise KeyError(tag)
         cache[tag] = v

@@ -60,6 +60,18 @@ def main():
         cases.append((st, ad + ["-u", "-f", "2"], dict(out_fmt=2, five_seq=five, three_seq=three, only_unit=1)))
     for fmt in (1, 2, 3, 4):
         cases.append(("testfq_all", ["-f", str(fmt)], dict(out_fmt=fmt)))
+    # -s: single-copy full-length reads (src/gen_cons.c:128-171), alone and next to tandem records
+    sets["syn_single"] = synth.gen_single_copy(24, (five, three))
+    ad = ["-5", os.path.join(REF, "test_data/5prime.fa"), "-3", os.path.join(REF, "test_data/3prime.fa")]
+    akw = dict(five_seq=five, three_seq=three, only_full_length=1, single_copy=1)
+    for st in ("syn_single", "full_length"):
+        cases.append((st, ad + ["-s", "-F", "-f", "2"], dict(out_fmt=2, **akw)))
+    cases.append(("syn_adapter", ad + ["-s", "-F", "-a", "0.6", "-f", "2"], dict(out_fmt=2, ada_match_rat=0.6, **akw)))
+    cases.append(("syn_single", ad + ["-s", "-F", "-f", "1"], dict(out_fmt=1, **akw)))
+    cases.append(("syn_single", ad + ["-s", "-F", "-f", "4"], dict(out_fmt=4, **akw)))
+    cases.append(("syn_single", ad + ["-s", "-F", "-u", "-f", "1"], dict(out_fmt=1, only_unit=1, **akw)))
+    cases.append(("syn_single", ad + ["-s", "-F", "-l", "-f", "2"], dict(out_fmt=2, only_longest=1, **akw)))
+    cases.append(("syn_single", ad + ["-s", "-F", "-a", "0.9", "-m", "1000", "-f", "2"], dict(out_fmt=2, ada_match_rat=0.9, min_len=1000, **akw)))
 
     out = {"inputs": {}, "cases": [], "adapters": {"five": five, "three": three}}
     for tag, (n, s) in sets.items():

@@ -66,5 +66,48 @@ def gen_reads(shape, n, start=0, seed=SEED, adapters=None):
     return names, seqs
 
 
+def _channel(rng, tmpl, e):
+    """The error channel of gen_reads on a template of codes 0..3."""
+    u = rng.random(len(tmpl))
+    sub = u < 0.4 * e
+    ins = (u >= 0.4 * e) & (u < 0.7 * e)
+    dele = (u >= 0.7 * e) & (u < e)
+    rb = rng.integers(0, 4, len(tmpl), dtype=np.uint8)
+    shift = rng.integers(1, 4, len(tmpl), dtype=np.uint8)
+    base = np.where(sub, (tmpl + shift) & 3, tmpl)
+    cnt = np.where(dele, 0, np.where(ins, 2, 1))
+    out = np.repeat(base, cnt)
+    pos = np.cumsum(cnt) - cnt
+    out[pos[ins]] = rb[ins]
+    return out
+
+
+def gen_single_copy(n, adapters, start=0, seed=SEED, err=0.08):
+    """Reads for the -s (single-copy full-length) path, src/gen_cons.c:128-171: flank + 5' adapter + one insert of
+    U{300..2500} bp + reverse complement of the 3' adapter + flank, every other read reverse-complemented as a whole,
+    through the same error channel (err lower than the R2C2 shape so that most adapters stay above -a 0.8).  Every fourth
+    read carries the insert twice in tandem, so chains and the single-copy scan both produce records."""
+    five, three = adapters
+    lut = np.zeros(256, dtype=np.uint8)
+    lut[ord("A")], lut[ord("C")], lut[ord("G")], lut[ord("T")] = 0, 1, 2, 3
+    a5 = lut[np.frombuffer(five.encode(), dtype=np.uint8)]
+    a3rc = (3 - lut[np.frombuffer(three.encode(), dtype=np.uint8)])[::-1]
+    names, seqs = [], []
+    for i in range(start, start + n):
+        rng = np.random.Generator(np.random.Philox(key=[seed + 7, i]))
+        ins_len = int(rng.integers(300, 2501))
+        insert = rng.integers(0, 4, ins_len, dtype=np.uint8)
+        body = np.concatenate([a5, insert, a3rc])
+        if i % 4 == 3:
+            body = np.concatenate([body, body, body[:len(body) // 2]])
+        tmpl = np.concatenate([rng.integers(0, 4, FLANK, dtype=np.uint8), body, rng.integers(0, 4, FLANK, dtype=np.uint8)])
+        if i % 2 == 1:
+            tmpl = (3 - tmpl)[::-1]
+        out = _channel(rng, tmpl, err)
+        seqs.append(_ACGT[out].tobytes())
+        names.append(("s%d" % i).encode())
+    return names, seqs
+
+
 def total_bases(seqs):
     return int(sum(len(s) for s in seqs))
