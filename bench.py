@@ -58,20 +58,28 @@ def _ref_runner():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
     if os.path.exists(O.REF_BIN):
-        def run(names, seqs, threads):
+        def run(names, seqs, threads, keep=None):
             with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
                 path = os.path.join(td, "sample.fa")
                 O.write_fasta(path, names, seqs)
+                opath = os.path.join(td, "out.fa") if keep is not None else os.devnull
                 t0 = time.perf_counter()
-                subprocess.run([O.REF_BIN, "-t", str(threads), "-f", "1", path], stdout=subprocess.DEVNULL,
+                subprocess.run([O.REF_BIN, "-t", str(threads), "-f", "1", "-o", opath, path], stdout=subprocess.DEVNULL,
                                stderr=subprocess.DEVNULL, check=True)
-                return time.perf_counter() - t0
+                dt = time.perf_counter() - t0
+                if keep is not None:
+                    with open(opath, "rb") as f:
+                        keep.append(f.read())
+                return dt
         return "reference", run
 
-    def run_port(names, seqs, threads):
+    def run_port(names, seqs, threads, keep=None):
         t0 = time.perf_counter()
-        O.run_batch(names, seqs, O.default_para(out_fmt=1), threads=threads)
-        return time.perf_counter() - t0
+        out = O.run_batch(names, seqs, O.default_para(out_fmt=1), threads=threads)[0]
+        dt = time.perf_counter() - t0
+        if keep is not None:
+            keep.append(out)
+        return dt
     return "port", run_port
 
 
@@ -304,7 +312,6 @@ def main():
         h2d += s["h2d_bytes"]; d2h += s["d2h_bytes"]
     barrier()
     dt_e2e = max_over_ranks(time.perf_counter() - t0)
-    th.close()
 
     tot_reads = sum_over_ranks(n) * args.steps
     tot_bases = sum_over_ranks(bases) * args.steps
@@ -383,9 +390,16 @@ def main():
         cores = os.cpu_count() or 1
         ns = cpu_sample_size(run, cores, 15.0)
         ns = min(ns, n)
-        t = run(names[:ns], seqs[:ns], cores)
+        ref_out = []
+        t = run(names[:ns], seqs[:ns], cores, keep=ref_out)
+        # parity at bench scale: the reference's output for the sample against ours for the same reads (untimed)
+        import hashlib
+        ours = th.run(names[:ns], seqs[:ns])
+        line["parity"] = {"reads": ns, "identical": bool(ours == ref_out[0]), "against": kind, "records": ours.count(b">"),
+                          "md5_ours": hashlib.md5(ours).hexdigest(), "md5_reference": hashlib.md5(ref_out[0]).hexdigest()}
         line["cpu_baseline"] = {"value": ns / t, "unit": "reads/s", "cores": cores, "kind": kind,
                                 "sample": "first %d reads of the step's batch (%d bases), TideHunter -t %d -f 1, %.1f s" % (ns, synth.total_bases(seqs[:ns]), cores, t)}
+    th.close()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
