@@ -397,7 +397,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
             // predecessors' row maxima, rounded to whole vectors (measured mean ~61 columns on 1 kb units)
             const int wband = 10 + T.qmax / 100;
             const size_t rows_typ = std::min<size_t>((size_t)T.ncap, (size_t)T.qmax * 5 / 2 + 64);
-            const size_t width_typ = std::min<size_t>((size_t)T.qmax + 64, (size_t)2 * wband + 256);
+            const size_t width_typ = std::min<size_t>((size_t)T.qmax + 64, (size_t)2 * wband + 64);
             const size_t typ = std::max<size_t>(rows_typ * width_typ * 10, (size_t)1 << 20);
             const size_t full = (size_t)T.ncap * ((size_t)T.qmax + 64) * 10;
             slab_typ = std::max(slab_typ, fixed + std::min(typ, full) + 4096);
@@ -430,6 +430,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         std::vector<int32_t> retry;
         for (int t = 0; t < nt; ++t) if (c->r_task_status[t] == TH_ERR_ARENA) retry.push_back(t);
         if (!retry.empty()) {
+            if (getenv("TH_GPU_DEBUG")) fprintf(stderr, "[th_gpu] %d of %d POA tasks overflowed their %zu-byte slab and are retried with %zu-byte slabs\n", (int)retry.size(), nt, slab_typ, slab_full);
             CK(cudaMemGetInfo(&free_b, &total_b));
             budget = (size_t)((double)(free_b + c->d_slabs.cap) * 0.8);
             int rw = (int)std::min<size_t>(retry.size(), std::max<size_t>(1, budget / slab_full));

@@ -129,7 +129,11 @@ __device__ __forceinline__ void poa_pred(const uint32_t *A32, const int4 pm, con
     Mx = __vmaxs2(Mx, __funnelshift_r(prev, Xh, 16));
 }
 
-struct PoaSmem { int4 desc[POA_RING]; int4 meta[POA_RING]; int4 pre[POA_MAXPRE]; uint4 last[32]; };
+#ifndef POA_SETUP_U
+#define POA_SETUP_U 2      // batches of 32 nodes whose edge-list walks are interleaved when the row descriptors are built
+#endif
+#define POA_PEQ_W 40     // words per match bit-plane kept in shared memory (queries up to ~1200 columns; longer ones use the slab)
+struct PoaSmem { int4 desc[POA_RING]; int4 meta[POA_RING]; int4 pre[POA_MAXPRE]; uint4 last[32]; uint32_t peq[4 * POA_PEQ_W]; };
 
 // same contributions when the predecessor is the row this warp computed last and it fits one 64-column chunk: its
 // {H, E1, E2} pairs are still in shared memory (lane l holds columns last_beg + 2l, +1), no trip to L2
@@ -143,6 +147,7 @@ __device__ __forceinline__ void poa_pred_last(const uint4 *last, const int4 pm, 
 }
 
 // one warp aligns sequence `query` to the graph and merges it in.  Returns an error code.
+template <int LP> // LP = log2 of the emulated vector width pn (4: AVX2 int16, the reference build; 3: SSE)
 __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *query, int qlen, int &node_n, int &edge_n,
                                 PoaSmem &sm, unsigned long long &cells, unsigned long long &rows, long long *ph) {
 #ifdef POA_PROFILE   // per-phase warp-cycle counters (tools/profile_step.py); cost ~16 registers, off in the product build
@@ -152,7 +157,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
 #define PH(k) do { } while (0)
 #endif
     const int lane = lane_id();
-    const int n = node_n, pn = P.pn, lp = P.pn == 16 ? 4 : 3;
+    const int n = node_n; constexpr int pn = 1 << LP, lp = LP;
     const int o1 = P.o1, e1 = P.e1, o2 = P.o2, e2 = P.e2, oe1 = o1 + e1, oe2 = o2 + e2;
     const int mis = P.mismatch > 0 ? P.mismatch : -P.mismatch, mat = P.match < 0 ? -P.match : P.match;
     { // int16 path only (simd_abpoa_align.c:1610-1621)
@@ -166,28 +171,66 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
     // ---- row descriptors: order index, predecessors by row, heaviest successor ----------------
     for (int i = lane; i < n; i += 32) w.n2i[w.ord[i]] = i;
     __syncwarp();
-    {
+    { // four batches of 32 nodes walk their edge lists in lock-step: the loads of a step are independent across the
+      // batches, so four of these dependent (DRAM/L2-latency) pointer chases are in flight per lane instead of one
+        constexpr int U = POA_SETUP_U;
         int pl_base = 0, bad = 0;
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            int np = 0, p0 = -1, p1 = -1, hi = 0x7fffffff, v = 0, b = 0;
-            if (i < n) {
-                v = w.ord[i]; b = w.base[v];
-                for (int e = w.in_head[v]; e >= 0; e = w.e_ni[e]) { const int pi = w.n2i[w.e_from[e]]; if (np == 0) p0 = pi; else if (np == 1) p1 = pi; ++np; }
-                int mw = -1, mt = -1; // first out-edge with maximum weight (abpoa_graph.c:216-226)
-                for (int e = w.out_head[v]; e >= 0; e = w.e_no[e]) if (w.e_w[e] > mw) { mw = w.e_w[e]; mt = w.e_to[e]; }
-                if (mt >= 0) hi = w.n2i[mt];
-            }
-            const int cnt = np > 2 ? np : 0;
-            int inc = cnt;
+        for (int i0 = 0; i0 < n; i0 += 32 * U) {
+            int np[U], p0[U], p1[U], hi[U], v[U], b[U], ei[U], eo[U], mw[U], mt[U];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(TH_FULL, inc, d); if (lane >= d) inc += o; }
-            const int off = pl_base + inc - cnt;
-            pl_base += __shfl_sync(TH_FULL, inc, 31);
-            if (i < n) {
-                if (np > 2) { int k = 0; for (int e = w.in_head[v]; e >= 0; e = w.e_ni[e]) w.plist[off + k++] = w.n2i[w.e_from[e]]; }
-                w.hi_idx[i] = hi; bad |= np > 1023;
-                w.rdesc[i] = make_int4(p0, min(np, 1023) | (min(b, 7) << 10) | (v << 13), 0, np > 2 ? off : p1);
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + 32 * u + lane;
+                np[u] = 0; p0[u] = -1; p1[u] = -1; hi[u] = 0x7fffffff; b[u] = 0; mw[u] = -1; mt[u] = -1;
+                v[u] = i < n ? w.ord[i] : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                ei[u] = -1; eo[u] = -1;
+                if (v[u] >= 0) { b[u] = w.base[v[u]]; ei[u] = w.in_head[v[u]]; eo[u] = w.out_head[v[u]]; }
+            }
+            while (true) { // predecessors by row, in in_id order
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < U; ++u) any |= ei[u] >= 0;
+                if (!any) break;
+                int fr[U], nx[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (ei[u] >= 0) { fr[u] = w.e_from[ei[u]]; nx[u] = w.e_ni[ei[u]]; }
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (ei[u] >= 0) {
+                    const int pi = w.n2i[fr[u]];
+                    if (np[u] == 0) p0[u] = pi; else if (np[u] == 1) p1[u] = pi;
+                    ++np[u]; ei[u] = nx[u];
+                }
+            }
+            while (true) { // first out-edge with maximum weight (abpoa_graph.c:216-226)
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < U; ++u) any |= eo[u] >= 0;
+                if (!any) break;
+                int ww[U], to[U], nx[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (eo[u] >= 0) { ww[u] = w.e_w[eo[u]]; to[u] = w.e_to[eo[u]]; nx[u] = w.e_no[eo[u]]; }
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (eo[u] >= 0) { if (ww[u] > mw[u]) { mw[u] = ww[u]; mt[u] = to[u]; } eo[u] = nx[u]; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (mt[u] >= 0) hi[u] = w.n2i[mt[u]];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + 32 * u + lane;
+                const int cnt = np[u] > 2 ? np[u] : 0;
+                int inc = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(TH_FULL, inc, d); if (lane >= d) inc += o; }
+                const int off = pl_base + inc - cnt;
+                pl_base += __shfl_sync(TH_FULL, inc, 31);
+                if (i < n) {
+                    if (np[u] > 2) { int k = 0; for (int e = w.in_head[v[u]]; e >= 0; e = w.e_ni[e]) w.plist[off + k++] = w.n2i[w.e_from[e]]; }
+                    w.hi_idx[i] = hi[u];
+                    bad |= np[u] > 1023 || (i > 0 && i < n - 1 && (unsigned)(np[u] - 1) >= POA_MAXPRE); // the row loop relies on 1 <= np <= POA_MAXPRE
+                    w.rdesc[i] = make_int4(p0[u], min(np[u], 1023) | (min(b[u], 7) << 10) | (v[u] << 13), 0, np[u] > 2 ? off : p1[u]);
+                }
             }
         }
         if (__any_sync(TH_FULL, bad)) return TH_ERR_CAP;
@@ -214,17 +257,24 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         }
         __syncwarp();
     }
-    // ---- query profile (simd_abpoa_align.c:438-446); N row/column score 0 -----------------
+    // ---- query profile (simd_abpoa_align.c:438-446) as four match bit-planes: bit j of plane b = (query[j-1] == b).
+    // The row score pair of columns (j, j+1) is then one word load, a shift and an IMAD instead of a trip to a 5 x qlen
+    // int16 table in the slab.  Columns 0 and > qlen score as mismatches here instead of 0: column 0 only feeds
+    // inf_min + s into a max that E wins, columns past the query end never flow back (M, F move right, E stays) and are
+    // excluded from the row maximum and the backtrack.  N (query or node) scores 0 in the reference: those rows take
+    // the literal path below.
     const int prof_w = ((qlen / pn + 1) * pn + 64 + 1) & ~1;
-    for (int j = lane; j < prof_w; j += 32) {
-        const int qc = (j >= 1 && j <= qlen) ? min((int)query[j - 1], 4) : -1;
-#pragma unroll
-        for (int b = 0; b < 5; ++b) {
-            int s = 0;
-            if (qc >= 0 && qc < 4 && b < 4) s = (qc == b) ? mat : -mis;
-            w.qp[b * w.qp_stride + j] = (int16_t)s;
-        }
+    const int peq_w = (prof_w >> 5) + 1;
+    uint32_t *const peq = peq_w <= POA_PEQ_W ? sm.peq : reinterpret_cast<uint32_t *>(w.qp);
+    bool q_has_n = false;
+    for (int j0 = 0; j0 < peq_w * 32; j0 += 32) {
+        const int j = j0 + lane;
+        const int qc = (j >= 1 && j <= qlen) ? (int)query[j - 1] : 7;
+        q_has_n |= qc >= 4 && qc != 7;
+        const uint32_t b0 = __ballot_sync(TH_FULL, qc == 0), b1 = __ballot_sync(TH_FULL, qc == 1), b2 = __ballot_sync(TH_FULL, qc == 2), b3 = __ballot_sync(TH_FULL, qc == 3);
+        if (lane < 4) peq[lane * peq_w + (j0 >> 5)] = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : b3;
     }
+    q_has_n = __any_sync(TH_FULL, q_has_n);
     // ---- first row (simd_abpoa_align.c:538-555, 591-610) ------------------------------------
     uint32_t used = 0;
     {
@@ -267,7 +317,9 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
     const uint32_t *A32 = reinterpret_cast<const uint32_t *>(w.arena);
     uint32_t *A32w = reinterpret_cast<uint32_t *>(w.arena);
     uint32_t last_off = 0xffffffffu; // arena offset of the row whose values sit in sm.last
-    const int16_t *const qp = w.qp; const int qps = w.qp_stride;
+    const uint32_t NEGMIS2 = pk(-mis, -mis), XMM = (uint32_t)(uint16_t)mat ^ (uint32_t)(uint16_t)(-mis); // -mis ^ XMM == mat per half
+    const uint32_t KLO = lamk_lo | 0xfffu, KHI = lamk_hi | 0xfffu;
+    const uint32_t used_rows0 = used;
     int4 *const rmeta_g = w.rmeta; const int4 *const rdesc_g = w.rdesc; const int32_t *const plist_g = w.plist;
     const uint32_t arena_cap = w.arena_cap;
     for (int i = 1; i < n - 1; ++i) {
@@ -277,8 +329,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
             __syncwarp();
         }
         const int4 d = sm.desc[i & (POA_RING - 1)];
-        const int np = d.y & 1023;
-        if ((unsigned)(np - 1) >= POA_MAXPRE) return TH_ERR_CAP;
+        const int np = d.y & 1023; // 1..POA_MAXPRE, checked when the descriptors were built
         // band: what the predecessors' row maxima and max_remain say (abpoa_align.h:34-35, simd_abpoa_align.c:846-854)
         const int4 pm0 = (i - d.x < POA_RING) ? sm.meta[d.x & (POA_RING - 1)] : rmeta_g[d.x];
         int mpl = min(n, pm0.w), mpr = max(0, pm0.w), min_pre_beg = pm0.y;
@@ -295,13 +346,18 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         const int beg = max((beg0 >> lp) << lp, min_pre_beg), esn = end0 >> lp, dend = ((esn + 1) << lp) - 1;
         if (beg > dend) return TH_ERR_BAND;
         const int bsn = beg >> lp, width = dend - beg + 1;
-        if (5u * (uint32_t)width > arena_cap - used) return TH_ERR_ARENA;
+        const uint32_t w5 = 5u * (uint32_t)width;
+        if (w5 > arena_cap - used) return TH_ERR_ARENA;
         const uint32_t row_off = used;
-        used += 5u * width; cells += width; rows += 1;
-        const int16_t *qrow = qp + ((d.y >> 10) & 7) * qps;
+        used += w5; // cells and rows are derived from `used` after the loop
+        const int vb = (d.y >> 10) & 7;
+        const bool fast_s = vb < 4 && !q_has_n;
+        const uint32_t *const prow = peq + (vb & 3) * peq_w;
+        uint4 *const rowp = reinterpret_cast<uint4 *>(A32w + (row_off >> 1)) + lane;        // this lane's record in chunk 0
+        uint32_t *const f2p = A32w + (row_off >> 1) + 2u * (uint32_t)width + lane;          // ... and its F2 pair
         const int jmax = esn == qsn ? qlen : dend;       // columns past the query end do not compete for the row maximum
         const int vlast = esn - bsn;                      // the row's last vector is visited first by the reference's arg-max
-        uint32_t best = 0, carryH = 0, carryF = POA_NEGP; // carryF: (F1 - e1, F2 - e2) of the previous chunk's last column
+        int best = INT_MIN; uint32_t carryH = 0, carryF = POA_NEGP; // carryF: (F1 - e1, F2 - e2) of the previous chunk's last column
         const int nchunk = (width + 63) >> 6;
         for (int ch = 0; ch < nchunk; ++ch) {
             const int j = beg + (ch << 6) + 2 * lane;
@@ -313,7 +369,14 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 if ((uint32_t)pm.x == last_off) poa_pred_last(sm.last, pm, j, INFP, Mx, E1x, E2x);
                 else poa_pred(A32, pm, j, INFP, Mx, E1x, E2x);
             }
-            const uint32_t S = ld32(qrow + j);
+            uint32_t S;
+            if (fast_s) {
+                const uint32_t t = (prow[j >> 5] >> (j & 31)) & 3u;            // match bits of columns j, j + 1 (j is even)
+                S = NEGMIS2 ^ (((t | (t << 15)) & 0x10001u) * XMM);
+            } else { // N in the query or an N node: score 0 (simd_abpoa_align.c:438-446 with the all-zero N row/column of the matrix)
+                const int c0 = (j >= 1 && j <= qlen) ? (int)query[j - 1] : 4, c1 = (j + 1 <= qlen) ? (int)query[j] : 4;
+                S = pk((c0 < 4 && vb < 4) ? (c0 == vb ? mat : -mis) : 0, (c1 < 4 && vb < 4) ? (c1 == vb ? mat : -mis) : 0);
+            }
             const uint32_t Ms = __vadd2(Mx, S);
             const uint32_t Hme = __vimax3_s16x2(Ms, E1x, E2x);
             uint32_t hp = __shfl_up_sync(TH_FULL, Hme, 1);
@@ -338,22 +401,19 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 carryF = __vadd2(__byte_perm(fa, fb, 0x7632), pk(-e1, -e2)); // G of column j0 - 1 in the next chunk's frame
             }
             if (nchunk == 1) sm.last[lane] = make_uint4(Hn, E1o, E2o, 0); // every reader of the old contents is past the scan's shuffles
-            if (j <= dend) {
-                const uint32_t wi = (row_off >> 1) + 2u * (uint32_t)(j - beg);
-                *reinterpret_cast<uint4 *>(A32w + wi) = make_uint4(Hn, E1o, E2o, Fa);
-                A32w[(row_off >> 1) + 2u * (uint32_t)width + ((uint32_t)(j - beg) >> 1)] = Fb;
-                // row arg-max key: value, then lane (j mod pn) ascending, then vector order with end_sn first
+            if (j <= dend) { rowp[ch << 5] = make_uint4(Hn, E1o, E2o, Fa); f2p[ch << 5] = Fb; }
+            { // row arg-max key (signed compare): value, then lane (j mod pn) ascending, then vector order with end_sn first
                 const int rel = lane_vec + (ch << (6 - lp));
-                const uint32_t tail = (uint32_t)(0xfff - (rel == vlast ? 0 : rel + 1));
-                if (j <= jmax) best = max(best, ((Hn << 16) ^ 0x80000000u) | lamk_lo | tail);
-                if (j < jmax) best = max(best, ((Hn & 0xffff0000u) ^ 0x80000000u) | lamk_hi | tail);
+                const uint32_t sub = rel == vlast ? 0u : (uint32_t)(rel + 1);
+                const int klo = (int)__byte_perm(Hn, KLO - sub, 0x1054), khi = (int)__byte_perm(Hn, KHI - sub, 0x3254);
+                best = max(best, max(j <= jmax ? klo : INT_MIN, j < jmax ? khi : INT_MIN)); // jmax <= dend
             }
         }
         best = __reduce_max_sync(TH_FULL, best);
         { // simd_abpoa_max_in_row + simd_abpoa_ada_max_i: successors pull max_i + 1 from this row's metadata
-            const int val = (int)(best >> 16) - 32768;
+            const int val = best >> 16;
             int max_i = -1;
-            if (best != 0 && val > inf_min) {
+            if (best != INT_MIN && val > inf_min) {
                 const int lam = lam_bits - (int)((best >> 12) & 0xf), vr = 0xfff - (int)(best & 0xfff);
                 const int vsn = vr == 0 ? esn : bsn + vr - 1;
                 max_i = vsn * pn + lam;
@@ -363,6 +423,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         last_off = nchunk == 1 ? row_off : 0xffffffffu;
         __syncwarp();
     }
+    cells += (used - used_rows0) / 5u; rows += (unsigned long long)max(n - 2, 0);
     PH(1);
     // ---- best end cell (simd_abpoa_align.c:976-989): sink's in-neighbours in in_id order, strict > ----
     int bi = 0, bj = 0;
@@ -407,10 +468,12 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                     const int4 m = w.rmeta[r];
                     sm.desc[r & (POA_RING - 1)] = w.rdesc[r]; sm.meta[r & (POA_RING - 1)] = m;
                     const int rw = m.z - m.y + 1;
-                    int jp = j - (i - r); jp = min(max(jp, m.y), m.z);
-                    const int c0 = max(jp - 8, m.y) - m.y, c1 = min(jp + 8, m.z) - m.y;
+                    // the path crosses a row close to that row's maximum (the column that steered the band); the graph holds
+                    // several nodes per query column, so extrapolating j along the row index would drift off within a few rows
+                    int jp = m.w > 0 ? m.w - 1 : j - (i - r); jp = min(max(jp, m.y), m.z);
+                    const int c0 = max(jp - 7, m.y) - m.y, c1 = max(jp - 2, m.y) - m.y, c2 = min(jp + 4, m.z) - m.y;
                     const uint32_t *Rr = A32 + (m.x >> 1);
-                    prefetch_l2(Rr + 4 * (c0 >> 1)); prefetch_l2(Rr + 4 * (c1 >> 1)); prefetch_l2(Rr + 2 * rw + ((jp - m.y) >> 1));
+                    prefetch_l2(Rr + 4 * (c0 >> 1)); prefetch_l2(Rr + 4 * (c1 >> 1)); prefetch_l2(Rr + 4 * (c2 >> 1)); prefetch_l2(Rr + 2 * rw + ((jp - m.y) >> 1));
                 }
                 wlo = max(0, top - 32); whi = min(whi, wlo + POA_RING - 1);
                 __syncwarp();
@@ -679,7 +742,7 @@ __device__ int poa_consensus(PoaWs &w, int node_n, int n_seq, uint8_t *cons, int
 
 // persistent warps pull tasks from an atomic counter
 #ifndef POA_MIN_BLOCKS
-#define POA_MIN_BLOCKS 5
+#define POA_MIN_BLOCKS 8   // 64 registers: 32 warps per SM.  Every phase of the kernel is a dependent chain, so resident warps are what hides latency
 #endif
 __global__ void __launch_bounds__(POA_WARPS * 32, POA_MIN_BLOCKS)
 poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const int32_t *__restrict__ task_order,
@@ -737,7 +800,8 @@ poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const in
         __syncwarp();
         int node_n = l0 + 2, edge_n = l0 + 1, err = TH_OK;
         for (int s = 1; s < T.n_seqs && err == TH_OK; ++s)
-            err = poa_add_sequence(w, P, rseq + u_start[T.unit_off + s], u_len[T.unit_off + s], node_n, edge_n, s_mem[wib], cells, rows, ph);
+            err = P.pn == 16 ? poa_add_sequence<4>(w, P, rseq + u_start[T.unit_off + s], u_len[T.unit_off + s], node_n, edge_n, s_mem[wib], cells, rows, ph)
+                             : poa_add_sequence<3>(w, P, rseq + u_start[T.unit_off + s], u_len[T.unit_off + s], node_n, edge_n, s_mem[wib], cells, rows, ph);
         int cl = 0;
 #ifdef POA_PROFILE
         long long t_c0 = clock64();
