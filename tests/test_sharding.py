@@ -21,8 +21,12 @@ def test_shard_ranges_tile_in_order():
             assert max(sizes) - min(sizes) <= 1
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, shm=False):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    if shm:  # what torchrun exports on a single node: the gather then goes through /dev/shm files
+        os.environ["LOCAL_WORLD_SIZE"] = str(world); os.environ["MASTER_PORT"] = str(port)
+    else:
+        os.environ.pop("LOCAL_WORLD_SIZE", None)
     import torch.distributed as dist
     import oracle_py as O
     from tidehunter_b200 import synth
@@ -40,13 +44,14 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_ordered_gather_matches_single_process(oracle):
+@pytest.mark.parametrize("shm", [False, True])
+def test_two_rank_ordered_gather_matches_single_process(oracle, shm):
     import torch.multiprocessing as mp
     from tidehunter_b200 import synth
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q, shm)) for r in range(2)]
     for p in ps:
         p.start()
     out = q.get(timeout=120)

@@ -94,6 +94,8 @@ __device__ inline void poa_carve(PoaWs &w, uint8_t *slab, size_t slab_bytes, int
 __device__ __forceinline__ uint32_t ld32(const int16_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
 __device__ __forceinline__ void st32(int16_t *p, uint32_t v) { *reinterpret_cast<uint32_t *>(p) = v; }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// whole-range L2 prefetch (sm_90+): p 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes)); }
 
 // graph edit used for the final edge into the sink (lane 0 only)
 __device__ inline void g_add_edge(PoaWs &w, int &edge_n, int from, int to, bool check) {
@@ -344,17 +346,16 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         }
         const int beg0 = max(0, min(mpl, d.z) - wband), end0 = min(qlen, max(mpr, d.z) + wband);
         const int beg = max((beg0 >> lp) << lp, min_pre_beg), esn = end0 >> lp, dend = ((esn + 1) << lp) - 1;
-        if (beg > dend) return TH_ERR_BAND;
         const int bsn = beg >> lp, width = dend - beg + 1;
         const uint32_t w5 = 5u * (uint32_t)width;
-        if (w5 > arena_cap - used) return TH_ERR_ARENA;
+        if ((beg > dend) | (w5 > arena_cap - used)) return beg > dend ? TH_ERR_BAND : TH_ERR_ARENA;
         const uint32_t row_off = used;
         used += w5; // cells and rows are derived from `used` after the loop
         const int vb = (d.y >> 10) & 7;
         const bool fast_s = vb < 4 && !q_has_n;
         const uint32_t *const prow = peq + (vb & 3) * peq_w;
-        uint4 *const rowp = reinterpret_cast<uint4 *>(A32w + (row_off >> 1)) + lane;        // this lane's record in chunk 0
-        uint32_t *const f2p = A32w + (row_off >> 1) + 2u * (uint32_t)width + lane;          // ... and its F2 pair
+        const uint32_t rec0 = (row_off >> 3) + lane;                                  // this lane's record in chunk 0 (16-byte units; row_off is a multiple of 40)
+        const uint32_t f20 = (row_off >> 1) + 2u * (uint32_t)width + lane;              // ... and its F2 pair (words)
         const int jmax = esn == qsn ? qlen : dend;       // columns past the query end do not compete for the row maximum
         const int vlast = esn - bsn;                      // the row's last vector is visited first by the reference's arg-max
         int best = INT_MIN; uint32_t carryH = 0, carryF = POA_NEGP; // carryF: (F1 - e1, F2 - e2) of the previous chunk's last column
@@ -401,7 +402,7 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 carryF = __vadd2(__byte_perm(fa, fb, 0x7632), pk(-e1, -e2)); // G of column j0 - 1 in the next chunk's frame
             }
             if (nchunk == 1) sm.last[lane] = make_uint4(Hn, E1o, E2o, 0); // every reader of the old contents is past the scan's shuffles
-            if (j <= dend) { rowp[ch << 5] = make_uint4(Hn, E1o, E2o, Fa); f2p[ch << 5] = Fb; }
+            if (j <= dend) { reinterpret_cast<uint4 *>(A32w)[rec0 + (ch << 5)] = make_uint4(Hn, E1o, E2o, Fa); A32w[f20 + (ch << 5)] = Fb; }
             { // row arg-max key (signed compare): value, then lane (j mod pn) ascending, then vector order with end_sn first
                 const int rel = lane_vec + (ch << (6 - lp));
                 const uint32_t sub = rel == vlast ? 0u : (uint32_t)(rel + 1);
@@ -468,12 +469,16 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                     const int4 m = w.rmeta[r];
                     sm.desc[r & (POA_RING - 1)] = w.rdesc[r]; sm.meta[r & (POA_RING - 1)] = m;
                     const int rw = m.z - m.y + 1;
-                    // the path crosses a row close to that row's maximum (the column that steered the band); the graph holds
-                    // several nodes per query column, so extrapolating j along the row index would drift off within a few rows
-                    int jp = m.w > 0 ? m.w - 1 : j - (i - r); jp = min(max(jp, m.y), m.z);
-                    const int c0 = max(jp - 7, m.y) - m.y, c1 = max(jp - 2, m.y) - m.y, c2 = min(jp + 4, m.z) - m.y;
+                    // the whole row (records + F2 = 10 bytes per column, a few hundred bytes for the usual band) goes to L2 with one
+                    // bulk prefetch: no guess about the column where the path will cross it.  Wide rows: around the row maximum.
                     const uint32_t *Rr = A32 + (m.x >> 1);
-                    prefetch_l2(Rr + 4 * (c0 >> 1)); prefetch_l2(Rr + 4 * (c1 >> 1)); prefetch_l2(Rr + 4 * (c2 >> 1)); prefetch_l2(Rr + 2 * rw + ((jp - m.y) >> 1));
+                    if (rw <= 256) prefetch_l2_bulk(Rr, 10u * (uint32_t)rw);
+                    else {
+                        int jp = m.w > 0 ? m.w - 1 : j - (i - r); jp = min(max(jp, m.y), m.z);
+                        const int c0 = (max(jp - 62, m.y) - m.y) & ~1; // 128 columns of records (16-byte aligned start) and their F2 words
+                        prefetch_l2_bulk(Rr + 4 * (c0 >> 1), (uint32_t)min(128, rw - c0) * 8u);
+                        prefetch_l2_bulk(Rr + 2 * rw + ((c0 >> 1) & ~3), (uint32_t)(min(128, rw - c0) * 2 + 16) & ~15u);
+                    }
                 }
                 wlo = max(0, top - 32); whi = min(whi, wlo + POA_RING - 1);
                 __syncwarp();

@@ -6,6 +6,7 @@ there is no data-path collective.  Output order = input order: rank 0 concatenat
 texts in rank order, exactly what mini_tandem_output (src/main.c:214-271) prints for the whole batch.
 The gather runs over a gloo (host) group; NCCL / NVLink are not on the data path.
 """
+import os
 
 
 def shard_range(n, rank, world):
@@ -15,13 +16,47 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+_gather_seq = 0
+
+
+def _same_node(world):
+    """All ranks on one node (the only layout the reference has: one process, one box)?"""
+    lw = os.environ.get("LOCAL_WORLD_SIZE")
+    return lw is not None and int(lw) == world and os.path.isdir("/dev/shm") and os.environ.get("TH_GATHER", "shm") == "shm"
+
+
 def ordered_gather(payload, rank, world, group=None, dst=0):
-    """Gather one bytes payload per rank on `dst`, in rank order.  Returns the list on dst, None elsewhere."""
+    """Gather one bytes payload per rank on `dst`, in rank order.  Returns the list on dst, None elsewhere.
+
+    On one node the texts travel through tmpfs files (/dev/shm) bracketed by two host-side barriers: memcpy speed,
+    no pickling of tens of MB per rank through the loopback.  Otherwise torch.distributed.gather_object over the
+    gloo group.  Either way it is a host-side gather; nothing touches the GPUs or NCCL."""
+    global _gather_seq
     if world == 1:
         return [payload]
     import torch.distributed as dist
-    out = [None] * world if rank == dst else None
-    dist.gather_object(payload, out, dst=dst, group=group)
+    if not _same_node(world):
+        out = [None] * world if rank == dst else None
+        dist.gather_object(payload, out, dst=dst, group=group)
+        return out
+    _gather_seq += 1
+    tag = "th_b200_%s_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "run"), _gather_seq)
+    path = os.path.join("/dev/shm", "%s_r%d" % (tag, rank))
+    if rank != dst:
+        with open(path, "wb") as f:
+            f.write(payload)
+    dist.barrier(group=group)            # every rank's file is complete
+    out = None
+    if rank == dst:
+        out = []
+        for r in range(world):
+            if r == dst:
+                out.append(payload)
+                continue
+            pr = os.path.join("/dev/shm", "%s_r%d" % (tag, r))
+            with open(pr, "rb") as f:
+                out.append(f.read())
+            os.unlink(pr)
     return out
 
 
