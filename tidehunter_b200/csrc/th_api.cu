@@ -419,7 +419,13 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         int nwarps = (int)std::min<size_t>((size_t)(c->n_sm * POA_MIN_BLOCKS * POA_WARPS * c->share), std::max<size_t>(1, budget / slab_typ));
         nwarps = std::min(nwarps, std::max(nt, 1));
         int grid = (nwarps + POA_WARPS - 1) / POA_WARPS;
-        if (c->d_slabs.ensure((size_t)grid * POA_WARPS * slab_typ)) return -1;
+        // several contexts of one process (the host layer's lanes) size their slabs from the same free-memory reading:
+        // if the allocation loses that race, run with fewer resident warps instead of failing the chunk
+        while (c->d_slabs.ensure((size_t)grid * POA_WARPS * slab_typ)) {
+            cudaGetLastError();
+            if (grid <= 8) return -1;
+            grid = (grid + 1) / 2;
+        }
         poa_kernel<<<grid, POA_WARPS * 32, 0, st>>>(P, nt, c->d_tasks.as<PoaTask>(), c->d_torder.as<int32_t>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(),
                                                  c->d_bseq.as<uint8_t>(), c->d_slabs.as<uint8_t>(), slab_typ, cnt32 + 1, c->d_consb.as<uint8_t>(), c->d_consc.as<int32_t>(),
                                                  c->d_consl.as<int32_t>(), c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2, cnt64 + 16);
