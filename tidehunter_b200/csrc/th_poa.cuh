@@ -118,33 +118,26 @@ __device__ inline void g_add_edge(PoaWs &w, int &edge_n, int from, int to, bool 
 __device__ __forceinline__ const uint4 *poa_recs(const uint32_t *A32, int off) { return reinterpret_cast<const uint4 *>(A32 + (off >> 1)); }
 __device__ __forceinline__ int s16_at(uint32_t word, int odd) { return odd ? hi16(word) : lo16(word); }
 
-// contributions of one predecessor row to columns (j, j+1) of the current row: M from H[p][j-1], H[p][j];
-// E1, E2 from the same columns.  pm = the predecessor's row metadata.  Cells outside the predecessor's band
-// count as inf_min (simd_abpoa_align.c:860-905).
-__device__ __forceinline__ void poa_pred(const uint32_t *A32, const int4 pm, const int j, const uint32_t INFP,
-                                         uint32_t &Mx, uint32_t &E1x, uint32_t &E2x) {
-    const int pb = pm.y;
-    const uint32_t wi = (uint32_t)(pm.x >> 1) + 2u * (uint32_t)(j - pb); // word index of record (j - pb) / 2
-    uint32_t Xh = INFP, prev = INFP;
-    if (j >= pb && j <= pm.z) { const uint4 r = *reinterpret_cast<const uint4 *>(A32 + wi); Xh = r.x; E1x = __vmaxs2(E1x, r.y); E2x = __vmaxs2(E2x, r.z); }
-    if (j > pb && j - 1 <= pm.z) prev = A32[wi - 4]; // H of the pair to the left; only its upper half (column j-1) is used
-    Mx = __vmaxs2(Mx, __funnelshift_r(prev, Xh, 16));
-}
-
 #ifndef POA_SETUP_U
 #define POA_SETUP_U 2      // batches of 32 nodes whose edge-list walks are interleaved when the row descriptors are built
 #endif
-#define POA_PEQ_W 40     // words per match bit-plane kept in shared memory (queries up to ~1200 columns; longer ones use the slab)
-struct PoaSmem { int4 desc[POA_RING]; int4 meta[POA_RING]; int4 pre[POA_MAXPRE]; uint4 last[32]; uint32_t peq[4 * POA_PEQ_W]; };
+#define POA_PEQ_W 40     // words per query bit-plane kept in shared memory (queries up to ~1200 columns; longer ones use the slab)
+struct PoaSmem { int4 desc[POA_RING]; int4 meta[POA_RING]; int4 pre[POA_MAXPRE]; uint4 last[32]; uint32_t peq[5 * POA_PEQ_W]; };
 
-// same contributions when the predecessor is the row this warp computed last and it fits one 64-column chunk: its
-// {H, E1, E2} pairs are still in shared memory (lane l holds columns last_beg + 2l, +1), no trip to L2
-__device__ __forceinline__ void poa_pred_last(const uint4 *last, const int4 pm, const int j, const uint32_t INFP,
-                                              uint32_t &Mx, uint32_t &E1x, uint32_t &E2x) {
-    const int pb = pm.y, l2 = (j - pb) >> 1;
+// contributions of one predecessor row to columns (j, j+1) of the current row: M from H[p][j-1], H[p][j];
+// E1, E2 from the same columns.  pm = the predecessor's row metadata, recs = its records ({H, E1, E2, F1} per column
+// pair).  Cells outside the predecessor's band count as inf_min (simd_abpoa_align.c:860-905).
+// The row this warp computed last (when it fits one 64-column chunk) is still in shared memory in the same record
+// layout, so `recs` is a generic pointer to either place and one code path serves both.
+__device__ __forceinline__ const uint4 *poa_row_recs(const uint32_t *A32, const uint4 *last, uint32_t off, uint32_t last_off) {
+    return off == last_off ? last : reinterpret_cast<const uint4 *>(A32) + (off >> 3); // row offsets are multiples of 40 int16
+}
+__device__ __forceinline__ void poa_pred(const uint4 *recs, const int4 pm, const int j, const uint32_t INFP,
+                                         uint32_t &Mx, uint32_t &E1x, uint32_t &E2x) {
+    const int pb = pm.y, l2 = (j - pb) >> 1; // band starts are even, so is j
     uint32_t Xh = INFP, prev = INFP;
-    if (j >= pb && j <= pm.z) { const uint4 r = last[l2]; Xh = r.x; E1x = __vmaxs2(E1x, r.y); E2x = __vmaxs2(E2x, r.z); }
-    if (j > pb && j - 1 <= pm.z) prev = last[l2 - 1].x;
+    if (j >= pb && j <= pm.z) { const uint4 r = recs[l2]; Xh = r.x; E1x = __vmaxs2(E1x, r.y); E2x = __vmaxs2(E2x, r.z); }
+    if (j > pb && j - 1 <= pm.z) prev = recs[l2 - 1].x; // H of the pair to the left; only its upper half (column j-1) is used
     Mx = __vmaxs2(Mx, __funnelshift_r(prev, Xh, 16));
 }
 
@@ -259,24 +252,21 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         }
         __syncwarp();
     }
-    // ---- query profile (simd_abpoa_align.c:438-446) as four match bit-planes: bit j of plane b = (query[j-1] == b).
-    // The row score pair of columns (j, j+1) is then one word load, a shift and an IMAD instead of a trip to a 5 x qlen
-    // int16 table in the slab.  Columns 0 and > qlen score as mismatches here instead of 0: column 0 only feeds
-    // inf_min + s into a max that E wins, columns past the query end never flow back (M, F move right, E stays) and are
-    // excluded from the row maximum and the backtrack.  N (query or node) scores 0 in the reference: those rows take
-    // the literal path below.
+    // ---- query profile (simd_abpoa_align.c:438-446) as bit-planes: bit j of plane b < 4 = (query[j-1] == b), bit j of
+    // plane 4 = (query[j-1] is A/C/G/T and 1 <= j <= qlen).  The score pair of columns (j, j+1) against node base b is
+    // then two word loads, shifts and IMADs: mat where the match bit is set, -mis where only the valid bit is set, 0
+    // elsewhere (N in the query, column 0, columns past the query end) or when the node itself is N -- exactly the
+    // reference's 5 x qlen table, without a trip to a table in the slab at the head of every row's dependency chain.
     const int prof_w = ((qlen / pn + 1) * pn + 64 + 1) & ~1;
     const int peq_w = (prof_w >> 5) + 1;
     uint32_t *const peq = peq_w <= POA_PEQ_W ? sm.peq : reinterpret_cast<uint32_t *>(w.qp);
-    bool q_has_n = false;
     for (int j0 = 0; j0 < peq_w * 32; j0 += 32) {
         const int j = j0 + lane;
         const int qc = (j >= 1 && j <= qlen) ? (int)query[j - 1] : 7;
-        q_has_n |= qc >= 4 && qc != 7;
-        const uint32_t b0 = __ballot_sync(TH_FULL, qc == 0), b1 = __ballot_sync(TH_FULL, qc == 1), b2 = __ballot_sync(TH_FULL, qc == 2), b3 = __ballot_sync(TH_FULL, qc == 3);
-        if (lane < 4) peq[lane * peq_w + (j0 >> 5)] = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : b3;
+        const uint32_t b0 = __ballot_sync(TH_FULL, qc == 0), b1 = __ballot_sync(TH_FULL, qc == 1), b2 = __ballot_sync(TH_FULL, qc == 2),
+                       b3 = __ballot_sync(TH_FULL, qc == 3), bv = __ballot_sync(TH_FULL, qc < 4);
+        if (lane < 5) peq[lane * peq_w + (j0 >> 5)] = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : lane == 3 ? b3 : bv;
     }
-    q_has_n = __any_sync(TH_FULL, q_has_n);
     // ---- first row (simd_abpoa_align.c:538-555, 591-610) ------------------------------------
     uint32_t used = 0;
     {
@@ -324,12 +314,13 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
     const uint32_t used_rows0 = used;
     int4 *const rmeta_g = w.rmeta; const int4 *const rdesc_g = w.rdesc; const int32_t *const plist_g = w.plist;
     const uint32_t arena_cap = w.arena_cap;
-    for (int i = 1; i < n - 1; ++i) {
-        if ((i & 31) == 0 || i == 1) { // descriptors of the next 32 rows
-            const int idx = (i & ~31) + lane;
-            if (idx < n) sm.desc[idx & (POA_RING - 1)] = rdesc_g[idx];
-            __syncwarp();
-        }
+    const uint32_t *const vrow = peq + 4 * peq_w; // valid plane
+    for (int i0 = 0; i0 < n - 1; i0 += 32) {
+      { const int idx = i0 + lane; // descriptors of the next 32 rows
+        if (idx < n) sm.desc[idx & (POA_RING - 1)] = rdesc_g[idx];
+        __syncwarp(); }
+      const int i_end = min(i0 + 32, n - 1);
+      for (int i = max(i0, 1); i < i_end; ++i) {
         const int4 d = sm.desc[i & (POA_RING - 1)];
         const int np = d.y & 1023; // 1..POA_MAXPRE, checked when the descriptors were built
         // band: what the predecessors' row maxima and max_remain say (abpoa_align.h:34-35, simd_abpoa_align.c:846-854)
@@ -352,32 +343,60 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
         const uint32_t row_off = used;
         used += w5; // cells and rows are derived from `used` after the loop
         const int vb = (d.y >> 10) & 7;
-        const bool fast_s = vb < 4 && !q_has_n;
         const uint32_t *const prow = peq + (vb & 3) * peq_w;
+        const uint32_t s_neg = vb < 4 ? NEGMIS2 : 0u, s_xm = vb < 4 ? XMM : 0u;  // an N node scores 0 against everything
         const uint32_t rec0 = (row_off >> 3) + lane;                                  // this lane's record in chunk 0 (16-byte units; row_off is a multiple of 40)
         const uint32_t f20 = (row_off >> 1) + 2u * (uint32_t)width + lane;              // ... and its F2 pair (words)
         const int jmax = esn == qsn ? qlen : dend;       // columns past the query end do not compete for the row maximum
         const int vlast = esn - bsn;                      // the row's last vector is visited first by the reference's arg-max
-        int best = INT_MIN; uint32_t carryH = 0, carryF = POA_NEGP; // carryF: (F1 - e1, F2 - e2) of the previous chunk's last column
+        int best = INT_MIN;
+        if (width <= 64) {
+            // ---- the usual row: one 64-column chunk, no carries between chunks --------------------------------------
+            const int j = beg + 2 * lane;
+            uint32_t Mx = INFP, E1x = INFP, E2x = INFP;
+            poa_pred(poa_row_recs(A32, sm.last, (uint32_t)pm0.x, last_off), pm0, j, INFP, Mx, E1x, E2x);
+            for (int p = 1; p < np; ++p) {
+                const int4 pm = sm.pre[p];
+                poa_pred(poa_row_recs(A32, sm.last, (uint32_t)pm.x, last_off), pm, j, INFP, Mx, E1x, E2x);
+            }
+            const uint32_t sh = j & 31, t = (prow[j >> 5] >> sh) & 3u, v = (vrow[j >> 5] >> sh) & 3u; // bits of columns j, j + 1 (j is even)
+            const uint32_t S = (s_neg ^ (((t | (t << 15)) & 0x10001u) * s_xm)) & (((v | (v << 15)) & 0x10001u) * 0xffffu);
+            const uint32_t Ms = __vadd2(Mx, S);
+            const uint32_t Hme = __vimax3_s16x2(Ms, E1x, E2x);
+            uint32_t hp = __shfl_up_sync(TH_FULL, Hme, 1);
+            if (lane == 0) hp = Ms << 16;
+            const uint32_t Hsh = __funnelshift_r(hp, Hme, 16);
+            uint32_t G1 = __vadd2(Hsh, C1), G2 = __vadd2(Hsh, C2);   // G = (Hme[j-1] - oe) + e (j - j0)
+            G1 = __vmaxs2(G1, (G1 << 16) | 0x8000u); G2 = __vmaxs2(G2, (G2 << 16) | 0x8000u); // odd column also sees the even one
+            uint32_t TT = __byte_perm(G1, G2, 0x7632); // lo = G1 at this lane's odd column, hi = G2
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) TT = __vmaxs2(TT, __shfl_up_sync(TH_FULL, TT, dd)); // lanes < dd get their own value back
+            uint32_t Pv = __shfl_up_sync(TH_FULL, TT, 1);
+            if (lane == 0) Pv = POA_NEGP;
+            G1 = __vmaxs2(G1, __byte_perm(Pv, Pv, 0x1010)); G2 = __vmaxs2(G2, __byte_perm(Pv, Pv, 0x3232));
+            const uint32_t Fa = __vadd2(G1, NJ1), Fb = __vadd2(G2, NJ2);
+            const uint32_t Hn = __vimax3_s16x2(Hme, Fa, Fb);
+            const uint32_t E1o = __viaddmax_s16x2(E1x, NE1P, __vadd2(Hn, NOE1P));
+            const uint32_t E2o = __viaddmax_s16x2(E2x, NE2P, __vadd2(Hn, NOE2P));
+            sm.last[lane] = make_uint4(Hn, E1o, E2o, 0); // every reader of the old contents is past the scan's shuffles
+            if (j <= dend) { reinterpret_cast<uint4 *>(A32w)[rec0] = make_uint4(Hn, E1o, E2o, Fa); A32w[f20] = Fb; }
+            const uint32_t sub = lane_vec == vlast ? 0u : (uint32_t)(lane_vec + 1);
+            const int klo = (int)__byte_perm(Hn, KLO - sub, 0x1054), khi = (int)__byte_perm(Hn, KHI - sub, 0x3254);
+            best = max(j <= jmax ? klo : INT_MIN, j < jmax ? khi : INT_MIN); // jmax <= dend
+            last_off = row_off;
+        } else {
+        uint32_t carryH = 0, carryF = POA_NEGP; // carryF: (F1 - e1, F2 - e2) of the previous chunk's last column
         const int nchunk = (width + 63) >> 6;
         for (int ch = 0; ch < nchunk; ++ch) {
             const int j = beg + (ch << 6) + 2 * lane;
             uint32_t Mx = INFP, E1x = INFP, E2x = INFP;
-            if ((uint32_t)pm0.x == last_off) poa_pred_last(sm.last, pm0, j, INFP, Mx, E1x, E2x);
-            else poa_pred(A32, pm0, j, INFP, Mx, E1x, E2x);
+            poa_pred(poa_row_recs(A32, sm.last, (uint32_t)pm0.x, last_off), pm0, j, INFP, Mx, E1x, E2x);
             for (int p = 1; p < np; ++p) {
                 const int4 pm = sm.pre[p];
-                if ((uint32_t)pm.x == last_off) poa_pred_last(sm.last, pm, j, INFP, Mx, E1x, E2x);
-                else poa_pred(A32, pm, j, INFP, Mx, E1x, E2x);
+                poa_pred(poa_row_recs(A32, sm.last, (uint32_t)pm.x, last_off), pm, j, INFP, Mx, E1x, E2x);
             }
-            uint32_t S;
-            if (fast_s) {
-                const uint32_t t = (prow[j >> 5] >> (j & 31)) & 3u;            // match bits of columns j, j + 1 (j is even)
-                S = NEGMIS2 ^ (((t | (t << 15)) & 0x10001u) * XMM);
-            } else { // N in the query or an N node: score 0 (simd_abpoa_align.c:438-446 with the all-zero N row/column of the matrix)
-                const int c0 = (j >= 1 && j <= qlen) ? (int)query[j - 1] : 4, c1 = (j + 1 <= qlen) ? (int)query[j] : 4;
-                S = pk((c0 < 4 && vb < 4) ? (c0 == vb ? mat : -mis) : 0, (c1 < 4 && vb < 4) ? (c1 == vb ? mat : -mis) : 0);
-            }
+            const uint32_t sh = j & 31, t = (prow[j >> 5] >> sh) & 3u, v = (vrow[j >> 5] >> sh) & 3u;
+            const uint32_t S = (s_neg ^ (((t | (t << 15)) & 0x10001u) * s_xm)) & (((v | (v << 15)) & 0x10001u) * 0xffffu);
             const uint32_t Ms = __vadd2(Mx, S);
             const uint32_t Hme = __vimax3_s16x2(Ms, E1x, E2x);
             uint32_t hp = __shfl_up_sync(TH_FULL, Hme, 1);
@@ -401,7 +420,6 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 const uint32_t fa = __shfl_sync(TH_FULL, Fa, 31), fb = __shfl_sync(TH_FULL, Fb, 31);
                 carryF = __vadd2(__byte_perm(fa, fb, 0x7632), pk(-e1, -e2)); // G of column j0 - 1 in the next chunk's frame
             }
-            if (nchunk == 1) sm.last[lane] = make_uint4(Hn, E1o, E2o, 0); // every reader of the old contents is past the scan's shuffles
             if (j <= dend) { reinterpret_cast<uint4 *>(A32w)[rec0 + (ch << 5)] = make_uint4(Hn, E1o, E2o, Fa); A32w[f20 + (ch << 5)] = Fb; }
             { // row arg-max key (signed compare): value, then lane (j mod pn) ascending, then vector order with end_sn first
                 const int rel = lane_vec + (ch << (6 - lp));
@@ -410,19 +428,18 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 best = max(best, max(j <= jmax ? klo : INT_MIN, j < jmax ? khi : INT_MIN)); // jmax <= dend
             }
         }
+        last_off = 0xffffffffu; // sm.last keeps an older row; it is matched by offset, and that offset is forgotten here
+        }
         best = __reduce_max_sync(TH_FULL, best);
         { // simd_abpoa_max_in_row + simd_abpoa_ada_max_i: successors pull max_i + 1 from this row's metadata
             const int val = best >> 16;
-            int max_i = -1;
-            if (best != INT_MIN && val > inf_min) {
-                const int lam = lam_bits - (int)((best >> 12) & 0xf), vr = 0xfff - (int)(best & 0xfff);
-                const int vsn = vr == 0 ? esn : bsn + vr - 1;
-                max_i = vsn * pn + lam;
-            }
+            const int lam = lam_bits - (int)((best >> 12) & 0xf), vr = 0xfff - (int)(best & 0xfff);
+            const int vsn = vr == 0 ? esn : bsn + vr - 1;
+            const int max_i = (best != INT_MIN && val > inf_min) ? vsn * pn + lam : -1;
             if (lane == 0) { const int4 m = make_int4((int)row_off, beg, dend, max_i + 1); sm.meta[i & (POA_RING - 1)] = m; rmeta_g[i] = m; }
         }
-        last_off = nchunk == 1 ? row_off : 0xffffffffu;
         __syncwarp();
+      }
     }
     cells += (used - used_rows0) / 5u; rows += (unsigned long long)max(n - 2, 0);
     PH(1);
