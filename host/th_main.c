@@ -51,49 +51,42 @@ static int usage(void) {
     return 1;
 }
 
-/* ---- FASTA/FASTQ(.gz) reader with kseq semantics (src/kseq.h:174-217): name = up to first whitespace ---- */
-typedef struct { gzFile fp; unsigned char *buf; int beg, end, eof; } stream_t;
-static int st_getc(stream_t *s) {
-    if (s->beg >= s->end) {
-        if (s->eof) return -1;
-        s->beg = 0; s->end = gzread(s->fp, s->buf, 1 << 20);
-        if (s->end <= 0) { s->eof = 1; s->end = 0; return -1; }
-    }
-    return s->buf[s->beg++];
-}
-typedef struct { char *s; size_t l, m; } kstr_t;
-static void ks_push(kstr_t *k, int c) { if (k->l + 2 > k->m) { k->m = k->m ? k->m * 2 : 256; k->s = (char *)realloc(k->s, k->m); } k->s[k->l++] = (char)c; k->s[k->l] = 0; }
-static int last_char = 0;
-static int read_record(stream_t *s, kstr_t *name, kstr_t *seq) {
-    int c;
-    if (last_char == 0) { while ((c = st_getc(s)) != -1 && c != '>' && c != '@') ; if (c == -1) return -1; last_char = c; }
-    name->l = seq->l = 0; ks_push(name, 0); name->l = 0; ks_push(seq, 0); seq->l = 0;
-    while ((c = st_getc(s)) != -1 && c != ' ' && c != '\t' && c != '\n' && c != '\r') ks_push(name, c);
-    if (c == -1) return -1;
-    if (c != '\n') while ((c = st_getc(s)) != -1 && c != '\n') ;
-    while ((c = st_getc(s)) != -1 && c != '>' && c != '+' && c != '@') {
-        if (c == '\n') continue;
-        if (c > 32 && c < 127) ks_push(seq, c); /* kseq keeps isgraph() characters */
-        while ((c = st_getc(s)) != -1 && c != '\n') if (c > 32 && c < 127) ks_push(seq, c);
-    }
-    if (c == '>' || c == '@') last_char = c;
-    if (c != '+') { if (c == -1) last_char = 0; return (int)seq->l; }
-    while ((c = st_getc(s)) != -1 && c != '\n') ; /* skip the rest of '+' line */
-    { size_t ql = 0; while (ql < seq->l && (c = st_getc(s)) != -1) if (c > 32 && c < 127) ++ql; }
-    last_char = 0;
-    return (int)seq->l;
+/* ---- input: host/th_reader.h parses batches on a reader thread while the GPU lanes work on the previous batch ---- */
+#include <pthread.h>
+#include "th_reader.h"
+
+static char *read_first_seq(const char *fn) { /* get_seq_from_fx, src/main.c:157-171: first record with a non-empty sequence */
+    th_reader *r = thr_open(fn); th_batch b; int stop = 0; char *res = NULL;
+    if (!r) { fprintf(stderr, "[%s] fail to open %s\n", PROG, fn); exit(1); }
+    memset(&b, 0, sizeof(b));
+    if (thr_read_batch(r, &b, 1, &stop) > 0 && b.lens[0] > 0) res = strdup(b.seqs[0]);
+    thr_batch_free(&b); thr_close(r);
+    if (!res) { fprintf(stderr, "[%s] No sequence found in %s.\n", PROG, fn); exit(1); }
+    return res;
 }
 
-static char *read_first_seq(const char *fn) { /* get_seq_from_fx, src/seq.c */
-    stream_t s; kstr_t name = {0, 0, 0}, seq = {0, 0, 0}; char *r = NULL;
-    memset(&s, 0, sizeof(s));
-    s.fp = gzopen(fn, "r"); if (!s.fp) { fprintf(stderr, "[%s] fail to open %s\n", PROG, fn); exit(1); }
-    s.buf = (unsigned char *)malloc(1 << 20);
-    last_char = 0;
-    if (read_record(&s, &name, &seq) > 0) r = strdup(seq.s);
-    gzclose(s.fp); free(s.buf); free(name.s); free(seq.s); last_char = 0;
-    if (!r) { fprintf(stderr, "[%s] No sequence found in %s.\n", PROG, fn); exit(1); }
-    return r;
+typedef struct {
+    th_reader *r; int batch_reads;
+    th_batch slot[2]; int state[2];       /* 0 = free, 1 = filled */
+    int done;                             /* reader reached the end of the input (or the reference's stop condition) */
+    pthread_mutex_t mu; pthread_cond_t cv;
+} prefetch_t;
+
+static void *reader_main(void *arg) {
+    prefetch_t *q = (prefetch_t *)arg; int k = 0, stop = 0;
+    for (;;) {
+        pthread_mutex_lock(&q->mu);
+        while (q->state[k] != 0) pthread_cond_wait(&q->cv, &q->mu);
+        pthread_mutex_unlock(&q->mu);
+        { const int n = stop ? 0 : thr_read_batch(q->r, &q->slot[k], q->batch_reads, &stop);
+          pthread_mutex_lock(&q->mu);
+          if (n > 0) q->state[k] = 1; else q->done = 1;
+          pthread_cond_broadcast(&q->cv);
+          pthread_mutex_unlock(&q->mu);
+          if (n <= 0) break; }
+        k ^= 1;
+    }
+    return NULL;
 }
 
 int main(int argc, char *argv[]) {
@@ -144,36 +137,35 @@ int main(int argc, char *argv[]) {
     if (five_fn && three_fn) { p.five_seq = read_first_seq(five_fn); p.three_seq = read_first_seq(three_fn); }
     {
         struct timespec t0, t1; FILE *out = out_fn ? fopen(out_fn, "w") : stdout;
-        th_host *h; stream_t st; kstr_t name = {0, 0, 0}, seq = {0, 0, 0};
-        int n = 0, m = 0, i, batch_reads; char **names = NULL, **seqs = NULL; int32_t *lens = NULL; long long tot_reads = 0;
+        th_host *h; prefetch_t q; pthread_t rt; int k = 0; long long tot_reads = 0;
         clock_gettime(CLOCK_MONOTONIC, &t0);
         if (!out) { fprintf(stderr, "[main] cannot open %s\n", out_fn); return 1; }
         h = th_host_create(&p, device);
         if (!h) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
+        memset(&q, 0, sizeof(q));
         /* one th_host_run covers several chunks so that its GPU lanes overlap (host/th_host.h) */
-        batch_reads = p.chunk_reads * (p.lanes > 0 ? p.lanes : 3) * 2;
-        memset(&st, 0, sizeof(st));
-        st.fp = strcmp(argv[optind], "-") ? gzopen(argv[optind], "r") : gzdopen(0, "r");
-        if (!st.fp) { fprintf(stderr, "[main] fail to open %s\n", argv[optind]); return 1; }
-        st.buf = (unsigned char *)malloc(1 << 20);
-        last_char = 0;
-        while (1) {
-            int l = read_record(&st, &name, &seq);
-            if (l >= 0) {
-                if (n == m) { m = m ? m * 2 : 1024; names = (char **)realloc(names, sizeof(char *) * m); seqs = (char **)realloc(seqs, sizeof(char *) * m); lens = (int32_t *)realloc(lens, sizeof(int32_t) * m); }
-                names[n] = strdup(name.s); seqs[n] = (char *)malloc(seq.l + 1); memcpy(seqs[n], seq.s, seq.l + 1); lens[n] = (int32_t)seq.l; ++n;
-            }
-            if (n == batch_reads || (l < 0 && n > 0)) {
-                size_t ol; const char *txt = th_host_run(h, n, (const char *const *)names, (const char *const *)seqs, lens, &ol);
-                if (!txt) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
-                fwrite(txt, 1, ol, out);
-                tot_reads += n;
-                for (i = 0; i < n; ++i) { free(names[i]); free(seqs[i]); }
-                n = 0;
-            }
-            if (l < 0) break;
+        q.batch_reads = p.chunk_reads * (p.lanes > 0 ? p.lanes : 3) * 2;
+        q.r = thr_open(argv[optind]);
+        if (!q.r) { fprintf(stderr, "[main] fail to open %s\n", argv[optind]); return 1; }
+        pthread_mutex_init(&q.mu, NULL); pthread_cond_init(&q.cv, NULL);
+        pthread_create(&rt, NULL, reader_main, &q);
+        for (;;) {
+            th_batch *b = &q.slot[k]; size_t ol; const char *txt; int have;
+            pthread_mutex_lock(&q.mu);
+            while (q.state[k] == 0 && !q.done) pthread_cond_wait(&q.cv, &q.mu);
+            have = q.state[k] == 1;
+            pthread_mutex_unlock(&q.mu);
+            if (!have) break;
+            txt = th_host_run(h, b->n, (const char *const *)b->names, (const char *const *)b->seqs, b->lens, &ol);
+            if (!txt) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
+            fwrite(txt, 1, ol, out);
+            tot_reads += b->n;
+            pthread_mutex_lock(&q.mu); q.state[k] = 0; pthread_cond_broadcast(&q.cv); pthread_mutex_unlock(&q.mu);
+            k ^= 1;
         }
-        gzclose(st.fp); free(st.buf); free(name.s); free(seq.s); free(names); free(seqs); free(lens);
+        pthread_join(rt, NULL);
+        thr_batch_free(&q.slot[0]); thr_batch_free(&q.slot[1]); thr_close(q.r);
+        pthread_mutex_destroy(&q.mu); pthread_cond_destroy(&q.cv);
         th_host_destroy(h);
         if (out != stdout) fclose(out);
         clock_gettime(CLOCK_MONOTONIC, &t1);

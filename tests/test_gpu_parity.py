@@ -175,3 +175,45 @@ def test_edge_reads(T, oracle):
     assert th.run(names, seqs) == oracle.run_batch(names, seqs, oracle.default_para())[0]
     assert th.run([], []) == b""
     th.close()
+
+
+def test_cli_golden_cases(T, golden, golden_inputs, tmp_path):
+    """The command line front end (host/tidehunter-b200: reader thread -> host layer -> C ABI) on files: every golden
+    case, with the input written as multi-line FASTA, as gzip, and (quality-format cases) as FASTQ."""
+    import gzip
+    import os
+    import subprocess
+    from tidehunter_b200 import build as B
+    cli = B.build()[2]
+    five, three = golden["adapters"]["five"], golden["adapters"]["three"]
+    p5, p3 = str(tmp_path / "5.fa"), str(tmp_path / "3.fa")
+    open(p5, "w").write(">5\n%s\n" % five)
+    open(p3, "w").write(">3 adapter\n%s\n%s\n" % (three[:10], three[10:]))
+    bad = []
+    for k, c in enumerate(golden["cases"]):
+        names, seqs = golden_inputs(c["input"])
+        style = k % 3
+        path = str(tmp_path / ("in%d.fx" % k))
+        with open(path, "wb") as f:
+            for n, s in zip(names, seqs):
+                if style == 1:      # FASTQ, quality may start with '@'
+                    f.write(b"@" + n + b" some comment\n" + s + b"\n+" + n + b"\n" + b"@" * len(s) + b"\n")
+                else:               # FASTA, 70 columns, CRLF for every third case
+                    eol = b"\r\n" if k % 9 == 0 else b"\n"
+                    f.write(b">" + n + b"\tcomment" + eol + eol.join(s[i:i + 70] for i in range(0, len(s), 70)) + eol)
+        if style == 2:
+            with open(path, "rb") as f, gzip.open(path + ".gz", "wb") as g:
+                g.write(f.read())
+            path += ".gz"
+        args = []
+        i = 0
+        while i < len(c["args"]):   # golden args name the reference's adapter files: point them at ours
+            a = c["args"][i]
+            if a in ("-5", "-3"):
+                args += [a, p5 if a == "-5" else p3]; i += 2
+            else:
+                args.append(a); i += 1
+        r = subprocess.run([cli] + args + [path], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        if r.returncode != 0 or hashlib.md5(r.stdout).hexdigest() != c["md5"]:
+            bad.append((c["input"], c["args"], style, r.returncode, r.stderr.decode()[-200:]))
+    assert not bad, bad[:5]

@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
     if force or _newer(HOST_SO, host_src):
         _run(["gcc", "-std=gnu99", "-O2", "-fPIC", "-ffp-contract=off", "-Wall", "-shared", "-o", HOST_SO,
               os.path.join(HOST, "th_host.c"), "-L" + PKG, "-lth_gpu", "-Wl,-rpath,$ORIGIN", "-lm", "-lpthread"])
-    if force or _newer(CLI, [os.path.join(HOST, "th_main.c"), HOST_SO]):
+    if force or _newer(CLI, [os.path.join(HOST, "th_main.c"), os.path.join(HOST, "th_reader.h"), HOST_SO]):
         _run(["gcc", "-std=gnu99", "-O2", "-ffp-contract=off", "-Wall", "-o", CLI, os.path.join(HOST, "th_main.c"),
               "-L" + PKG, "-lth_host", "-lth_gpu", "-Wl,-rpath,$ORIGIN/../tidehunter_b200", "-lz", "-lm", "-lpthread"])
     return GPU_SO, HOST_SO, CLI
