@@ -36,7 +36,7 @@ static void set_err(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnpr
 void th_host_default_para(th_host_para *p) {
     memset(p, 0, sizeof(*p));
     th_gpu_default_params(&p->gpu);
-    p->out_fmt = 1; p->min_len = 30; p->ada_match_rat = 0.8f; p->chunk_reads = 8192;
+    p->out_fmt = 1; p->min_len = 30; p->ada_match_rat = 0.8f; p->chunk_reads = 4096;
 }
 
 static void str_reserve(str_t *s, size_t extra) {
@@ -66,8 +66,8 @@ th_host *th_host_create(const th_host_para *p, int device) {
     th_host *h = (th_host *)calloc(1, sizeof(th_host));
     h->p = *p;
     h->p.gpu.need_cov = (p->out_fmt == 3 || p->out_fmt == 4 || p->min_cov > 0 || p->min_frac > 0.0) ? 1 : 0;
-    if (h->p.chunk_reads <= 0) h->p.chunk_reads = 8192;
-    if (h->p.lanes <= 0) { const char *e = getenv("TH_HOST_LANES"); h->p.lanes = e ? atoi(e) : 3; }
+    if (h->p.chunk_reads <= 0) h->p.chunk_reads = 4096;
+    if (h->p.lanes <= 0) { const char *e = getenv("TH_HOST_LANES"); h->p.lanes = e ? atoi(e) : 4; } /* 4 contexts x 4096 reads: the best end-to-end setting measured on B200 (profiles/) */
     if (h->p.lanes < 1) h->p.lanes = 1;
     if (h->p.lanes > TH_MAX_LANES) h->p.lanes = TH_MAX_LANES;
     for (h->n_lanes = 0; h->n_lanes < h->p.lanes; ++h->n_lanes) {

@@ -47,7 +47,7 @@ static int usage(void) {
                     "  -o STR  output file [stdout]           -m INT  min consensus length [30]  -r FLT|INT min coverage\n"
                     "  -u unit sequences only   -l longest only   -F full-length only   -s single-copy full-length (with -F -5 -3)\n"
                     "  -f INT  1 FASTA, 2 tabular, 3 FASTQ, 4 tabular+quality [1]\n"
-                    "  -t INT  accepted, ignored              --device INT CUDA device [0]       --chunk INT reads per GPU chunk [8192]\n          --lanes INT GPU contexts the chunks rotate over [3]\n\n");
+                    "  -t INT  accepted, ignored              --device INT CUDA device [0]       --chunk INT reads per GPU chunk [4096]\n          --lanes INT GPU contexts the chunks rotate over [4]\n\n");
     return 1;
 }
 
@@ -144,7 +144,7 @@ int main(int argc, char *argv[]) {
         if (!h) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
         memset(&q, 0, sizeof(q));
         /* one th_host_run covers several chunks so that its GPU lanes overlap (host/th_host.h) */
-        q.batch_reads = p.chunk_reads * (p.lanes > 0 ? p.lanes : 3) * 2;
+        q.batch_reads = p.chunk_reads * (p.lanes > 0 ? p.lanes : 4) * 2;
         q.r = thr_open(argv[optind]);
         if (!q.r) { fprintf(stderr, "[main] fail to open %s\n", argv[optind]); return 1; }
         pthread_mutex_init(&q.mu, NULL); pthread_cond_init(&q.cv, NULL);
