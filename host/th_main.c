@@ -140,15 +140,15 @@ int main(int argc, char *argv[]) {
         th_host *h; prefetch_t q; pthread_t rt; int k = 0; long long tot_reads = 0;
         clock_gettime(CLOCK_MONOTONIC, &t0);
         if (!out) { fprintf(stderr, "[main] cannot open %s\n", out_fn); return 1; }
-        h = th_host_create(&p, device);
-        if (!h) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
         memset(&q, 0, sizeof(q));
         /* one th_host_run covers several chunks so that its GPU lanes overlap (host/th_host.h) */
         q.batch_reads = p.chunk_reads * (p.lanes > 0 ? p.lanes : 4) * 2;
         q.r = thr_open(argv[optind]);
         if (!q.r) { fprintf(stderr, "[main] fail to open %s\n", argv[optind]); return 1; }
         pthread_mutex_init(&q.mu, NULL); pthread_cond_init(&q.cv, NULL);
-        pthread_create(&rt, NULL, reader_main, &q);
+        pthread_create(&rt, NULL, reader_main, &q);   /* the first batch is parsed while the CUDA contexts come up */
+        h = th_host_create(&p, device);
+        if (!h) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
         for (;;) {
             th_batch *b = &q.slot[k]; size_t ol; const char *txt; int have;
             pthread_mutex_lock(&q.mu);
