@@ -287,11 +287,10 @@ def main():
     serial = {k: 0.0 for k in STAGES}
     serial_cnt = {}
     if L > 1:
-        for _ in range(2):
-            s = ctxs[0].process_resident().stats.as_dict()
-            for st in STAGES:
-                serial[st] += s["ms_" + st] / 2
-            serial_cnt = s
+        runs = [ctxs[0].process_resident().stats.as_dict() for _ in range(3)]
+        for st in STAGES:   # median of three launches: the per-launch time of the POA kernel varies by ~10 % between launches
+            serial[st] = statistics.median(r["ms_" + st] for r in runs)
+        serial_cnt = runs[-1]
     for c in ctxs:
         c.close()
 

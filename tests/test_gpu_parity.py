@@ -217,3 +217,21 @@ def test_cli_golden_cases(T, golden, golden_inputs, tmp_path):
         if r.returncode != 0 or hashlib.md5(r.stdout).hexdigest() != c["md5"]:
             bad.append((c["input"], c["args"], style, r.returncode, r.stderr.decode()[-200:]))
     assert not bad, bad[:5]
+
+
+def test_baseline_workload_chunk_matches_reference_md5(T):
+    """One 16,384-read chunk of the full BASELINE configs[1] workload (1,048,576 reads) against the md5 of the unmodified
+    reference's output for it (tests/golden/r2c2_1m_md5.json, made by tools/million_parity.py --make-md5).  The
+    whole set is checked by tools/million_parity.py --check (profiles/r1_million_parity.json)."""
+    import json
+    import os
+    from tidehunter_b200 import synth
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "r2c2_1m_md5.json")))
+    assert len(fx["chunks"]) == 64 and sum(c["reads"] for c in fx["chunks"]) == 1048576
+    c = fx["chunks"][37]
+    names, seqs = synth.gen_reads("r2c2", c["reads"], start=c["first_read"])
+    assert hashlib.md5(b"".join(seqs)).hexdigest() == c["input_md5"]
+    th = T.TideHunter(out_fmt=1)
+    out = th.run(names, seqs)
+    th.close()
+    assert len(out) == c["bytes"] and hashlib.md5(out).hexdigest() == c["md5"]

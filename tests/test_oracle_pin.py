@@ -78,3 +78,15 @@ def test_edge_cases(oracle):
     names = [b"e", b"s", b"n", b"u"]
     seqs = [b"", b"ACGT", b"N" * 500, b"ACGTTGCA" * 4 + b"GATTACAGATTACCA"]
     assert oracle.run_batch(names, seqs, oracle.default_para())[0] == b""
+
+
+def test_million_read_fixture_is_complete():
+    """tests/golden/r2c2_1m_md5.json covers BASELINE configs[1] end to end: 64 consecutive chunks of 16,384 reads."""
+    import json
+    import os
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "r2c2_1m_md5.json")))
+    ch = fx["chunks"]
+    assert [c["chunk"] for c in ch] == list(range(64))
+    assert all(c["first_read"] == 16384 * c["chunk"] and c["reads"] == 16384 for c in ch)
+    assert sum(c["reads"] for c in ch) == 1048576 and sum(c["records"] for c in ch) > 1000000
+    assert len({c["md5"] for c in ch}) == 64

@@ -69,6 +69,7 @@ struct th_gpu_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[16];
     cudaEvent_t mark[4]; // th_gpu_mark: step brackets for callers that time several contexts together
+    cudaEvent_t ev_block; // host waits go through a blocking-sync event: a waiting lane thread sleeps instead of spinning on a core
     // resident chunk
     int n_reads = 0; int64_t bpad = 0; int max_len = 0;
     std::vector<int64_t> h_roff; std::vector<int32_t> h_rlen;
@@ -119,6 +120,7 @@ extern "C" th_gpu_ctx *th_gpu_create(const th_gpu_params *p, int device) {
     CKP(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) CKP(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 4; ++i) CKP(cudaEventCreate(&c->mark[i]));
+    CKP(cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
     CKP(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_CAP * 8));
     memset(&c->stats, 0, sizeof(c->stats));
     return c;
@@ -138,11 +140,19 @@ extern "C" void th_gpu_destroy(th_gpu_ctx *c) {
     for (HBuf *b : hs) b->release();
     for (int i = 0; i < 16; ++i) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(c->mark[i]);
+    cudaEventDestroy(c->ev_block);
     cudaStreamDestroy(c->stream);
     delete c;
 }
 
 // ---------------------------------------------------------------------------------------------
+// Wait for the context's stream without burning a host core: with several contexts per GPU and one process per GPU,
+// spinning waits (the runtime's default on a lightly loaded host) starve the threads that format records.
+static cudaError_t th_wait(th_gpu_ctx *c) {
+    cudaError_t e = cudaEventRecord(c->ev_block, c->stream);
+    return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_block);
+}
+
 extern "C" int th_gpu_upload(th_gpu_ctx *c, int32_t n_reads, const char *const *seq, const int32_t *seq_len) {
     CK(cudaSetDevice(c->device));
     c->n_reads = n_reads;
@@ -166,7 +176,7 @@ extern "C" int th_gpu_upload(th_gpu_ctx *c, int32_t n_reads, const char *const *
     CK(cudaMemcpyAsync(c->d_roff.p, c->h_roff.data(), sizeof(int64_t) * (n_reads + 1), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_rlen.p, c->h_rlen.data(), sizeof(int32_t) * n_reads, cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(c->ev[1], c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(th_wait(c));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
     c->stats.ms_h2d = ms;
     c->stats.h2d_bytes = off + (int64_t)(sizeof(int64_t) + sizeof(int32_t)) * n_reads;
@@ -310,7 +320,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     std::vector<int32_t> used(n), nhits_h(n);
     CK(cudaMemcpyAsync(used.data(), c->d_parused.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(nhits_h.data(), c->d_nhits.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(th_wait(c));
     std::vector<int64_t> doff(n + 1, 0), soff(n);
     for (int i = 0; i < n; ++i) { doff[i + 1] = doff[i] + used[i]; soff[i] = 2 * c->h_roff[i]; S.n_hits += nhits_h[i]; }
     const int64_t tot_stream = doff[n];
@@ -321,7 +331,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     S.n_launches++;
     c->dbg_par_stream.resize(tot_stream); c->dbg_par_doff = doff;
     CK(cudaMemcpyAsync(c->dbg_par_stream.data(), c->d_dense_c.p, 4 * (size_t)tot_stream, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(th_wait(c));
     S.d2h_bytes += 4 * tot_stream + 8 * (int64_t)n;
     // ---- host: split runs into tasks exactly as seqs_msa (src/gen_cons.c:191-200) ----
     std::vector<PoaTask> tasks; std::vector<int32_t> ustart, ulen; std::vector<KswItem> items;
@@ -431,7 +441,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
                                                  c->d_consl.as<int32_t>(), c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2, cnt64 + 16);
         S.n_launches++;
         CK(cudaMemcpyAsync(c->r_task_status.data(), c->d_tstatus.p, 4 * (size_t)nt, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(th_wait(c));
         // retry tasks whose DP arena overflowed, with full-width slabs
         std::vector<int32_t> retry;
         for (int t = 0; t < nt; ++t) if (c->r_task_status[t] == TH_ERR_ARENA) retry.push_back(t);
@@ -496,7 +506,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         CK(cudaMemcpyAsync(c->r_task_status.data(), c->d_tstatus.p, 4 * (size_t)nt, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(c->r_iden.data(), c->d_iden.p, 4 * c->r_pos.size(), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(c->r_ext.data(), c->d_ext.p, 16 * (size_t)nt, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(th_wait(c));
         std::vector<int64_t> gs(nt), gd(nt);
         int64_t tot = 0;
         for (int t = 0; t < nt; ++t) { gs[t] = tasks[t].cons_off; gd[t] = tot; c->r_task_cons_off[t] = (int32_t)tot; tot += cl[t]; }
@@ -516,16 +526,16 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
             }
         }
         CK(cudaEventRecord(c->ev[ei++], st)); // 11
-        CK(cudaStreamSynchronize(st));
+        CK(th_wait(c));
         S.d2h_bytes += 4ll * nt * 2 + 4ll * (int64_t)c->r_pos.size() + 16ll * nt + tot * (c->params.need_cov ? 5 : 1);
         S.ms_poa = ev_ms(c, 8, 9); S.ms_ksw = ev_ms(c, 9, 10); S.ms_d2h = ev_ms(c, 10, 11);
     } else {
         CK(cudaEventRecord(c->ev[ei++], st)); CK(cudaEventRecord(c->ev[ei++], st)); CK(cudaEventRecord(c->ev[ei++], st));
-        CK(cudaStreamSynchronize(st));
+        CK(th_wait(c));
     }
     // per-read status -> tasks of that read
     { std::vector<int32_t> rs(n);
-      CK(cudaMemcpy(rs.data(), c->d_rstatus.p, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpyAsync(rs.data(), c->d_rstatus.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st)); CK(th_wait(c));
       for (int r = 0; r < n; ++r) if (rs[r]) for (int t = c->r_read_task_off[r]; t < c->r_read_task_off[r + 1]; ++t) if (!c->r_task_status[t]) c->r_task_status[t] = rs[r]; }
     unsigned long long hc[4];
     CK(cudaMemcpy(hc, c->d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost));

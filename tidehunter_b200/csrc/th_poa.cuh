@@ -94,8 +94,6 @@ __device__ inline void poa_carve(PoaWs &w, uint8_t *slab, size_t slab_bytes, int
 __device__ __forceinline__ uint32_t ld32(const int16_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
 __device__ __forceinline__ void st32(int16_t *p, uint32_t v) { *reinterpret_cast<uint32_t *>(p) = v; }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// whole-range L2 prefetch (sm_90+): p 16-byte aligned, bytes a multiple of 16
-__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes)); }
 
 // graph edit used for the final edge into the sink (lane 0 only)
 __device__ inline void g_add_edge(PoaWs &w, int &edge_n, int from, int to, bool check) {
@@ -486,16 +484,14 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                     const int4 m = w.rmeta[r];
                     sm.desc[r & (POA_RING - 1)] = w.rdesc[r]; sm.meta[r & (POA_RING - 1)] = m;
                     const int rw = m.z - m.y + 1;
-                    // the whole row (records + F2 = 10 bytes per column, a few hundred bytes for the usual band) goes to L2 with one
-                    // bulk prefetch: no guess about the column where the path will cross it.  Wide rows: around the row maximum.
+                    // the path crosses a row close to that row's maximum (the column that steered the band); the graph holds
+                    // several nodes per query column, so extrapolating j along the row index would drift off within a few rows.
+                    // (Prefetching whole rows with cp.async.bulk.prefetch.L2 was measured: +25 GB of DRAM reads per 8192 reads
+                    // and no shorter backtrack, so only the sectors around the predicted crossing are requested.)
+                    int jp = m.w > 0 ? m.w - 1 : j - (i - r); jp = min(max(jp, m.y), m.z);
+                    const int c0 = max(jp - 7, m.y) - m.y, c1 = max(jp - 2, m.y) - m.y, c2 = min(jp + 4, m.z) - m.y;
                     const uint32_t *Rr = A32 + (m.x >> 1);
-                    if (rw <= 256) prefetch_l2_bulk(Rr, 10u * (uint32_t)rw);
-                    else {
-                        int jp = m.w > 0 ? m.w - 1 : j - (i - r); jp = min(max(jp, m.y), m.z);
-                        const int c0 = (max(jp - 62, m.y) - m.y) & ~1; // 128 columns of records (16-byte aligned start) and their F2 words
-                        prefetch_l2_bulk(Rr + 4 * (c0 >> 1), (uint32_t)min(128, rw - c0) * 8u);
-                        prefetch_l2_bulk(Rr + 2 * rw + ((c0 >> 1) & ~3), (uint32_t)(min(128, rw - c0) * 2 + 16) & ~15u);
-                    }
+                    prefetch_l2(Rr + 4 * (c0 >> 1)); prefetch_l2(Rr + 4 * (c1 >> 1)); prefetch_l2(Rr + 4 * (c2 >> 1)); prefetch_l2(Rr + 2 * rw + ((jp - m.y) >> 1));
                 }
                 wlo = max(0, top - 32); whi = min(whi, wlo + POA_RING - 1);
                 __syncwarp();
