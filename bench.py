@@ -33,8 +33,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # DRAM bytes per banded POA cell from the ncu --set full capture in profiles/ (dram__bytes_read.sum + dram__bytes_write.sum
-# of poa_kernel over its cell count): r1 capture at 8192 reads = (57.67 + 67.70) GB / 5.686 G cells
-NCU_POA_TRAFFIC_PER_CELL = 22.05
+# of poa_kernel over its cell count): r1 final capture at 8192 reads = (55.58 + 67.88) GB / 5.693 G cells
+# (profiles/r1_ncu_full_summary_8192reads_final.txt)
+NCU_POA_TRAFFIC_PER_CELL = 21.69
 
 WORKLOAD = "synthetic ONT R2C2-style reads: 10 kb, 1 kb unit x 10 copies, 15% error (BASELINE.json configs[1])"
 
