@@ -43,7 +43,7 @@ def main():
             O.write_fasta(path, names, seqs)
             ref = subprocess.run([O.REF_BIN, "-t", str(os.cpu_count() or 1), "-f", "2", path], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
         rep = {"world_size": world, "reads": n, "identical": text == ref, "bytes": len(ref), "md5_reference": hashlib.md5(ref).hexdigest(),
-               "md5_ours": hashlib.md5(text).hexdigest(), "options": "-f 2", "gather": "gloo gather_object in rank order, no data-path collective"}
+               "md5_ours": hashlib.md5(text).hexdigest(), "options": "-f 2", "gather": "host-side, rank order (tmpfs files + gloo barrier on one node, gather_object otherwise); no data-path collective"}
         print(json.dumps(rep))
         rc = 0 if text == ref else 1
     if world > 1:
