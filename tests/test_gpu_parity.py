@@ -235,3 +235,21 @@ def test_baseline_workload_chunk_matches_reference_md5(T):
     out = th.run(names, seqs)
     th.close()
     assert len(out) == c["bytes"] and hashlib.md5(out).hexdigest() == c["md5"]
+
+
+def test_sse_vector_width_mode(T):
+    """simd_lanes16 = 8: the GPU path emulating abPOA's SSE4.1 build (template instance LP = 3 of the POA kernel)
+    against the output of the reference built that way (tests/golden/pn8_golden.json)."""
+    import json
+    import os
+    from tidehunter_b200 import synth
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pn8_golden.json")))
+    names, seqs = [], []
+    for shape, start, n in fx["sets"]:
+        a, b = synth.gen_reads(shape, n, start=start)
+        names += a; seqs += b
+    for lanes16, md5 in ((8, fx["md5_pn8"]), (16, fx["md5_pn16"])):
+        th = T.TideHunter(out_fmt=2, simd_lanes16=lanes16)
+        out = th.run(names, seqs)
+        th.close()
+        assert hashlib.md5(out).hexdigest() == md5, "simd_lanes16 = %d" % lanes16

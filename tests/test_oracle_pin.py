@@ -90,3 +90,27 @@ def test_million_read_fixture_is_complete():
     assert all(c["first_read"] == 16384 * c["chunk"] and c["reads"] == 16384 for c in ch)
     assert sum(c["reads"] for c in ch) == 1048576 and sum(c["records"] for c in ch) > 1000000
     assert len({c["md5"] for c in ch}) == 64
+
+
+def _pn8_sample():
+    import json
+    import os
+    from tidehunter_b200 import synth
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pn8_golden.json")))
+    names, seqs = [], []
+    for shape, start, n in fx["sets"]:
+        a, b = synth.gen_reads(shape, n, start=start)
+        names += a; seqs += b
+    return fx, names, seqs
+
+
+def test_oracle_sse_vector_width_matches_sse_build_of_the_reference(oracle):
+    """pn16 = 8 (abPOA compiled for SSE4.1: 8 int16 lanes per vector) changes band rounding and the row arg-max
+    tie-break; the fixture holds the output of the reference built that way (tests/golden/make_pn8_golden.py) on a
+    sample that separates the two widths."""
+    import hashlib
+    fx, names, seqs = _pn8_sample()
+    out8 = oracle.run_batch(names, seqs, oracle.default_para(out_fmt=2, pn16=8), threads=4)[0]
+    out16 = oracle.run_batch(names, seqs, oracle.default_para(out_fmt=2), threads=4)[0]
+    assert out8.decode() == fx["text_pn8"] and hashlib.md5(out8).hexdigest() == fx["md5_pn8"]
+    assert hashlib.md5(out16).hexdigest() == fx["md5_pn16"] and out8 != out16
