@@ -14,7 +14,7 @@
 #include "th_host.h"
 
 #define TH_SLOTS 4096 /* CHUNK_READ_N, src/tidehunter.h:10: tandem_seq_t slots are reused every 4096 reads */
-#define TH_MAX_LANES 8
+#define TH_MAX_LANES 64 /* e.g. 8 GPUs x 8 contexts */
 
 typedef struct { char *s; size_t l, m; } str_t;
 
@@ -62,16 +62,24 @@ static char *revcomp(const char *s, int l) { /* src/seq.c:89-95 */
     return r;
 }
 
-th_host *th_host_create(const th_host_para *p, int device) {
+th_host *th_host_create(const th_host_para *p, int device) { return th_host_create_multi(p, 1, &device); }
+
+/* One process, several GPUs: `lanes` contexts on each device, chunk c of a th_host_run goes to lane c % n_lanes and
+ * consecutive lanes sit on different devices.  Reads are independent, so this is the whole multi-GPU story of the
+ * command line front end: no exchange between devices, results are formatted in input order by the caller's thread. */
+th_host *th_host_create_multi(const th_host_para *p, int n_devices, const int *devices) {
     th_host *h = (th_host *)calloc(1, sizeof(th_host));
+    if (n_devices < 1 || !devices) { set_err("th_host_create_multi: no device given"); free(h); return NULL; }
     h->p = *p;
     h->p.gpu.need_cov = (p->out_fmt == 3 || p->out_fmt == 4 || p->min_cov > 0 || p->min_frac > 0.0) ? 1 : 0;
     if (h->p.chunk_reads <= 0) h->p.chunk_reads = 4096;
     if (h->p.lanes <= 0) { const char *e = getenv("TH_HOST_LANES"); h->p.lanes = e ? atoi(e) : 4; } /* 4 contexts x 4096 reads: the best end-to-end setting measured on B200 (profiles/) */
     if (h->p.lanes < 1) h->p.lanes = 1;
+    h->p.lanes *= n_devices;
     if (h->p.lanes > TH_MAX_LANES) h->p.lanes = TH_MAX_LANES;
     for (h->n_lanes = 0; h->n_lanes < h->p.lanes; ++h->n_lanes) {
-        h->lane[h->n_lanes] = th_gpu_create(&h->p.gpu, device < 0 ? 0 : device);
+        { const int dev = devices[h->n_lanes % n_devices];
+          h->lane[h->n_lanes] = th_gpu_create(&h->p.gpu, dev < 0 ? 0 : dev); }
         if (!h->lane[h->n_lanes]) { int i; set_err("%s", th_gpu_last_error()); for (i = 0; i < h->n_lanes; ++i) th_gpu_destroy(h->lane[i]); free(h); return NULL; }
     }
     h->gpu = h->lane[0];

@@ -31,7 +31,7 @@ typedef struct {
     int chunk_reads;        /* reads per GPU chunk (the reference uses 4096, src/tidehunter.h:10) */
     int lanes;              /* GPU contexts (own stream + buffers) the chunks of one th_host_run rotate over; chunk c+1 is
                                uploaded and processed while chunk c is formatted, and their kernels fill each other's
-                               tails.  <= 0: default (TH_HOST_LANES or 3); 1 = strictly serial */
+                               tails.  <= 0: default (TH_HOST_LANES or 4); 1 = strictly serial.  Per device with th_host_create_multi */
 } th_host_para;
 
 void th_host_default_para(th_host_para *p);
@@ -40,6 +40,8 @@ typedef struct th_host th_host;
 
 /* device < 0: use CUDA device 0.  NULL on failure (see th_host_last_error). */
 th_host *th_host_create(const th_host_para *p, int device);
+/* `lanes` contexts on each of n_devices CUDA devices (one process drives several GPUs; reads are independent) */
+th_host *th_host_create_multi(const th_host_para *p, int n_devices, const int *devices);
 void th_host_destroy(th_host *h);
 
 /* Process reads [0,n) and append the text the reference would print for them to an internal buffer;

@@ -26,7 +26,7 @@ static const struct option long_opt[] = {
     {"output", 1, NULL, 'o'}, {"min-len", 1, NULL, 'm'}, {"min-cov", 1, NULL, 'r'}, {"unit-seq", 0, NULL, 'u'},
     {"longest", 0, NULL, 'l'}, {"full-len", 0, NULL, 'F'}, {"single-copy", 0, NULL, 's'}, {"out-fmt", 1, NULL, 'f'},
     {"thread", 1, NULL, 't'}, {"help", 0, NULL, 'h'}, {"version", 0, NULL, 'v'},
-    {"device", 1, NULL, 1001}, {"chunk", 1, NULL, 1002}, {"lanes", 1, NULL, 1003},
+    {"device", 1, NULL, 1001}, {"chunk", 1, NULL, 1002}, {"lanes", 1, NULL, 1003}, {"devices", 1, NULL, 1004},
     {0, 0, 0, 0}};
 
 static long long parse_num(const char *str) { /* th_parse_num, src/main.c:54-64 */
@@ -47,7 +47,7 @@ static int usage(void) {
                     "  -o STR  output file [stdout]           -m INT  min consensus length [30]  -r FLT|INT min coverage\n"
                     "  -u unit sequences only   -l longest only   -F full-length only   -s single-copy full-length (with -F -5 -3)\n"
                     "  -f INT  1 FASTA, 2 tabular, 3 FASTQ, 4 tabular+quality [1]\n"
-                    "  -t INT  accepted, ignored              --device INT CUDA device [0]       --chunk INT reads per GPU chunk [4096]\n          --lanes INT GPU contexts the chunks rotate over [4]\n\n");
+                    "  -t INT  accepted, ignored              --device INT CUDA device [0]       --chunk INT reads per GPU chunk [4096]\n          --lanes INT GPU contexts per device the chunks rotate over [4]\n          --devices LIST  comma-separated CUDA devices driven by this one process, e.g. 0,1,2,3 [--device]\n\n");
     return 1;
 }
 
@@ -90,7 +90,7 @@ static void *reader_main(void *arg) {
 }
 
 int main(int argc, char *argv[]) {
-    th_host_para p; int c, device = 0; const char *out_fn = NULL, *five_fn = NULL, *three_fn = NULL; char *s;
+    th_host_para p; int c, device = 0, n_dev = 0, devs[16]; const char *out_fn = NULL, *five_fn = NULL, *three_fn = NULL; char *s;
     th_host_default_para(&p);
     if (argc < 2) return usage();
     while ((c = getopt_long(argc, argv, "k:w:m:Hhvc:e:p:P:M:X:E:O:5:3:a:o:ur:qslFf:t:", long_opt, NULL)) >= 0) {
@@ -122,6 +122,7 @@ int main(int argc, char *argv[]) {
         case 1001: device = atoi(optarg); break;
         case 1002: p.chunk_reads = atoi(optarg); break;
         case 1003: p.lanes = atoi(optarg); break;
+        case 1004: { char *q = optarg; n_dev = 0; while (*q && n_dev < 16) { devs[n_dev++] = (int)strtol(q, &q, 10); if (*q == ',') ++q; else break; } break; }
         case 'v': printf("%s (TideHunter v1.5.5 compatible)\n", PROG); return 0;
         case 'h': default: return usage();
         }
@@ -142,12 +143,13 @@ int main(int argc, char *argv[]) {
         if (!out) { fprintf(stderr, "[main] cannot open %s\n", out_fn); return 1; }
         memset(&q, 0, sizeof(q));
         /* one th_host_run covers several chunks so that its GPU lanes overlap (host/th_host.h) */
-        q.batch_reads = p.chunk_reads * (p.lanes > 0 ? p.lanes : 4) * 2;
+        q.batch_reads = p.chunk_reads * (p.lanes > 0 ? p.lanes : 4) * (n_dev > 0 ? n_dev : 1) * 2;
         q.r = thr_open(argv[optind]);
         if (!q.r) { fprintf(stderr, "[main] fail to open %s\n", argv[optind]); return 1; }
         pthread_mutex_init(&q.mu, NULL); pthread_cond_init(&q.cv, NULL);
         pthread_create(&rt, NULL, reader_main, &q);   /* the first batch is parsed while the CUDA contexts come up */
-        h = th_host_create(&p, device);
+        if (n_dev == 0) { devs[0] = device; n_dev = 1; }
+        h = th_host_create_multi(&p, n_dev, devs);
         if (!h) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
         for (;;) {
             th_batch *b = &q.slot[k]; size_t ol; const char *txt; int have;

@@ -253,3 +253,16 @@ def test_sse_vector_width_mode(T):
         out = th.run(names, seqs)
         th.close()
         assert hashlib.md5(out).hexdigest() == md5, "simd_lanes16 = %d" % lanes16
+
+
+def test_one_process_several_devices(T, golden, golden_inputs):
+    """th_host_create_multi: lanes spread over a device list (here every visible GPU, and device 0 listed twice so the
+    path is exercised on a one-GPU box too); output must not depend on it."""
+    c = next(c for c in golden["cases"] if c["input"] == "testfq_all" and c["args"] == ["-f", "4"])
+    names, seqs = golden_inputs(c["input"])
+    n_dev = T.gpu_lib().th_gpu_device_count()
+    for devs in ([0, 0], list(range(n_dev))):
+        th = T.TideHunter(devices=devs, lanes=2, chunk_reads=7, **c["para"])
+        out = th.run(names, seqs)
+        th.close()
+        assert hashlib.md5(out).hexdigest() == c["md5"], devs

@@ -86,6 +86,8 @@ def _load():
         h.th_host_default_para.argtypes = [C.POINTER(HostPara)]
         h.th_host_create.argtypes = [C.POINTER(HostPara), C.c_int]
         h.th_host_create.restype = C.c_void_p
+        h.th_host_create_multi.argtypes = [C.POINTER(HostPara), C.c_int, C.POINTER(C.c_int)]
+        h.th_host_create_multi.restype = C.c_void_p
         h.th_host_destroy.argtypes = [C.c_void_p]
         h.th_host_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]
         h.th_host_run.restype = C.c_void_p
@@ -130,10 +132,12 @@ def _arrays(seqs):
 class TideHunter:
     """Drop-in for the reference's per-chunk loop (src/main.c:402-425): reads in, output text out."""
 
-    def __init__(self, device=0, **para):
+    def __init__(self, device=0, devices=None, **para):
+        """`devices`: list of CUDA devices driven by this one object (`lanes` contexts on each); default [device]."""
         _, h = _load()
         self.para = default_host_para(**para)
-        self._h = h.th_host_create(C.byref(self.para), device)
+        devs = list(devices) if devices else [device]
+        self._h = h.th_host_create_multi(C.byref(self.para), len(devs), (C.c_int * len(devs))(*devs))
         if not self._h:
             raise RuntimeError("th_host_create failed: %s" % h.th_host_last_error().decode())
 
