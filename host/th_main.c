@@ -66,19 +66,20 @@ static char *read_first_seq(const char *fn) { /* get_seq_from_fx, src/main.c:157
 }
 
 typedef struct {
-    th_reader *r; int batch_reads;
+    th_reader *r; int batch_reads, first_batch;
     th_batch slot[2]; int state[2];       /* 0 = free, 1 = filled */
     int done;                             /* reader reached the end of the input (or the reference's stop condition) */
     pthread_mutex_t mu; pthread_cond_t cv;
 } prefetch_t;
 
 static void *reader_main(void *arg) {
-    prefetch_t *q = (prefetch_t *)arg; int k = 0, stop = 0;
+    prefetch_t *q = (prefetch_t *)arg; int k = 0, stop = 0, first = 1;
     for (;;) {
         pthread_mutex_lock(&q->mu);
         while (q->state[k] != 0) pthread_cond_wait(&q->cv, &q->mu);
         pthread_mutex_unlock(&q->mu);
-        { const int n = stop ? 0 : thr_read_batch(q->r, &q->slot[k], q->batch_reads, &stop);
+        { const int n = stop ? 0 : thr_read_batch(q->r, &q->slot[k], first ? q->first_batch : q->batch_reads, &stop);
+          first = 0;
           pthread_mutex_lock(&q->mu);
           if (n > 0) q->state[k] = 1; else q->done = 1;
           pthread_cond_broadcast(&q->cv);
@@ -138,29 +139,39 @@ int main(int argc, char *argv[]) {
     if (five_fn && three_fn) { p.five_seq = read_first_seq(five_fn); p.three_seq = read_first_seq(three_fn); }
     {
         struct timespec t0, t1; FILE *out = out_fn ? fopen(out_fn, "w") : stdout;
-        th_host *h; prefetch_t q; pthread_t rt; int k = 0; long long tot_reads = 0;
+        th_host *h; prefetch_t q; pthread_t rt; int k = 0; long long tot_reads = 0; double t_wait = 0, t_run = 0, t_write = 0, t_create;
+        struct timespec ta, tb;
+#define TSPAN(a, b) ((b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec))
         clock_gettime(CLOCK_MONOTONIC, &t0);
         if (!out) { fprintf(stderr, "[main] cannot open %s\n", out_fn); return 1; }
         memset(&q, 0, sizeof(q));
-        /* one th_host_run covers several chunks so that its GPU lanes overlap (host/th_host.h) */
-        q.batch_reads = p.chunk_reads * (p.lanes > 0 ? p.lanes : 4) * (n_dev > 0 ? n_dev : 1) * 2;
+        /* one th_host_run covers several chunks so that its GPU lanes overlap (host/th_host.h): four chunks per lane,
+         * so the lanes drain only once per 16 chunks; the first batch is one chunk per lane to get the GPUs going early */
+        q.first_batch = p.chunk_reads * (p.lanes > 0 ? p.lanes : 4) * (n_dev > 0 ? n_dev : 1);
+        q.batch_reads = q.first_batch * 4;
         q.r = thr_open(argv[optind]);
         if (!q.r) { fprintf(stderr, "[main] fail to open %s\n", argv[optind]); return 1; }
         pthread_mutex_init(&q.mu, NULL); pthread_cond_init(&q.cv, NULL);
         pthread_create(&rt, NULL, reader_main, &q);   /* the first batch is parsed while the CUDA contexts come up */
         if (n_dev == 0) { devs[0] = device; n_dev = 1; }
+        clock_gettime(CLOCK_MONOTONIC, &ta);
         h = th_host_create_multi(&p, n_dev, devs);
         if (!h) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
+        clock_gettime(CLOCK_MONOTONIC, &tb); t_create = TSPAN(ta, tb);
         for (;;) {
             th_batch *b = &q.slot[k]; size_t ol; const char *txt; int have;
+            clock_gettime(CLOCK_MONOTONIC, &ta);
             pthread_mutex_lock(&q.mu);
             while (q.state[k] == 0 && !q.done) pthread_cond_wait(&q.cv, &q.mu);
             have = q.state[k] == 1;
             pthread_mutex_unlock(&q.mu);
+            clock_gettime(CLOCK_MONOTONIC, &tb); t_wait += TSPAN(ta, tb);
             if (!have) break;
             txt = th_host_run(h, b->n, (const char *const *)b->names, (const char *const *)b->seqs, b->lens, &ol);
             if (!txt) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
+            clock_gettime(CLOCK_MONOTONIC, &ta); t_run += TSPAN(tb, ta);
             fwrite(txt, 1, ol, out);
+            clock_gettime(CLOCK_MONOTONIC, &tb); t_write += TSPAN(ta, tb);
             tot_reads += b->n;
             pthread_mutex_lock(&q.mu); q.state[k] = 0; pthread_cond_broadcast(&q.cv); pthread_mutex_unlock(&q.mu);
             k ^= 1;
@@ -172,6 +183,7 @@ int main(int argc, char *argv[]) {
         if (out != stdout) fclose(out);
         clock_gettime(CLOCK_MONOTONIC, &t1);
         fprintf(stderr, "[main] Real time: %.3f sec; reads: %lld\n", (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec), tot_reads);
+        if (getenv("TH_HOST_TIMING")) fprintf(stderr, "[main] contexts %.2f s, waiting for the reader %.2f s, th_host_run %.2f s, writing %.2f s\n", t_create, t_wait, t_run, t_write);
     }
     return 0;
 }

@@ -36,19 +36,22 @@ def main():
                 done += 1
     size = os.path.getsize(path)
     rep = {"reads": n, "fasta_bytes": size}
-    for tag, cmd in (("cli_fa", [cli, "-f", "1", "-o", os.path.join(d, "th_cli_out.fa"), path]),):
+    devs = os.environ.get("TH_CLI_DEVICES")     # e.g. "0,1": one process drives several GPUs
+    extra = ["--devices", devs] if devs else []
+    rep["devices"] = devs or "0"
+    for tag, cmd in (("cli_fa", [cli] + extra + ["-f", "1", "-o", os.path.join(d, "th_cli_out.fa"), path]),):
         subprocess.run(cmd[:1] + ["-f", "1", "-o", os.devnull, pref], check=True, stderr=subprocess.DEVNULL)   # warm-up (context creation, allocations)
         t0 = time.perf_counter()
         r = subprocess.run(cmd, stderr=subprocess.PIPE, check=True)
         dt = time.perf_counter() - t0
-        rep[tag] = {"seconds_incl_process_start": round(dt, 2), "reads_per_s": round(n / dt, 1), "MB_per_s_input": round(size / dt / 1e6, 1), "stderr": r.stderr.decode().strip()[-120:]}
+        rep[tag] = {"seconds_incl_process_start": round(dt, 2), "reads_per_s": round(n / dt, 1), "MB_per_s_input": round(size / dt / 1e6, 1), "stderr": r.stderr.decode().strip()[-1500:]}
     # parity of the prefix: CLI vs the reference binary
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "TideHunter")
     if os.path.exists(ref_bin):
         t0 = time.perf_counter()
         ref = subprocess.run([ref_bin, "-t", str(os.cpu_count() or 1), "-f", "1", pref], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
         t_ref = time.perf_counter() - t0
-        ours = subprocess.run([cli, "-f", "1", pref], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+        ours = subprocess.run([cli] + extra + ["-f", "1", pref], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
         rep["prefix_parity"] = {"reads": nref, "identical": ours == ref, "md5": hashlib.md5(ref).hexdigest(), "reference_reads_per_s": round(nref / t_ref, 1), "cores": os.cpu_count()}
     for p in (path, pref, os.path.join(d, "th_cli_out.fa")):
         try:
@@ -57,7 +60,7 @@ def main():
             pass
     print(json.dumps(rep))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "cli_bench.json"), "w"), indent=1)
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "cli_bench_dev%s.json" % (devs or "0").replace(",", "_")), "w"), indent=1)
 
 
 if __name__ == "__main__":
