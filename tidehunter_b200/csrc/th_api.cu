@@ -271,7 +271,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     CK(cudaEventRecord(c->ev[ei++], st)); // 4
     // ---- chain DP ----
     {
-        const int grid = std::min((n + CHAIN_WARPS - 1) / CHAIN_WARPS, std::max(1, (int)(c->n_sm * 8 * c->share)));
+        const int grid = std::min((n + CHAIN_WARPS - 1) / CHAIN_WARPS, std::max(1, (int)(c->n_sm * CHAIN_BLOCKS_PER_SM * c->share)));
         if (P.max_p < (1u << 27)) // hit periods are <= max_p (src/tandem_hit.c:204): the 1.8x gate fits 32-bit products
             chain_dp_kernel<true><<<grid, CHAIN_WARPS * 32, 0, st>>>(P, n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(),
                                                                   c->d_score.as<int32_t>(), c->d_from.as<int32_t>(), c->d_gflag.as<int32_t>(), cnt64 + 0);
@@ -301,7 +301,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     }
     CK(cudaEventRecord(c->ev[ei++], st)); // 6
     // ---- partition ----
-    const int n_pwarps = std::min(n, std::max(4, (int)(c->n_sm * 16 * c->share)));
+    const int n_pwarps = std::min(n, std::max(4, (int)(c->n_sm * PART_MIN_BLOCKS * PART_WARPS * c->share)));
     const int64_t bnd_stride = 2 * (int64_t)(c->max_len + 64);
     {
         if (c->d_bnd.ensure((size_t)n_pwarps * bnd_stride * sizeof(int4))) return -1;
@@ -478,7 +478,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
             const int64_t rev_stride = 2 * (int64_t)(c->max_len + 64);
             const KswItem *d_pairs = c->d_items.as<KswItem>(), *d_singles = d_pairs + n_pairs, *d_exts = d_singles + n_singles;
             auto grid_for = [&](int n_work, int min_blocks) { const int kw = std::min(std::max(n_work, 1), std::max(4, (int)(c->n_sm * min_blocks * KSW_WARPS * c->share))); return (kw + KSW_WARPS - 1) / KSW_WARPS; };
-            const int g_pair = grid_for(n_pairs, KSW_PAIR_MIN_BLOCKS), g_single = grid_for(n_singles + 64, KSW_MIN_BLOCKS), g_ext = grid_for(n_exts, KSW_MIN_BLOCKS);
+            const int g_pair = grid_for(n_pairs, KSW_PAIR_MIN_BLOCKS), g_single = grid_for(n_singles + 64, KSW_MIN_BLOCKS), g_ext = grid_for(n_exts, KSW_EXT_MIN_BLOCKS);
             const int g_max = std::max(g_pair, std::max(g_single, g_ext));
             if (c->d_bnd.ensure((size_t)g_max * KSW_WARPS * bnd_stride * sizeof(int4)) || c->d_rev.ensure((size_t)g_ext * KSW_WARPS * rev_stride) ||
                 c->d_redo.ensure(4 * (size_t)n_pairs + 64)) return -1;

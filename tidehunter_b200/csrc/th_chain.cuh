@@ -34,6 +34,9 @@ __device__ __forceinline__ int con_score(int cs, int ce, int ps, int pe, int k, 
 }
 
 #define CHAIN_WARPS 4
+#ifndef CHAIN_BLOCKS_PER_SM
+#define CHAIN_BLOCKS_PER_SM 8   // persistent grid: blocks per SM (tuning knob)
+#endif
 template <bool SMALL>
 __global__ void __launch_bounds__(CHAIN_WARPS * 32)
 chain_dp_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ nhits,

@@ -15,7 +15,10 @@
 #include "th_ksw.cuh"
 
 #define PART_WARPS 4
-__global__ void __launch_bounds__(PART_WARPS * 32)
+#ifndef PART_MIN_BLOCKS
+#define PART_MIN_BLOCKS 4   // resident blocks per SM the grid is sized for (tuning knob)
+#endif
+__global__ void __launch_bounds__(PART_WARPS * 32, PART_MIN_BLOCKS)
 partition_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ rlen,
                  const uint8_t *__restrict__ bseq, const int32_t *__restrict__ hend, const int32_t *__restrict__ hper,
                  const int32_t *__restrict__ cells, const int32_t *__restrict__ pch_n, const int32_t *__restrict__ pch_off,
@@ -99,6 +102,9 @@ __device__ __forceinline__ bool warp_has_n(const uint8_t *s, int l) {
 #define KSW2_C 16
 #endif
 #define KSW_MIN_BLOCKS 4
+#ifndef KSW_EXT_MIN_BLOCKS
+#define KSW_EXT_MIN_BLOCKS 4
+#endif
 
 // Post-consensus alignments of seqs_msa (src/gen_cons.c:208-223) run as three kernels with their own register
 // budgets, persistent warps on atomic work counters:
@@ -172,7 +178,7 @@ ksw_single_kernel(int n_single, const KswItem *__restrict__ singles, const KswIt
     if (lane == 0 && ncell) atomicAdd(stat_cells, ncell);
 }
 
-__global__ void __launch_bounds__(KSW_WARPS * 32, KSW_MIN_BLOCKS)
+__global__ void __launch_bounds__(KSW_WARPS * 32, KSW_EXT_MIN_BLOCKS)
 ksw_ext_kernel(int n_items, const KswItem *__restrict__ items, const uint8_t *__restrict__ bseq,
                const uint8_t *__restrict__ cons_base, const int32_t *__restrict__ cons_off, const int32_t *__restrict__ cons_len,
                uint8_t *rev_all, int64_t rev_stride, int4 *bnd_all, int64_t bnd_stride, int *counter,
