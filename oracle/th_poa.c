@@ -267,16 +267,22 @@ static int poa_align(pgraph_t *g, const tho_para_t *p, const uint8_t *query, int
     }
     int max_mat = p->match < 0 ? -p->match : p->match, min_mis = p->mismatch > 0 ? p->mismatch : -p->mismatch;
     int o1 = p->gap_open1, e1 = p->gap_ext1, o2 = p->gap_open2, e2 = p->gap_ext2, oe1 = o1 + e1, oe2 = o2 + e2;
+    const int oe2_raw = oe2, e2_raw = e2; /* inf_min and the int16 choice use the options as given in every gap mode (:1613-1614) */
+    /* affine mode (gap_open2 == 0, abpoa_align.c:85-88; DP simd_abpoa_align.c:160-246, 649-833: H = max(M, E, F)) is evaluated
+     * with the convex recurrences and a second gap function equal to the first plus one: E2 <= E1 - 1 and F2 <= F1 - 1 by
+     * induction, so the second pair never wins a max nor a backtrack comparison.  Pinned on outputs of the reference run
+     * with -O 4,0 (tests/golden/gapmode_golden.json). */
+    if (p->gap_open2 == 0) { o2 = o1 + 1; e2 = e1; oe2 = o2 + e2; }
     int beg_index = g->node_id_to_index[0], end_index = g->node_id_to_index[1], gn = end_index - beg_index + 1;
     pdp_t D, *d = &D; memset(d, 0, sizeof(D));
     { /* simd_abpoa_align.c:1610-1621 */
         int len = qlen > gn ? qlen : gn, max_score = MAX2(qlen * max_mat, len * e1 + o1);
-        if (max_score <= INT16_MAX - min_mis - oe1 - oe2) {
+        if (max_score <= INT16_MAX - min_mis - oe1 - oe2_raw) {
             d->bits = 16; d->pn = p->pn16;
-            d->inf_min = MAX3(INT16_MIN + min_mis, INT16_MIN + oe1, INT16_MIN + oe2) + 31 * MAX2(e1, e2);
+            d->inf_min = MAX3(INT16_MIN + min_mis, INT16_MIN + oe1, INT16_MIN + oe2_raw) + 31 * MAX2(e1, e2_raw);
         } else {
             d->bits = 32; d->pn = p->pn16 / 2;
-            d->inf_min = MAX3(INT32_MIN + min_mis, INT32_MIN + oe1, INT32_MIN + oe2) + 31 * MAX2(e1, e2);
+            d->inf_min = MAX3(INT32_MIN + min_mis, INT32_MIN + oe1, INT32_MIN + oe2_raw) + 31 * MAX2(e1, e2_raw);
         }
     }
     int pn = d->pn, inf_min = d->inf_min;

@@ -266,3 +266,20 @@ def test_one_process_several_devices(T, golden, golden_inputs):
         out = th.run(names, seqs)
         th.close()
         assert hashlib.md5(out).hexdigest() == c["md5"], devs
+
+
+def test_gap_modes(T):
+    """Convex (default) and affine (-O x,0) abPOA gap modes on long-indel reads against the reference's outputs
+    (tests/golden/gapmode_golden.json); the linear mode (-O 0,...) is rejected with a message."""
+    import json
+    import os
+    from tidehunter_b200 import synth
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gapmode_golden.json")))
+    names, seqs = synth.gen_long_indel_reads(fx["n_reads"])
+    for tag, m in fx["modes"].items():
+        th = T.TideHunter(out_fmt=2, **m["para"])
+        out = th.run(names, seqs)
+        th.close()
+        assert hashlib.md5(out).hexdigest() == m["md5"], tag
+    with pytest.raises(RuntimeError, match="linear gap mode"):
+        T.TideHunter(out_fmt=2, gap_open1=0)

@@ -114,3 +114,23 @@ def test_oracle_sse_vector_width_matches_sse_build_of_the_reference(oracle):
     out16 = oracle.run_batch(names, seqs, oracle.default_para(out_fmt=2), threads=4)[0]
     assert out8.decode() == fx["text_pn8"] and hashlib.md5(out8).hexdigest() == fx["md5_pn8"]
     assert hashlib.md5(out16).hexdigest() == fx["md5_pn16"] and out8 != out16
+
+
+def _gapmode():
+    import json
+    import os
+    from tidehunter_b200 import synth
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gapmode_golden.json")))
+    names, seqs = synth.gen_long_indel_reads(fx["n_reads"])
+    return fx, names, seqs
+
+
+def test_oracle_gap_modes_match_reference(oracle):
+    """abPOA's convex (default) and affine (-O x,0) gap modes on reads with 22-59 bp indels, where the two modes give
+    different consensus sequences (tests/golden/make_gapmode_golden.py ran the unmodified reference)."""
+    import hashlib
+    fx, names, seqs = _gapmode()
+    assert fx["lines_differing_convex_vs_affine"] > 10
+    for tag, m in fx["modes"].items():
+        out = oracle.run_batch(names, seqs, oracle.default_para(out_fmt=2, **m["para"]), threads=4)[0]
+        assert hashlib.md5(out).hexdigest() == m["md5"], tag

@@ -106,7 +106,7 @@ extern "C" th_gpu_ctx *th_gpu_create(const th_gpu_params *p, int device) {
     if (p->k < 2 || p->k > 16) { set_err("k must be in 2..16"); return nullptr; }
     if (p->w < 1 || p->w > 255) { set_err("w must be in 1..255"); return nullptr; }
     if (p->simd_lanes16 != 16 && p->simd_lanes16 != 8) { set_err("simd_lanes16 must be 8 or 16"); return nullptr; }
-    if (p->gap_open1 <= 0 || p->gap_open2 <= 0) { set_err("only the convex gap mode (O1 > 0, O2 > 0) is implemented on the GPU path"); return nullptr; }
+    if (p->gap_open1 <= 0 || p->gap_open2 < 0 || p->gap_ext1 <= 0 || p->gap_ext2 < 0) { set_err("abPOA's linear gap mode (O1 = 0) is not implemented on the GPU path; convex (O1, O2 > 0) and affine (O2 = 0) are"); return nullptr; }
     CKP(cudaSetDevice(device));
     th_gpu_ctx *c = new th_gpu_ctx();
     c->device = device; c->params = *p;
@@ -116,6 +116,11 @@ extern "C" th_gpu_ctx *th_gpu_create(const th_gpu_params *p, int device) {
     DevParams &d = c->dp;
     d.k = p->k; d.w = p->w; d.hpc = p->hpc; d.min_copy = p->min_copy; d.min_p = (uint32_t)p->min_p; d.max_p = (uint32_t)p->max_p;
     d.max_div = p->max_div; d.match = p->match; d.mismatch = p->mismatch; d.o1 = p->gap_open1; d.e1 = p->gap_ext1; d.o2 = p->gap_open2; d.e2 = p->gap_ext2;
+    d.o2_raw = p->gap_open2; d.e2_raw = p->gap_ext2;
+    // abPOA's affine mode (gap_open2 == 0, abpoa_align.c:85-88: H = max(M, E1, F1)) runs on the convex kernel with a second
+    // gap function that is the first one plus one: E2 <= E1 - 1 and F2 <= F1 - 1 hold by induction over the recurrences, so
+    // the second pair never wins a max nor a backtrack comparison, and every H, E1, F1 equals the affine model's.
+    if (p->gap_open2 == 0) { d.o2 = d.o1 + 1; d.e2 = d.e1; }
     d.pn = p->simd_lanes16; d.only_unit = p->only_unit;
     CKP(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) CKP(cudaEventCreate(&c->ev[i]));

@@ -156,9 +156,10 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
     { // int16 path only (simd_abpoa_align.c:1610-1621)
         int len = qlen > n ? qlen : n;
         int max_score = max(qlen * mat, len * e1 + o1);
-        if (max_score > 32767 - mis - oe1 - oe2 - 64 * max(e1, e2)) return TH_ERR_LEN;
+        if (max_score > 32767 - mis - oe1 - max(oe2, P.o2_raw + P.e2_raw) - 64 * max(max(e1, e2), P.e2_raw)) return TH_ERR_LEN;
     }
-    const int inf_min = max(max(-32768 + mis, -32768 + oe1), -32768 + oe2) + 31 * max(e1, e2);
+    // simd_abpoa_align.c:1613-1614 uses the option values as given, whatever the gap mode
+    const int inf_min = max(max(-32768 + mis, -32768 + oe1), -32768 + P.o2_raw + P.e2_raw) + 31 * max(e1, P.e2_raw);
     const uint32_t INFP = pk(inf_min, inf_min);
     const int wband = 10 + (int)(0.01f * (float)qlen); // wb + (int)(wf*qlen), float (simd_abpoa_align.c:393)
     // ---- row descriptors: order index, predecessors by row, heaviest successor ----------------

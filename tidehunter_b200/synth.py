@@ -111,3 +111,32 @@ def gen_single_copy(n, adapters, start=0, seed=SEED, err=0.08):
 
 def total_bases(seqs):
     return int(sum(len(s) for s in seqs))
+
+
+def gen_long_indel_reads(n, start=0, seed=SEED + 7, err=0.08):
+    """Tandem repeats (unit 300-900 bp, 4-8 copies) whose copies carry up to two 22-59 bp deletions or insertions on top
+    of the per-base error channel: gaps long enough for the second gap function of abPOA's convex model (O2 = 24, E2 = 1
+    beats O1 = 4, E1 = 2 beyond 20 columns) to decide the alignment, which the BASELINE shapes (single-base errors) never
+    do.  Used for the convex-vs-affine gap mode tests.  Read i depends only on (seed, i)."""
+    names, seqs = [], []
+    for i in range(start, start + n):
+        rng = np.random.Generator(np.random.Philox(key=[seed, i]))
+        ulen = int(rng.integers(300, 900))
+        copies = int(rng.integers(4, 9))
+        unit = rng.integers(0, 4, ulen, dtype=np.uint8)
+        parts = [rng.integers(0, 4, 40, dtype=np.uint8)]
+        for _ in range(copies):
+            u = unit.copy()
+            for _ in range(int(rng.integers(0, 3))):
+                gl = int(rng.integers(22, 60))
+                pos = int(rng.integers(10, len(u) - gl - 10))
+                if rng.random() < 0.5:
+                    u = np.concatenate([u[:pos], u[pos + gl:]])
+                else:
+                    u = np.concatenate([u[:pos], rng.integers(0, 4, gl, dtype=np.uint8), u[pos:]])
+            parts.append(u)
+        parts.append(rng.integers(0, 4, 40, dtype=np.uint8))
+        out = _channel(rng, np.concatenate(parts), err)
+        seqs.append(_ACGT[out].tobytes())
+        names.append(("g%d" % i).encode())
+    return names, seqs
