@@ -431,6 +431,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         size_t free_b = 0, total_b = 0; CK(cudaMemGetInfo(&free_b, &total_b));
         if (slab_typ == 0) slab_typ = 1 << 20;
         size_t budget = (size_t)((double)(free_b + c->d_slabs.cap) * 0.6);
+        budget = std::min(budget, total_b / 5); // several contexts share the device (the host layer runs four): none may take it all
         int nwarps = (int)std::min<size_t>((size_t)(c->n_sm * POA_MIN_BLOCKS * POA_WARPS * c->share), std::max<size_t>(1, budget / slab_typ));
         nwarps = std::min(nwarps, std::max(nt, 1));
         int grid = (nwarps + POA_WARPS - 1) / POA_WARPS;
