@@ -22,6 +22,7 @@ struct th_host {
     th_host_para p;
     th_gpu_ctx *gpu;                        /* = lane[0] */
     th_gpu_ctx *lane[TH_MAX_LANES]; int n_lanes;
+    long long n_failed;       /* consensus tasks the GPU path reported as failed since th_host_create (their records are missing) */
     char *five_rc, *three_rc; int five_len, three_len;
     str_t out;
     str_t qual[TH_SLOTS];     /* persistent quality buffers: qual.l is never reset in the reference */
@@ -99,6 +100,7 @@ void th_host_destroy(th_host *h) {
     free(h->out.s); free(h);
 }
 void th_host_stats(const th_host *h, th_gpu_stats *s) { *s = h->stats; }
+long long th_host_failed_tasks(const th_host *h) { return h->n_failed; }
 th_gpu_ctx *th_host_gpu(th_host *h) { return h->gpu; }
 
 /* Infix edit distance with threshold (edlib_align_HW, src/edlib_align.c:73-85): edit distance,
@@ -195,7 +197,10 @@ static void emit_read(th_host *h, const th_gpu_result *R, int r, const char *nam
             memset(&rec[n_rec], 0, sizeof(rec_t)); rec[n_rec].pos_n = pos_n; rec[n_rec].sub_pos = pos; ++n_rec;
             continue;
         }
-        if (R->task_status[t] != 0) { fprintf(stderr, "[th_host] read %s: consensus task failed on the GPU (code %d); record dropped\n", name, R->task_status[t]); continue; }
+        if (R->task_status[t] != 0) { /* e.g. TH_ERR_LEN: a unit beyond the int16 score range (the reference switches to int32 there) */
+            if (h->n_failed++ < 20) fprintf(stderr, "[th_host] read %s: consensus task failed on the GPU (code %d); record dropped\n", name, R->task_status[t]);
+            continue;
+        }
         {
             const int c0 = R->task_cons_off[t]; int cons_len = R->task_cons_off[t + 1] - c0;
             const int n_seqs = R->task_n_seqs[t];

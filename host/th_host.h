@@ -51,6 +51,9 @@ const char *th_host_run(th_host *h, int n, const char *const *names, const char 
 
 /* stats of the last th_host_run (summed over its chunks) */
 void th_host_stats(const th_host *h, th_gpu_stats *s);
+/* consensus tasks that failed on the GPU since th_host_create (status != 0, e.g. a unit beyond the int16 score range);
+ * their records are missing from the output and a message went to stderr */
+long long th_host_failed_tasks(const th_host *h);
 th_gpu_ctx *th_host_gpu(th_host *h);
 const char *th_host_last_error(void);
 

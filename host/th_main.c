@@ -179,6 +179,7 @@ int main(int argc, char *argv[]) {
         pthread_join(rt, NULL);
         thr_batch_free(&q.slot[0]); thr_batch_free(&q.slot[1]); thr_close(q.r);
         pthread_mutex_destroy(&q.mu); pthread_cond_destroy(&q.cv);
+        if (th_host_failed_tasks(h) > 0) fprintf(stderr, "[main] WARNING: %lld consensus task(s) could not run on the GPU path; their records are missing from the output\n", th_host_failed_tasks(h));
         th_host_destroy(h);
         if (out != stdout) fclose(out);
         clock_gettime(CLOCK_MONOTONIC, &t1);
