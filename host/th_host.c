@@ -11,6 +11,7 @@
 #include <math.h>
 #include <pthread.h>
 #include <time.h>
+#include <unistd.h>
 #include "th_host.h"
 
 #define TH_SLOTS 4096 /* CHUNK_READ_N, src/tidehunter.h:10: tandem_seq_t slots are reused every 4096 reads */
@@ -180,7 +181,7 @@ typedef struct { /* one record of tandem_seq_t */
 } rec_t;
 
 /* one read: turn its tasks into records (seqs_msa tail + write_tandem_cons_seq) and print them */
-static void emit_read(th_host *h, const th_gpu_result *R, int r, const char *name, const char *seq, int len, int64_t global_index) {
+static void emit_read(th_host *h, str_t *out, long long *n_failed, const th_gpu_result *R, int r, const char *name, const char *seq, int len, int64_t global_index) {
     const th_host_para *p = &h->p;
     const int with_qual = (p->out_fmt == 3 || p->out_fmt == 4);
     int t, i, n_rec = 0, m_rec = 0;
@@ -198,7 +199,7 @@ static void emit_read(th_host *h, const th_gpu_result *R, int r, const char *nam
             continue;
         }
         if (R->task_status[t] != 0) { /* e.g. TH_ERR_LEN: a unit beyond the int16 score range (the reference switches to int32 there) */
-            if (h->n_failed++ < 20) fprintf(stderr, "[th_host] read %s: consensus task failed on the GPU (code %d); record dropped\n", name, R->task_status[t]);
+            if ((*n_failed)++ < 20) fprintf(stderr, "[th_host] read %s: consensus task failed on the GPU (code %d); record dropped\n", name, R->task_status[t]);
             continue;
         }
         {
@@ -334,7 +335,7 @@ WRITE_CONS:
     }
     /* mini_tandem_output, src/main.c:214-271 */
     {
-        str_t *o = &h->out; int ci, j; size_t qoff = 0;
+        str_t *o = out; int ci, j; size_t qoff = 0;
         for (ci = 0; ci < n_rec; ++ci) {
             const rec_t *c = rec + ci;
             if (p->gpu.only_unit) {
@@ -416,8 +417,48 @@ static void *lane_main(void *arg_) {
     return NULL;
 }
 
+/* Formats the m reads of one finished chunk into h->out, in input order, on several threads: a read's records depend
+ * only on that read (and on its own quality slot, src/main.c:266-267 -- distinct for reads less than TH_SLOTS apart), so
+ * blocks of at most TH_SLOTS reads are split into contiguous segments with a buffer each.  The adapter searches of the
+ * full-length / single-copy modes (src/gen_cons.c:85-171) are the heavy part; the reference runs them on its thread pool. */
+typedef struct { th_host *h; const th_gpu_result *R; const char *const *names, *const *seqs; const int32_t *lens; int r0, r1; int64_t g0; str_t out; long long failed; } fmt_arg;
+static void *fmt_main(void *a_) {
+    fmt_arg *a = (fmt_arg *)a_; int r;
+    for (r = a->r0; r < a->r1; ++r) emit_read(a->h, &a->out, &a->failed, a->R, r, a->names[r], a->seqs[r], a->lens[r], a->g0 + r);
+    return NULL;
+}
+static int fmt_threads(void) {
+    static int n = 0;
+    if (n == 0) { const char *e = getenv("TH_HOST_FMT_THREADS"); long c = sysconf(_SC_NPROCESSORS_ONLN); n = e ? atoi(e) : (int)(c >= 16 ? 8 : c >= 4 ? c / 2 : 1); if (n < 1) n = 1; if (n > 32) n = 32; }
+    return n;
+}
+static void emit_chunk(th_host *h, const th_gpu_result *R, int m, const char *const *names, const char *const *seqs, const int32_t *lens) {
+    int b0;
+    for (b0 = 0; b0 < m; b0 += TH_SLOTS) {
+        const int b1 = b0 + TH_SLOTS < m ? b0 + TH_SLOTS : m, nb = b1 - b0;
+        int T = fmt_threads(), t;
+        { const char *e = getenv("TH_HOST_FMT_GRAIN"); const int grain = e && atoi(e) > 0 ? atoi(e) : 64; /* reads per thread worth a thread */
+          if (nb < grain * T) T = nb / grain > 0 ? nb / grain : 1; }
+        if (T <= 1) { int r; for (r = b0; r < b1; ++r) emit_read(h, &h->out, &h->n_failed, R, r, names[r], seqs[r], lens[r], h->read_counter + r); continue; }
+        {
+            fmt_arg *fa = (fmt_arg *)calloc((size_t)T, sizeof(fmt_arg)); pthread_t *th = (pthread_t *)calloc((size_t)T, sizeof(pthread_t));
+            for (t = 0; t < T; ++t) {
+                fa[t].h = h; fa[t].R = R; fa[t].names = names; fa[t].seqs = seqs; fa[t].lens = lens; fa[t].g0 = h->read_counter;
+                fa[t].r0 = b0 + (int)((long long)nb * t / T); fa[t].r1 = b0 + (int)((long long)nb * (t + 1) / T);
+                pthread_create(&th[t], NULL, fmt_main, &fa[t]);
+            }
+            for (t = 0; t < T; ++t) {
+                pthread_join(th[t], NULL);
+                if (fa[t].out.l) str_write(&h->out, fa[t].out.s, fa[t].out.l);
+                h->n_failed += fa[t].failed; free(fa[t].out.s);
+            }
+            free(fa); free(th);
+        }
+    }
+}
+
 const char *th_host_run(th_host *h, int n, const char *const *names, const char *const *seqs, const int32_t *lens, size_t *out_len) {
-    int c, r, n_chunks = (n + h->p.chunk_reads - 1) / h->p.chunk_reads;
+    int c, n_chunks = (n + h->p.chunk_reads - 1) / h->p.chunk_reads;
     h->out.l = 0; str_reserve(&h->out, 16); h->out.s[0] = 0;
     memset(&h->stats, 0, sizeof(h->stats));
     if (n_chunks <= 1 || h->n_lanes == 1) {
@@ -425,7 +466,7 @@ const char *th_host_run(th_host *h, int n, const char *const *names, const char 
             const int c0 = c * h->p.chunk_reads, m = n - c0 < h->p.chunk_reads ? n - c0 : h->p.chunk_reads;
             th_gpu_result R;
             if (th_gpu_process_chunk(h->gpu, m, seqs + c0, lens + c0, &R)) { set_err("%s", th_gpu_last_error()); *out_len = 0; return NULL; }
-            for (r = 0; r < m; ++r) emit_read(h, &R, r, names[c0 + r], seqs[c0 + r], lens[c0 + r], h->read_counter + r);
+            emit_chunk(h, &R, m, names + c0, seqs + c0, lens + c0);
             h->read_counter += m;
             add_stats(&h->stats, &R.stats);
         }
@@ -447,7 +488,7 @@ const char *th_host_run(th_host *h, int n, const char *const *names, const char 
             t_mwait += now_s() - t0;
             if (failed) break;
             t0 = now_s();
-            for (r = 0; r < m; ++r) emit_read(h, &J.res[c], r, names[c0 + r], seqs[c0 + r], lens[c0 + r], h->read_counter + r);
+            emit_chunk(h, &J.res[c], m, names + c0, seqs + c0, lens + c0);
             t_emit += now_s() - t0;
             h->read_counter += m;
             add_stats(&h->stats, &J.res[c].stats);

@@ -139,6 +139,21 @@ def test_all_golden_cases(T, golden, golden_inputs):
     assert not bad, bad[:6]
 
 
+def test_parallel_formatting_does_not_change_output(T, golden, golden_inputs, monkeypatch):
+    """th_host formats a finished chunk on several threads (segments of reads, own buffers, concatenated in order);
+    with a grain of 3 reads per thread the 100-read FASTQ cases (quality slot quirk included) and the adapter cases
+    run through that path."""
+    monkeypatch.setenv("TH_HOST_FMT_GRAIN", "3")
+    bad = []
+    for c in golden["cases"]:
+        if c["input"] not in ("testfq_all", "full_length"):
+            continue
+        out, _ = _run_case(T, golden_inputs, c)
+        if hashlib.md5(out).hexdigest() != c["md5"]:
+            bad.append((c["input"], c["args"]))
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("lanes", [1, 2, 4])
 def test_chunking_does_not_change_output(T, golden, golden_inputs, lanes):
     """Chunks rotate over `lanes` GPU contexts on their own host threads (host/th_host.c); the text, including the
