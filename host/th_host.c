@@ -106,8 +106,10 @@ th_gpu_ctx *th_host_gpu(th_host *h) { return h->gpu; }
 
 /* Infix edit distance with threshold (edlib_align_HW, src/edlib_align.c:73-85): edit distance,
  * first end location, and for it the smallest start reaching that distance (edlib/src/edlib.cpp:141-236).
- * Plain DP over the adapter (<= ~100 bp) x 2*cons_len; case-insensitive equality. */
-static int infix_ed(const char *q, int ql, const char *t, int tl, int *start, int *end, int k) {
+ * Case-insensitive equality.  infix_ed_plain is the column-by-column definition; infix_ed evaluates the same two
+ * passes with Myers' bit-vector recurrences (Myers 1999, block form of Hyyro 2003: vertical deltas Pv/Mv per 64 rows,
+ * horizontal delta carried from block to block), 64 DP cells per word operation. */
+static int infix_ed_plain(const char *q, int ql, const char *t, int tl, int *start, int *end, int k) {
     int i, j, best = -1, best_end = -1, best_start = -1;
     int *col;
     if (ql <= 0 || tl <= 0) return -1;
@@ -141,6 +143,86 @@ static int infix_ed(const char *q, int ql, const char *t, int tl, int *start, in
     free(col);
     *start = best_start; *end = best_end;
     return best;
+}
+
+#define ED_MAXW 4 /* adapters up to 256 bases take the bit-vector path */
+/* one text column through the W blocks; hin0 = horizontal delta along the top row (0: a match may start anywhere,
+ * +1: the top row counts text characters); returns the delta of the bottom row (pattern row ql) */
+static inline int ed_column(int W, uint64_t last_bit, const uint64_t *eq, uint64_t *Pv, uint64_t *Mv, int hin0) {
+    int hin = hin0, b;
+    for (b = 0; b < W; ++b) {
+        const uint64_t top = b == W - 1 ? last_bit : (uint64_t)1 << 63;
+        uint64_t Eq = eq[b], pv = Pv[b], mv = Mv[b], Xv, Xh, Ph, Mh;
+        int hout = 0;
+        Xv = Eq | mv;
+        if (hin < 0) Eq |= 1;
+        Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+        Ph = mv | ~(Xh | pv);
+        Mh = pv & Xh;
+        if (Ph & top) hout = 1; else if (Mh & top) hout = -1;
+        Ph <<= 1; Mh <<= 1;
+        if (hin < 0) Mh |= 1; else if (hin > 0) Ph |= 1;
+        Pv[b] = Mh | ~(Xv | Ph);
+        Mv[b] = Ph & Xv;
+        hin = hout;
+    }
+    return hin;
+}
+static int infix_ed(const char *q, int ql, const char *t, int tl, int *start, int *end, int k) {
+    uint64_t peq[256][ED_MAXW], Pv[ED_MAXW], Mv[ED_MAXW];
+    int W, i, j, b, score, best = -1, best_end = -1, best_start = -1;
+    uint64_t last_bit;
+    if (ql <= 0 || tl <= 0) return -1;
+    if (ql > 64 * ED_MAXW) return infix_ed_plain(q, ql, t, tl, start, end, k);
+    W = (ql + 63) / 64; last_bit = (uint64_t)1 << ((ql - 1) & 63);
+    memset(peq, 0, sizeof(peq));
+    for (i = 0; i < ql; ++i) peq[(unsigned char)(q[i] | 0x20)][i >> 6] |= (uint64_t)1 << (i & 63);
+    for (b = 0; b < W; ++b) { Pv[b] = ~(uint64_t)0; Mv[b] = 0; }
+    score = ql;
+    for (j = 0; j < tl; ++j) {
+        score += ed_column(W, last_bit, peq[(unsigned char)(t[j] | 0x20)], Pv, Mv, 0);
+        if (best < 0 || score < best) { best = score; best_end = j; }
+    }
+    if (best > ql) best = ql;
+    if (k >= 0 && best > k) return -1;
+    /* backwards from the end location: reversed adapter against the reversed text prefix, top row counting text */
+    memset(peq, 0, sizeof(peq));
+    for (i = 0; i < ql; ++i) peq[(unsigned char)(q[ql - 1 - i] | 0x20)][i >> 6] |= (uint64_t)1 << (i & 63);
+    for (b = 0; b < W; ++b) { Pv[b] = ~(uint64_t)0; Mv[b] = 0; }
+    score = ql;
+    for (j = 0; j <= best_end; ++j) {
+        score += ed_column(W, last_bit, peq[(unsigned char)(t[best_end - j] | 0x20)], Pv, Mv, 1);
+        if (score == best) best_start = best_end - j;
+    }
+    *start = best_start; *end = best_end;
+    return best;
+}
+
+/* self-test hook for tests/: random adapters and texts through both implementations; returns the number of disagreements */
+int th_host_selftest_infix(int trials, unsigned seed) {
+    int bad = 0, it;
+    unsigned long long x = seed * 2654435761ull + 88172645463325252ull;
+#define RND() (x ^= x << 13, x ^= x >> 7, x ^= x << 17, (unsigned)(x >> 11))
+    for (it = 0; it < trials; ++it) {
+        const int ql = 1 + (int)(RND() % (it % 7 == 0 ? 300 : 130));
+        const int tl = 1 + (int)(RND() % (it % 5 == 0 ? 3000 : 400));
+        const int sigma = 2 + (int)(RND() % 4);
+        char *q = (char *)malloc((size_t)ql + 1), *t = (char *)malloc((size_t)tl + 1);
+        int i, s1 = -7, e1 = -7, s2 = -7, e2 = -7, r1, r2, k;
+        static const char al[] = "ACGTNacgtn";
+        for (i = 0; i < ql; ++i) { const unsigned c = RND() % sigma, lower = RND() % 4 == 0; q[i] = al[c + (lower ? 5 : 0)]; }
+        for (i = 0; i < tl; ++i) { const unsigned c = RND() % sigma, lower = RND() % 4 == 0; t[i] = al[c + (lower ? 5 : 0)]; }
+        if (it % 3 == 0 && tl > ql + 10) { /* plant a noisy copy of the adapter */
+            const int off = (int)(RND() % (unsigned)(tl - ql));
+            for (i = 0; i < ql; ++i) if (RND() % 8) t[off + i] = q[i];
+        }
+        k = it % 4 == 0 ? -1 : (int)(ql * (RND() % 100) / 100.0);
+        r1 = infix_ed_plain(q, ql, t, tl, &s1, &e1, k); r2 = infix_ed(q, ql, t, tl, &s2, &e2, k);
+        if (r1 != r2 || (r1 >= 0 && (s1 != s2 || e1 != e2))) ++bad;
+        free(q); free(t);
+    }
+#undef RND
+    return bad;
 }
 
 /* -s: collect_ed_res (src/gen_cons.c:89-110) -- the best infix hit of an adapter in the read and one more on each side */

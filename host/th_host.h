@@ -56,6 +56,9 @@ void th_host_stats(const th_host *h, th_gpu_stats *s);
 long long th_host_failed_tasks(const th_host *h);
 th_gpu_ctx *th_host_gpu(th_host *h);
 const char *th_host_last_error(void);
+/* test hook: the bit-vector adapter search against its column-by-column definition on random inputs; returns the
+ * number of disagreements (0 expected) */
+int th_host_selftest_infix(int trials, unsigned seed);
 
 #ifdef __cplusplus
 }

@@ -65,3 +65,15 @@ def test_product_never_touches_the_oracle():
                     if re.search(r"oracle_py|th_oracle|libth_oracle|oracle/", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_adapter_search_bitvector_equals_definition():
+    """host/th_host.c: the Myers bit-vector infix search (adapter detection of -5/-3/-F/-s, restating edlib_align_HW)
+    against the plain column DP on 30,000 random adapter/text pairs (1-300 bp adapters incl. the > 256 bp fallback,
+    mixed case, planted noisy copies, thresholds).  Host code only, no GPU needed."""
+    import ctypes as C
+    import tidehunter_b200 as T
+    h = T.host_lib()
+    h.th_host_selftest_infix.argtypes = [C.c_int, C.c_uint]
+    h.th_host_selftest_infix.restype = C.c_int
+    assert h.th_host_selftest_infix(30000, 20260117) == 0
