@@ -23,7 +23,7 @@ FLANK = 50
 _ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
-def gen_reads(shape, n, start=0, seed=SEED, adapters=None):
+def gen_reads(shape, n, start=0, seed=SEED, adapters=None, three_rc=False):
     """Return (names, seqs): `n` reads of `shape`, read indices start..start+n-1.
 
     Read i depends only on (seed, shape, i).  `adapters` = (five, three) splices
@@ -43,7 +43,9 @@ def gen_reads(shape, n, start=0, seed=SEED, adapters=None):
             a3 = np.frombuffer(three.encode(), dtype=np.uint8)
             lut = np.zeros(256, dtype=np.uint8)
             lut[ord("A")], lut[ord("C")], lut[ord("G")], lut[ord("T")] = 0, 1, 2, 3
-            unit = np.concatenate([lut[a5], unit, lut[a3]])
+            # three_rc: the splint structure -F looks for (5' adapter, insert, reverse complement of the 3' adapter:
+            # src/gen_cons.c:224-291 searches five_seq and revcomp(three_seq) on the same strand)
+            unit = np.concatenate([lut[a5], unit, (3 - lut[a3])[::-1] if three_rc else lut[a3]])
             ulen = len(unit)
         rot = int(rng.integers(0, ulen))
         body = np.tile(unit, copies + 1)[rot:rot + ulen * copies]

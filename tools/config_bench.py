@@ -32,7 +32,7 @@ def main():
         ("configs[3] long units 4-5 kb x 2-4, -f 2", lambda n: synth.gen_reads("long", n, start=600000), 8192, ["-f", "2"], dict(out_fmt=2)),
         ("configs[4] adapters -5 -3 -u -f 2", lambda n: synth.gen_reads("r2c2", n, start=600000, adapters=(five, three)), 16384, ["ADAPTERS", "-u", "-f", "2"],
          dict(out_fmt=2, five_seq=five, three_seq=three, only_unit=1)),
-        ("configs[4] adapters -5 -3 -F -f 2 (full-length consensus)", lambda n: synth.gen_reads("r2c2", n, start=600000, adapters=(five, three)), 16384, ["ADAPTERS", "-F", "-f", "2"],
+        ("configs[4] adapters -5 -3 -F -f 2 (full-length consensus)", lambda n: synth.gen_reads("r2c2", n, start=600000, adapters=(five, three), three_rc=True), 16384, ["ADAPTERS", "-F", "-f", "2"],
          dict(out_fmt=2, five_seq=five, three_seq=three, only_full_length=1)),
     ]
     rows = []

@@ -47,8 +47,10 @@ def main():
         ("r2c2 -u -f 2", lambda: synth.gen_reads("r2c2", n_of(8192), start=400000), ["-u", "-f", "2"], dict(out_fmt=2, only_unit=1)),
         ("adapter -5 -3 -f 2", lambda: synth.gen_reads("r2c2", n_of(4096), start=200000, adapters=(five, three)), ["ADAPTERS", "-f", "2"],
          dict(out_fmt=2, five_seq=five, three_seq=three)),
-        ("adapter -5 -3 -F -f 2", lambda: synth.gen_reads("r2c2", n_of(2048), start=210000, adapters=(five, three)), ["ADAPTERS", "-F", "-f", "2"],
+        ("adapter -5 -3 -F -f 2", lambda: synth.gen_reads("r2c2", n_of(2048), start=210000, adapters=(five, three), three_rc=True), ["ADAPTERS", "-F", "-f", "2"],
          dict(out_fmt=2, five_seq=five, three_seq=three, only_full_length=1)),
+        ("splint -5 -3 -f 3", lambda: synth.gen_reads("r2c2", n_of(3000), start=220000, adapters=(five, three), three_rc=True), ["ADAPTERS", "-f", "3"],
+         dict(out_fmt=3, five_seq=five, three_seq=three)),
         ("single -s -F -f 2", lambda: synth.gen_single_copy(n_of(4096), (five, three), start=200000), ["ADAPTERS", "-s", "-F", "-f", "2"],
          dict(out_fmt=2, five_seq=five, three_seq=three, only_full_length=1, single_copy=1)),
         ("r2c2 -k 12 -w 5 -f 2", lambda: synth.gen_reads("r2c2", n_of(4096), start=500000), ["-k", "12", "-w", "5", "-f", "2"], dict(out_fmt=2, k=12, w=5)),
