@@ -22,7 +22,8 @@
 //  * The consensus DFS (msa rank) and column vote are literal.
 //
 // HBM layout (per warp "slab"): graph arrays (SoA, int32), edge pool with per-node in/out linked lists
-// in insertion order, two order buffers, per-row band metadata, query profile (5 x int16 rows), cigar,
+// in insertion order, two order buffers, per-row band metadata, room for the query bit-planes of long queries
+// (short ones keep them in shared memory), cigar,
 // and the DP arena holding, per row, H|E1|E2|F1|F2 as int16 over the row's band only.
 #pragma once
 #include "th_common.cuh"
@@ -91,8 +92,6 @@ __device__ inline void poa_carve(PoaWs &w, uint8_t *slab, size_t slab_bytes, int
     w.arena_cap = (uint32_t)ne;
 }
 
-__device__ __forceinline__ uint32_t ld32(const int16_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
-__device__ __forceinline__ void st32(int16_t *p, uint32_t v) { *reinterpret_cast<uint32_t *>(p) = v; }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // graph edit used for the final edge into the sink (lane 0 only)
@@ -113,7 +112,6 @@ __device__ inline void g_add_edge(PoaWs &w, int &edge_n, int from, int to, bool 
 //   W/2 records of 16 bytes, record q = columns (beg + 2q, beg + 2q + 1) as four s16x2 words {H, E1, E2, F1},
 //   followed by W/2 words of F2 pairs.  One 16-byte access moves everything the next rows need from a column
 //   pair, and a backtrack step touches one or two sectors per row instead of five.
-__device__ __forceinline__ const uint4 *poa_recs(const uint32_t *A32, int off) { return reinterpret_cast<const uint4 *>(A32 + (off >> 1)); }
 __device__ __forceinline__ int s16_at(uint32_t word, int odd) { return odd ? hi16(word) : lo16(word); }
 
 #ifndef POA_SETUP_U
