@@ -298,3 +298,18 @@ def test_gap_modes(T):
         assert hashlib.md5(out).hexdigest() == m["md5"], tag
     with pytest.raises(RuntimeError, match="linear gap mode"):
         T.TideHunter(out_fmt=2, gap_open1=0)
+
+
+def test_very_long_reads(T, oracle):
+    """~100 kb reads: 60 and 800 copies in one consensus task, 6 kb units -- capacities (sorts beyond shared memory, slab
+    sizing with the full-width retry, sink in-degree, cigar lengths), not throughput."""
+    from tidehunter_b200 import synth
+    names, seqs = synth.gen_very_long_reads()
+    exp, cnt = oracle.run_batch(names, seqs, oracle.default_para(out_fmt=2), threads=3)
+    assert exp.count(b"\n") >= 3
+    th = T.TideHunter(out_fmt=2)
+    out = th.run(names, seqs)
+    st = th.stats()
+    th.close()
+    assert out == exp
+    assert st["n_poa_cells"] == cnt["poa_cells"] and st["n_chain_evals"] == cnt["chain_evals"]

@@ -142,3 +142,16 @@ def gen_long_indel_reads(n, start=0, seed=SEED + 7, err=0.08):
         seqs.append(_ACGT[out].tobytes())
         names.append(("g%d" % i).encode())
     return names, seqs
+
+
+def gen_very_long_reads(seed=SEED + 11):
+    """Three ~100 kb reads that stress capacities rather than throughput: 2 kb x 60 copies, 150 bp x 800 copies (a
+    consensus task with 800 sequences), 6 kb x 12 copies (units close to the int16 score range of abPOA)."""
+    names, seqs = [], []
+    for i, (ulen, copies) in enumerate(((2000, 60), (150, 800), (6000, 12))):
+        rng = np.random.Generator(np.random.Philox(key=[seed, i]))
+        unit = rng.integers(0, 4, ulen, dtype=np.uint8)
+        tmpl = np.concatenate([rng.integers(0, 4, FLANK, dtype=np.uint8), np.tile(unit, copies), rng.integers(0, 4, FLANK, dtype=np.uint8)])
+        seqs.append(_ACGT[_channel(rng, tmpl, 0.10)].tobytes())
+        names.append(("vl%d" % i).encode())
+    return names, seqs
