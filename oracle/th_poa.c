@@ -282,6 +282,7 @@ static int poa_align(pgraph_t *g, const tho_para_t *p, const uint8_t *query, int
             d->inf_min = MAX3(INT16_MIN + min_mis, INT16_MIN + oe1, INT16_MIN + oe2_raw) + 31 * MAX2(e1, e2_raw);
         } else {
             d->bits = 32; d->pn = p->pn16 / 2;
+            if (getenv("THO_DEBUG")) fprintf(stderr, "[tho] int32 alignment: qlen %d, graph rows %d\n", qlen, gn);
             d->inf_min = MAX3(INT32_MIN + min_mis, INT32_MIN + oe1, INT32_MIN + oe2_raw) + 31 * MAX2(e1, e2_raw);
         }
     }

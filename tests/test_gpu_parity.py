@@ -313,3 +313,20 @@ def test_very_long_reads(T, oracle):
     th.close()
     assert out == exp
     assert st["n_poa_cells"] == cnt["poa_cells"] and st["n_chain_evals"] == cnt["chain_evals"]
+
+
+def test_int32_range_units_fail_loudly(T):
+    """The GPU path has no 32-bit POA: a unit whose graph leaves abPOA's int16 score range (synth.gen_int32_read; the
+    reference switches to 32-bit vectors there, the oracle follows) is reported as a failed task -- counted, announced on
+    stderr, its record absent -- and the reads around it are unaffected."""
+    from tidehunter_b200 import synth
+    n0, s0 = synth.gen_reads("r2c2", 3, start=42)
+    nw, sw = synth.gen_int32_read()
+    th = T.TideHunter(out_fmt=2)
+    ref3 = th.run(n0, s0)
+    assert th.failed_tasks() == 0
+    out = th.run(n0[:2] + nw + n0[2:], s0[:2] + sw + s0[2:])
+    failed = th.failed_tasks()
+    th.close()
+    assert failed == 1
+    assert out == ref3 and b"w0" not in out

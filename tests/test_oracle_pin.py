@@ -134,3 +134,18 @@ def test_oracle_gap_modes_match_reference(oracle):
     for tag, m in fx["modes"].items():
         out = oracle.run_batch(names, seqs, oracle.default_para(out_fmt=2, **m["para"]), threads=4)[0]
         assert hashlib.md5(out).hexdigest() == m["md5"], tag
+
+
+def test_oracle_int32_path_matches_reference(oracle, capfd, monkeypatch):
+    """A 98 kb read whose graph outgrows abPOA's int16 score range: the last alignments run with 32-bit vectors (pn = 8)
+    in the reference; the oracle follows and reproduces the reference's record (tests/golden/int32_golden.json)."""
+    import hashlib
+    import json
+    import os
+    from tidehunter_b200 import synth
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "int32_golden.json")))
+    monkeypatch.setenv("THO_DEBUG", "1")
+    names, seqs = synth.gen_int32_read()
+    out = oracle.run_batch(names, seqs, oracle.default_para(out_fmt=2), threads=1)[0]
+    assert hashlib.md5(out).hexdigest() == fx["md5"] and len(out) == fx["bytes"]
+    assert "int32 alignment" in capfd.readouterr().err

@@ -157,6 +157,13 @@ class TideHunter:
         host_lib().th_host_stats(self._h, C.byref(s))
         return s.as_dict()
 
+    def failed_tasks(self):
+        """Consensus tasks the GPU path reported as failed since construction (their records are missing; stderr says why)."""
+        h = host_lib()
+        h.th_host_failed_tasks.argtypes = [C.c_void_p]
+        h.th_host_failed_tasks.restype = C.c_longlong
+        return int(h.th_host_failed_tasks(self._h))
+
     @property
     def gpu_ctx(self):
         return host_lib().th_host_gpu(self._h)

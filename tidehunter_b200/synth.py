@@ -155,3 +155,13 @@ def gen_very_long_reads(seed=SEED + 11):
         seqs.append(_ACGT[_channel(rng, tmpl, 0.10)].tobytes())
         names.append(("vl%d" % i).encode())
     return names, seqs
+
+
+def gen_int32_read(seed=SEED + 13):
+    """One 98 kb read, unit 9.8 kb x 10 copies at 15 % error: the partial-order graph grows beyond 16.4 k rows, where
+    abPOA leaves its int16 score range and switches to 32-bit vectors (simd_abpoa_align.c:1610-1621) for the last
+    alignments.  The oracle follows (pinned on the reference's output); the GPU path reports the task as failed."""
+    rng = np.random.Generator(np.random.Philox(key=[seed, 0]))
+    unit = rng.integers(0, 4, 9800, dtype=np.uint8)
+    tmpl = np.concatenate([rng.integers(0, 4, FLANK, dtype=np.uint8), np.tile(unit, 10), rng.integers(0, 4, FLANK, dtype=np.uint8)])
+    return [b"w0"], [_ACGT[_channel(rng, tmpl, 0.15)].tobytes()]
