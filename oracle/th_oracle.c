@@ -389,7 +389,13 @@ static void write_cons(tho_read_t *r, const tho_para_t *p, const char *cons_seq,
                        const tho_cons_t *raw) {
     if (cons_len < p->min_len || cons_len > p->max_p) return;
     if (p->only_longest && r->n_cons == 1) {
-        if (end - start > r->cons[0].cons_end - r->cons[0].cons_start) { free_cons(r->cons); r->n_cons = 0; }
+        if (end - start > r->cons[0].cons_end - r->cons[0].cons_start) {
+            if (r->cons[0].cons_qual) { /* the replaced record's quality bytes stay in the buffer (qual.l is not rewound) */
+                r->dropped_qual = (char *)realloc(r->dropped_qual, r->dropped_l + r->cons[0].cons_len + 1);
+                memcpy(r->dropped_qual + r->dropped_l, r->cons[0].cons_qual, r->cons[0].cons_len); r->dropped_l += r->cons[0].cons_len;
+            }
+            free_cons(r->cons); r->n_cons = 0;
+        }
         else return;
     }
     tho_cons_t *c = push_cons(r);
@@ -678,7 +684,7 @@ void tho_process_read(const char *seq, int len, const tho_para_t *p, tho_read_t 
 void tho_read_free(tho_read_t *r) {
     int i;
     for (i = 0; i < r->n_cons; ++i) free_cons(r->cons + i);
-    free(r->cons);
+    free(r->cons); free(r->dropped_qual);
     memset(r, 0, sizeof(*r));
 }
 
@@ -784,7 +790,7 @@ char *tho_run_batch(int n, const char *const *names, const char *const *seqs, co
     for (i = 0; i < n; ++i) {
         const char *qov = NULL;
         if (with_qual) {
-            slot_t *s = slots + i % CHUNK_READ_N; int ci; size_t need = 0;
+            slot_t *s = slots + i % CHUNK_READ_N; int ci; size_t need = res[i].dropped_l;
             for (ci = 0; ci < res[i].n_cons; ++ci) need += res[i].cons[ci].cons_len;
             if (s->qual_l + need + 1 > s->qual_m) {
                 size_t m2 = (s->qual_l + need + 1) * 2;
@@ -792,6 +798,7 @@ char *tho_run_batch(int n, const char *const *names, const char *const *seqs, co
                 memset(s->qual_s + s->qual_m, '?', m2 - s->qual_m); /* the reference would print uninitialised heap here */
                 s->qual_m = m2;
             }
+            if (res[i].dropped_l) { memcpy(s->qual_s + s->qual_l, res[i].dropped_qual, res[i].dropped_l); s->qual_l += res[i].dropped_l; }
             for (ci = 0; ci < res[i].n_cons; ++ci) {
                 memcpy(s->qual_s + s->qual_l, res[i].cons[ci].cons_qual, res[i].cons[ci].cons_len);
                 s->qual_l += res[i].cons[ci].cons_len;

@@ -95,6 +95,9 @@ typedef struct {
     tho_cons_t *cons;
     /* work counters for roofline numerators */
     int64_t n_hits, n_chain_evals, n_poa_cells, n_ksw_cells;
+    /* qualities of records that -l replaced by a longer one: write_tandem_cons_seq rewinds seq.l but not qual.l
+     * (src/gen_cons.c:12-16 vs :23-30), so they stay in the slot's quality buffer in front of the kept record's */
+    char *dropped_qual; size_t dropped_l;
 } tho_read_t;
 
 /* src/tidehunter.c:23-60 */

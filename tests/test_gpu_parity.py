@@ -330,3 +330,17 @@ def test_int32_range_units_fail_loudly(T):
     th.close()
     assert failed == 1
     assert out == ref3 and b"w0" not in out
+
+
+def test_option_sets_found_by_fuzzing(T):
+    """The same option sets (tests/golden/fuzz_found_golden.json: -l with quality formats) through the host layer."""
+    import json
+    import os
+    from tidehunter_b200 import synth
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuzz_found_golden.json")))["cases"]
+    for c in fx:
+        names, seqs = synth.gen_reads(c["shape"], c["n"], start=c["start"])
+        th = T.TideHunter(**c["para"])
+        out = th.run(names, seqs)
+        th.close()
+        assert hashlib.md5(out).hexdigest() == c["md5"], c["args"]

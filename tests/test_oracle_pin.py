@@ -149,3 +149,21 @@ def test_oracle_int32_path_matches_reference(oracle, capfd, monkeypatch):
     out = oracle.run_batch(names, seqs, oracle.default_para(out_fmt=2), threads=1)[0]
     assert hashlib.md5(out).hexdigest() == fx["md5"] and len(out) == fx["bytes"]
     assert "int32 alignment" in capfd.readouterr().err
+
+
+def _fuzz_found():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuzz_found_golden.json")))["cases"]
+
+
+def test_option_sets_found_by_fuzzing(oracle):
+    """Option sets where tools/oracle_fuzz.py once separated the oracle from the reference: -l replacing a record while a
+    quality format is printed (the reference rewinds seq.l but not qual.l, so the replaced record's quality bytes are
+    printed for the kept one)."""
+    import hashlib
+    from tidehunter_b200 import synth
+    for c in _fuzz_found():
+        names, seqs = synth.gen_reads(c["shape"], c["n"], start=c["start"])
+        out = oracle.run_batch(names, seqs, oracle.default_para(**c["para"]), threads=4)[0]
+        assert hashlib.md5(out).hexdigest() == c["md5"], c["args"]
