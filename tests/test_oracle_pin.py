@@ -158,7 +158,7 @@ def _fuzz_found():
 
 
 def test_option_sets_found_by_fuzzing(oracle):
-    """Option sets where tools/oracle_fuzz.py once separated the oracle from the reference: -l replacing a record while a
+    """Option sets where tools/option_fuzz.py once separated the oracle from the reference: -l replacing a record while a
     quality format is printed (the reference rewinds seq.l but not qual.l, so the replaced record's quality bytes are
     printed for the kept one)."""
     import hashlib

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
-"""Option-space fuzz on CPU: random TideHunter option sets on seeded synthetic reads, the oracle's C restatement
-(oracle/libth_oracle.so) against the unmodified reference binary (oracle/_ref/TideHunter).  Test infrastructure; run in
-the container that has /root/reference:  python tools/oracle_fuzz.py [n_trials] [seed]"""
+"""Option-space fuzz: random TideHunter option sets on seeded synthetic reads against the unmodified reference binary
+(oracle/_ref/TideHunter).
+  python tools/option_fuzz.py [n_trials] [seed]          the oracle's C restatement (CPU, needs no GPU)
+  python tools/option_fuzz.py [n_trials] [seed] gpu      the product: host layer over the C ABI on cuda:0
+Test infrastructure (it executes oracle/_ref); writes gpurun_out/option_fuzz_<engine>.json."""
 import gzip
 import hashlib
 import json
@@ -19,7 +21,10 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 def main():
     n_trials = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     rnd = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    engine = sys.argv[3] if len(sys.argv) > 3 else "oracle"
     import oracle_py as O
+    if engine == "gpu":
+        import tidehunter_b200 as T
     from tidehunter_b200 import synth
     with gzip.open(os.path.join(ROOT, "tests", "golden", "golden.json.gz"), "rt") as f:
         ad = json.load(f)["adapters"]
@@ -81,7 +86,12 @@ def main():
             O.write_fasta(path, names, seqs)
             r = subprocess.run([O.REF_BIN, "-t", "4"] + argv + [path], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
             try:
-                out = O.run_batch(names, seqs, O.default_para(**kw), threads=4)[0]
+                if engine == "gpu":
+                    th = T.TideHunter(device=0, lanes=2, **kw)
+                    out = th.run(names, seqs)
+                    th.close()
+                else:
+                    out = O.run_batch(names, seqs, O.default_para(**kw), threads=4)[0]
             except Exception as e:  # noqa: BLE001
                 out = ("EXC %s" % e).encode()
             same = r.returncode == 0 and out == r.stdout
@@ -90,7 +100,10 @@ def main():
             if not same:
                 bad.append({"trial": it, "shape": shape, "start": start, "argv": [a if not a.startswith("/") else "<ad>" for a in argv], "ref_rc": r.returncode,
                             "ref_md5": hashlib.md5(r.stdout).hexdigest(), "ours_md5": hashlib.md5(out).hexdigest(), "ref_err": r.stderr.decode()[-200:]})
-    print(json.dumps({"trials": n_trials, "different": len(bad), "cases": bad[:10]}, indent=1))
+    rep = {"engine": engine, "trials": n_trials, "seed": int(sys.argv[2]) if len(sys.argv) > 2 else 1, "different": len(bad), "cases": bad[:10]}
+    print(json.dumps(rep, indent=1))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "option_fuzz_%s.json" % engine), "w"), indent=1)
     return 1 if bad else 0
 
 
