@@ -268,11 +268,13 @@ static int poa_align(pgraph_t *g, const tho_para_t *p, const uint8_t *query, int
     int max_mat = p->match < 0 ? -p->match : p->match, min_mis = p->mismatch > 0 ? p->mismatch : -p->mismatch;
     int o1 = p->gap_open1, e1 = p->gap_ext1, o2 = p->gap_open2, e2 = p->gap_ext2, oe1 = o1 + e1, oe2 = o2 + e2;
     const int oe2_raw = oe2, e2_raw = e2; /* inf_min and the int16 choice use the options as given in every gap mode (:1613-1614) */
-    /* affine mode (gap_open2 == 0, abpoa_align.c:85-88; DP simd_abpoa_align.c:160-246, 649-833: H = max(M, E, F)) is evaluated
-     * with the convex recurrences and a second gap function equal to the first plus one: E2 <= E1 - 1 and F2 <= F1 - 1 by
-     * induction, so the second pair never wins a max nor a backtrack comparison.  Pinned on outputs of the reference run
-     * with -O 4,0 (tests/golden/gapmode_golden.json). */
-    if (p->gap_open2 == 0) { o2 = o1 + 1; e2 = e1; oe2 = o2 + e2; }
+    /* affine mode (gap_open2 == 0, abpoa_align.c:85-88): simd_abpoa_ag_dp (:739-833) is NOT the convex recurrence with
+     * one gap function removed: an insertion opens from M only (F from the row's diagonal values, before E is folded
+     * in, :807-815), and the E handed to the next row is inf_min wherever F strictly won the cell (SIMDSetIfEqual,
+     * :822-827) -- insertions and deletions cannot be adjacent.  The second pair (E2, F2) is held at inf_min, so the
+     * convex backtrack (:248-377) degenerates to simd_abpoa_ag_backtrack (:160-246).  Pinned on reference outputs
+     * (tests/golden/gapmode_golden.json, tools/option_fuzz.py). */
+    const int affine = p->gap_open2 == 0;
     int beg_index = g->node_id_to_index[0], end_index = g->node_id_to_index[1], gn = end_index - beg_index + 1;
     pdp_t D, *d = &D; memset(d, 0, sizeof(D));
     { /* simd_abpoa_align.c:1610-1621 */
@@ -323,9 +325,9 @@ static int poa_align(pgraph_t *g, const tho_para_t *p, const uint8_t *query, int
     {
         int _end_sn = MIN2(d->dp_end_sn[0] + 1, dp_sn - 1);
         for (j = 0; j < (_end_sn + 1) * pn; ++j) AT(d->H, 0, j) = AT(d->E1, 0, j) = AT(d->E2, 0, j) = inf_min;
-        AT(d->H, 0, 0) = 0; AT(d->E1, 0, 0) = -oe1; AT(d->E2, 0, 0) = -oe2; AT(d->F1, 0, 0) = AT(d->F2, 0, 0) = inf_min;
+        AT(d->H, 0, 0) = 0; AT(d->E1, 0, 0) = -oe1; AT(d->E2, 0, 0) = affine ? inf_min : -oe2; AT(d->F1, 0, 0) = AT(d->F2, 0, 0) = inf_min;
         for (j = 1; j <= d->dp_end[0]; ++j) {
-            AT(d->F1, 0, j) = Wv(d, -o1 - e1 * j); AT(d->F2, 0, j) = Wv(d, -o2 - e2 * j);
+            AT(d->F1, 0, j) = Wv(d, -o1 - e1 * j); AT(d->F2, 0, j) = affine ? inf_min : Wv(d, -o2 - e2 * j);
             AT(d->H, 0, j) = MAX2(AT(d->F1, 0, j), AT(d->F2, 0, j));
         }
         if (cells) *cells += (int64_t)(d->dp_end_sn[0] + 1) * pn;
@@ -388,6 +390,18 @@ static int poa_align(pgraph_t *g, const tho_para_t *p, const uint8_t *query, int
             if (sn < min_pre_beg_sn) { fprintf(stderr, "[tho] sn_i < min_pre_beg_sn\n"); exit(1); }
             else if (sn > max_pre_end_sn) set_num = sn == max_pre_end_sn + 1 ? 2 : 1;
             else set_num = pn;
+            if (affine) { /* simd_abpoa_ag_dp: F from M, E masked where F won */
+                for (l = 0; l < pn; ++l) f1[l] = Wv(d, (int64_t)(l ? h[l - 1] : first) - oe1);
+                set_F(d, f1, set_num, e1);
+                first = MAX2(h[pn - 1], Wv(d, (int64_t)f1[pn - 1] + o1));
+                for (l = 0; l < pn; ++l) {
+                    const int32_t tmp = MAX2(h[l], x1[l]);
+                    h[l] = MAX2(tmp, f1[l]);
+                    x1[l] = h[l] == tmp ? MAX2(Wv(d, (int64_t)x1[l] - e1), Wv(d, (int64_t)h[l] - oe1)) : inf_min;
+                    x2[l] = inf_min; f2[l] = inf_min;
+                }
+                continue;
+            }
             for (l = 0; l < pn; ++l) h[l] = MAX3(h[l], x1[l], x2[l]);
             for (l = 0; l < pn; ++l) {
                 f1[l] = Wv(d, (int64_t)(l ? h[l - 1] : first) - oe1);

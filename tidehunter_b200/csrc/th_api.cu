@@ -117,11 +117,10 @@ extern "C" th_gpu_ctx *th_gpu_create(const th_gpu_params *p, int device) {
     d.k = p->k; d.w = p->w; d.hpc = p->hpc; d.min_copy = p->min_copy; d.min_p = (uint32_t)p->min_p; d.max_p = (uint32_t)p->max_p;
     d.max_div = p->max_div; d.match = p->match; d.mismatch = p->mismatch; d.o1 = p->gap_open1; d.e1 = p->gap_ext1; d.o2 = p->gap_open2; d.e2 = p->gap_ext2;
     d.o2_raw = p->gap_open2; d.e2_raw = p->gap_ext2;
-    // abPOA's affine mode (gap_open2 == 0, abpoa_align.c:85-88: H = max(M, E1, F1)) runs on the convex kernel with a second
-    // gap function that is the first one plus one: E2 <= E1 - 1 and F2 <= F1 - 1 hold by induction over the recurrences, so
-    // the second pair never wins a max nor a backtrack comparison, and every H, E1, F1 equals the affine model's.
-    if (p->gap_open2 == 0) { d.o2 = d.o1 + 1; d.e2 = d.e1; }
-    d.pn = p->simd_lanes16; d.only_unit = p->only_unit;
+    // abPOA's affine mode (gap_open2 == 0, abpoa_align.c:85-88) has its own recurrences (template parameter AFFINE of
+    // poa_add_sequence); the unused second gap function only has to stay inside the int16 headroom checks
+    d.affine = p->gap_open2 == 0;
+    if (d.affine) { d.o2 = d.o1 + 1; d.e2 = d.e1; }
     CKP(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) CKP(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 4; ++i) CKP(cudaEventCreate(&c->mark[i]));

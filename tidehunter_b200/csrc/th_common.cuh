@@ -15,6 +15,7 @@ struct DevParams {
     uint32_t min_p, max_p;
     double max_div;
     int match, mismatch, o1, e1, o2, e2; // o2/e2 as used in the recurrences (affine mode: o1 + 1 / e1, see th_gpu_create)
+    int affine;                          // abPOA's affine gap mode (gap_open2 == 0): own recurrences, see th_poa.cuh
     int o2_raw, e2_raw;                  // the caller's values: abPOA derives inf_min and the int16 range check from them in every gap mode
     int pn;          // int16 lanes of the emulated abPOA vector (16)
     int only_unit;

@@ -138,7 +138,12 @@ __device__ __forceinline__ void poa_pred(const uint4 *recs, const int4 pm, const
 }
 
 // one warp aligns sequence `query` to the graph and merges it in.  Returns an error code.
-template <int LP> // LP = log2 of the emulated vector width pn (4: AVX2 int16, the reference build; 3: SSE)
+// AFFINE: abPOA's affine gap mode (gap_open2 == 0, simd_abpoa_ag_dp, simd_abpoa_align.c:739-833).  It is not the convex
+// recurrence minus one gap function: an insertion opens from M only (F is built from the row's diagonal values before E
+// is folded in), and the E handed to the next row is inf_min wherever F strictly won the cell (SIMDSetIfEqual), so
+// insertions and deletions are never adjacent.  The second pair (E2, F2) is held at inf_min, which makes the convex
+// backtrack below behave exactly as simd_abpoa_ag_backtrack (:160-246).
+template <int LP, bool AFFINE> // LP = log2 of the emulated vector width pn (4: AVX2 int16, the reference build; 3: SSE)
 __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *query, int qlen, int &node_n, int &edge_n,
                                 PoaSmem &sm, unsigned long long &cells, unsigned long long &rows, long long *ph) {
 #ifdef POA_PROFILE   // per-phase warp-cycle counters (tools/profile_step.py); cost ~16 registers, off in the product build
@@ -278,8 +283,8 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
             for (int h = 0; h < 2; ++h) {
                 const int j = 2 * q + h;
                 const int f1 = -o1 - e1 * j, f2 = -o2 - e2 * j;
-                const int vh = j == 0 ? 0 : max((int)(int16_t)f1, (int)(int16_t)f2);
-                const int v1 = j == 0 ? -oe1 : inf_min, v2 = j == 0 ? -oe2 : inf_min, vf1 = j == 0 ? inf_min : f1, vf2 = j == 0 ? inf_min : f2;
+                const int vh = j == 0 ? 0 : (AFFINE ? (int)(int16_t)f1 : max((int)(int16_t)f1, (int)(int16_t)f2));
+                const int v1 = j == 0 ? -oe1 : inf_min, v2 = (j == 0 && !AFFINE) ? -oe2 : inf_min, vf1 = j == 0 ? inf_min : f1, vf2 = (j == 0 || AFFINE) ? inf_min : f2;
                 hh |= (uint32_t)(uint16_t)vh << (16 * h); ee1 |= (uint32_t)(uint16_t)v1 << (16 * h); ee2 |= (uint32_t)(uint16_t)v2 << (16 * h);
                 ff1 |= (uint32_t)(uint16_t)vf1 << (16 * h); ff2 |= (uint32_t)(uint16_t)vf2 << (16 * h);
             }
@@ -360,9 +365,10 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
             const uint32_t S = (s_neg ^ (((t | (t << 15)) & 0x10001u) * s_xm)) & (((v | (v << 15)) & 0x10001u) * 0xffffu);
             const uint32_t Ms = __vadd2(Mx, S);
             const uint32_t Hme = __vimax3_s16x2(Ms, E1x, E2x);
-            uint32_t hp = __shfl_up_sync(TH_FULL, Hme, 1);
+            const uint32_t Hf = AFFINE ? Ms : Hme;        // what an insertion may open from
+            uint32_t hp = __shfl_up_sync(TH_FULL, Hf, 1);
             if (lane == 0) hp = Ms << 16;
-            const uint32_t Hsh = __funnelshift_r(hp, Hme, 16);
+            const uint32_t Hsh = __funnelshift_r(hp, Hf, 16);
             uint32_t G1 = __vadd2(Hsh, C1), G2 = __vadd2(Hsh, C2);   // G = (Hme[j-1] - oe) + e (j - j0)
             G1 = __vmaxs2(G1, (G1 << 16) | 0x8000u); G2 = __vmaxs2(G2, (G2 << 16) | 0x8000u); // odd column also sees the even one
             uint32_t TT = __byte_perm(G1, G2, 0x7632); // lo = G1 at this lane's odd column, hi = G2
@@ -371,10 +377,11 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
             uint32_t Pv = __shfl_up_sync(TH_FULL, TT, 1);
             if (lane == 0) Pv = POA_NEGP;
             G1 = __vmaxs2(G1, __byte_perm(Pv, Pv, 0x1010)); G2 = __vmaxs2(G2, __byte_perm(Pv, Pv, 0x3232));
-            const uint32_t Fa = __vadd2(G1, NJ1), Fb = __vadd2(G2, NJ2);
+            const uint32_t Fa = __vadd2(G1, NJ1), Fb = AFFINE ? INFP : __vadd2(G2, NJ2);
             const uint32_t Hn = __vimax3_s16x2(Hme, Fa, Fb);
-            const uint32_t E1o = __viaddmax_s16x2(E1x, NE1P, __vadd2(Hn, NOE1P));
-            const uint32_t E2o = __viaddmax_s16x2(E2x, NE2P, __vadd2(Hn, NOE2P));
+            uint32_t E1o = __viaddmax_s16x2(E1x, NE1P, __vadd2(Hn, NOE1P));
+            if (AFFINE) { const uint32_t keep = __vcmpeq2(Hn, Hme); E1o = (E1o & keep) | (INFP & ~keep); } // F won the cell: no deletion from it
+            const uint32_t E2o = AFFINE ? INFP : __viaddmax_s16x2(E2x, NE2P, __vadd2(Hn, NOE2P));
             sm.last[lane] = make_uint4(Hn, E1o, E2o, 0); // every reader of the old contents is past the scan's shuffles
             if (j <= dend) { reinterpret_cast<uint4 *>(A32w)[rec0] = make_uint4(Hn, E1o, E2o, Fa); A32w[f20] = Fb; }
             const uint32_t sub = lane_vec == vlast ? 0u : (uint32_t)(lane_vec + 1);
@@ -396,9 +403,10 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
             const uint32_t S = (s_neg ^ (((t | (t << 15)) & 0x10001u) * s_xm)) & (((v | (v << 15)) & 0x10001u) * 0xffffu);
             const uint32_t Ms = __vadd2(Mx, S);
             const uint32_t Hme = __vimax3_s16x2(Ms, E1x, E2x);
-            uint32_t hp = __shfl_up_sync(TH_FULL, Hme, 1);
+            const uint32_t Hf = AFFINE ? Ms : Hme;
+            uint32_t hp = __shfl_up_sync(TH_FULL, Hf, 1);
             if (lane == 0) hp = ch == 0 ? (Ms << 16) : carryH;
-            const uint32_t Hsh = __funnelshift_r(hp, Hme, 16);
+            const uint32_t Hsh = __funnelshift_r(hp, Hf, 16);
             uint32_t G1 = __vadd2(Hsh, C1), G2 = __vadd2(Hsh, C2);   // G = (Hme[j-1] - oe) + e (j - j0)
             if (lane == 0) { G1 = __vmaxs2(G1, (carryF & 0xffffu) | 0x80000000u); G2 = __vmaxs2(G2, (carryF >> 16) | 0x80000000u); }
             G1 = __vmaxs2(G1, (G1 << 16) | 0x8000u); G2 = __vmaxs2(G2, (G2 << 16) | 0x8000u); // odd column also sees the even one
@@ -408,12 +416,13 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
             uint32_t Pv = __shfl_up_sync(TH_FULL, TT, 1);
             if (lane == 0) Pv = POA_NEGP;
             G1 = __vmaxs2(G1, __byte_perm(Pv, Pv, 0x1010)); G2 = __vmaxs2(G2, __byte_perm(Pv, Pv, 0x3232));
-            const uint32_t Fa = __vadd2(G1, NJ1), Fb = __vadd2(G2, NJ2);
+            const uint32_t Fa = __vadd2(G1, NJ1), Fb = AFFINE ? INFP : __vadd2(G2, NJ2);
             const uint32_t Hn = __vimax3_s16x2(Hme, Fa, Fb);
-            const uint32_t E1o = __viaddmax_s16x2(E1x, NE1P, __vadd2(Hn, NOE1P));
-            const uint32_t E2o = __viaddmax_s16x2(E2x, NE2P, __vadd2(Hn, NOE2P));
+            uint32_t E1o = __viaddmax_s16x2(E1x, NE1P, __vadd2(Hn, NOE1P));
+            if (AFFINE) { const uint32_t keep = __vcmpeq2(Hn, Hme); E1o = (E1o & keep) | (INFP & ~keep); } // F won the cell: no deletion from it
+            const uint32_t E2o = AFFINE ? INFP : __viaddmax_s16x2(E2x, NE2P, __vadd2(Hn, NOE2P));
             if (ch + 1 < nchunk) {
-                carryH = __shfl_sync(TH_FULL, Hme, 31) & 0xffff0000u;
+                carryH = __shfl_sync(TH_FULL, Hf, 31) & 0xffff0000u;
                 const uint32_t fa = __shfl_sync(TH_FULL, Fa, 31), fb = __shfl_sync(TH_FULL, Fb, 31);
                 carryF = __vadd2(__byte_perm(fa, fb, 0x7632), pk(-e1, -e2)); // G of column j0 - 1 in the next chunk's frame
             }
@@ -817,8 +826,13 @@ poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const in
         __syncwarp();
         int node_n = l0 + 2, edge_n = l0 + 1, err = TH_OK;
         for (int s = 1; s < T.n_seqs && err == TH_OK; ++s)
-            err = P.pn == 16 ? poa_add_sequence<4>(w, P, rseq + u_start[T.unit_off + s], u_len[T.unit_off + s], node_n, edge_n, s_mem[wib], cells, rows, ph)
-                             : poa_add_sequence<3>(w, P, rseq + u_start[T.unit_off + s], u_len[T.unit_off + s], node_n, edge_n, s_mem[wib], cells, rows, ph);
+        {
+            const uint8_t *q = rseq + u_start[T.unit_off + s]; const int ql = u_len[T.unit_off + s];
+            if (!P.affine) err = P.pn == 16 ? poa_add_sequence<4, false>(w, P, q, ql, node_n, edge_n, s_mem[wib], cells, rows, ph)
+                                            : poa_add_sequence<3, false>(w, P, q, ql, node_n, edge_n, s_mem[wib], cells, rows, ph);
+            else err = P.pn == 16 ? poa_add_sequence<4, true>(w, P, q, ql, node_n, edge_n, s_mem[wib], cells, rows, ph)
+                                  : poa_add_sequence<3, true>(w, P, q, ql, node_n, edge_n, s_mem[wib], cells, rows, ph);
+        }
         int cl = 0;
 #ifdef POA_PROFILE
         long long t_c0 = clock64();

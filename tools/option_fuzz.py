@@ -65,10 +65,10 @@ def main():
                 opt("-m", "min_len", rnd.choice([5, 30, 100, 500]))
             if rnd.random() < 0.2:
                 argv.append("-l"); kw["only_longest"] = 1
-            if rnd.random() < 0.25:
-                o1 = rnd.choice([2, 4, 6]); o2 = rnd.choice([0, 12, 24, 40])
+            if rnd.random() < 0.25 or os.environ.get("TH_FUZZ_AFFINE"):
+                o1 = rnd.choice([2, 4, 6]); o2 = 0 if os.environ.get("TH_FUZZ_AFFINE") else rnd.choice([0, 12, 24, 40])
                 argv.extend(["-O", "%d,%d" % (o1, o2)]); kw["gap_open1"] = o1; kw["gap_open2"] = o2
-            if rnd.random() < 0.15:
+            if rnd.random() < (0.6 if os.environ.get("TH_FUZZ_AFFINE") else 0.15):
                 e1 = rnd.choice([1, 2, 3])
                 argv.extend(["-E", "%d,1" % e1]); kw["gap_ext1"] = e1; kw["gap_ext2"] = 1
             if shape == "splint" or rnd.random() < 0.15:
