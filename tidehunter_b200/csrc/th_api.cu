@@ -121,6 +121,7 @@ extern "C" th_gpu_ctx *th_gpu_create(const th_gpu_params *p, int device) {
     // poa_add_sequence); the unused second gap function only has to stay inside the int16 headroom checks
     d.affine = p->gap_open2 == 0;
     if (d.affine) { d.o2 = d.o1 + 1; d.e2 = d.e1; }
+    d.pn = p->simd_lanes16; d.only_unit = p->only_unit;
     CKP(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) CKP(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 4; ++i) CKP(cudaEventCreate(&c->mark[i]));
