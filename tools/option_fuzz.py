@@ -35,10 +35,12 @@ def main():
         open(p5, "w").write(">5\n%s\n" % five)
         open(p3, "w").write(">3\n%s\n" % three)
         for it in range(n_trials):
-            shape = rnd.choice(["short", "short", "r2c2", "long", "indel", "splint"])
+            shape = rnd.choice(["short", "short", "r2c2", "long", "indel", "splint", "single"])
             start = rnd.randrange(0, 10 ** 6)
             if shape == "indel":
                 names, seqs = synth.gen_long_indel_reads(rnd.randrange(6, 16), start=start)
+            elif shape == "single":
+                names, seqs = synth.gen_single_copy(rnd.randrange(8, 24), (five, three), start=start)
             elif shape == "splint":
                 names, seqs = synth.gen_reads("r2c2", rnd.randrange(3, 8), start=start, adapters=(five, three), three_rc=rnd.random() < 0.7)
             else:
@@ -71,9 +73,11 @@ def main():
             if rnd.random() < (0.6 if os.environ.get("TH_FUZZ_AFFINE") else 0.15):
                 e1 = rnd.choice([1, 2, 3])
                 argv.extend(["-E", "%d,1" % e1]); kw["gap_ext1"] = e1; kw["gap_ext2"] = 1
-            if shape == "splint" or rnd.random() < 0.15:
+            if shape in ("splint", "single") or rnd.random() < 0.15:
                 argv.extend(["-5", p5, "-3", p3]); kw["five_seq"] = five; kw["three_seq"] = three
-                if rnd.random() < 0.5:
+                if shape == "single" and rnd.random() < 0.8:
+                    argv.extend(["-s", "-F"]); kw["single_copy"] = 1; kw["only_full_length"] = 1
+                elif rnd.random() < 0.5:
                     argv.append("-F"); kw["only_full_length"] = 1
                 if rnd.random() < 0.3:
                     opt("-a", "ada_match_rat", rnd.choice([0.6, 0.7, 0.9]))
