@@ -99,6 +99,29 @@ extern "C" void th_gpu_default_params(th_gpu_params *p) {
 extern "C" const char *th_gpu_last_error(void) { return g_err.c_str(); }
 extern "C" int th_gpu_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
+// the kernels' view of the options (pure host code: no device is touched, so the mapping is testable without a GPU)
+static DevParams dev_params_from(const th_gpu_params *p) {
+    DevParams d; memset(&d, 0, sizeof(d));
+    d.k = p->k; d.w = p->w; d.hpc = p->hpc; d.min_copy = p->min_copy; d.min_p = (uint32_t)p->min_p; d.max_p = (uint32_t)p->max_p;
+    d.max_div = p->max_div; d.match = p->match; d.mismatch = p->mismatch; d.o1 = p->gap_open1; d.e1 = p->gap_ext1; d.o2 = p->gap_open2; d.e2 = p->gap_ext2;
+    d.o2_raw = p->gap_open2; d.e2_raw = p->gap_ext2;
+    // abPOA's affine mode (gap_open2 == 0, abpoa_align.c:85-88) has its own recurrences (template parameter AFFINE of
+    // poa_add_sequence); the unused second gap function only has to stay inside the int16 headroom checks
+    d.affine = p->gap_open2 == 0;
+    if (d.affine) { d.o2 = d.o1 + 1; d.e2 = d.e1; }
+    d.pn = p->simd_lanes16; d.only_unit = p->only_unit;
+    return d;
+}
+// test hook: the fields of DevParams as int32 in declaration order (max_div as round(max_div * 1e6)); returns the count
+extern "C" int th_gpu_debug_dev_params(const th_gpu_params *p, int32_t cap, int32_t *out) {
+    const DevParams d = dev_params_from(p);
+    const int32_t v[] = {d.k, d.w, d.hpc, d.min_copy, (int32_t)d.min_p, (int32_t)d.max_p, (int32_t)(d.max_div * 1e6 + 0.5), d.match, d.mismatch,
+                         d.o1, d.e1, d.o2, d.e2, d.affine, d.o2_raw, d.e2_raw, d.pn, d.only_unit};
+    const int n = (int)(sizeof(v) / sizeof(v[0]));
+    for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
+    return n;
+}
+
 extern "C" th_gpu_ctx *th_gpu_create(const th_gpu_params *p, int device) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { set_err("no CUDA device available (there is no CPU fallback)"); return nullptr; }
@@ -113,15 +136,7 @@ extern "C" th_gpu_ctx *th_gpu_create(const th_gpu_params *p, int device) {
     cudaDeviceProp prop; CKP(cudaGetDeviceProperties(&prop, device));
     c->n_sm = prop.multiProcessorCount;
     if (const char *e = getenv("TH_GPU_SHARE")) { const double v = atof(e); if (v > 0.05 && v <= 1.0) c->share = v; }
-    DevParams &d = c->dp;
-    d.k = p->k; d.w = p->w; d.hpc = p->hpc; d.min_copy = p->min_copy; d.min_p = (uint32_t)p->min_p; d.max_p = (uint32_t)p->max_p;
-    d.max_div = p->max_div; d.match = p->match; d.mismatch = p->mismatch; d.o1 = p->gap_open1; d.e1 = p->gap_ext1; d.o2 = p->gap_open2; d.e2 = p->gap_ext2;
-    d.o2_raw = p->gap_open2; d.e2_raw = p->gap_ext2;
-    // abPOA's affine mode (gap_open2 == 0, abpoa_align.c:85-88) has its own recurrences (template parameter AFFINE of
-    // poa_add_sequence); the unused second gap function only has to stay inside the int16 headroom checks
-    d.affine = p->gap_open2 == 0;
-    if (d.affine) { d.o2 = d.o1 + 1; d.e2 = d.e1; }
-    d.pn = p->simd_lanes16; d.only_unit = p->only_unit;
+    c->dp = dev_params_from(p);
     CKP(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) CKP(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 4; ++i) CKP(cudaEventCreate(&c->mark[i]));
