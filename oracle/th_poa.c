@@ -274,7 +274,11 @@ static int poa_align(pgraph_t *g, const tho_para_t *p, const uint8_t *query, int
      * :822-827) -- insertions and deletions cannot be adjacent.  The second pair (E2, F2) is held at inf_min, so the
      * convex backtrack (:248-377) degenerates to simd_abpoa_ag_backtrack (:160-246).  Pinned on reference outputs
      * (tests/golden/gapmode_golden.json, tools/option_fuzz.py). */
-    const int affine = p->gap_open2 == 0;
+    const int affine = p->gap_open1 > 0 && p->gap_open2 == 0;
+    /* linear mode (gap_open1 == 0, abpoa_align.c:86): simd_abpoa_lg_first_dp / lg_dp / lg_backtrack (:557-570, :649-736,
+     * :108-158) -- a single matrix H = max(M, max_pre H[pre][j] - e, H[j-1] - e); the oracle only (the GPU path rejects
+     * the option), pinned by tools/option_fuzz.py against the reference */
+    const int linear = p->gap_open1 == 0;
     int beg_index = g->node_id_to_index[0], end_index = g->node_id_to_index[1], gn = end_index - beg_index + 1;
     pdp_t D, *d = &D; memset(d, 0, sizeof(D));
     { /* simd_abpoa_align.c:1610-1621 */
@@ -326,7 +330,8 @@ static int poa_align(pgraph_t *g, const tho_para_t *p, const uint8_t *query, int
         int _end_sn = MIN2(d->dp_end_sn[0] + 1, dp_sn - 1);
         for (j = 0; j < (_end_sn + 1) * pn; ++j) AT(d->H, 0, j) = AT(d->E1, 0, j) = AT(d->E2, 0, j) = inf_min;
         AT(d->H, 0, 0) = 0; AT(d->E1, 0, 0) = -oe1; AT(d->E2, 0, 0) = affine ? inf_min : -oe2; AT(d->F1, 0, 0) = AT(d->F2, 0, 0) = inf_min;
-        for (j = 1; j <= d->dp_end[0]; ++j) {
+        if (linear) for (j = 1; j <= d->dp_end[0]; ++j) { AT(d->H, 0, j) = Wv(d, -e1 * j); AT(d->F1, 0, j) = AT(d->F2, 0, j) = inf_min; }
+        else for (j = 1; j <= d->dp_end[0]; ++j) {
             AT(d->F1, 0, j) = Wv(d, -o1 - e1 * j); AT(d->F2, 0, j) = affine ? inf_min : Wv(d, -o2 - e2 * j);
             AT(d->H, 0, j) = MAX2(AT(d->F1, 0, j), AT(d->F2, 0, j));
         }
@@ -353,6 +358,41 @@ static int poa_align(pgraph_t *g, const tho_para_t *p, const uint8_t *query, int
         int32_t *rH = &AT(d->H, dp_i, beg_sn * pn) - (size_t)beg_sn * pn; /* column-indexed views */
         int32_t *rE1 = &AT(d->E1, dp_i, beg_sn * pn) - (size_t)beg_sn * pn, *rE2 = &AT(d->E2, dp_i, beg_sn * pn) - (size_t)beg_sn * pn;
         int32_t *rF1 = &AT(d->F1, dp_i, beg_sn * pn) - (size_t)beg_sn * pn, *rF2 = &AT(d->F2, dp_i, beg_sn * pn) - (size_t)beg_sn * pn;
+        if (linear) { /* simd_abpoa_lg_dp (:649-736) */
+            for (i = 0; i < pre_n[dp_i]; ++i) {
+                int pre = pre_index[dp_i][i], _beg_sn, _end_sn; int32_t first;
+                int pre_beg_sn = d->dp_beg_sn[pre], pre_end = d->dp_end[pre];
+                if (pre_beg_sn < beg_sn) { _beg_sn = beg_sn; first = stored(d, pre, beg_sn - 1) ? AT(d->H, pre, (beg_sn - 1) * pn + pn - 1) : inf_min; }
+                else { _beg_sn = pre_beg_sn; first = inf_min; }
+                _end_sn = MIN3((pre_end + 1) / pn, end_sn, dp_sn - 1);
+                if (i == 0) {
+                    for (sn = beg_sn; sn < _beg_sn && sn <= end_sn + 1; ++sn) for (l = 0; l < pn; ++l) rH[sn * pn + l] = inf_min;
+                    for (sn = MAX2(_end_sn + 1, beg_sn); sn <= MIN2(end_sn + 1, dp_sn - 1); ++sn) for (l = 0; l < pn; ++l) rH[sn * pn + l] = inf_min;
+                }
+                for (sn = _beg_sn; sn <= _end_sn; ++sn) {
+                    for (l = 0; l < pn; ++l) {
+                        const int32_t mm = Wv(d, (int64_t)(l ? AT(d->H, pre, sn * pn + l - 1) : first) + q[sn * pn + l]);
+                        const int32_t ee = Wv(d, (int64_t)AT(d->H, pre, sn * pn + l) - e1);
+                        const int32_t v = MAX2(mm, ee);
+                        if (i == 0 || v > rH[sn * pn + l]) rH[sn * pn + l] = v;
+                    }
+                    first = AT(d->H, pre, sn * pn + pn - 1);
+                }
+            }
+            {
+                int32_t first = rH[beg_sn * pn]; /* lane 0 of the first vector, the other lanes hold inf_min (:719) */
+                for (sn = beg_sn; sn <= end_sn; ++sn) {
+                    int set_num; int32_t *h = rH + sn * pn;
+                    if (sn < min_pre_beg_sn) { fprintf(stderr, "[tho] sn_i < min_pre_beg_sn\n"); exit(1); }
+                    else if (sn > max_pre_end_sn) set_num = sn == max_pre_end_sn + 1 ? 1 : 0;
+                    else set_num = pn;
+                    if (first > h[0]) h[0] = first;
+                    set_F(d, h, set_num, e1);
+                    first = Wv(d, (int64_t)h[pn - 1] - e1);
+                }
+                for (j = beg_sn * pn; j < (end_sn + 1) * pn; ++j) rE1[j] = rE2[j] = rF1[j] = rF2[j] = inf_min;
+            }
+        } else {
         for (i = 0; i < pre_n[dp_i]; ++i) { /* M and E from every predecessor (:862-915) */
             int pre = pre_index[dp_i][i], _beg_sn, _end_sn; int32_t first;
             int pre_beg_sn = d->dp_beg_sn[pre], pre_end_sn = d->dp_end_sn[pre], pre_end = d->dp_end[pre];
@@ -416,6 +456,7 @@ static int poa_align(pgraph_t *g, const tho_para_t *p, const uint8_t *query, int
                 x2[l] = MAX2(Wv(d, (int64_t)x2[l] - e2), Wv(d, (int64_t)h[l] - oe2));
             }
         }
+        } /* !linear */
         /* row arg-max with the lane-ordered tie-break (:991-1005), then widen out-neighbours (:1007-1015) */
         {
             int32_t a[64], b[64]; int max = inf_min, max_i = -1;
@@ -447,6 +488,30 @@ static int poa_align(pgraph_t *g, const tho_para_t *p, const uint8_t *query, int
     if (best_j < qlen) { pcig_t c = {OP_I, -1, qlen - 1, qlen - j}; PUSH(cig, n_c, m_c, pcig_t, c); }
 #define INBAND(r, c) ((c) >= d->dp_beg[r] && (c) <= d->dp_end[r])
 #define PUSH_I1(qpos) do { if (n_c && cig[n_c - 1].op == OP_I) cig[n_c - 1].len += 1; else { pcig_t c_ = {OP_I, -1, (qpos), 1}; PUSH(cig, n_c, m_c, pcig_t, c_); } } while (0)
+    while (linear && i > 0 && j > 0) { /* simd_abpoa_lg_backtrack (:108-158): match, then deletion, else insertion */
+        int s = mat[m * g->node[id].base + query[j - 1]];
+        int32_t hij = AT(d->H, i, j);
+        hit = 0;
+        for (k = 0; k < pre_n[i]; ++k) {
+            int pre = pre_index[i][k];
+            if (!INBAND(pre, j - 1)) continue;
+            if ((int64_t)AT(d->H, pre, j - 1) + s == (int64_t)hij) {
+                pcig_t c = {OP_M, id, j - 1, 1}; PUSH(cig, n_c, m_c, pcig_t, c);
+                hit = 1; i = pre; --j; id = g->index_to_node_id[i + beg_index];
+                break;
+            }
+        }
+        if (hit == 0) for (k = 0; k < pre_n[i]; ++k) {
+            int pre = pre_index[i][k];
+            if (!INBAND(pre, j)) continue;
+            if ((int64_t)AT(d->H, pre, j) - e1 == (int64_t)hij) {
+                pcig_t c = {OP_D, id, j - 1, 1}; PUSH(cig, n_c, m_c, pcig_t, c);
+                hit = 1; i = pre; id = g->index_to_node_id[i + beg_index];
+                break;
+            }
+        }
+        if (hit == 0) { PUSH_I1(j - 1); --j; }
+    }
     while (i > 0 && j > 0) {
         int s = mat[m * g->node[id].base + query[j - 1]];
         int32_t hij = AT(d->H, i, j);

@@ -131,7 +131,7 @@ def test_oracle_gap_modes_match_reference(oracle):
     import hashlib
     fx, names, seqs = _gapmode()
     assert fx["lines_differing_convex_vs_affine"] > 10
-    for tag, m in fx["modes"].items():
+    for tag, m in list(fx["modes"].items()) + list(fx["oracle_only_modes"].items()):   # + the linear mode (-O 0,...)
         out = oracle.run_batch(names, seqs, oracle.default_para(out_fmt=2, **m["para"]), threads=4)[0]
         assert hashlib.md5(out).hexdigest() == m["md5"], tag
 

@@ -67,10 +67,12 @@ def main():
                 opt("-m", "min_len", rnd.choice([5, 30, 100, 500]))
             if rnd.random() < 0.2:
                 argv.append("-l"); kw["only_longest"] = 1
-            if rnd.random() < 0.25 or os.environ.get("TH_FUZZ_AFFINE"):
+            if os.environ.get("TH_FUZZ_LINEAR") and engine != "gpu":      # abPOA's linear gap mode: the oracle restates it, the GPU path rejects it
+                o2 = rnd.choice([0, 24]); argv.extend(["-O", "0,%d" % o2]); kw["gap_open1"] = 0; kw["gap_open2"] = o2
+            elif rnd.random() < 0.25 or os.environ.get("TH_FUZZ_AFFINE"):
                 o1 = rnd.choice([2, 4, 6]); o2 = 0 if os.environ.get("TH_FUZZ_AFFINE") else rnd.choice([0, 12, 24, 40])
                 argv.extend(["-O", "%d,%d" % (o1, o2)]); kw["gap_open1"] = o1; kw["gap_open2"] = o2
-            if rnd.random() < (0.6 if os.environ.get("TH_FUZZ_AFFINE") else 0.15):
+            if rnd.random() < (0.6 if os.environ.get("TH_FUZZ_AFFINE") or os.environ.get("TH_FUZZ_LINEAR") else 0.15):
                 e1 = rnd.choice([1, 2, 3])
                 argv.extend(["-E", "%d,1" % e1]); kw["gap_ext1"] = e1; kw["gap_ext2"] = 1
             if shape in ("splint", "single") or rnd.random() < 0.15:
