@@ -112,7 +112,9 @@ int main(int argc, char *argv[]) {
         case 'a': p.ada_match_rat = (float)atof(optarg); break;
         case 'o': out_fn = optarg; break;
         case 'm': p.min_len = atoi(optarg); break;
-        case 'r': { double v = atof(optarg); if (v > 0 && v < 1) p.min_frac = v; else p.min_cov = (int)v; break; }
+        case 'r': { double v = strtod(optarg, &s); /* src/main.c:492-495 */
+                    if (v < 1.0) { p.min_frac = v; p.min_cov = 0; } else { p.min_cov = (int)(v + .499); p.min_frac = 0.0; }
+                    break; }
         case 'u': p.gpu.only_unit = 1; break;
         case 'l': p.only_longest = 1; break;
         case 'F': p.only_full_length = 1; break;
@@ -132,6 +134,7 @@ int main(int argc, char *argv[]) {
     if (p.gpu.k > 16) { fprintf(stderr, "[main] k-mer length must be no larger than 16\n"); return 1; }
     if (p.gpu.min_copy < 2) { fprintf(stderr, "[main] min copy number must be >= 2\n"); return 1; }
     if (p.gpu.min_p < 2) { fprintf(stderr, "[main] min period must be >= 2\n"); return 1; }
+    if (p.gpu.max_p > 4294967295LL) { fprintf(stderr, "[main] max period must be <= 4294967295\n"); return 1; } /* MAX_PERIOD, src/tidehunter.h:23 */
     if (p.out_fmt < 1 || p.out_fmt > 4) { fprintf(stderr, "[main] unknown output format %d\n", p.out_fmt); return 1; }
     if (p.gpu.only_unit && p.out_fmt > 2) { fprintf(stderr, "[main] -u only works with -f 1/2\n"); return 1; }
     if (p.only_full_length && !(five_fn && three_fn)) { fprintf(stderr, "[main] -F needs -5 and -3\n"); return 1; }
