@@ -13,6 +13,7 @@
 #include <string.h>
 #include <algorithm>
 #include <vector>
+#include <limits.h>
 #include <string>
 #include "../../include/th_gpu.h"
 #include "th_common.cuh"
@@ -110,6 +111,17 @@ static DevParams dev_params_from(const th_gpu_params *p) {
     d.affine = p->gap_open2 == 0;
     if (d.affine) { d.o2 = d.o1 + 1; d.e2 = d.e1; }
     d.pn = p->simd_lanes16; d.only_unit = p->only_unit;
+    d.lp = d.pn == 16 ? 4 : 3;
+    d.mat_abs = d.match < 0 ? -d.match : d.match; d.mis_abs = d.mismatch < 0 ? -d.mismatch : d.mismatch;
+    d.oe1 = d.o1 + d.e1; d.oe2 = d.o2 + d.e2;
+    { // simd_abpoa_align.c:1613-1614 uses the option values as given, whatever the gap mode
+        const int a = -32768 + d.mis_abs, b = -32768 + d.oe1, c2 = -32768 + d.o2_raw + d.e2_raw;
+        d.inf_min = std::max(std::max(a, b), c2) + 31 * std::max(d.e1, d.e2_raw);
+    }
+    auto pk2 = [](int lo, int hi) { return ((uint32_t)(uint16_t)lo) | ((uint32_t)(uint16_t)hi << 16); };
+    d.INFP = pk2(d.inf_min, d.inf_min); d.NOE1P = pk2(-d.oe1, -d.oe1); d.NOE2P = pk2(-d.oe2, -d.oe2);
+    d.NE1P = pk2(-d.e1, -d.e1); d.NE2P = pk2(-d.e2, -d.e2); d.PE12 = pk2(-d.e1, -d.e2);
+    d.NEGMIS2 = pk2(-d.mis_abs, -d.mis_abs); d.XMM = ((uint32_t)(uint16_t)d.mat_abs ^ (uint32_t)(uint16_t)(-d.mis_abs)) * 0x10001u;
     return d;
 }
 // test hook: the fields of DevParams as int32 in declaration order (max_div as round(max_div * 1e6)); returns the count
@@ -142,6 +154,8 @@ extern "C" th_gpu_ctx *th_gpu_create(const th_gpu_params *p, int device) {
     for (int i = 0; i < 4; ++i) CKP(cudaEventCreate(&c->mark[i]));
     CKP(cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
     CKP(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_CAP * 8));
+    CKP(cudaFuncSetAttribute(poa_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PoaSmem<16>) * POA_WARPS * 2 + sizeof(PoaLaneK) * 16)));
+    CKP(cudaFuncSetAttribute(poa_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PoaSmem<32>) * POA_WARPS + sizeof(PoaLaneK) * 32)));
     memset(&c->stats, 0, sizeof(c->stats));
     return c;
 }
@@ -418,22 +432,22 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         std::vector<int32_t> order(nt);
         for (int i = 0; i < nt; ++i) order[i] = i;
         std::sort(order.begin(), order.end(), [&](int a, int b) { return (int64_t)tasks[a].ncap * tasks[a].n_seqs > (int64_t)tasks[b].ncap * tasks[b].n_seqs; });
-        size_t slab_typ = 0, slab_full = 0;
-        for (const PoaTask &T : tasks) {
-            if (T.n_seqs <= 2) continue;
+        // Slabs: graph arrays + the DP arena of ONE alignment (recycled for every unit): rows <= nodes, three int16 planes
+        // (H, E1, E2) per banded cell.  Typical: the graph holds <= ~2.5 units worth of nodes; the adaptive band is 2w+1
+        // columns around the predecessors' row maxima, rounded to whole vectors (measured mean ~61 columns on 1 kb units)
+        auto slab_need = [](const PoaTask &T, bool full) -> size_t {
             const size_t fixed = poa_fixed_bytes(T.ncap, T.qmax, T.n_seqs);
-            // DP arena of ONE alignment (it is recycled for every unit): rows <= nodes, 5 int16 states per banded cell.
-            // typical: the graph holds <= ~2.5 units worth of nodes; the adaptive band is 2w+1 columns around the
-            // predecessors' row maxima, rounded to whole vectors (measured mean ~61 columns on 1 kb units)
+            const size_t fullb = (size_t)T.ncap * ((size_t)T.qmax + 64) * 6;
+            if (full) return fixed + fullb + 4096;
             const int wband = 10 + T.qmax / 100;
             const size_t rows_typ = std::min<size_t>((size_t)T.ncap, (size_t)T.qmax * 5 / 2 + 64);
             const size_t width_typ = std::min<size_t>((size_t)T.qmax + 64, (size_t)2 * wband + 64);
-            const size_t typ = std::max<size_t>(rows_typ * width_typ * 10, (size_t)1 << 20);
-            const size_t full = (size_t)T.ncap * ((size_t)T.qmax + 64) * 10;
-            slab_typ = std::max(slab_typ, fixed + std::min(typ, full) + 4096);
-            slab_full = std::max(slab_full, fixed + full + 4096);
-        }
-        slab_typ = (slab_typ + 255) & ~(size_t)255; slab_full = (slab_full + 255) & ~(size_t)255; // slabs hold 32-bit and 16x2 accesses
+            const size_t typ = std::max<size_t>(rows_typ * width_typ * 6, (size_t)1 << 20);
+            return fixed + std::min(typ, fullb) + 4096;
+        };
+        size_t slab_typ = 0;
+        for (const PoaTask &T : tasks) if (T.n_seqs > 2) slab_typ = std::max(slab_typ, slab_need(T, false));
+        slab_typ = (slab_typ + 255) & ~(size_t)255; // slabs hold 16-byte accesses
         if (c->d_tasks.ensure(sizeof(PoaTask) * (size_t)nt) || c->d_torder.ensure(4 * (size_t)nt) || c->d_ustart.ensure(4 * ustart.size() + 64) ||
             c->d_ulen.ensure(4 * ulen.size() + 64) || c->d_consb.ensure((size_t)cons_total + 64) || c->d_consc.ensure(4 * (size_t)cons_total + 64) ||
             c->d_consl.ensure(4 * (size_t)nt) || c->d_tstatus.ensure(4 * (size_t)nt)) return -1;
@@ -447,38 +461,57 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         if (slab_typ == 0) slab_typ = 1 << 20;
         size_t budget = (size_t)((double)(free_b + c->d_slabs.cap) * 0.6);
         budget = std::min(budget, total_b / 5); // several contexts share the device (the host layer runs four): none may take it all
-        int nwarps = (int)std::min<size_t>((size_t)(c->n_sm * POA_MIN_BLOCKS * POA_WARPS * c->share), std::max<size_t>(1, budget / slab_typ));
-        nwarps = std::min(nwarps, std::max(nt, 1));
-        int grid = (nwarps + POA_WARPS - 1) / POA_WARPS;
+        // first pass: 16-lane groups, two tasks per warp
+        constexpr int GPB16 = POA_WARPS * 2, GPB32 = POA_WARPS;
+        int ngroups = (int)std::min<size_t>((size_t)(c->n_sm * POA_MIN_BLOCKS16 * GPB16 * c->share), std::max<size_t>(1, budget / slab_typ));
+        ngroups = std::min(ngroups, std::max(nt, 1));
+        int grid = (ngroups + GPB16 - 1) / GPB16;
         // several contexts of one process (the host layer's lanes) size their slabs from the same free-memory reading:
-        // if the allocation loses that race, run with fewer resident warps instead of failing the chunk
-        while (c->d_slabs.ensure((size_t)grid * POA_WARPS * slab_typ)) {
+        // if the allocation loses that race, run with fewer resident groups instead of failing the chunk
+        while (c->d_slabs.ensure((size_t)grid * GPB16 * slab_typ)) {
             cudaGetLastError();
-            if (grid <= 8) return -1;
+            if (grid <= 4) return -1;
             grid = (grid + 1) / 2;
         }
-        poa_kernel<<<grid, POA_WARPS * 32, 0, st>>>(P, nt, c->d_tasks.as<PoaTask>(), c->d_torder.as<int32_t>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(),
+        poa_kernel<16><<<grid, POA_WARPS * 32, sizeof(PoaSmem<16>) * GPB16 + sizeof(PoaLaneK) * 16, st>>>(P, nt, c->d_tasks.as<PoaTask>(), c->d_torder.as<int32_t>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(),
                                                  c->d_bseq.as<uint8_t>(), c->d_slabs.as<uint8_t>(), slab_typ, cnt32 + 1, c->d_consb.as<uint8_t>(), c->d_consc.as<int32_t>(),
-                                                 c->d_consl.as<int32_t>(), c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2, cnt64 + 16);
+                                                 c->d_consl.as<int32_t>(), c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2, cnt64 + 16, grid * GPB16);
         S.n_launches++;
         CK(cudaMemcpyAsync(c->r_task_status.data(), c->d_tstatus.p, 4 * (size_t)nt, cudaMemcpyDeviceToHost, st));
         CK(th_wait(c));
-        // retry tasks whose DP arena overflowed, with full-width slabs
+        // second pass, one task per warp with full-width slabs: tasks whose DP arena overflowed the typical slab, and rows
+        // with more than 16 predecessors.  The slab is sized for the retried tasks only; when memory is short the pass
+        // runs with fewer resident warps, and if even one slab cannot be had the tasks keep their error status (the host
+        // layer reports and drops those records) -- the chunk goes on.
         std::vector<int32_t> retry;
-        for (int t = 0; t < nt; ++t) if (c->r_task_status[t] == TH_ERR_ARENA) retry.push_back(t);
+        for (int t = 0; t < nt; ++t) if (c->r_task_status[t] == TH_ERR_ARENA || c->r_task_status[t] == TH_ERR_CAP) retry.push_back(t);
         if (!retry.empty()) {
-            if (getenv("TH_GPU_DEBUG")) fprintf(stderr, "[th_gpu] %d of %d POA tasks overflowed their %zu-byte slab and are retried with %zu-byte slabs\n", (int)retry.size(), nt, slab_typ, slab_full);
+            size_t slab_full = 0;
+            for (int t : retry) slab_full = std::max(slab_full, slab_need(tasks[t], true));
+            slab_full = (slab_full + 255) & ~(size_t)255;
+            if (getenv("TH_GPU_DEBUG")) fprintf(stderr, "[th_gpu] %d of %d POA tasks are retried with %zu-byte slabs (first pass: %zu)\n", (int)retry.size(), nt, slab_full, slab_typ);
             CK(cudaMemGetInfo(&free_b, &total_b));
             budget = (size_t)((double)(free_b + c->d_slabs.cap) * 0.8);
-            int rw = (int)std::min<size_t>(retry.size(), std::max<size_t>(1, budget / slab_full));
-            int rgrid = (rw + POA_WARPS - 1) / POA_WARPS;
-            if (c->d_slabs.ensure((size_t)rgrid * POA_WARPS * slab_full)) return -1;
-            CK(cudaMemcpyAsync(c->d_torder.p, retry.data(), 4 * retry.size(), cudaMemcpyHostToDevice, st));
-            CK(cudaMemsetAsync(cnt32 + 1, 0, 4, st));
-            poa_kernel<<<rgrid, POA_WARPS * 32, 0, st>>>(P, (int)retry.size(), c->d_tasks.as<PoaTask>(), c->d_torder.as<int32_t>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(),
-                                                      c->d_bseq.as<uint8_t>(), c->d_slabs.as<uint8_t>(), slab_full, cnt32 + 1, c->d_consb.as<uint8_t>(), c->d_consc.as<int32_t>(),
-                                                      c->d_consl.as<int32_t>(), c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2, cnt64 + 16);
-            S.n_launches++;
+            int rg = (int)std::min<size_t>(retry.size(), std::max<size_t>(1, budget / slab_full));
+            rg = std::min(rg, (int)(c->n_sm * POA_MIN_BLOCKS32 * GPB32));
+            bool have = false;
+            while (true) {
+                const int rgrid = (rg + GPB32 - 1) / GPB32;
+                // fewer groups than a block holds: the extra groups of the last block find no task and never touch their slab
+                if (!c->d_slabs.ensure((size_t)std::min(rg, rgrid * GPB32) * slab_full)) { have = true; break; }
+                cudaGetLastError();
+                if (rg <= 1) break;
+                rg = (rg + 1) / 2;
+            }
+            if (have) {
+                const int rgrid = (rg + GPB32 - 1) / GPB32;
+                CK(cudaMemcpyAsync(c->d_torder.p, retry.data(), 4 * retry.size(), cudaMemcpyHostToDevice, st));
+                CK(cudaMemsetAsync(cnt32 + 1, 0, 4, st));
+                poa_kernel<32><<<rgrid, POA_WARPS * 32, sizeof(PoaSmem<32>) * GPB32 + sizeof(PoaLaneK) * 32, st>>>(P, std::min((int)retry.size(), INT_MAX), c->d_tasks.as<PoaTask>(), c->d_torder.as<int32_t>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(),
+                                                          c->d_bseq.as<uint8_t>(), c->d_slabs.as<uint8_t>(), slab_full, cnt32 + 1, c->d_consb.as<uint8_t>(), c->d_consc.as<int32_t>(),
+                                                          c->d_consl.as<int32_t>(), c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2, cnt64 + 16, rg);
+                S.n_launches++;
+            } else set_err("POA retry: no memory for one %zu-byte slab; %d tasks keep their error status", slab_full, (int)retry.size());
         }
         CK(cudaEventRecord(c->ev[ei++], st)); // 9
         // ---- post-consensus ksw items ----

@@ -19,6 +19,10 @@ struct DevParams {
     int o2_raw, e2_raw;                  // the caller's values: abPOA derives inf_min and the int16 range check from them in every gap mode
     int pn;          // int16 lanes of the emulated abPOA vector (16)
     int only_unit;
+    // derived once on the host (dev_params_from): the POA kernel reads them straight from the constant bank
+    int lp;                              // log2(pn)
+    int mat_abs, mis_abs, oe1, oe2, inf_min; // |match|, |mismatch|, o + e, abPOA's int16 "minus infinity" (simd_abpoa_align.c:1613-1614)
+    uint32_t INFP, NOE1P, NOE2P, NE1P, NE2P, PE12, NEGMIS2, XMM; // the same as s16x2 pairs: (inf, inf), (-oe1, -oe1), ..., (-e1, -e2), (-mis, -mis), mat ^ -mis
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

@@ -1,30 +1,39 @@
-// th_poa.cuh -- adaptive-banded partial-order alignment + heaviest-column consensus, one warp per task.
+// th_poa.cuh -- adaptive-banded partial-order alignment + heaviest-column consensus on lane groups.
 //
 // Replaces (reference, /root/reference): src/abpoa_cons.c:30-120 (abpoa_gen_cons) and the abPOA calls
 // below it: abPOA/src/abpoa_align.c:293-411 (abpoa_msa / abpoa_poa), abPOA/src/simd_abpoa_align.c
-// (convex-gap banded DP :835-958, row arg-max :991-1015, best cell :976-989, backtrack :248-377),
+// (convex-gap banded DP :835-958, affine :739-833, row arg-max :991-1015, best cell :976-989, backtrack :248-377),
 // abPOA/src/abpoa_graph.c (:197-238 max_remain, :1020-1124 node/edge/aligned, :1218-1288 add alignment,
 // :279-359 + :604-648 heaviest-column consensus).
 //
+// Mapping.  A task (one consensus) is worked on by a GROUP of LPT lanes: LPT = 16 puts two tasks in one warp, LPT = 32
+// one.  A lane owns four adjacent columns of a row chunk (two s16x2 registers), so a chunk is 4 LPT columns: the usual
+// band of a 1 kb unit (48-80 columns) is one chunk of a 16-lane group.  The kernel is bound by instructions issued per
+// row (band bookkeeping, address arithmetic, scan rounds), not by cell throughput: with two groups in a warp every
+// one of those instructions serves two rows.  Both groups of a warp run the same instruction stream ("lockstep"):
+// every loop that contains a warp-synchronous operation runs while ANY group needs it, a group that has nothing to do
+// executes it with its loads and stores predicated off, and the cross-lane operations are full-warp shuffles of
+// width LPT.  Groups fetch their tasks independently, so a finished group starts its next task while its neighbour
+// is still in the middle of one; only the phases of one alignment (setup, rows, backtrack, merge) are shared.
+//
 // What is kept bit-exact and why it is enough:
-//  * DP values are 16-bit wrapping integers exactly as the reference's AVX2 int16 path; two adjacent
-//    columns are packed in one register (s16x2) and updated with DPX/video SIMD ops.
-//  * Band edges are rounded to whole emulated SIMD vectors of `pn` lanes (pn = 16), and the row
-//    arg-max that steers the adaptive band uses the reference's lane-ordered tie-break.
-//  * Rows are processed in a topological order that keeps aligned-node groups contiguous; it is NOT
-//    the reference's BFS order.  The alignment does not depend on which topological order is used:
-//    a row's band and values depend only on its predecessors' rows, the backtrack walks in_id order,
-//    and max_remain is a function of graph structure only.  The order is maintained incrementally
-//    (new nodes are merged in right before the next existing node of the alignment path), which
-//    replaces the per-sequence BFS (abpoa_graph.c:150-195) by a parallel merge.
-//  * read-id bitsets are not stored: popcount(read_ids) of a node equals the sum of its out-edge
-//    weights, because every sequence adds weight 1 to exactly one out-edge of each node it visits.
+//  * DP values are 16-bit wrapping integers exactly as the reference's AVX2 int16 path (DPX / video SIMD ops).
+//  * Band edges are rounded to whole emulated SIMD vectors of `pn` lanes, and the row arg-max that steers the
+//    adaptive band uses the reference's lane-ordered tie-break.
+//  * Rows are processed in a topological order that keeps aligned-node groups contiguous; it is NOT the reference's
+//    BFS order.  The alignment does not depend on which topological order is used: a row's band and values depend
+//    only on its predecessors' rows, the backtrack walks in_id order, and max_remain is a function of graph
+//    structure only.  The order is maintained incrementally (new nodes are merged in right before the next existing
+//    node of the alignment path), which replaces the per-sequence BFS (abpoa_graph.c:150-195) by a parallel merge.
+//  * read-id bitsets are not stored: popcount(read_ids) of a node equals the sum of its out-edge weights.
 //  * The consensus DFS (msa rank) and column vote are literal.
 //
-// HBM layout (per warp "slab"): graph arrays (SoA, int32), edge pool with per-node in/out linked lists
-// in insertion order, two order buffers, per-row band metadata, room for the query bit-planes of long queries
-// (short ones keep them in shared memory), cigar,
-// and the DP arena holding, per row, H|E1|E2|F1|F2 as int16 over the row's band only.
+// DP storage: 6 bytes per banded cell.  A row of W columns owns three int16 planes H | E1 | E2 (what successor rows and
+// the backtrack's match / deletion tests read).  F1 / F2 are NOT stored: the backtrack only needs them at the few
+// cells where an insertion is taken, and recomputes that row chunk from the predecessors' planes (same code as the
+// forward pass).  The last POA_NRING rows (when they fit one chunk) also stay in shared memory, where the next rows
+// read them; the backtrack stages the metadata of a 64-row window plus a 16-column H segment around each row's
+// arg-max (where the path crosses the row) in shared memory, so a match step touches no global memory.
 #pragma once
 #include "th_common.cuh"
 
@@ -37,23 +46,24 @@ struct PoaTask {
 };
 
 #define POA_WARPS 4
-#define POA_MAXPRE 32
+#define POA_MAXPRE 32     // most predecessors a row may have in the 32-lane kernel (16 in the 16-lane kernel): more -> TH_ERR_CAP
 #define POA_NEGP 0x80008000u
-#define POA_RING 64       // rows of metadata kept in shared memory per warp (power of two)
+#define POA_NRING 4       // rows kept in shared memory for their successors (power of two)
+#define POA_WIN 64        // rows of metadata kept in shared memory (power of two)
 
 // Row descriptor (static per alignment, by row index):  x = first predecessor row (-1: none),
 //   y = np | base << 10 | node << 13,  z = qlen - max_remain term of the band centre,
 //   w = second predecessor row (np == 2) or offset into plist (np > 2).
-// Row metadata (written when the row is computed):  x = arena offset, y = first column, z = last column,
+// Row metadata (written when the row is computed):  x = arena offset (int16 units), y = first column, z = last column,
 //   w = max_i + 1 of the row (what the reference scatters into max_pos_left/right of the successors).
 struct PoaWs {
     int4 *rdesc, *rmeta;
     int32_t *out_head, *out_tail, *in_head, *in_tail, *aln_n, *aln, *n2i, *ri, *hs;
     int32_t *e_to, *e_from, *e_w, *e_no, *e_ni, *plist;
     int32_t *ord, *ord2, *ev_anchor, *ev_node, *hi_idx;
-    int16_t *qp; uint32_t *cigar; int32_t *cigq; uint8_t *base;
+    uint32_t *q8g; uint32_t *cigar; int32_t *cigq; uint8_t *base;
     int16_t *arena; uint32_t arena_cap;
-    int32_t qp_stride, ncap;
+    int32_t ncap;
 };
 
 __host__ __device__ inline size_t poa_fixed_bytes(int ncap, int qmax, int nseq) {
@@ -64,7 +74,7 @@ __host__ __device__ inline size_t poa_fixed_bytes(int ncap, int qmax, int nseq) 
     b += ecap * 4 * 6;                                 // 5 edge arrays + plist
     b += (size_t)ncap * 4 * 3;                         // ord, ord2, hi_idx
     b += (size_t)(qmax + 2) * 4 * 2;                   // events
-    b += (size_t)5 * (qmax + 1 + 128) * 2 + 8;         // profile
+    b += (size_t)(qmax + 512) + 8;                     // query bytes (when they do not fit shared memory)
     b += (size_t)(qmax + ncap + 8) * 4 * 2;            // cigar, cigq
     b += (size_t)ncap + 64;                            // base
     return (b + 4095) & ~(size_t)4095;
@@ -80,21 +90,21 @@ __device__ inline void poa_carve(PoaWs &w, uint8_t *slab, size_t slab_bytes, int
     w.e_to = p; p += ecap; w.e_from = p; p += ecap; w.e_w = p; p += ecap; w.e_no = p; p += ecap; w.e_ni = p; p += ecap; w.plist = p; p += ecap;
     w.ord = p; p += ncap; w.ord2 = p; p += ncap; w.hi_idx = p; p += ncap;
     w.ev_anchor = p; p += qmax + 2; w.ev_node = p; p += qmax + 2;
-    w.qp_stride = (qmax + 1 + 128) & ~1;
-    w.qp = reinterpret_cast<int16_t *>(p); p += ((size_t)5 * w.qp_stride * 2 + 3) / 4;
+    w.q8g = reinterpret_cast<uint32_t *>(p); p += (qmax + 512 + 3) / 4 + 1;
     w.cigar = reinterpret_cast<uint32_t *>(p); p += qmax + ncap + 8;
     w.cigq = p; p += qmax + ncap + 8;
     w.base = reinterpret_cast<uint8_t *>(p);
     size_t fixed = poa_fixed_bytes(ncap, qmax, nseq);
     w.arena = reinterpret_cast<int16_t *>(slab + fixed);
     size_t ab = slab_bytes > fixed ? slab_bytes - fixed : 0;
-    size_t ne = ab / 2; if (ne > 0xfffffff0ull) ne = 0xfffffff0ull;
+    size_t ne = ab / 2; if (ne > 0x7ffffff0ull) ne = 0x7ffffff0ull; // row offsets are kept in an int; the sign bit marks "in the shared-memory ring"
     w.arena_cap = (uint32_t)ne;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int s16_at(uint32_t word, int odd) { return odd ? hi16(word) : lo16(word); }
 
-// graph edit used for the final edge into the sink (lane 0 only)
+// graph edit used for the final edge into the sink (one lane of the group)
 __device__ inline void g_add_edge(PoaWs &w, int &edge_n, int from, int to, bool check) {
     if (check) {
         for (int e = w.out_head[from]; e >= 0; e = w.e_no[e])
@@ -108,77 +118,221 @@ __device__ inline void g_add_edge(PoaWs &w, int &edge_n, int from, int to, bool 
     w.in_tail[to] = e;
 }
 
-// DP arena layout.  A row of W columns (W a multiple of pn) that starts at int16 offset `off` owns 5 W int16:
-//   W/2 records of 16 bytes, record q = columns (beg + 2q, beg + 2q + 1) as four s16x2 words {H, E1, E2, F1},
-//   followed by W/2 words of F2 pairs.  One 16-byte access moves everything the next rows need from a column
-//   pair, and a backtrack step touches one or two sectors per row instead of five.
-__device__ __forceinline__ int s16_at(uint32_t word, int odd) { return odd ? hi16(word) : lo16(word); }
+// ---- lane groups --------------------------------------------------------------------------------------------------
+// Every member function is a warp-synchronous operation over ALL 32 lanes (full mask); the group only sees its own part
+// of the result.  They must be called from code all lanes of the warp execute together.
+template <int LPT> struct PoaG {
+    int gl, gofs;
+    __device__ __forceinline__ PoaG() { const int l = threadIdx.x & 31; gl = l & (LPT - 1); gofs = l & ~(LPT - 1); }
+    __device__ __forceinline__ unsigned ballot(bool p) const {
+        const unsigned b = __ballot_sync(TH_FULL, p);
+        if (LPT == 32) return b;
+        return (b >> gofs) & 0xffffu;
+    }
+    __device__ __forceinline__ bool any(bool p) const { return ballot(p) != 0; }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(TH_FULL, v, src, LPT); }
+    template <class T> __device__ __forceinline__ T shfl_up(T v, int d) const { return __shfl_up_sync(TH_FULL, v, d, LPT); }
+    __device__ __forceinline__ int rmax(int v) const {
+        if (LPT == 32) return __reduce_max_sync(TH_FULL, v);
+        const int a = __reduce_max_sync(TH_FULL, gofs ? INT_MIN : v), b = __reduce_max_sync(TH_FULL, gofs ? v : INT_MIN);
+        return gofs ? b : a;
+    }
+};
 
-#ifndef POA_SETUP_U
-#define POA_SETUP_U 2      // batches of 32 nodes whose edge-list walks are interleaved when the row descriptors are built
-#endif
-#define POA_PEQ_W 40     // words per query bit-plane kept in shared memory (queries up to ~1200 columns; longer ones use the slab)
-struct PoaSmem { int4 desc[POA_RING]; int4 meta[POA_RING]; int4 pre[POA_MAXPRE]; uint4 last[32]; uint32_t peq[5 * POA_PEQ_W]; };
+template <int LPT> struct PoaSmem {
+    static constexpr int CW = LPT * 4;               // columns per chunk
+    static constexpr int RINGW = 3 * CW / 2;         // words per ring slot (three planes of CW int16)
+    static constexpr int Q8W = LPT == 16 ? 320 : 1536; // words of query bytes kept in shared memory
+    int4 meta[POA_WIN];
+    int4 desc[POA_WIN];                               // backtrack window only
+    union { uint32_t ring[POA_NRING * RINGW]; uint4 seg[POA_WIN * 2]; } u; // forward: recent rows; backtrack: 16 H columns per window row
+    int4 pre[POA_MAXPRE];                             // metadata of predecessors 1.. of the row being computed
+    uint32_t q8[Q8W];
+    int plist_n;
+    PoaWs ws;
+};
 
-// contributions of one predecessor row to columns (j, j+1) of the current row: M from H[p][j-1], H[p][j];
-// E1, E2 from the same columns.  pm = the predecessor's row metadata, recs = its records ({H, E1, E2, F1} per column
-// pair).  Cells outside the predecessor's band count as inf_min (simd_abpoa_align.c:860-905).
-// The row this warp computed last (when it fits one 64-column chunk) is still in shared memory in the same record
-// layout, so `recs` is a generic pointer to either place and one code path serves both.
-__device__ __forceinline__ const uint4 *poa_row_recs(const uint32_t *A32, const uint4 *last, uint32_t off, uint32_t last_off) {
-    return off == last_off ? last : reinterpret_cast<const uint4 *>(A32) + (off >> 3); // row offsets are multiples of 40 int16
+// Per-lane constants of the row chunk: for the lane's registers r = 0, 1 (columns c = 4 gl + 2 r, c + 1 of the chunk)
+//   C1 = (e1 c - oe1, e1 (c + 1) - oe1), C2 likewise: what turns H[j - 1] into the scan's G;  NJ1 / NJ2 = (-e c, -e (c + 1)): G back to F;
+//   KLO / KHI: the tie-break bits of the row arg-max key for the even / odd column.
+// They depend on the lane and the options only; a table in shared memory is filled once per block and read where needed
+// (a volatile load: held in registers across the row loop they would push its other state out).
+struct PoaLaneK { uint32_t C1[2], C2[2], NJ1[2], NJ2[2], KLO[2], KHI[2]; };
+__device__ __forceinline__ uint4 lds128v(uint32_t saddr) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr)); return v;
 }
-__device__ __forceinline__ void poa_pred(const uint4 *recs, const int4 pm, const int j, const uint32_t INFP,
-                                         uint32_t &Mx, uint32_t &E1x, uint32_t &E2x) {
-    const int pb = pm.y, l2 = (j - pb) >> 1; // band starts are even, so is j
-    uint32_t Xh = INFP, prev = INFP;
-    if (j >= pb && j <= pm.z) { const uint4 r = recs[l2]; Xh = r.x; E1x = __vmaxs2(E1x, r.y); E2x = __vmaxs2(E2x, r.z); }
-    if (j > pb && j - 1 <= pm.z) prev = recs[l2 - 1].x; // H of the pair to the left; only its upper half (column j-1) is used
-    Mx = __vmaxs2(Mx, __funnelshift_r(prev, Xh, 16));
+__device__ inline void poa_fill_lane_k(PoaLaneK *tab, int lpt, const DevParams &P) {
+    const int lam_bits = P.pn - 1;
+    for (int gl = threadIdx.x; gl < lpt; gl += blockDim.x) {
+        PoaLaneK k;
+        for (int r = 0; r < 2; ++r) {
+            const int c = 4 * gl + 2 * r;
+            k.C1[r] = pk(P.e1 * c - P.oe1, P.e1 * (c + 1) - P.oe1); k.C2[r] = pk(P.e2 * c - P.oe2, P.e2 * (c + 1) - P.oe2);
+            k.NJ1[r] = pk(-P.e1 * c, -P.e1 * (c + 1)); k.NJ2[r] = pk(-P.e2 * c, -P.e2 * (c + 1));
+            k.KLO[r] = ((uint32_t)(lam_bits - (c & lam_bits)) << 12) | 0xfffu; k.KHI[r] = ((uint32_t)(lam_bits - ((c + 1) & lam_bits)) << 12) | 0xfffu;
+        }
+        tab[gl] = k;
+    }
 }
 
-// one warp aligns sequence `query` to the graph and merges it in.  Returns an error code.
+// One predecessor row's contribution to the four columns (j0 .. j0 + 3) of a lane: m = H[p][j - 1] (the diagonal), x1 / x2 =
+// E1 / E2[p][j].  pm.x = source of the row's planes (sign bit: slot of the shared-memory ring, else arena offset in int16
+// units), pm.y / pm.z = its first / last column.  Cells outside the predecessor's band count as inf_min
+// (simd_abpoa_align.c:860-905).  Band edges are multiples of 8 columns, j0 of 4: a lane's columns are all inside or all outside.
+template <int LPT, bool AFFINE>
+__device__ __forceinline__ void poa_pred(const uint32_t *A32, const uint32_t *ring, const int4 pm, const bool act, const int j0, const uint32_t INFP,
+                                         uint32_t (&m)[2], uint32_t (&x1)[2], uint32_t (&x2)[2]) {
+    const int pb = pm.y, ps = (pm.z - pb + 1) >> 1, wi = (j0 - pb) >> 1;
+    // a plane holds ps words; wi and ps are even.  Columns j0 .. j0 + 3 inside the band <=> 0 <= wi < ps;  column j0 - 1 inside <=> 2 <= wi <= ps
+    const bool in0 = act && (unsigned)wi < (unsigned)ps, in1 = act && (unsigned)(wi - 2) < (unsigned)ps;
+    uint2 h = make_uint2(INFP, INFP), a = h, b = h; uint32_t left = INFP;
+    if (pm.x < 0) { // one of the last POA_NRING rows: shared memory
+        const uint32_t *Pp = ring + (pm.x & (POA_NRING - 1)) * PoaSmem<LPT>::RINGW + wi;
+        if (in0) { h = *reinterpret_cast<const uint2 *>(Pp); a = *reinterpret_cast<const uint2 *>(Pp + ps); if (!AFFINE) b = *reinterpret_cast<const uint2 *>(Pp + 2 * ps); }
+        if (in1) left = Pp[-1]; // upper half = H[p][j0 - 1]
+    } else {
+        const uint32_t *Pp = A32 + ((uint32_t)pm.x >> 1) + wi;
+        if (in0) { h = *reinterpret_cast<const uint2 *>(Pp); a = *reinterpret_cast<const uint2 *>(Pp + ps); if (!AFFINE) b = *reinterpret_cast<const uint2 *>(Pp + 2 * ps); }
+        if (in1) left = Pp[-1];
+    }
+    m[0] = __funnelshift_r(left, h.x, 16); m[1] = __funnelshift_r(h.x, h.y, 16);
+    x1[0] = a.x; x1[1] = a.y; x2[0] = b.x; x2[1] = b.y;
+}
+
+// One chunk (4 LPT columns) of one row: M / E from the predecessors, scores, the F scans, H and the E handed on.
+// `act` is false for a group that only keeps the warp company: it loads nothing, and what it computes is discarded.
+// pm0 / pre[1..np-1]: predecessor metadata with x = source of the row's planes (sign bit: slot of the shared-memory ring,
+// else arena offset in int16 units), y / z = its first / last column.  Cells outside a predecessor's band count as
+// inf_min (simd_abpoa_align.c:860-905).  j0 = first column of this lane.  ch0: first chunk of the row.
 // AFFINE: abPOA's affine gap mode (gap_open2 == 0, simd_abpoa_ag_dp, simd_abpoa_align.c:739-833).  It is not the convex
 // recurrence minus one gap function: an insertion opens from M only (F is built from the row's diagonal values before E
 // is folded in), and the E handed to the next row is inf_min wherever F strictly won the cell (SIMDSetIfEqual), so
-// insertions and deletions are never adjacent.  The second pair (E2, F2) is held at inf_min, which makes the convex
-// backtrack below behave exactly as simd_abpoa_ag_backtrack (:160-246).
-template <int LP, bool AFFINE> // LP = log2 of the emulated vector width pn (4: AVX2 int16, the reference build; 3: SSE)
-__device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *query, int qlen, int &node_n, int &edge_n,
-                                PoaSmem &sm, unsigned long long &cells, unsigned long long &rows, long long *ph) {
-#ifdef POA_PROFILE   // per-phase warp-cycle counters (tools/profile_step.py); cost ~16 registers, off in the product build
+// insertions and deletions are never adjacent.  The second pair (E2, F2) is held at inf_min.
+template <int LPT, bool AFFINE>
+__device__ __forceinline__ void poa_chunk(const PoaG<LPT> &g, const DevParams &P, const uint32_t lk, const uint32_t *A32, const uint32_t *ring, const int4 *pre,
+                                          const int4 pm0, const int np, const bool act, const int j0, const bool ch0,
+                                          const uint32_t carryH, const uint32_t carryF, const uint32_t basew, const uint32_t *q8,
+                                          uint32_t (&Hn)[2], uint32_t (&E1o)[2], uint32_t (&E2o)[2], uint32_t (&Fa)[2], uint32_t (&Fb)[2], uint32_t (&Hf)[2]) {
+    const uint32_t INFP = P.INFP;
+    uint32_t Mx[2], E1x[2], E2x[2];
+    poa_pred<LPT, AFFINE>(A32, ring, pm0, act, j0, INFP, Mx, E1x, E2x);
+#pragma unroll 1
+    for (int p = 1; p < np; ++p) { // no warp-synchronous operation in here: groups may run different trip counts
+        uint32_t m[2], x1[2], x2[2];
+        poa_pred<LPT, AFFINE>(A32, ring, pre[p], act, j0, INFP, m, x1, x2);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) { Mx[r] = __vmaxs2(Mx[r], m[r]); E1x[r] = __vmaxs2(E1x[r], x1[r]); if (!AFFINE) E2x[r] = __vmaxs2(E2x[r], x2[r]); }
+    }
+    // scores of the lane's four columns against the node base: query bytes q8[j] = query[j-1] (0..3) or 0x40 where the
+    // score is 0 (column 0, N in the query, columns past the query end); basew = the node base in every byte, 0x20 for an
+    // N node (scores 0 against everything).  x = q ^ base: 0 = match, 1..3 = mismatch, >= 0x20 = no score.
+    uint32_t S[2];
+    {
+        const uint32_t x = (act ? q8[j0 >> 2] : 0x40404040u) ^ basew;
+        const uint32_t hb = 0x80808080u - x, vb = x + 0x60606060u; // sign bit of each byte: match / no score (bytes are <= 0x63: no borrows or carries)
+        const uint32_t m0 = prmt(hb, 0, 0x9988), m1 = prmt(hb, 0, 0xbbaa), v0 = prmt(vb, 0, 0x9988), v1 = prmt(vb, 0, 0xbbaa);
+        S[0] = (P.NEGMIS2 ^ (m0 & P.XMM)) & ~v0; S[1] = (P.NEGMIS2 ^ (m1 & P.XMM)) & ~v1;
+    }
+    uint32_t Ms[2], Hme[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        Ms[r] = __vadd2(Mx[r], S[r]);
+        Hme[r] = AFFINE ? __vmaxs2(Ms[r], E1x[r]) : __vimax3_s16x2(Ms[r], E1x[r], E2x[r]);
+        Hf[r] = AFFINE ? Ms[r] : Hme[r];               // what an insertion may open from
+    }
+    // F1[j] = max_k<=j (A1[k] - e1 (j-k)) with A1[k] = Hf[k-1] - oe1 is evaluated as a prefix MAX of G[k] = A1[k] + e1 (k - j0)
+    // over the chunk (no subtraction inside the scan, hence no underflow), F = G - e1 (j - j0).  The int16 range check of
+    // the alignment leaves 4 LPT max(e1, e2) of headroom for G.  The row's first cell feeds its own F (:924).
+    uint32_t hp = g.shfl_up(Hf[1], 1);
+    if (g.gl == 0) hp = ch0 ? (Ms[0] << 16) : carryH;
+    const uint32_t Hsh0 = __funnelshift_r(hp, Hf[0], 16), Hsh1 = __funnelshift_r(Hf[0], Hf[1], 16);
+    uint32_t G1[2], G2[2];
+    { const uint4 c = lds128v(lk);                        // C1[0], C1[1], C2[0], C2[1]
+      G1[0] = __vadd2(Hsh0, c.x); G1[1] = __vadd2(Hsh1, c.y); G2[0] = __vadd2(Hsh0, c.z); G2[1] = __vadd2(Hsh1, c.w); }
+    if (!ch0 && g.gl == 0) { G1[0] = __vmaxs2(G1[0], (carryF & 0xffffu) | 0x80000000u); G2[0] = __vmaxs2(G2[0], (carryF >> 16) | 0x80000000u); }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) { // the odd column also sees the even one
+        G1[r] = __vmaxs2(G1[r], (G1[r] << 16) | 0x8000u);
+        if (!AFFINE) G2[r] = __vmaxs2(G2[r], (G2[r] << 16) | 0x8000u);
+    }
+    G1[1] = __vmaxs2(G1[1], prmt(G1[0], 0, 0x3232));
+    if (!AFFINE) G2[1] = __vmaxs2(G2[1], prmt(G2[0], 0, 0x3232));
+    uint32_t TT = prmt(G1[1], G2[1], 0x7632); // lo = G1 at this lane's last column, hi = G2
+#pragma unroll
+    for (int dd = 1; dd < LPT; dd <<= 1) TT = __vmaxs2(TT, g.shfl_up(TT, dd)); // lanes < dd get their own value back
+    uint32_t Pv = g.shfl_up(TT, 1);
+    if (g.gl == 0) Pv = POA_NEGP;
+    const uint32_t P1 = prmt(Pv, 0, 0x1010), P2 = prmt(Pv, 0, 0x3232);
+    const uint4 nj = lds128v(lk + 16);                    // NJ1[0], NJ1[1], NJ2[0], NJ2[1]
+    const uint32_t NJ1[2] = {nj.x, nj.y}, NJ2[2] = {nj.z, nj.w};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        G1[r] = __vmaxs2(G1[r], P1);
+        Fa[r] = __vadd2(G1[r], NJ1[r]);
+        if (AFFINE) { Fb[r] = INFP; Hn[r] = __vmaxs2(Hme[r], Fa[r]); }
+        else { G2[r] = __vmaxs2(G2[r], P2); Fb[r] = __vadd2(G2[r], NJ2[r]); Hn[r] = __vimax3_s16x2(Hme[r], Fa[r], Fb[r]); }
+        // Value bounds that make plain 16-bit adds exact here: every H is >= inf_min - mis (the M term), so H - oe and
+        // E - e never reach -32768: the reference's saturating subtractions only ever clip candidates that lose the max.
+        E1o[r] = __viaddmax_s16x2(E1x[r], P.NE1P, __vadd2(Hn[r], P.NOE1P));
+        if (AFFINE) { const uint32_t keep = __vcmpeq2(Hn[r], Hme[r]); E1o[r] = (E1o[r] & keep) | (INFP & ~keep); E2o[r] = INFP; } // F won the cell: no deletion from it
+        else E2o[r] = __viaddmax_s16x2(E2x[r], P.NE2P, __vadd2(Hn[r], P.NOE2P));
+    }
+}
+
+// carries from this chunk to the next one of the same row (all lanes call)
+template <int LPT>
+__device__ __forceinline__ void poa_chunk_carry(const PoaG<LPT> &g, const DevParams &P, const uint32_t (&Hf)[2], const uint32_t (&Fa)[2], const uint32_t (&Fb)[2],
+                                                uint32_t &carryH, uint32_t &carryF) {
+    carryH = g.shfl(Hf[1], LPT - 1) & 0xffff0000u;
+    const uint32_t fa = g.shfl(Fa[1], LPT - 1), fb = g.shfl(Fb[1], LPT - 1);
+    carryF = __vadd2(prmt(fa, fb, 0x7632), P.PE12); // G of column j0 - 1 in the next chunk's frame
+}
+
+// Aligns sequence `query` of every active group to its graph and merges it in.  ALL lanes of the warp call; `act` says
+// whether this lane's group takes part.  err is the group's status (TH_OK going in).
+template <int LPT, bool AFFINE>
+__device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uint32_t lk, const bool act, const uint8_t *query, const int qlen_in,
+                                 int &node_n, int &edge_n, int &err, unsigned long long &cells, unsigned long long &rows, long long *ph) {
+#ifdef POA_PROFILE   // per-phase warp-cycle counters (tools/profile_step.py); off in the product build
     long long t_ph = clock64();
 #define PH(k) do { long long t_ = clock64(); ph[k] += t_ - t_ph; t_ph = t_; } while (0)
 #else
 #define PH(k) do { } while (0)
 #endif
-    const int lane = lane_id();
-    const int n = node_n; constexpr int pn = 1 << LP, lp = LP;
-    const int o1 = P.o1, e1 = P.e1, o2 = P.o2, e2 = P.e2, oe1 = o1 + e1, oe2 = o2 + e2;
-    const int mis = P.mismatch > 0 ? P.mismatch : -P.mismatch, mat = P.match < 0 ? -P.match : P.match;
-    { // int16 path only (simd_abpoa_align.c:1610-1621)
-        int len = qlen > n ? qlen : n;
-        int max_score = max(qlen * mat, len * e1 + o1);
-        if (max_score > 32767 - mis - oe1 - max(oe2, P.o2_raw + P.e2_raw) - 64 * max(max(e1, e2), P.e2_raw)) return TH_ERR_LEN;
+    constexpr int CW = PoaSmem<LPT>::CW, RINGW = PoaSmem<LPT>::RINGW;
+    const PoaG<LPT> g;
+    const int gl = g.gl;
+    PoaWs &w = sm.ws;
+    bool ok = act;                                     // this group is (still) working on the alignment
+    const int n = act ? node_n : 0, qlen = act ? qlen_in : 0;
+    const int lp = P.lp, pn = P.pn;                   // log2 / width of the emulated vector (16: AVX2 int16, the reference build; 8: SSE)
+    const int o1 = P.o1, e1 = P.e1, o2 = P.o2, e2 = P.e2, oe1 = P.oe1, oe2 = P.oe2;
+    const int mis = P.mis_abs, mat = P.mat_abs;
+    if (ok) { // int16 path only (simd_abpoa_align.c:1610-1621); CW max(e) of headroom for the scan frame
+        const int len = qlen > n ? qlen : n;
+        const int max_score = max(qlen * mat, len * e1 + o1);
+        if (max_score > 32767 - mis - oe1 - max(oe2, P.o2_raw + P.e2_raw) - CW * max(max(e1, e2), P.e2_raw)) { err = TH_ERR_LEN; ok = false; }
     }
-    // simd_abpoa_align.c:1613-1614 uses the option values as given, whatever the gap mode
-    const int inf_min = max(max(-32768 + mis, -32768 + oe1), -32768 + P.o2_raw + P.e2_raw) + 31 * max(e1, P.e2_raw);
-    const uint32_t INFP = pk(inf_min, inf_min);
+    const int inf_min = P.inf_min;
     const int wband = 10 + (int)(0.01f * (float)qlen); // wb + (int)(wf*qlen), float (simd_abpoa_align.c:393)
+    int4 *const rmeta_g = w.rmeta; int4 *const rdesc_g = w.rdesc; int32_t *const plist_g = w.plist;
     // ---- row descriptors: order index, predecessors by row, heaviest successor ----------------
-    for (int i = lane; i < n; i += 32) w.n2i[w.ord[i]] = i;
+    { const int nn = ok ? n : 0;
+      for (int i = gl; i < nn; i += LPT) w.n2i[w.ord[i]] = i; }
+    if (gl == 0) sm.plist_n = 0;
     __syncwarp();
-    { // four batches of 32 nodes walk their edge lists in lock-step: the loads of a step are independent across the
-      // batches, so four of these dependent (DRAM/L2-latency) pointer chases are in flight per lane instead of one
-        constexpr int U = POA_SETUP_U;
-        int pl_base = 0, bad = 0;
-        for (int i0 = 0; i0 < n; i0 += 32 * U) {
+    { // two batches of LPT nodes walk their edge lists in lock-step: the loads of a step are independent across the
+      // batches, so two of these dependent (DRAM/L2-latency) pointer chases are in flight per lane instead of one
+        constexpr int U = 2;
+        int bad = 0;
+        const int nn = ok ? n : 0;
+        for (int i0 = 0; i0 < nn; i0 += LPT * U) {
             int np[U], p0[U], p1[U], hi[U], v[U], b[U], ei[U], eo[U], mw[U], mt[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int i = i0 + 32 * u + lane;
+                const int i = i0 + LPT * u + gl;
                 np[u] = 0; p0[u] = -1; p1[u] = -1; hi[u] = 0x7fffffff; b[u] = 0; mw[u] = -1; mt[u] = -1;
-                v[u] = i < n ? w.ord[i] : -1;
+                v[u] = i < nn ? w.ord[i] : -1;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -186,10 +340,10 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 if (v[u] >= 0) { b[u] = w.base[v[u]]; ei[u] = w.in_head[v[u]]; eo[u] = w.out_head[v[u]]; }
             }
             while (true) { // predecessors by row, in in_id order
-                bool any = false;
+                bool anyp = false;
 #pragma unroll
-                for (int u = 0; u < U; ++u) any |= ei[u] >= 0;
-                if (!any) break;
+                for (int u = 0; u < U; ++u) anyp |= ei[u] >= 0;
+                if (!anyp) break;
                 int fr[U], nx[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) if (ei[u] >= 0) { fr[u] = w.e_from[ei[u]]; nx[u] = w.e_ni[ei[u]]; }
@@ -201,10 +355,10 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 }
             }
             while (true) { // first out-edge with maximum weight (abpoa_graph.c:216-226)
-                bool any = false;
+                bool anyp = false;
 #pragma unroll
-                for (int u = 0; u < U; ++u) any |= eo[u] >= 0;
-                if (!any) break;
+                for (int u = 0; u < U; ++u) anyp |= eo[u] >= 0;
+                if (!anyp) break;
                 int ww[U], to[U], nx[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) if (eo[u] >= 0) { ww[u] = w.e_w[eo[u]]; to[u] = w.e_to[eo[u]]; nx[u] = w.e_no[eo[u]]; }
@@ -215,395 +369,391 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
             for (int u = 0; u < U; ++u) if (mt[u] >= 0) hi[u] = w.n2i[mt[u]];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int i = i0 + 32 * u + lane;
-                const int cnt = np[u] > 2 ? np[u] : 0;
-                int inc = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(TH_FULL, inc, d); if (lane >= d) inc += o; }
-                const int off = pl_base + inc - cnt;
-                pl_base += __shfl_sync(TH_FULL, inc, 31);
-                if (i < n) {
-                    if (np[u] > 2) { int k = 0; for (int e = w.in_head[v[u]]; e >= 0; e = w.e_ni[e]) w.plist[off + k++] = w.n2i[w.e_from[e]]; }
+                const int i = i0 + LPT * u + gl;
+                if (i < nn) {
+                    int off = p1[u];
+                    if (np[u] > 2) { // predecessor rows beyond the second go to a list; the lists' order among rows does not matter
+                        off = atomicAdd(&sm.plist_n, np[u]);
+                        int k = 0; for (int e = w.in_head[v[u]]; e >= 0; e = w.e_ni[e]) plist_g[off + k++] = w.n2i[w.e_from[e]];
+                    }
                     w.hi_idx[i] = hi[u];
-                    bad |= np[u] > 1023 || (i > 0 && i < n - 1 && (unsigned)(np[u] - 1) >= POA_MAXPRE); // the row loop relies on 1 <= np <= POA_MAXPRE
-                    w.rdesc[i] = make_int4(p0[u], min(np[u], 1023) | (min(b[u], 7) << 10) | (v[u] << 13), 0, np[u] > 2 ? off : p1[u]);
+                    bad |= np[u] > 1023 || (i > 0 && i < nn - 1 && (unsigned)(np[u] - 1) >= (unsigned)min(LPT, POA_MAXPRE)); // the row loop relies on 1 <= np <= LPT
+                    rdesc_g[i] = make_int4(p0[u], min(np[u], 1023) | (min(b[u], 7) << 10) | (v[u] << 13), 0, off);
                 }
             }
         }
-        if (__any_sync(TH_FULL, bad)) return TH_ERR_CAP;
+        if (g.any(bad)) { if (ok) err = TH_ERR_CAP; ok = false; }
     }
     __syncwarp();
-    // max_remain by index, 32 indices at a time from the sink backwards; chains inside a chunk are
+    // max_remain by index, LPT indices at a time from the sink backwards; chains inside a chunk are
     // collapsed by pointer jumping on shuffles (remain[v] = remain[heaviest successor] + 1)
     int32_t *ri = w.ri;
-    for (int cb = ((n - 1) / 32) * 32; cb >= 0; cb -= 32) {
-        const int idx = cb + lane;
-        int ptr = 0x7fffffff, dist = 0;
-        if (idx < n) { ptr = w.hi_idx[idx]; dist = 1; if (idx == n - 1) { ptr = 0x7fffffff; dist = -1; } }
+    {
+        int cb = ok ? ((n - 1) / LPT) * LPT : -1;
+        while (__any_sync(TH_FULL, cb >= 0)) {
+            const bool a = cb >= 0;
+            const int idx = cb + gl;
+            int ptr = 0x7fffffff, dist = 0;
+            if (a && idx < n) { ptr = w.hi_idx[idx]; dist = 1; if (idx == n - 1) { ptr = 0x7fffffff; dist = -1; } }
 #pragma unroll
-        for (int rnd = 0; rnd < 5; ++rnd) {
-            const bool inside = ptr < cb + 32;
-            const int tl = inside ? ptr - cb : 0;
-            const int pd = __shfl_sync(TH_FULL, dist, tl), pp = __shfl_sync(TH_FULL, ptr, tl);
-            if (inside) { dist += pd; ptr = pp; }
+            for (int rnd = 0; (1 << rnd) < LPT; ++rnd) {
+                const bool inside = a && ptr < cb + LPT;
+                const int tl = inside ? ptr - cb : 0;
+                const int pd = g.shfl(dist, tl), pp = g.shfl(ptr, tl);
+                if (inside) { dist += pd; ptr = pp; }
+            }
+            if (a && idx < n) {
+                const int val = (ptr == 0x7fffffff ? 0 : ri[ptr]) + dist;
+                ri[idx] = val;
+                reinterpret_cast<int32_t *>(rdesc_g + idx)[2] = qlen - val;
+            }
+            __syncwarp();
+            if (a) cb -= LPT;
         }
-        if (idx < n) {
-            const int val = (ptr == 0x7fffffff ? 0 : ri[ptr]) + dist;
-            ri[idx] = val;
-            reinterpret_cast<int32_t *>(w.rdesc + idx)[2] = qlen - val;
-        }
-        __syncwarp();
     }
-    // ---- query profile (simd_abpoa_align.c:438-446) as bit-planes: bit j of plane b < 4 = (query[j-1] == b), bit j of
-    // plane 4 = (query[j-1] is A/C/G/T and 1 <= j <= qlen).  The score pair of columns (j, j+1) against node base b is
-    // then two word loads, shifts and IMADs: mat where the match bit is set, -mis where only the valid bit is set, 0
-    // elsewhere (N in the query, column 0, columns past the query end) or when the node itself is N -- exactly the
-    // reference's 5 x qlen table, without a trip to a table in the slab at the head of every row's dependency chain.
-    const int prof_w = ((qlen / pn + 1) * pn + 64 + 1) & ~1;
-    const int peq_w = (prof_w >> 5) + 1;
-    uint32_t *const peq = peq_w <= POA_PEQ_W ? sm.peq : reinterpret_cast<uint32_t *>(w.qp);
-    for (int j0 = 0; j0 < peq_w * 32; j0 += 32) {
-        const int j = j0 + lane;
-        const int qc = (j >= 1 && j <= qlen) ? (int)query[j - 1] : 7;
-        const uint32_t b0 = __ballot_sync(TH_FULL, qc == 0), b1 = __ballot_sync(TH_FULL, qc == 1), b2 = __ballot_sync(TH_FULL, qc == 2),
-                       b3 = __ballot_sync(TH_FULL, qc == 3), bv = __ballot_sync(TH_FULL, qc < 4);
-        if (lane < 5) peq[lane * peq_w + (j0 >> 5)] = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : lane == 3 ? b3 : bv;
+    // ---- query bytes (the reference's 5 x qlen profile, simd_abpoa_align.c:438-446, reduced to what it encodes):
+    // q8[j] = query[j-1] for an A/C/G/T base, 0x40 (score 0 against every node) for column 0, N and columns past the end
+    const int q8n = (qlen + pn + CW + 8) >> 2;          // words: every column a lane of any chunk may look at
+    uint32_t *const q8 = q8n <= PoaSmem<LPT>::Q8W ? sm.q8 : w.q8g;
+    if (ok) for (int wi = gl; wi < q8n; wi += LPT) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = 4 * wi + b;
+            uint32_t qc = 0x40;
+            if (j >= 1 && j <= qlen) { qc = query[j - 1]; if (qc > 3) qc = 0x40; }
+            word |= qc << (8 * b);
+        }
+        q8[wi] = word;
     }
     // ---- first row (simd_abpoa_align.c:538-555, 591-610) ------------------------------------
     uint32_t used = 0;
-    {
+    uint32_t *const A32w = reinterpret_cast<uint32_t *>(w.arena);
+    const uint32_t *const A32 = A32w;
+    const uint32_t arena_cap = w.arena_cap;
+    uint32_t *const ring = sm.u.ring;
+    if (ok) {
         const int end = min(qlen, max(0, qlen - ri[0]) + wband);
         const int esn = end >> lp, width = (esn + 1) << lp;
-        if ((uint64_t)used + 5ull * width > w.arena_cap) return TH_ERR_ARENA;
-        if (lane == 0) { const int4 m = make_int4(0, 0, width - 1, 1); w.rmeta[0] = m; sm.meta[0] = m; } // the source hands 1 to its successors (:549-552)
-        uint4 *R = reinterpret_cast<uint4 *>(w.arena); uint32_t *F2w = reinterpret_cast<uint32_t *>(w.arena) + 2 * width;
-        for (int q = lane; q < width / 2; q += 32) {
-            uint32_t hh = 0, ee1 = 0, ee2 = 0, ff1 = 0, ff2 = 0;
+        if (3ull * width > arena_cap) { err = TH_ERR_ARENA; ok = false; }
+        else {
+            if (gl == 0) { const int4 m = make_int4(0, 0, width - 1, 1); rmeta_g[0] = m; sm.meta[0] = m; } // the source hands 1 to its successors (:549-552)
+            const int ps = width >> 1;
+            for (int q = gl; q < ps; q += LPT) {
+                uint32_t hh = 0, ee1 = 0, ee2 = 0;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = 2 * q + h;
-                const int f1 = -o1 - e1 * j, f2 = -o2 - e2 * j;
-                const int vh = j == 0 ? 0 : (AFFINE ? (int)(int16_t)f1 : max((int)(int16_t)f1, (int)(int16_t)f2));
-                const int v1 = j == 0 ? -oe1 : inf_min, v2 = (j == 0 && !AFFINE) ? -oe2 : inf_min, vf1 = j == 0 ? inf_min : f1, vf2 = (j == 0 || AFFINE) ? inf_min : f2;
-                hh |= (uint32_t)(uint16_t)vh << (16 * h); ee1 |= (uint32_t)(uint16_t)v1 << (16 * h); ee2 |= (uint32_t)(uint16_t)v2 << (16 * h);
-                ff1 |= (uint32_t)(uint16_t)vf1 << (16 * h); ff2 |= (uint32_t)(uint16_t)vf2 << (16 * h);
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 2 * q + h;
+                    const int f1 = -o1 - e1 * j, f2 = -o2 - e2 * j;
+                    const int vh = j == 0 ? 0 : (AFFINE ? (int)(int16_t)f1 : max((int)(int16_t)f1, (int)(int16_t)f2));
+                    const int v1 = j == 0 ? -oe1 : inf_min, v2 = (j == 0 && !AFFINE) ? -oe2 : inf_min;
+                    hh |= (uint32_t)(uint16_t)vh << (16 * h); ee1 |= (uint32_t)(uint16_t)v1 << (16 * h); ee2 |= (uint32_t)(uint16_t)v2 << (16 * h);
+                }
+                A32w[q] = hh; A32w[ps + q] = ee1; if (!AFFINE) A32w[2 * ps + q] = ee2;
+                if (width <= CW) { ring[q] = hh; ring[ps + q] = ee1; if (!AFFINE) ring[2 * ps + q] = ee2; }
             }
-            R[q] = make_uint4(hh, ee1, ee2, ff1); F2w[q] = ff2;
+            used = 3u * width; cells += width; rows += 1;
         }
-        used += 5u * width; cells += width; rows += 1;
     }
     __syncwarp();
     PH(0);
     // ---- rows in topological order ----------------------------------------------------------
-    // Value bounds that make plain 16-bit adds exact here: every H is >= inf_min - mis (the M term), so
-    // H - oe, E - e and the final F never reach -32768: the reference's saturating subtractions
-    // (_mm256_subs_epi16 in SIMD_SET_F) only ever clip intermediate candidates that lose the max anyway.
-    // F1[j] = max_k<=j (A1[k] - e1 (j-k)) is evaluated as a prefix MAX of G[k] = A1[k] + e1 (k - j0) over the
-    // chunk (no subtraction inside the scan, hence no underflow), F = G - e1 (j - j0).  The int16 range check
-    // above leaves 64 max(e1,e2) of headroom for G.
-    const uint32_t NOE1P = pk(-oe1, -oe1), NOE2P = pk(-oe2, -oe2), NE1P = pk(-e1, -e1), NE2P = pk(-e2, -e2);
-    const uint32_t C1 = pk(e1 * 2 * lane - oe1, e1 * (2 * lane + 1) - oe1), C2 = pk(e2 * 2 * lane - oe2, e2 * (2 * lane + 1) - oe2);
-    const uint32_t NJ1 = pk(-e1 * 2 * lane, -e1 * (2 * lane + 1)), NJ2 = pk(-e2 * 2 * lane, -e2 * (2 * lane + 1));
     const int lam_bits = pn - 1;
-    const uint32_t lamk_lo = (uint32_t)(lam_bits - ((2 * lane) & lam_bits)) << 12, lamk_hi = (uint32_t)(lam_bits - ((2 * lane + 1) & lam_bits)) << 12;
-    const int lane_vec = (2 * lane) >> lp;
+    const int lane_vec = (4 * gl) >> lp;
     const int qsn = qlen >> lp;
-    const uint32_t *A32 = reinterpret_cast<const uint32_t *>(w.arena);
-    uint32_t *A32w = reinterpret_cast<uint32_t *>(w.arena);
-    uint32_t last_off = 0xffffffffu; // arena offset of the row whose values sit in sm.last
-    const uint32_t NEGMIS2 = pk(-mis, -mis), XMM = (uint32_t)(uint16_t)mat ^ (uint32_t)(uint16_t)(-mis); // -mis ^ XMM == mat per half
-    const uint32_t KLO = lamk_lo | 0xfffu, KHI = lamk_hi | 0xfffu;
     const uint32_t used_rows0 = used;
-    int4 *const rmeta_g = w.rmeta; const int4 *const rdesc_g = w.rdesc; const int32_t *const plist_g = w.plist;
-    const uint32_t arena_cap = w.arena_cap;
-    const uint32_t *const vrow = peq + 4 * peq_w; // valid plane
-    for (int i0 = 0; i0 < n - 1; i0 += 32) {
-      { const int idx = i0 + lane; // descriptors of the next 32 rows
-        if (idx < n) sm.desc[idx & (POA_RING - 1)] = rdesc_g[idx];
-        __syncwarp(); }
-      const int i_end = min(i0 + 32, n - 1);
-      for (int i = max(i0, 1); i < i_end; ++i) {
-        const int4 d = sm.desc[i & (POA_RING - 1)];
-        const int np = d.y & 1023; // 1..POA_MAXPRE, checked when the descriptors were built
-        // band: what the predecessors' row maxima and max_remain say (abpoa_align.h:34-35, simd_abpoa_align.c:846-854)
-        const int4 pm0 = (i - d.x < POA_RING) ? sm.meta[d.x & (POA_RING - 1)] : rmeta_g[d.x];
-        int mpl = min(n, pm0.w), mpr = max(0, pm0.w), min_pre_beg = pm0.y;
-        if (np > 1) {
-            for (int p = 1; p < np; ++p) {
-                const int pi = np == 2 ? d.w : plist_g[d.w + p];
-                const int4 m = (i - pi < POA_RING) ? sm.meta[pi & (POA_RING - 1)] : rmeta_g[pi];
-                mpl = min(mpl, m.w); mpr = max(mpr, m.w); min_pre_beg = min(min_pre_beg, m.y);
-                if (lane == 0) sm.pre[p] = m;
+    {
+        int i = 1;
+        bool ract = ok && n > 2;
+        int4 dn = ract ? rdesc_g[1] : make_int4(0, 0, 0, 0);
+        while (__any_sync(TH_FULL, ract)) {
+            // ---- band and predecessors of row i (no warp-synchronous operation before the chunk)
+            const int4 d = dn;
+            int4 pm0 = make_int4(0, 0, -1, 0);
+            int np = 0, beg = 0, dend = -1, esn = 0, width = 0;
+            uint32_t row_off = 0;
+            bool go = false;
+            if (ract) {
+                if (i + 1 < n - 1) dn = rdesc_g[i + 1];   // next row's descriptor: in flight while this row is computed
+                np = d.y & 1023;                           // 1..LPT, checked when the descriptors were built
+                // band: what the predecessors' row maxima and max_remain say (abpoa_align.h:34-35, simd_abpoa_align.c:846-854)
+                int4 m = (i - d.x < POA_WIN) ? sm.meta[d.x & (POA_WIN - 1)] : rmeta_g[d.x];
+                int mpl = min(n, m.w), mpr = max(0, m.w), min_pre_beg = m.y;
+                if (i - d.x <= POA_NRING && m.z - m.y < CW) m.x = (int)(0x80000000u | (uint32_t)(d.x & (POA_NRING - 1)));
+                pm0 = m;
+                if (np > 1) {
+#pragma unroll 1
+                    for (int p = 1; p < np; ++p) {
+                        const int pi = np == 2 ? d.w : plist_g[d.w + p];
+                        int4 q = (i - pi < POA_WIN) ? sm.meta[pi & (POA_WIN - 1)] : rmeta_g[pi];
+                        mpl = min(mpl, q.w); mpr = max(mpr, q.w); min_pre_beg = min(min_pre_beg, q.y);
+                        if (i - pi <= POA_NRING && q.z - q.y < CW) q.x = (int)(0x80000000u | (uint32_t)(pi & (POA_NRING - 1)));
+                        sm.pre[p] = q;                     // every lane of the group writes the same value and reads back its own write
+                    }
+                }
+                const int beg0 = max(0, min(mpl, d.z) - wband), end0 = min(qlen, max(mpr, d.z) + wband);
+                beg = max((beg0 >> lp) << lp, min_pre_beg); esn = end0 >> lp; dend = ((esn + 1) << lp) - 1;
+                width = dend - beg + 1;
+                if (beg > dend) err = TH_ERR_BAND;
+                else if (3ull * (uint32_t)width > (unsigned long long)(arena_cap - used)) err = TH_ERR_ARENA;
+                else { go = true; row_off = used; used += 3u * (uint32_t)width; } // cells and rows are derived from `used` after the loop
+                if (!go) { ract = false; ok = false; width = 0; }
+            }
+            const int ps = width >> 1, nchunk = (width + CW - 1) / CW;
+            const bool cache_row = width <= CW;
+            const int vb = (d.y >> 10) & 7;
+            const uint32_t basew = (uint32_t)(vb < 4 ? vb : 0x20) * 0x01010101u;
+            const int jmax = esn == qsn ? qlen : dend;   // columns past the query end do not compete for the row maximum
+            const int vlast = esn - (beg >> lp);          // the row's last vector is visited first by the reference's arg-max
+            int best = INT_MIN;
+            uint32_t carryH = 0, carryF = POA_NEGP;
+            const bool multi = __any_sync(TH_FULL, go && nchunk > 1);
+            auto chunk = [&](const int ch, const bool more) {
+                const bool a = go && ch < nchunk;
+                const int j0 = beg + ch * CW + 4 * gl;
+                uint32_t Hn[2], E1o[2], E2o[2], Fa[2], Fb[2], Hf[2];
+                poa_chunk<LPT, AFFINE>(g, P, lk, A32, ring, sm.pre, pm0, a ? np : 0, a, j0, ch == 0, carryH, carryF, basew, q8, Hn, E1o, E2o, Fa, Fb, Hf);
+                if (a && j0 <= dend) {
+                    const uint32_t wo = (row_off >> 1) + (uint32_t)((j0 - beg) >> 1);
+                    *reinterpret_cast<uint2 *>(A32w + wo) = make_uint2(Hn[0], Hn[1]);
+                    *reinterpret_cast<uint2 *>(A32w + wo + ps) = make_uint2(E1o[0], E1o[1]);
+                    if (!AFFINE) *reinterpret_cast<uint2 *>(A32w + wo + 2 * ps) = make_uint2(E2o[0], E2o[1]);
+                    if (cache_row) { // every reader of the slot's old contents is past the scan's shuffles
+                        uint32_t *rs = ring + (i & (POA_NRING - 1)) * RINGW + 2 * gl;
+                        *reinterpret_cast<uint2 *>(rs) = make_uint2(Hn[0], Hn[1]);
+                        *reinterpret_cast<uint2 *>(rs + ps) = make_uint2(E1o[0], E1o[1]);
+                        if (!AFFINE) *reinterpret_cast<uint2 *>(rs + 2 * ps) = make_uint2(E2o[0], E2o[1]);
+                    }
+                }
+                if (a) { // row arg-max key (signed compare): value, then lane (j mod pn) ascending, then vector order with end_sn first
+                    const int rel = lane_vec + ch * (CW >> lp);
+                    const uint32_t sub = rel == vlast ? 0u : (uint32_t)(rel + 1);
+                    const uint4 kk = lds128v(lk + 32);    // KLO[0], KLO[1], KHI[0], KHI[1]
+                    const uint32_t KLO[2] = {kk.x, kk.y}, KHI[2] = {kk.z, kk.w};
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int j = j0 + 2 * r;
+                        const int klo = (int)prmt(Hn[r], KLO[r] - sub, 0x1054), khi = (int)prmt(Hn[r], KHI[r] - sub, 0x3254);
+                        best = max(best, max(j <= jmax ? klo : INT_MIN, j < jmax ? khi : INT_MIN)); // jmax <= dend
+                    }
+                }
+                if (more) poa_chunk_carry<LPT>(g, P, Hf, Fa, Fb, carryH, carryF);
+            };
+            chunk(0, multi);
+            if (multi) for (int ch = 1; __any_sync(TH_FULL, go && ch < nchunk); ++ch) chunk(ch, true); // rows wider than one chunk: the other group keeps the warp company
+            const int rbest = g.rmax(best);
+            if (go) { // simd_abpoa_max_in_row + simd_abpoa_ada_max_i: successors pull max_i + 1 from this row's metadata
+                const int val = rbest >> 16;
+                const int lam = lam_bits - (int)((rbest >> 12) & 0xf), vr = 0xfff - (int)(rbest & 0xfff);
+                const int vsn = vr == 0 ? esn : (beg >> lp) + vr - 1;
+                const int max_i = (rbest != INT_MIN && val > inf_min) ? vsn * pn + lam : -1;
+                if (gl == 0) { const int4 m = make_int4((int)row_off, beg, dend, max_i + 1); sm.meta[i & (POA_WIN - 1)] = m; rmeta_g[i] = m; }
+                ++i; ract = i < n - 1;
             }
             __syncwarp();
         }
-        const int beg0 = max(0, min(mpl, d.z) - wband), end0 = min(qlen, max(mpr, d.z) + wband);
-        const int beg = max((beg0 >> lp) << lp, min_pre_beg), esn = end0 >> lp, dend = ((esn + 1) << lp) - 1;
-        const int bsn = beg >> lp, width = dend - beg + 1;
-        const uint32_t w5 = 5u * (uint32_t)width;
-        if ((beg > dend) | (w5 > arena_cap - used)) return beg > dend ? TH_ERR_BAND : TH_ERR_ARENA;
-        const uint32_t row_off = used;
-        used += w5; // cells and rows are derived from `used` after the loop
-        const int vb = (d.y >> 10) & 7;
-        const uint32_t *const prow = peq + (vb & 3) * peq_w;
-        const uint32_t s_neg = vb < 4 ? NEGMIS2 : 0u, s_xm = vb < 4 ? XMM : 0u;  // an N node scores 0 against everything
-        const uint32_t rec0 = (row_off >> 3) + lane;                                  // this lane's record in chunk 0 (16-byte units; row_off is a multiple of 40)
-        const uint32_t f20 = (row_off >> 1) + 2u * (uint32_t)width + lane;              // ... and its F2 pair (words)
-        const int jmax = esn == qsn ? qlen : dend;       // columns past the query end do not compete for the row maximum
-        const int vlast = esn - bsn;                      // the row's last vector is visited first by the reference's arg-max
-        int best = INT_MIN;
-        if (width <= 64) {
-            // ---- the usual row: one 64-column chunk, no carries between chunks --------------------------------------
-            const int j = beg + 2 * lane;
-            uint32_t Mx = INFP, E1x = INFP, E2x = INFP;
-            poa_pred(poa_row_recs(A32, sm.last, (uint32_t)pm0.x, last_off), pm0, j, INFP, Mx, E1x, E2x);
-            for (int p = 1; p < np; ++p) {
-                const int4 pm = sm.pre[p];
-                poa_pred(poa_row_recs(A32, sm.last, (uint32_t)pm.x, last_off), pm, j, INFP, Mx, E1x, E2x);
-            }
-            const uint32_t sh = j & 31, t = (prow[j >> 5] >> sh) & 3u, v = (vrow[j >> 5] >> sh) & 3u; // bits of columns j, j + 1 (j is even)
-            const uint32_t S = (s_neg ^ (((t | (t << 15)) & 0x10001u) * s_xm)) & (((v | (v << 15)) & 0x10001u) * 0xffffu);
-            const uint32_t Ms = __vadd2(Mx, S);
-            const uint32_t Hme = __vimax3_s16x2(Ms, E1x, E2x);
-            const uint32_t Hf = AFFINE ? Ms : Hme;        // what an insertion may open from
-            uint32_t hp = __shfl_up_sync(TH_FULL, Hf, 1);
-            if (lane == 0) hp = Ms << 16;
-            const uint32_t Hsh = __funnelshift_r(hp, Hf, 16);
-            uint32_t G1 = __vadd2(Hsh, C1), G2 = __vadd2(Hsh, C2);   // G = (Hme[j-1] - oe) + e (j - j0)
-            G1 = __vmaxs2(G1, (G1 << 16) | 0x8000u); G2 = __vmaxs2(G2, (G2 << 16) | 0x8000u); // odd column also sees the even one
-            uint32_t TT = __byte_perm(G1, G2, 0x7632); // lo = G1 at this lane's odd column, hi = G2
-#pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) TT = __vmaxs2(TT, __shfl_up_sync(TH_FULL, TT, dd)); // lanes < dd get their own value back
-            uint32_t Pv = __shfl_up_sync(TH_FULL, TT, 1);
-            if (lane == 0) Pv = POA_NEGP;
-            G1 = __vmaxs2(G1, __byte_perm(Pv, Pv, 0x1010)); G2 = __vmaxs2(G2, __byte_perm(Pv, Pv, 0x3232));
-            const uint32_t Fa = __vadd2(G1, NJ1), Fb = AFFINE ? INFP : __vadd2(G2, NJ2);
-            const uint32_t Hn = __vimax3_s16x2(Hme, Fa, Fb);
-            uint32_t E1o = __viaddmax_s16x2(E1x, NE1P, __vadd2(Hn, NOE1P));
-            if (AFFINE) { const uint32_t keep = __vcmpeq2(Hn, Hme); E1o = (E1o & keep) | (INFP & ~keep); } // F won the cell: no deletion from it
-            const uint32_t E2o = AFFINE ? INFP : __viaddmax_s16x2(E2x, NE2P, __vadd2(Hn, NOE2P));
-            sm.last[lane] = make_uint4(Hn, E1o, E2o, 0); // every reader of the old contents is past the scan's shuffles
-            if (j <= dend) { reinterpret_cast<uint4 *>(A32w)[rec0] = make_uint4(Hn, E1o, E2o, Fa); A32w[f20] = Fb; }
-            const uint32_t sub = lane_vec == vlast ? 0u : (uint32_t)(lane_vec + 1);
-            const int klo = (int)__byte_perm(Hn, KLO - sub, 0x1054), khi = (int)__byte_perm(Hn, KHI - sub, 0x3254);
-            best = max(j <= jmax ? klo : INT_MIN, j < jmax ? khi : INT_MIN); // jmax <= dend
-            last_off = row_off;
-        } else {
-        uint32_t carryH = 0, carryF = POA_NEGP; // carryF: (F1 - e1, F2 - e2) of the previous chunk's last column
-        const int nchunk = (width + 63) >> 6;
-        for (int ch = 0; ch < nchunk; ++ch) {
-            const int j = beg + (ch << 6) + 2 * lane;
-            uint32_t Mx = INFP, E1x = INFP, E2x = INFP;
-            poa_pred(poa_row_recs(A32, sm.last, (uint32_t)pm0.x, last_off), pm0, j, INFP, Mx, E1x, E2x);
-            for (int p = 1; p < np; ++p) {
-                const int4 pm = sm.pre[p];
-                poa_pred(poa_row_recs(A32, sm.last, (uint32_t)pm.x, last_off), pm, j, INFP, Mx, E1x, E2x);
-            }
-            const uint32_t sh = j & 31, t = (prow[j >> 5] >> sh) & 3u, v = (vrow[j >> 5] >> sh) & 3u;
-            const uint32_t S = (s_neg ^ (((t | (t << 15)) & 0x10001u) * s_xm)) & (((v | (v << 15)) & 0x10001u) * 0xffffu);
-            const uint32_t Ms = __vadd2(Mx, S);
-            const uint32_t Hme = __vimax3_s16x2(Ms, E1x, E2x);
-            const uint32_t Hf = AFFINE ? Ms : Hme;
-            uint32_t hp = __shfl_up_sync(TH_FULL, Hf, 1);
-            if (lane == 0) hp = ch == 0 ? (Ms << 16) : carryH;
-            const uint32_t Hsh = __funnelshift_r(hp, Hf, 16);
-            uint32_t G1 = __vadd2(Hsh, C1), G2 = __vadd2(Hsh, C2);   // G = (Hme[j-1] - oe) + e (j - j0)
-            if (lane == 0) { G1 = __vmaxs2(G1, (carryF & 0xffffu) | 0x80000000u); G2 = __vmaxs2(G2, (carryF >> 16) | 0x80000000u); }
-            G1 = __vmaxs2(G1, (G1 << 16) | 0x8000u); G2 = __vmaxs2(G2, (G2 << 16) | 0x8000u); // odd column also sees the even one
-            uint32_t TT = __byte_perm(G1, G2, 0x7632); // lo = G1 at this lane's odd column, hi = G2
-#pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) TT = __vmaxs2(TT, __shfl_up_sync(TH_FULL, TT, dd)); // lanes < dd get their own value back
-            uint32_t Pv = __shfl_up_sync(TH_FULL, TT, 1);
-            if (lane == 0) Pv = POA_NEGP;
-            G1 = __vmaxs2(G1, __byte_perm(Pv, Pv, 0x1010)); G2 = __vmaxs2(G2, __byte_perm(Pv, Pv, 0x3232));
-            const uint32_t Fa = __vadd2(G1, NJ1), Fb = AFFINE ? INFP : __vadd2(G2, NJ2);
-            const uint32_t Hn = __vimax3_s16x2(Hme, Fa, Fb);
-            uint32_t E1o = __viaddmax_s16x2(E1x, NE1P, __vadd2(Hn, NOE1P));
-            if (AFFINE) { const uint32_t keep = __vcmpeq2(Hn, Hme); E1o = (E1o & keep) | (INFP & ~keep); } // F won the cell: no deletion from it
-            const uint32_t E2o = AFFINE ? INFP : __viaddmax_s16x2(E2x, NE2P, __vadd2(Hn, NOE2P));
-            if (ch + 1 < nchunk) {
-                carryH = __shfl_sync(TH_FULL, Hf, 31) & 0xffff0000u;
-                const uint32_t fa = __shfl_sync(TH_FULL, Fa, 31), fb = __shfl_sync(TH_FULL, Fb, 31);
-                carryF = __vadd2(__byte_perm(fa, fb, 0x7632), pk(-e1, -e2)); // G of column j0 - 1 in the next chunk's frame
-            }
-            if (j <= dend) { reinterpret_cast<uint4 *>(A32w)[rec0 + (ch << 5)] = make_uint4(Hn, E1o, E2o, Fa); A32w[f20 + (ch << 5)] = Fb; }
-            { // row arg-max key (signed compare): value, then lane (j mod pn) ascending, then vector order with end_sn first
-                const int rel = lane_vec + (ch << (6 - lp));
-                const uint32_t sub = rel == vlast ? 0u : (uint32_t)(rel + 1);
-                const int klo = (int)__byte_perm(Hn, KLO - sub, 0x1054), khi = (int)__byte_perm(Hn, KHI - sub, 0x3254);
-                best = max(best, max(j <= jmax ? klo : INT_MIN, j < jmax ? khi : INT_MIN)); // jmax <= dend
-            }
-        }
-        last_off = 0xffffffffu; // sm.last keeps an older row; it is matched by offset, and that offset is forgotten here
-        }
-        best = __reduce_max_sync(TH_FULL, best);
-        { // simd_abpoa_max_in_row + simd_abpoa_ada_max_i: successors pull max_i + 1 from this row's metadata
-            const int val = best >> 16;
-            const int lam = lam_bits - (int)((best >> 12) & 0xf), vr = 0xfff - (int)(best & 0xfff);
-            const int vsn = vr == 0 ? esn : bsn + vr - 1;
-            const int max_i = (best != INT_MIN && val > inf_min) ? vsn * pn + lam : -1;
-            if (lane == 0) { const int4 m = make_int4((int)row_off, beg, dend, max_i + 1); sm.meta[i & (POA_RING - 1)] = m; rmeta_g[i] = m; }
-        }
-        __syncwarp();
-      }
     }
-    cells += (used - used_rows0) / 5u; rows += (unsigned long long)max(n - 2, 0);
+    if (ok) { cells += (used - used_rows0) / 3u; rows += (unsigned long long)max(n - 2, 0); }
     PH(1);
     // ---- best end cell (simd_abpoa_align.c:976-989): sink's in-neighbours in in_id order, strict > ----
+    const int16_t *const A16 = w.arena;
     int bi = 0, bj = 0;
     {
-        const int4 ds = w.rdesc[n - 1];
-        const int nps = ds.y & 1023;
+        const int4 ds = ok ? rdesc_g[n - 1] : make_int4(0, 0, 0, 0);
+        const int nps = ok ? (ds.y & 1023) : 0;
         int best_score = inf_min;
-        for (int p0 = 0; p0 < nps; p0 += 32) {
-            const int p = p0 + lane;
+        for (int p0 = 0; __any_sync(TH_FULL, p0 < nps); p0 += LPT) {
+            const int p = p0 + gl;
             int s = -0x7fffffff, pi = 0, end = 0;
             if (p < nps) {
-                pi = p == 0 ? ds.x : (nps == 2 ? ds.w : w.plist[ds.w + p]);
-                const int4 m = w.rmeta[pi];
+                pi = p == 0 ? ds.x : (nps == 2 ? ds.w : plist_g[ds.w + p]);
+                const int4 m = rmeta_g[pi];
                 end = qlen > m.z ? m.z : qlen;
-                s = s16_at(A32[(m.x >> 1) + 4 * ((end - m.y) >> 1)], (end - m.y) & 1);
+                s = A16[(uint32_t)m.x + (uint32_t)(end - m.y)];
             }
-            const int mx = __reduce_max_sync(TH_FULL, s);
-            if (mx > best_score) {
-                const unsigned bm = __ballot_sync(TH_FULL, s == mx);
-                const int f = __ffs(bm) - 1;
-                best_score = mx; bi = __shfl_sync(TH_FULL, pi, f); bj = __shfl_sync(TH_FULL, end, f);
-            }
+            const int mx = g.rmax(s);
+            const unsigned bm = g.ballot(s == mx);
+            const int f = bm ? __ffs(bm) - 1 : 0;
+            const int fpi = g.shfl(pi, f), fend = g.shfl(end, f);
+            if (p0 < nps && mx > best_score) { best_score = mx; bi = fpi; bj = fend; }
         }
     }
-    // ---- backtrack by value comparison (simd_abpoa_align.c:248-377).  The walk is sequential, but every
-    // step's loads (own row, all predecessors) are issued together by the warp, row metadata comes from a
-    // shared-memory window filled 32 rows at a time, and the DP values of the rows ahead are prefetched into L2.
-    int n_cig = 0, err = TH_OK;
+    // ---- backtrack by value comparison (simd_abpoa_align.c:248-377).  The walk is sequential; lane p of the group holds
+    // predecessor p.  Row metadata and descriptors come from a shared-memory window filled 32 rows at a time, and so do
+    // 16 columns of H around each window row's arg-max: a match step reads shared memory only.
+    int n_cig = 0;
     {
         enum { M_OP = 1, E1_OP = 2, E2_OP = 4, E_OP = 6, F1_OP = 8, F2_OP = 16, F_OP = 24, ALL_OP = 31 };
-        int i = bi, j = bj, cur_op = ALL_OP;
+        int i = ok ? bi : 0, j = ok ? bj : 0, cur_op = ALL_OP;
         uint32_t *cg = w.cigar; int32_t *cq = w.cigq;
-        for (int t = lane; t < qlen - bj; t += 32) { cg[t] = 1; cq[t] = qlen - 1 - t; } // unaligned query tail
-        if (bj < qlen) n_cig = qlen - bj;
+        if (ok) {
+            for (int t = gl; t < qlen - bj; t += LPT) { cg[t] = 1; cq[t] = qlen - 1 - t; } // unaligned query tail
+            if (bj < qlen) n_cig = qlen - bj;
+        }
         int wlo = n, whi = -1; // rows [wlo, whi] are in the window
-        while (i > 0 && j > 0) {
-            if (i < wlo || (i < wlo + 32 && wlo > 0)) {
-                const int top = i < wlo ? i + 1 : wlo; // load rows [top-32, top)
-                if (i < wlo) whi = i;
-                const int r = top - 32 + lane;
-                if (r >= 0) {
-                    const int4 m = w.rmeta[r];
-                    sm.desc[r & (POA_RING - 1)] = w.rdesc[r]; sm.meta[r & (POA_RING - 1)] = m;
-                    const int rw = m.z - m.y + 1;
-                    // the path crosses a row close to that row's maximum (the column that steered the band); the graph holds
-                    // several nodes per query column, so extrapolating j along the row index would drift off within a few rows.
-                    // (Prefetching whole rows with cp.async.bulk.prefetch.L2 was measured: +25 GB of DRAM reads per 8192 reads
-                    // and no shorter backtrack, so only the sectors around the predicted crossing are requested.)
-                    int jp = m.w > 0 ? m.w - 1 : j - (i - r); jp = min(max(jp, m.y), m.z);
-                    const int c0 = max(jp - 7, m.y) - m.y, c1 = max(jp - 2, m.y) - m.y, c2 = min(jp + 4, m.z) - m.y;
-                    const uint32_t *Rr = A32 + (m.x >> 1);
-                    prefetch_l2(Rr + 4 * (c0 >> 1)); prefetch_l2(Rr + 4 * (c1 >> 1)); prefetch_l2(Rr + 4 * (c2 >> 1)); prefetch_l2(Rr + 2 * rw + ((jp - m.y) >> 1));
+        const uint8_t *const q8b = reinterpret_cast<const uint8_t *>(q8);
+        const int16_t *const segs = reinterpret_cast<const int16_t *>(sm.u.seg);
+        bool bact;
+        while (__any_sync(TH_FULL, bact = (ok && i > 0 && j > 0))) {
+            const bool need = bact && (i < wlo || (i < wlo + 32 && wlo > 0));
+            if (__any_sync(TH_FULL, need)) {
+                if (need) {
+                    const int top = i < wlo ? i + 1 : wlo; // load rows [top-32, top)
+                    if (i < wlo) whi = i;
+                    for (int r = top - 32 + gl; r < top; r += LPT) if (r >= 0) {
+                        int4 m = rmeta_g[r];
+                        // the path crosses a row close to that row's maximum (the column that steered the band)
+                        const int jp = m.w > 0 ? m.w - 1 : j - (i - r);
+                        int sb = (jp - 6) & ~7; sb = max(m.y, min(sb, m.z - 15));
+                        const uint4 *src = reinterpret_cast<const uint4 *>(A16 + (uint32_t)m.x + (uint32_t)(sb - m.y));
+                        const uint4 s0 = src[0], s1 = src[1]; // a row holds at least 24 int16, so this stays inside it
+                        sm.u.seg[2 * (r & (POA_WIN - 1))] = s0; sm.u.seg[2 * (r & (POA_WIN - 1)) + 1] = s1;
+                        sm.desc[r & (POA_WIN - 1)] = rdesc_g[r];
+                        m.w = sb; sm.meta[r & (POA_WIN - 1)] = m;
+                    }
+                    wlo = max(0, top - 32); whi = min(whi, wlo + POA_WIN - 1);
                 }
-                wlo = max(0, top - 32); whi = min(whi, wlo + POA_RING - 1);
                 __syncwarp();
             }
-            const int4 d = sm.desc[i & (POA_RING - 1)], mi = sm.meta[i & (POA_RING - 1)];
+            const int4 d = sm.desc[i & (POA_WIN - 1)], mi = sm.meta[i & (POA_WIN - 1)];
             const int np = d.y & 1023, vb = (d.y >> 10) & 7, v = d.y >> 13;
-            if (np > 32) { err = TH_ERR_CAP; break; }
-            const int qb = query[j - 1];
+            const int qb = bact ? q8b[j] : 0x40;
             const int s = (qb < 4 && vb < 4) ? (qb == vb ? mat : -mis) : 0;
             const int ib = mi.y, iw = mi.z - mi.y + 1;
-            const int c = j - ib, q = c >> 1, odd = c & 1;
-            const uint32_t rb = (uint32_t)(mi.x >> 1);
-            // lane p holds predecessor p.  Most steps are matches: test those first, with the two loads they need.
-            int pi = 0; bool in1 = false, in0 = false, podd = false; uint32_t pbw = 0;
-            if (lane < np) {
-                pi = lane == 0 ? d.x : (np == 2 ? d.w : w.plist[d.w + lane]);
-                const int4 pm = pi >= wlo ? sm.meta[pi & (POA_RING - 1)] : w.rmeta[pi];
-                const int cp = j - pm.y;
-                podd = cp & 1; pbw = (uint32_t)(pm.x >> 1) + 4 * (cp >> 1);
-                in1 = cp >= 1 && j - 1 <= pm.z; in0 = cp >= 0 && j <= pm.z;
+            int hij;
+            { const unsigned dj = (unsigned)(j - mi.w);
+              hij = !bact ? 0 : (dj < 16u ? segs[16 * (i & (POA_WIN - 1)) + dj] : A16[(uint32_t)mi.x + (uint32_t)(j - ib)]); }
+            // lane p holds predecessor p.  Most steps are matches: test those first.
+            int pi = 0; bool in1 = false, in0 = false; int4 pm = make_int4(0, 0, -1, 0); bool pwin = false;
+            if (bact && gl < np) {
+                pi = gl == 0 ? d.x : (np == 2 ? d.w : plist_g[d.w + gl]);
+                pwin = pi >= wlo;
+                pm = pwin ? sm.meta[pi & (POA_WIN - 1)] : rmeta_g[pi];
+                in1 = j - 1 >= pm.y && j - 1 <= pm.z; in0 = j >= pm.y && j <= pm.z;
             }
-            const int hij = s16_at(A32[rb + 4 * q], odd);
-            if (cur_op & M_OP) {
-                uint32_t hpw = 0; // the H word that holds column j-1 of the predecessor
-                if (in1) hpw = A32[podd ? pbw : pbw - 4];
-                const int a = podd ? lo16(hpw) : hi16(hpw);
-                const unsigned mm = __ballot_sync(TH_FULL, in1 && a + s == hij);
+            bool stepped = false;
+            {
+                int a = 0;
+                if (in1 && (cur_op & M_OP)) {
+                    const unsigned dj = (unsigned)(j - 1 - pm.w);
+                    a = (pwin && dj < 16u) ? segs[16 * (pi & (POA_WIN - 1)) + dj] : A16[(uint32_t)pm.x + (uint32_t)(j - 1 - pm.y)];
+                }
+                const unsigned mm = g.ballot(in1 && (cur_op & M_OP) && a + s == hij);
+                const int f = mm ? __ffs(mm) - 1 : 0;
+                const int fpi = g.shfl(pi, f);
                 if (mm) {
-                    const int f = __ffs(mm) - 1;
-                    if (lane == 0) { cg[n_cig] = ((uint32_t)v << 2) | 0; cq[n_cig] = j - 1; }
-                    ++n_cig; cur_op = ALL_OP; i = __shfl_sync(TH_FULL, pi, f); --j;
-                    continue;
+                    if (gl == 0) { cg[n_cig] = ((uint32_t)v << 2) | 0; cq[n_cig] = j - 1; }
+                    ++n_cig; cur_op = ALL_OP; i = fpi; --j; stepped = true;
                 }
             }
-            // not a match: the other states of this cell, of the cell to its left, and of the predecessors at column j
-            const uint4 r0 = *reinterpret_cast<const uint4 *>(A32 + rb + 4 * q);
-            const uint32_t g0 = A32[rb + 2 * iw + q];
-            uint4 r1 = r0; uint32_t g1 = g0;
-            if (!odd && c >= 2) { r1 = *reinterpret_cast<const uint4 *>(A32 + rb + 4 * (q - 1)); g1 = A32[rb + 2 * iw + q - 1]; }
-            const int e1ij = s16_at(r0.y, odd), e2ij = s16_at(r0.z, odd), f1 = s16_at(r0.w, odd), f2 = s16_at(g0, odd);
-            const int hm1 = s16_at(r1.x, !odd), f1m1 = s16_at(r1.w, !odd), f2m1 = s16_at(g1, !odd); // column j-1 (used only when c >= 1)
-            int b = 0, x1 = 0, x2 = 0;
-            if (in0) { const uint4 rp = *reinterpret_cast<const uint4 *>(A32 + pbw); b = s16_at(rp.x, podd); x1 = s16_at(rp.y, podd); x2 = s16_at(rp.z, podd); }
-            if (cur_op & E_OP) {
-                const bool ok1 = (cur_op & E1_OP) && in0 && ((cur_op & M_OP) ? (hij == x1) : (e1ij == x1 - e1));
-                const bool ok2 = (cur_op & E2_OP) && in0 && ((cur_op & M_OP) ? (hij == x2) : (e2ij == x2 - e2));
-                const unsigned em = __ballot_sync(TH_FULL, ok1 || ok2);
-                if (em) {
-                    const int f = __ffs(em) - 1;
+            if (__any_sync(TH_FULL, bact && !stepped)) { // not a match (for some group)
+                const bool todo = bact && !stepped;
+                if (__any_sync(TH_FULL, todo && (cur_op & E_OP))) { // deletions: predecessors at column j
+                    const bool te = todo && (cur_op & E_OP);
+                    int b = 0, x1 = 0, x2 = inf_min, e1ij = 0, e2ij = inf_min;
+                    if (te && in0) {
+                        const uint32_t pw = (uint32_t)(pm.z - pm.y + 1), po = (uint32_t)pm.x + (uint32_t)(j - pm.y);
+                        b = A16[po]; x1 = A16[po + pw]; if (!AFFINE) x2 = A16[po + 2 * pw];
+                    }
+                    if (te && !(cur_op & M_OP)) { const uint32_t io = (uint32_t)mi.x + (uint32_t)(j - ib); e1ij = A16[io + iw]; if (!AFFINE) e2ij = A16[io + 2 * iw]; }
+                    const bool ok1 = te && (cur_op & E1_OP) && in0 && ((cur_op & M_OP) ? (hij == x1) : (e1ij == x1 - e1));
+                    const bool ok2 = te && (cur_op & E2_OP) && in0 && ((cur_op & M_OP) ? (hij == x2) : (e2ij == x2 - e2));
+                    const unsigned em = g.ballot(ok1 || ok2);
+                    const int f = em ? __ffs(em) - 1 : 0;
                     int nop;
                     if (ok1) nop = (b - oe1 == x1) ? (M_OP | F_OP) : E1_OP;
                     else nop = (b - oe2 == x2) ? (M_OP | F_OP) : E2_OP;
-                    cur_op = __shfl_sync(TH_FULL, nop, f);
-                    if (lane == 0) { cg[n_cig] = ((uint32_t)v << 2) | 2; cq[n_cig] = j - 1; }
-                    ++n_cig; i = __shfl_sync(TH_FULL, pi, f);
-                    continue;
-                }
-            }
-            if (cur_op & F_OP) {
-                if (c < 1) { err = TH_ERR_BACKTRACK; break; }
-                bool hit = false;
-                if (cur_op & F1_OP) {
-                    if (!(cur_op & M_OP) || hij == f1) {
-                        if (hm1 - oe1 == f1) { cur_op = M_OP | E_OP; hit = true; }
-                        else if (f1m1 - e1 == f1) { cur_op = F1_OP; hit = true; }
-                        else { err = TH_ERR_BACKTRACK; break; }
+                    const int fop = g.shfl(nop, f), fpi = g.shfl(pi, f);
+                    if (em) {
+                        cur_op = fop;
+                        if (gl == 0) { cg[n_cig] = ((uint32_t)v << 2) | 2; cq[n_cig] = j - 1; }
+                        ++n_cig; i = fpi; stepped = true;
                     }
                 }
-                if (!hit && (cur_op & F2_OP)) {
-                    if (!(cur_op & M_OP) || hij == f2) {
-                        if (hm1 - oe2 == f2) { cur_op = M_OP | E_OP; hit = true; }
-                        else if (f2m1 - e2 == f2) { cur_op = F2_OP; hit = true; }
-                        else { err = TH_ERR_BACKTRACK; break; }
+                if (__any_sync(TH_FULL, bact && !stepped)) { // insertions: F1 / F2 of this row at columns j and j - 1, recomputed
+                    const bool tf = bact && !stepped && (cur_op & F_OP) && j > ib;
+                    if (bact && !stepped && !tf) { err = TH_ERR_BACKTRACK; ok = false; }
+                    // predecessors' planes from the arena (the ring belongs to the forward pass)
+                    int4 p0m = make_int4(0, 0, -1, 0);
+                    if (tf) {
+                        p0m = d.x >= wlo ? sm.meta[d.x & (POA_WIN - 1)] : rmeta_g[d.x];
+                        for (int p = 1; p < np; ++p) { const int pp = np == 2 ? d.w : plist_g[d.w + p]; sm.pre[p] = pp >= wlo ? sm.meta[pp & (POA_WIN - 1)] : rmeta_g[pp]; }
+                    }
+                    const uint32_t basew = (uint32_t)(vb < 4 ? vb : 0x20) * 0x01010101u;
+                    const int cj = tf ? (j - ib) / CW : -1;
+                    int f1 = 0, f2 = 0, f1m1 = 0, f2m1 = 0;
+                    uint32_t carryH = 0, carryF = POA_NEGP;
+                    for (int ch = 0; __any_sync(TH_FULL, ch <= cj); ++ch) {
+                        const bool a = ch <= cj;
+                        const int j0 = ib + ch * CW + 4 * gl;
+                        uint32_t Hn[2], E1o[2], E2o[2], Fa[2], Fb[2], Hf[2];
+                        poa_chunk<LPT, AFFINE>(g, P, lk, A32, ring, sm.pre, p0m, a ? np : 0, a, j0, ch == 0, carryH, carryF, basew, q8, Hn, E1o, E2o, Fa, Fb, Hf);
+#pragma unroll
+                        for (int x = 0; x < 2; ++x) { // x = 0: column j, x = 1: column j - 1
+                            const int rel = j - x - ib - ch * CW;
+                            const bool inch = a && rel >= 0 && rel < CW;
+                            const int own = (rel >> 2) & (LPT - 1), r = (rel >> 1) & 1, hf = rel & 1;
+                            const int va = s16_at(r ? Fa[1] : Fa[0], hf), vbb = s16_at(r ? Fb[1] : Fb[0], hf);
+                            const int ta = g.shfl(va, own), tb = g.shfl(vbb, own);
+                            if (inch) { if (x == 0) { f1 = ta; f2 = tb; } else { f1m1 = ta; f2m1 = tb; } }
+                        }
+                        poa_chunk_carry<LPT>(g, P, Hf, Fa, Fb, carryH, carryF);
+                    }
+                    if (tf) {
+                        int hm1;
+                        { const unsigned dj = (unsigned)(j - 1 - mi.w);
+                          hm1 = dj < 16u ? segs[16 * (i & (POA_WIN - 1)) + dj] : A16[(uint32_t)mi.x + (uint32_t)(j - 1 - ib)]; }
+                        bool hit = false, bad = false;
+                        if (cur_op & F1_OP) {
+                            if (!(cur_op & M_OP) || hij == f1) {
+                                if (hm1 - oe1 == f1) { cur_op = M_OP | E_OP; hit = true; }
+                                else if (f1m1 - e1 == f1) { cur_op = F1_OP; hit = true; }
+                                else bad = true;
+                            }
+                        }
+                        if (!hit && !bad && (cur_op & F2_OP)) {
+                            if (!(cur_op & M_OP) || hij == f2) {
+                                if (hm1 - oe2 == f2) { cur_op = M_OP | E_OP; hit = true; }
+                                else if (f2m1 - e2 == f2) { cur_op = F2_OP; hit = true; }
+                                else bad = true;
+                            }
+                        }
+                        if (bad) { err = TH_ERR_BACKTRACK; ok = false; }
+                        else { // simd_abpoa_align.c:357-361: the insertion is taken whether or not a test above fired
+                            if (gl == 0) { cg[n_cig] = 1; cq[n_cig] = j - 1; }
+                            ++n_cig; --j;
+                        }
                     }
                 }
-                if (lane == 0) { cg[n_cig] = 1; cq[n_cig] = j - 1; }
-                ++n_cig; --j;
-                continue;
             }
-            err = TH_ERR_BACKTRACK; break;
         }
-        if (err != TH_OK) return err;
-        for (int t = lane; t < j; t += 32) { cg[n_cig + t] = 1; cq[n_cig + t] = j - 1 - t; } // unaligned query head
-        if (j > 0) n_cig += j;
+        if (ok) {
+            for (int t = gl; t < j; t += LPT) { cg[n_cig + t] = 1; cq[n_cig + t] = j - 1 - t; } // unaligned query head
+            if (j > 0) n_cig += j;
+        }
         __syncwarp();
     }
     PH(2);
-    // ---- merge the alignment into the graph (abpoa_graph.c:1218-1284), 32 path steps at a time ----------
+    // ---- merge the alignment into the graph (abpoa_graph.c:1218-1284), LPT path steps at a time ----------
     // A path visits every node and every aligned group at most once, so all steps touch distinct adjacency lists
     // and groups; ids of new nodes/edges are creation-ordered prefix sums, exactly what the sequential walk yields.
     int n_ev = 0;
     {
         const int node_n0 = node_n;
         int last_id = 0, last_new = 0, pend_lo = 0; // events [pend_lo, n_ev) wait for the next match column
-        for (int k0 = 0; k0 < n_cig; k0 += 32) {
-            const int k = k0 + lane;
+        if (!ok) n_cig = 0;
+        const unsigned below = (1u << gl) - 1;
+        for (int k0 = 0; __any_sync(TH_FULL, ok && k0 < n_cig); k0 += LPT) {
+            const bool ma = ok && k0 < n_cig;
+            const int k = k0 + gl;
             int op = 2, v = 0, q = 0;
-            if (k < n_cig) { const uint32_t cv = w.cigar[n_cig - 1 - k]; op = cv & 3; v = (int)(cv >> 2); q = w.cigq[n_cig - 1 - k]; }
+            if (ma && k < n_cig) { const uint32_t cv = w.cigar[n_cig - 1 - k]; op = cv & 3; v = (int)(cv >> 2); q = w.cigq[n_cig - 1 - k]; }
             const bool prod = op != 2;
             int tgt = -1, isnew = 0, bf = 0, bl = 0, an = 0, al[4] = {0, 0, 0, 0};
             uint8_t qb = 0;
             if (prod) qb = query[q];
             if (op == 0) {
-                bf = w.n2i[v]; bl = bf; an = w.aln_n[v];
+                bf = w.n2i[v]; bl = bf; an = min(w.aln_n[v], 4);
                 int aid = -1;
                 for (int a = 0; a < an; ++a) {
                     al[a] = w.aln[v * 4 + a];
@@ -612,41 +762,42 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
                 }
                 if (w.base[v] == qb) tgt = v; else if (aid >= 0) tgt = aid; else isnew = 1;
             } else if (op == 1) isnew = 1;
-            const unsigned newm = __ballot_sync(TH_FULL, isnew), prodm = __ballot_sync(TH_FULL, prod), mm = __ballot_sync(TH_FULL, op == 0);
-            const unsigned below = (1u << lane) - 1;
+            const unsigned newm = g.ballot(isnew), prodm = g.ballot(prod), mm = g.ballot(op == 0);
             const int ev = n_ev + __popc(newm & below); // event id == rank of the new node
             if (isnew) tgt = node_n0 + ev;
             // previous producing step
             int from = last_id, from_new = last_new;
             { const unsigned lower = prodm & below; const int src = lower ? 31 - __clz(lower) : 0;
-              const int pt = __shfl_sync(TH_FULL, tgt, src), pnw = __shfl_sync(TH_FULL, isnew, src);
+              const int pt = g.shfl(tgt, src), pnw = g.shfl(isnew, src);
               if (lower) { from = pt; from_new = pnw; } }
             // new nodes first (their adjacency heads must exist before edges are linked)
+            int lerr = 0;
             if (isnew) {
-                if (tgt >= w.ncap) err = TH_ERR_CAP;
-                else { w.base[tgt] = qb; w.out_head[tgt] = w.out_tail[tgt] = w.in_head[tgt] = w.in_tail[tgt] = -1; w.aln_n[tgt] = 0; w.ev_node[ev] = tgt; }
+                if (tgt >= w.ncap) lerr = 1;
+                else { w.base[tgt] = qb; w.out_head[tgt] = w.out_tail[tgt] = w.in_head[tgt] = w.in_tail[tgt] = -1; w.aln_n[tgt] = 0; w.hs[tgt] = 0; w.ev_node[ev] = tgt; }
             }
-            if (__any_sync(TH_FULL, err != TH_OK)) return TH_ERR_CAP;
-            if (isnew && op == 0) { // abpoa_add_graph_aligned_node (:1036-1044): all-pairs with the old group
-                if (an >= 4) err = TH_ERR_CAP; // a column holds at most 5 distinct codes (ACGT + N): 4 aligned nodes per node
-                else {
-                    for (int a = 0; a < an; ++a) { const int y = al[a]; w.aln[y * 4 + w.aln_n[y]] = tgt; w.aln_n[y] += 1; w.aln[tgt * 4 + a] = y; }
-                    w.aln[v * 4 + an] = tgt; w.aln_n[v] = an + 1; w.aln[tgt * 4 + an] = v; w.aln_n[tgt] = an + 1;
-                    w.ev_anchor[ev] = bl + 1;
+            if (isnew && op == 0 && an >= 4) lerr = 1; // a column holds at most 5 distinct codes (ACGT + N): 4 aligned nodes per node
+            if (g.any(lerr)) { err = TH_ERR_CAP; ok = false; }
+            const bool go = ok && ma;
+            if (go && prod) w.hs[tgt] += 1;              // reads through the node (a path visits a node once: no two lanes share a target)
+            if (go && isnew && op == 0) { // abpoa_add_graph_aligned_node (:1036-1044): all-pairs with the old group
+                for (int a = 0; a < an; ++a) { const int y = al[a]; w.aln[y * 4 + w.aln_n[y]] = tgt; w.aln_n[y] += 1; w.aln[tgt * 4 + a] = y; }
+                w.aln[v * 4 + an] = tgt; w.aln_n[v] = an + 1; w.aln[tgt * 4 + an] = v; w.aln_n[tgt] = an + 1;
+                w.ev_anchor[ev] = bl + 1;
+            }
+            // insertion events take the first index of the next match column's group
+            {
+                const int fm = mm ? __ffs(mm) - 1 : 0, bff = g.shfl(bf, fm);
+                if (go && mm) {
+                    const int hi_ev = n_ev + __popc(newm & ((1u << fm) - 1)); // events created before that step
+                    for (int e = pend_lo + gl; e < hi_ev; e += LPT) w.ev_anchor[e] = bff;
                 }
             }
-            if (__any_sync(TH_FULL, err != TH_OK)) return TH_ERR_CAP;
-            // insertion events take the first index of the next match column's group
-            if (mm) {
-                const int fm = __ffs(mm) - 1, bff = __shfl_sync(TH_FULL, bf, fm);
-                const int hi_ev = n_ev + __popc(newm & ((1u << fm) - 1)); // events created before that step
-                for (int e = pend_lo + lane; e < hi_ev; e += 32) w.ev_anchor[e] = bff;
-            }
             {
-                const unsigned higher = mm & ~(below | (1u << lane));
+                const unsigned higher = mm & ~(below | (1u << gl));
                 const int src = higher ? __ffs(higher) - 1 : 0;
-                const int bfn = __shfl_sync(TH_FULL, bf, src);
-                if (op == 1 && higher) w.ev_anchor[ev] = bfn;
+                const int bfn = g.shfl(bf, src);
+                if (go && op == 1 && higher) w.ev_anchor[ev] = bfn;
             }
             { // events after the last match column of this batch stay pending
                 const int lastm = mm ? 31 - __clz(mm) : -1;
@@ -655,10 +806,10 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
             __syncwarp();
             // edges (abpoa_add_graph_edge :1063-1106): weight + 1 on an existing edge, else append to both lists
             int found = -1;
-            if (prod && !from_new && !isnew)
+            if (go && prod && !from_new && !isnew)
                 for (int e = w.out_head[from]; e >= 0; e = w.e_no[e]) if (w.e_to[e] == tgt) { found = e; break; }
-            const bool mk = prod && found < 0;
-            const unsigned mkm = __ballot_sync(TH_FULL, mk);
+            const bool mk = go && prod && found < 0;
+            const unsigned mkm = g.ballot(mk);
             if (found >= 0) w.e_w[found] += 1;
             if (mk) {
                 const int e = edge_n + __popc(mkm & below);
@@ -672,42 +823,92 @@ __device__ int poa_add_sequence(PoaWs &w, const DevParams &P, const uint8_t *que
             }
             edge_n += __popc(mkm);
             n_ev += __popc(newm);
-            if (prodm) { const int src = 31 - __clz(prodm); last_id = __shfl_sync(TH_FULL, tgt, src); last_new = __shfl_sync(TH_FULL, isnew, src); }
+            { const int src = prodm ? 31 - __clz(prodm) : 0;
+              const int lt = g.shfl(tgt, src), ln = g.shfl(isnew, src);
+              if (prodm) { last_id = lt; last_new = ln; } }
             __syncwarp();
         }
-        node_n = node_n0 + n_ev;
-        if (lane == 0) g_add_edge(w, edge_n, last_id, 1, !last_new);
-        edge_n = __shfl_sync(TH_FULL, edge_n, 0);
-        for (int e = pend_lo + lane; e < n_ev; e += 32) w.ev_anchor[e] = n - 1; // before the sink
+        if (ok) {
+            node_n = node_n0 + n_ev;
+            if (gl == 0) g_add_edge(w, edge_n, last_id, 1, !last_new);
+        }
+        edge_n = g.shfl(edge_n, 0);
+        if (ok) for (int e = pend_lo + gl; e < n_ev; e += LPT) w.ev_anchor[e] = n - 1; // before the sink
     }
     __syncwarp();
     PH(3);
     // new order: old node at index i moves to i + #(events with anchor <= i); event e lands at anchor_e + e
-    for (int i = lane; i < n; i += 32) {
-        int lo = 0, hi = n_ev;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (w.ev_anchor[mid] <= i) lo = mid + 1; else hi = mid; }
-        w.ord2[i + lo] = w.ord[i];
+    if (ok) {
+        for (int i = gl; i < n; i += LPT) {
+            int lo = 0, hi = n_ev;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (w.ev_anchor[mid] <= i) lo = mid + 1; else hi = mid; }
+            w.ord2[i + lo] = w.ord[i];
+        }
+        for (int e = gl; e < n_ev; e += LPT) w.ord2[w.ev_anchor[e] + e] = w.ev_node[e];
     }
-    for (int e = lane; e < n_ev; e += 32) w.ord2[w.ev_anchor[e] + e] = w.ev_node[e];
     __syncwarp();
-    if (lane == 0) { int32_t *t = w.ord; w.ord = w.ord2; w.ord2 = t; }
+    if (ok && gl == 0) { int32_t *t = w.ord; w.ord = w.ord2; w.ord2 = t; }
     __syncwarp();
     PH(4);
 #undef PH
-    return TH_OK;
 }
 
-// heaviest-column consensus (abpoa_graph.c:279-359, 604-648, 467-478).  All lanes call; returns cons_len.
-// The DFS that assigns MSA ranks is order dependent (stack discipline, abpoa_graph.c:279-339) and stays on lane 0;
-// in-degrees, column weights and the column vote are data parallel.
-__device__ int poa_consensus(PoaWs &w, int node_n, int n_seq, uint8_t *cons, int32_t *cov) {
-    const int lane = lane_id();
+// Heaviest-column consensus without the rank DFS.  The reference orders the MSA columns (aligned groups) by a stack-driven
+// DFS (abpoa_graph.c:279-339), which is one topological order of the column DAG; `ord` is another one, with every group
+// contiguous.  Only columns that EMIT a base matter (max_w >= n_seq - sum_w, :604-629), and two emitted columns that no
+// path orders would have disjoint read sets, hence max_w = sum_w = n_seq / 2 in both: unless at least two such columns
+// exist (counted in `ambiguous`), every topological order yields the same consensus, and this one is data parallel.
+// The weight of a node (popcount of its read ids) is the number of reads through it, kept in hs[] by the merge.
+template <int LPT>
+__device__ int poa_consensus_fast(PoaSmem<LPT> &sm, const bool act, const int node_n, const int n_seq, uint8_t *cons, int32_t *cov, int &ambiguous) {
+    const PoaG<LPT> g;
+    const int gl = g.gl;
+    PoaWs &w = sm.ws;
+    const int n = act ? node_n : 0;
+    for (int i = gl; i < n; i += LPT) w.n2i[w.ord[i]] = i;
+    __syncwarp();
+    int cons_i = 0; ambiguous = 0;
+    for (int i0 = 1; __any_sync(TH_FULL, i0 < n - 1); i0 += LPT) {
+        const int i = i0 + gl;
+        bool sel = false, amb = false; int max_w = 0, node = 0;
+        if (i < n - 1) {
+            const int v = w.ord[i], an = min(w.aln_n[v], 4);
+            bool first = true;
+            int sum = 0, key = 0;
+            { const int b = w.base[v], hw = w.hs[v]; if (b < 4) { sum += hw; key = (hw << 3) | (7 - b); node = v; } }
+            for (int a = 0; a < an; ++a) {
+                const int x = w.aln[v * 4 + a];
+                if (w.n2i[x] < i) first = false;
+                const int b = w.base[x], hw = w.hs[x];
+                if (b < 4) { sum += hw; const int k = (hw << 3) | (7 - b); if (k > key) { key = k; node = x; } } // first heaviest base in A, C, G, T order
+            }
+            max_w = key >> 3;
+            const int gap_w = n_seq - sum;
+            sel = first && max_w > 0 && max_w >= gap_w;
+            amb = sel && max_w == gap_w && sum == max_w;
+        }
+        const unsigned m = g.ballot(sel), am = g.ballot(amb);
+        if (sel) { const int pos = cons_i + __popc(m & ((1u << gl) - 1)); cons[pos] = w.base[node]; cov[pos] = max_w; }
+        cons_i += __popc(m); ambiguous += __popc(am);
+    }
+    return cons_i;
+}
+
+// heaviest-column consensus (abpoa_graph.c:279-359, 604-648, 467-478).  All lanes of the warp call; returns cons_len of the
+// lane's group (-1: the arena is too small).  The DFS that assigns MSA ranks is order dependent (stack discipline,
+// abpoa_graph.c:279-339) and runs on one lane per group; in-degrees, column weights and the column vote are data parallel.
+template <int LPT>
+__device__ int poa_consensus(PoaSmem<LPT> &sm, const bool act, int node_n, int n_seq, uint8_t *cons, int32_t *cov) {
+    const PoaG<LPT> g;
+    const int gl = g.gl;
+    PoaWs &w = sm.ws;
     int32_t *deg = w.n2i, *stk = w.ord2, *rank = w.ri;
     int32_t *rcw = reinterpret_cast<int32_t *>(w.arena); // 5 x msa_l weights, then 5 x msa_l node ids
-    for (int i = lane; i < node_n; i += 32) { int d = 0; for (int e = w.in_head[i]; e >= 0; e = w.e_ni[e]) ++d; deg[i] = d; }
+    if (!act) node_n = 0;
+    for (int i = gl; i < node_n; i += LPT) { int d = 0; for (int e = w.in_head[i]; e >= 0; e = w.e_ni[e]) ++d; deg[i] = d; }
     __syncwarp();
     int msa_l = 0;
-    if (lane == 0) {
+    if (act && gl == 0) {
         int sp = 0, msa_rank = 0;
         stk[sp++] = 0; rank[0] = -1;
         while (sp > 0) {
@@ -721,10 +922,10 @@ __device__ int poa_consensus(PoaWs &w, int node_n, int n_seq, uint8_t *cons, int
             for (int e = w.out_head[cur]; e >= 0; e = w.e_no[e]) {
                 const int o = w.e_to[e];
                 if (--deg[o] == 0) {
-                    bool ok = true;
+                    bool okk = true;
                     const int an = w.aln_n[o];
-                    for (int a = 0; a < an; ++a) if (deg[w.aln[o * 4 + a]] != 0) { ok = false; break; }
-                    if (!ok) continue;
+                    for (int a = 0; a < an; ++a) if (deg[w.aln[o * 4 + a]] != 0) { okk = false; break; }
+                    if (!okk) continue;
                     stk[sp++] = o; rank[o] = -1;
                     for (int a = 0; a < an; ++a) { const int x = w.aln[o * 4 + a]; stk[sp++] = x; rank[x] = -1; }
                 }
@@ -732,16 +933,17 @@ __device__ int poa_consensus(PoaWs &w, int node_n, int n_seq, uint8_t *cons, int
         }
         msa_l = rank[1] - 1;
     }
-    msa_l = __shfl_sync(TH_FULL, msa_l, 0);
+    msa_l = g.shfl(msa_l, 0);
     __syncwarp();
-    if (msa_l <= 0) return 0;
-    if ((uint64_t)msa_l * 10 * 2 > w.arena_cap) return -1;
+    int ret = 0;
+    if (msa_l <= 0) msa_l = 0;
+    else if ((uint64_t)msa_l * 10 * 2 > w.arena_cap) { ret = -1; msa_l = 0; }
     int32_t *nodeid = rcw + 5 * (size_t)msa_l;
-    for (int i = lane; i < 5 * msa_l; i += 32) { rcw[i] = 0; nodeid[i] = 0; }
+    for (int i = gl; i < 5 * msa_l; i += LPT) { rcw[i] = 0; nodeid[i] = 0; }
     __syncwarp();
     // abpoa_set_row_column_weight; popcount(read_ids) == sum of out weights.  A column is one aligned group and a
     // group holds one node per base, so every (column, base) slot has a single writer.
-    for (int i = 2 + lane; i < node_n; i += 32) {
+    if (msa_l > 0) for (int i = 2 + gl; i < node_n; i += LPT) {
         int rk = rank[i];
         for (int a = 0; a < w.aln_n[i]; ++a) rk = max(rk, rank[w.aln[i * 4 + a]]);
         int wsum = 0;
@@ -752,105 +954,144 @@ __device__ int poa_consensus(PoaWs &w, int node_n, int n_seq, uint8_t *cons, int
     }
     __syncwarp();
     int cons_i = 0;
-    for (int c0 = 0; c0 < msa_l; c0 += 32) { // abpoa_heaviest_column_consensus (:604-629): first heaviest base, kept iff max_w >= gap weight
-        const int c = c0 + lane;
+    for (int c0 = 0; __any_sync(TH_FULL, c0 < msa_l); c0 += LPT) { // abpoa_heaviest_column_consensus (:604-629): first heaviest base, kept iff max_w >= gap weight
+        const int c = c0 + gl;
         int max_w = 0, max_base = 5, gap_w = n_seq; bool sel = false;
         if (c < msa_l) {
             for (int b = 0; b < 4; ++b) { const int x = rcw[c * 5 + b]; if (x > max_w) { max_base = b; max_w = x; } gap_w -= x; }
             sel = max_w >= gap_w && max_base < 5;
         }
-        const unsigned m = __ballot_sync(TH_FULL, sel);
-        if (sel) { const int pos = cons_i + __popc(m & ((1u << lane) - 1)); cons[pos] = w.base[nodeid[c * 5 + max_base]]; cov[pos] = max_w; }
+        const unsigned m = g.ballot(sel);
+        if (sel) { const int pos = cons_i + __popc(m & ((1u << gl) - 1)); cons[pos] = w.base[nodeid[c * 5 + max_base]]; cov[pos] = max_w; }
         cons_i += __popc(m);
     }
-    return cons_i;
+    return ret < 0 ? -1 : cons_i;
 }
 
-// persistent warps pull tasks from an atomic counter
-#ifndef POA_MIN_BLOCKS
-#define POA_MIN_BLOCKS 8   // 64 registers: 32 warps per SM.  Every phase of the kernel is a dependent chain, so resident warps are what hides latency
+// persistent warps; every group pulls its tasks from an atomic counter
+#ifndef POA_MIN_BLOCKS16
+#define POA_MIN_BLOCKS16 4   // 16-lane groups: 16 warps = 32 tasks per SM, 128 registers
 #endif
-__global__ void __launch_bounds__(POA_WARPS * 32, POA_MIN_BLOCKS)
+#ifndef POA_MIN_BLOCKS32
+#define POA_MIN_BLOCKS32 4
+#endif
+template <int LPT>
+__global__ void __launch_bounds__(POA_WARPS * 32, LPT == 16 ? POA_MIN_BLOCKS16 : POA_MIN_BLOCKS32)
 poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const int32_t *__restrict__ task_order,
            const int32_t *__restrict__ u_start, const int32_t *__restrict__ u_len, const uint8_t *__restrict__ bseq,
            uint8_t *slabs, size_t slab_bytes, int *task_counter,
            uint8_t *__restrict__ cons_base, int32_t *__restrict__ cons_cov, int32_t *__restrict__ cons_len,
            int32_t *__restrict__ task_status, unsigned long long *__restrict__ stat_cells, unsigned long long *__restrict__ stat_rows,
-           unsigned long long *__restrict__ stat_phase) {
-    __shared__ PoaSmem s_mem[POA_WARPS];
-    __shared__ PoaWs s_ws[POA_WARPS]; // workspace pointers live in shared memory: one LDS instead of re-deriving them under register pressure
-    const int lane = lane_id(), wib = threadIdx.x >> 5;
-    const int gw = blockIdx.x * POA_WARPS + wib;
-    uint8_t *slab = slabs + (size_t)gw * slab_bytes;
+           unsigned long long *__restrict__ stat_phase, int max_groups) {
+    constexpr int GPW = 32 / LPT;                      // groups per warp
+    extern __shared__ __align__(16) unsigned char poa_smem_raw[];
+    PoaSmem<LPT> *s_all = reinterpret_cast<PoaSmem<LPT> *>(poa_smem_raw);
+    PoaLaneK *lk_tab = reinterpret_cast<PoaLaneK *>(s_all + POA_WARPS * GPW);
+    poa_fill_lane_k(lk_tab, LPT, P);
+    __syncthreads();
+    const PoaG<LPT> g;
+    const int gl = g.gl, wib = threadIdx.x >> 5, gib = wib * GPW + (g.gofs ? 1 : 0);
+    PoaSmem<LPT> &sm = s_all[gib];
+    const uint32_t lk = (uint32_t)__cvta_generic_to_shared(lk_tab + gl);
+    const int gg = blockIdx.x * (POA_WARPS * GPW) + gib;
+    uint8_t *slab = slabs + (size_t)gg * slab_bytes;
     unsigned long long cells = 0, rows = 0;
 #ifdef POA_PROFILE
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_all = clock64();
 #else
     long long *ph = nullptr;
 #endif
+    // group state
+    bool has = false, done = gg >= max_groups; // groups beyond max_groups have no slab
+    int t = 0, s = 0, node_n = 0, edge_n = 0, err = TH_OK;
+    PoaTask T; T.n_seqs = 0; T.unit_off = 0; T.seq_off = 0; T.cons_off = 0; T.ncap = 0; T.qmax = 0; T.read = 0;
     while (true) {
-#ifdef POA_PROFILE
-        long long t_task = clock64();
-#endif
-        int ti = 0;
-        if (lane == 0) ti = atomicAdd(task_counter, 1);
-        ti = __shfl_sync(TH_FULL, ti, 0);
-        if (ti >= n_tasks) break;
-        const int t = task_order ? task_order[ti] : ti;
-        const PoaTask T = tasks[t];
+        // ---- groups without a task fetch one -----------------------------------------------------------------------
+        bool fresh = false;
+        {
+            int ti = 0;
+            if (!has && !done && gl == 0) ti = atomicAdd(task_counter, 1);
+            ti = g.shfl(ti, 0);
+            if (!has && !done) {
+                if (ti >= n_tasks) done = true;
+                else { t = task_order ? task_order[ti] : ti; T = tasks[t]; has = true; fresh = true; s = 1; err = TH_OK; }
+            }
+        }
+        if (!__any_sync(TH_FULL, has)) break;
         const uint8_t *rseq = bseq + T.seq_off;
         uint8_t *cons = cons_base + T.cons_off; int32_t *cov = cons_cov + T.cons_off;
-        if (T.n_seqs < 2) { if (lane == 0) { cons_len[t] = 0; task_status[t] = TH_ERR_CAP; } continue; } // the reference aborts here (abpoa_cons.c:58)
-        if (T.n_seqs <= 2) { // src/abpoa_cons.c:57-80: the first unit verbatim
+        if (fresh) { // tasks that need no graph
+            if (T.n_seqs < 2) { if (gl == 0) { cons_len[t] = 0; task_status[t] = TH_ERR_CAP; } has = false; } // the reference aborts here (abpoa_cons.c:58)
+            else if (T.n_seqs <= 2) { // src/abpoa_cons.c:57-80: the first unit verbatim
+                const int l0 = u_len[T.unit_off]; const uint8_t *s0 = rseq + u_start[T.unit_off];
+                for (int i = gl; i < l0; i += LPT) { cons[i] = s0[i]; cov[i] = 0; }
+                if (gl == 0) { cons_len[t] = l0; task_status[t] = TH_OK; }
+                has = false;
+            } else if (poa_fixed_bytes(T.ncap, T.qmax, T.n_seqs) + 4096 > slab_bytes) { if (gl == 0) { cons_len[t] = 0; task_status[t] = TH_ERR_ARENA; } has = false; }
+            if (!has) fresh = false;
+        }
+        __syncwarp();
+        if (fresh && gl == 0) poa_carve(sm.ws, slab, slab_bytes, T.ncap, T.qmax, T.n_seqs);
+        __syncwarp();
+        if (fresh) { // first sequence: a chain of new nodes (abpoa_graph.c:1108-1124)
+            PoaWs &w = sm.ws;
+            const int l0 = u_len[T.unit_off];
+            for (int i = gl; i < l0 + 2; i += LPT) { w.out_head[i] = w.out_tail[i] = w.in_head[i] = w.in_tail[i] = -1; w.aln_n[i] = 0; }
+        }
+        __syncwarp();
+        if (fresh) {
+            PoaWs &w = sm.ws;
             const int l0 = u_len[T.unit_off]; const uint8_t *s0 = rseq + u_start[T.unit_off];
-            for (int i = lane; i < l0; i += 32) { cons[i] = s0[i]; cov[i] = 0; }
-            if (lane == 0) { cons_len[t] = l0; task_status[t] = TH_OK; }
-            continue;
+            for (int i = gl; i <= l0; i += LPT) {
+                const int from = i == 0 ? 0 : 1 + i, to = i == l0 ? 1 : 2 + i;
+                w.e_to[i] = to; w.e_from[i] = from; w.e_w[i] = 1; w.e_no[i] = -1; w.e_ni[i] = -1;
+                w.out_head[from] = w.out_tail[from] = i; w.in_head[to] = w.in_tail[to] = i;
+                if (i < l0) { w.base[2 + i] = s0[i]; w.ord[1 + i] = 2 + i; w.hs[2 + i] = 1; }
+            }
+            if (gl == 0) { w.ord[0] = 0; w.ord[l0 + 1] = 1; w.base[0] = w.base[1] = 4; }
+            node_n = l0 + 2; edge_n = l0 + 1;
         }
-        if (poa_fixed_bytes(T.ncap, T.qmax, T.n_seqs) + 4096 > slab_bytes) { if (lane == 0) { cons_len[t] = 0; task_status[t] = TH_ERR_ARENA; } continue; }
-        PoaWs &w = s_ws[wib];
         __syncwarp();
-        if (lane == 0) poa_carve(w, slab, slab_bytes, T.ncap, T.qmax, T.n_seqs);
-        __syncwarp();
-        // first sequence: a chain of new nodes (abpoa_graph.c:1108-1124)
-        const int l0 = u_len[T.unit_off]; const uint8_t *s0 = rseq + u_start[T.unit_off];
-        for (int i = lane; i < l0 + 2; i += 32) { w.out_head[i] = w.out_tail[i] = w.in_head[i] = w.in_tail[i] = -1; w.aln_n[i] = 0; }
-        __syncwarp();
-        for (int i = lane; i <= l0; i += 32) {
-            const int from = i == 0 ? 0 : 1 + i, to = i == l0 ? 1 : 2 + i;
-            w.e_to[i] = to; w.e_from[i] = from; w.e_w[i] = 1; w.e_no[i] = -1; w.e_ni[i] = -1;
-            w.out_head[from] = w.out_tail[from] = i; w.in_head[to] = w.in_tail[to] = i;
-            if (i < l0) { w.base[2 + i] = s0[i]; w.ord[1 + i] = 2 + i; }
+        // ---- one more sequence for every group that has a task -----------------------------------------------------
+        if (__any_sync(TH_FULL, has)) {
+            const bool act = has && err == TH_OK && s < T.n_seqs;
+            const uint8_t *q = rseq; int ql = 0;
+            if (act) { q = rseq + u_start[T.unit_off + s]; ql = u_len[T.unit_off + s]; }
+            if (!P.affine) poa_add_sequence<LPT, false>(sm, P, lk, act, q, ql, node_n, edge_n, err, cells, rows, ph);
+            else poa_add_sequence<LPT, true>(sm, P, lk, act, q, ql, node_n, edge_n, err, cells, rows, ph);
+            if (act) ++s;
         }
-        if (lane == 0) { w.ord[0] = 0; w.ord[l0 + 1] = 1; w.base[0] = w.base[1] = 4; }
-        __syncwarp();
-        int node_n = l0 + 2, edge_n = l0 + 1, err = TH_OK;
-        for (int s = 1; s < T.n_seqs && err == TH_OK; ++s)
-        {
-            const uint8_t *q = rseq + u_start[T.unit_off + s]; const int ql = u_len[T.unit_off + s];
-            if (!P.affine) err = P.pn == 16 ? poa_add_sequence<4, false>(w, P, q, ql, node_n, edge_n, s_mem[wib], cells, rows, ph)
-                                            : poa_add_sequence<3, false>(w, P, q, ql, node_n, edge_n, s_mem[wib], cells, rows, ph);
-            else err = P.pn == 16 ? poa_add_sequence<4, true>(w, P, q, ql, node_n, edge_n, s_mem[wib], cells, rows, ph)
-                                  : poa_add_sequence<3, true>(w, P, q, ql, node_n, edge_n, s_mem[wib], cells, rows, ph);
-        }
-        int cl = 0;
+        // ---- finished tasks: consensus -----------------------------------------------------------------------------
+        const bool fin = has && (err != TH_OK || s >= T.n_seqs);
+        if (__any_sync(TH_FULL, fin)) {
 #ifdef POA_PROFILE
-        long long t_c0 = clock64();
+            long long t_c0 = clock64();
 #endif
-        if (err == TH_OK) {
-            cl = poa_consensus(w, node_n, T.n_seqs, cons, cov);
-            if (cl < 0) { err = TH_ERR_ARENA; cl = 0; }
-        }
-        if (lane == 0) { cons_len[t] = cl; task_status[t] = err; }
-        __syncwarp();
+            int amb = 0;
+            int cl = poa_consensus_fast<LPT>(sm, fin && err == TH_OK, node_n, T.n_seqs, cons, cov, amb);
+            if (__any_sync(TH_FULL, fin && err == TH_OK && amb >= 2)) { // column order not settled by the graph: the reference's DFS decides
+                const bool dfs = fin && err == TH_OK && amb >= 2;
+                const int cl2 = poa_consensus<LPT>(sm, dfs, node_n, T.n_seqs, cons, cov);
+                if (dfs) cl = cl2;
+            }
+            if (fin) {
+                if (err == TH_OK && cl < 0) err = TH_ERR_ARENA;
+                if (err != TH_OK) cl = 0;
+                if (gl == 0) { cons_len[t] = cl; task_status[t] = err; }
+                has = false;
+            }
 #ifdef POA_PROFILE
-        { long long t_ = clock64(); ph[5] += t_ - t_c0; ph[6] += t_ - t_task; }
+            ph[5] += clock64() - t_c0;
 #endif
+        }
+        __syncwarp();
     }
-    if (lane == 0 && cells) {
-        atomicAdd(stat_cells, cells); atomicAdd(stat_rows, rows);
+    if (gl == 0 && cells) { atomicAdd(stat_cells, cells); atomicAdd(stat_rows, rows); }
 #ifdef POA_PROFILE
+    if ((threadIdx.x & 31) == 0) {
+        ph[6] = clock64() - t_all;
         for (int k = 0; k < 7; ++k) atomicAdd(stat_phase + k, (unsigned long long)ph[k]);
-#endif
     }
+#endif
 }

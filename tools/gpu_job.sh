@@ -1,0 +1,30 @@
+#!/bin/bash
+# One GPU-box visit, parameterised (replaces the per-round lease scripts).  usage: tools/gpu_job.sh <job> [args...]
+#   tests [pytest args]      GPU parity tests
+#   step N [steps] [shape]   one device-resident step (tools/profile_step.py)
+#   phases N [shape]         rebuild with -DPOA_PROFILE on the box and print the POA phase split
+#   ncu NAME N regex [count] ncu --set full capture of kernels matching regex -> gpurun_out/NAME.ncu-rep + summary
+#   launches NAME N          ncu launch list (gpu__time_duration) of one step -> gpurun_out/NAME.csv
+#   bench [args]             bench.py
+set -u
+mkdir -p gpurun_out
+job=$1; shift
+case $job in
+  tests) timeout 1500 python -m pytest tests -m gpu -x -q "$@" 2>&1 | tail -15 ;;
+  step) timeout 600 python tools/profile_step.py "$@" 2>&1 | tail -6 ;;
+  phases)
+    cp tidehunter_b200/libth_gpu.so /tmp/libth_gpu.so.keep
+    TH_NVCC_FLAGS="-DPOA_PROFILE" python -c "import tidehunter_b200.build as b; b.build(force=True)" && timeout 600 python tools/profile_step.py "$@" 2>&1 | tail -4
+    cp /tmp/libth_gpu.so.keep tidehunter_b200/libth_gpu.so ;;
+  ncu)
+    name=$1; n=$2; regex=$3; cnt=${4:-1}; shape=${5:-r2c2}
+    timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$regex" -c "$cnt" -o gpurun_out/$name -f python tools/profile_step.py "$n" 1 "$shape" > gpurun_out/$name.log 2>&1
+    tail -3 gpurun_out/$name.log | cut -c1-400
+    python tools/ncu_summary.py gpurun_out/$name.ncu-rep > gpurun_out/$name.summary.txt 2>&1; cat gpurun_out/$name.summary.txt ;;
+  launches)
+    name=$1; n=$2
+    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/$name.csv python tools/profile_step.py "$n" 2 > gpurun_out/$name.log 2>&1
+    tail -2 gpurun_out/$name.log | cut -c1-300 ;;
+  bench) timeout 1500 python bench.py "$@" ;;
+  *) echo "unknown job $job"; exit 2 ;;
+esac
