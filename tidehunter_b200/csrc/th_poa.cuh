@@ -56,8 +56,11 @@ struct PoaTask {
 //   w = second predecessor row (np == 2) or offset into plist (np > 2).
 // Row metadata (written when the row is computed):  x = arena offset (int16 units), y = first column, z = last column,
 //   w = max_i + 1 of the row (what the reference scatters into max_pos_left/right of the successors).
+// Node records (kept up to date by the merge, so that the per-alignment setup walks no adjacency list):
+//   nrec[v] = in-degree, then the first three in-neighbours in in_id order;
+//   brec[v] = heaviest out-edge (the first one of maximum weight, abpoa_graph.c:216-226): target node, weight, edge id.
 struct PoaWs {
-    int4 *rdesc, *rmeta;
+    int4 *rdesc, *rmeta, *nrec, *brec;
     int32_t *out_head, *out_tail, *in_head, *in_tail, *aln_n, *aln, *n2i, *ri, *hs;
     int32_t *e_to, *e_from, *e_w, *e_no, *e_ni, *plist;
     int32_t *ord, *ord2, *ev_anchor, *ev_node, *hi_idx;
@@ -69,7 +72,7 @@ struct PoaWs {
 __host__ __device__ inline size_t poa_fixed_bytes(int ncap, int qmax, int nseq) {
     size_t ecap = (size_t)ncap + nseq + 2;
     size_t b = 0;
-    b += (size_t)ncap * 16 * 2;                        // rdesc, rmeta
+    b += (size_t)ncap * 16 * 4;                        // rdesc, rmeta, nrec, brec
     b += (size_t)ncap * 4 * (9 + 3);                   // 9 node arrays (aln counts as 4) = 12 x int32
     b += ecap * 4 * 6;                                 // 5 edge arrays + plist
     b += (size_t)ncap * 4 * 3;                         // ord, ord2, hi_idx
@@ -83,8 +86,8 @@ __host__ __device__ inline size_t poa_fixed_bytes(int ncap, int qmax, int nseq) 
 __device__ inline void poa_carve(PoaWs &w, uint8_t *slab, size_t slab_bytes, int ncap, int qmax, int nseq) {
     size_t ecap = (size_t)ncap + nseq + 2;
     w.ncap = ncap;
-    w.rdesc = reinterpret_cast<int4 *>(slab); w.rmeta = w.rdesc + ncap;
-    int32_t *p = reinterpret_cast<int32_t *>(w.rmeta + ncap);
+    w.rdesc = reinterpret_cast<int4 *>(slab); w.rmeta = w.rdesc + ncap; w.nrec = w.rmeta + ncap; w.brec = w.nrec + ncap;
+    int32_t *p = reinterpret_cast<int32_t *>(w.brec + ncap);
     w.out_head = p; p += ncap; w.out_tail = p; p += ncap; w.in_head = p; p += ncap; w.in_tail = p; p += ncap;
     w.aln_n = p; p += ncap; w.aln = p; p += 4 * (size_t)ncap; w.n2i = p; p += ncap; w.ri = p; p += ncap; w.hs = p; p += ncap;
     w.e_to = p; p += ecap; w.e_from = p; p += ecap; w.e_w = p; p += ecap; w.e_no = p; p += ecap; w.e_ni = p; p += ecap; w.plist = p; p += ecap;
@@ -104,13 +107,28 @@ __device__ inline void poa_carve(PoaWs &w, uint8_t *slab, size_t slab_bytes, int
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 __device__ __forceinline__ int s16_at(uint32_t word, int odd) { return odd ? hi16(word) : lo16(word); }
 
+// a new edge `from -> to` with id e enters the node records (one lane per `to` and per `from` at a time)
+__device__ __forceinline__ void g_note_in(PoaWs &w, int to, int from) {
+    int32_t *r = reinterpret_cast<int32_t *>(w.nrec + to);
+    const int k = r[0];
+    if (k < 3) r[1 + k] = from;
+    r[0] = k + 1;
+}
+// edge e out of `from` now has weight wt: it becomes the heaviest one if it beats the current one, or ties with it
+// and comes earlier in the out list (edge ids grow along a node's out list)
+__device__ __forceinline__ void g_note_out(PoaWs &w, int from, int to, int e, int wt) {
+    int32_t *r = reinterpret_cast<int32_t *>(w.brec + from);
+    const int bw = r[1], be = r[2];
+    if (wt > bw || (wt == bw && e <= be)) { r[0] = to; r[1] = wt; r[2] = e; }
+}
 // graph edit used for the final edge into the sink (one lane of the group)
 __device__ inline void g_add_edge(PoaWs &w, int &edge_n, int from, int to, bool check) {
     if (check) {
         for (int e = w.out_head[from]; e >= 0; e = w.e_no[e])
-            if (w.e_to[e] == to) { w.e_w[e] += 1; return; }
+            if (w.e_to[e] == to) { const int wt = w.e_w[e] + 1; w.e_w[e] = wt; g_note_out(w, from, to, e, wt); return; }
     }
     int e = edge_n++;
+    g_note_in(w, to, from); g_note_out(w, from, to, e, 1);
     w.e_to[e] = to; w.e_from[e] = from; w.e_w[e] = 1; w.e_no[e] = -1; w.e_ni[e] = -1;
     if (w.out_tail[from] < 0) w.out_head[from] = e; else w.e_no[w.out_tail[from]] = e;
     w.out_tail[from] = e;
@@ -321,64 +339,40 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
       for (int i = gl; i < nn; i += LPT) w.n2i[w.ord[i]] = i; }
     if (gl == 0) sm.plist_n = 0;
     __syncwarp();
-    { // two batches of LPT nodes walk their edge lists in lock-step: the loads of a step are independent across the
-      // batches, so two of these dependent (DRAM/L2-latency) pointer chases are in flight per lane instead of one
-        constexpr int U = 2;
+    { // the node records hold each node's first three in-neighbours and its heaviest out-edge: a descriptor costs three
+      // dependent loads (node, records, their indices) and no list walk; four nodes per lane are in flight
+        constexpr int U = 4;
         int bad = 0;
         const int nn = ok ? n : 0;
         for (int i0 = 0; i0 < nn; i0 += LPT * U) {
-            int np[U], p0[U], p1[U], hi[U], v[U], b[U], ei[U], eo[U], mw[U], mt[U];
+            int v[U], b[U]; int4 nr[U], br[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { const int i = i0 + LPT * u + gl; v[u] = i < nn ? w.ord[i] : -1; }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int i = i0 + LPT * u + gl;
-                np[u] = 0; p0[u] = -1; p1[u] = -1; hi[u] = 0x7fffffff; b[u] = 0; mw[u] = -1; mt[u] = -1;
-                v[u] = i < nn ? w.ord[i] : -1;
+                nr[u] = make_int4(0, -1, -1, -1); br[u] = make_int4(-1, 0, 0, 0); b[u] = 0;
+                if (v[u] >= 0) { nr[u] = w.nrec[v[u]]; br[u] = w.brec[v[u]]; b[u] = w.base[v[u]]; }
             }
+            int p0[U], p1[U], p2[U], hi[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                ei[u] = -1; eo[u] = -1;
-                if (v[u] >= 0) { b[u] = w.base[v[u]]; ei[u] = w.in_head[v[u]]; eo[u] = w.out_head[v[u]]; }
+                p0[u] = nr[u].x > 0 ? w.n2i[nr[u].y] : -1; p1[u] = nr[u].x > 1 ? w.n2i[nr[u].z] : -1; p2[u] = nr[u].x > 2 ? w.n2i[nr[u].w] : -1;
+                hi[u] = br[u].x >= 0 ? w.n2i[br[u].x] : 0x7fffffff;
             }
-            while (true) { // predecessors by row, in in_id order
-                bool anyp = false;
-#pragma unroll
-                for (int u = 0; u < U; ++u) anyp |= ei[u] >= 0;
-                if (!anyp) break;
-                int fr[U], nx[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) if (ei[u] >= 0) { fr[u] = w.e_from[ei[u]]; nx[u] = w.e_ni[ei[u]]; }
-#pragma unroll
-                for (int u = 0; u < U; ++u) if (ei[u] >= 0) {
-                    const int pi = w.n2i[fr[u]];
-                    if (np[u] == 0) p0[u] = pi; else if (np[u] == 1) p1[u] = pi;
-                    ++np[u]; ei[u] = nx[u];
-                }
-            }
-            while (true) { // first out-edge with maximum weight (abpoa_graph.c:216-226)
-                bool anyp = false;
-#pragma unroll
-                for (int u = 0; u < U; ++u) anyp |= eo[u] >= 0;
-                if (!anyp) break;
-                int ww[U], to[U], nx[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) if (eo[u] >= 0) { ww[u] = w.e_w[eo[u]]; to[u] = w.e_to[eo[u]]; nx[u] = w.e_no[eo[u]]; }
-#pragma unroll
-                for (int u = 0; u < U; ++u) if (eo[u] >= 0) { if (ww[u] > mw[u]) { mw[u] = ww[u]; mt[u] = to[u]; } eo[u] = nx[u]; }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) if (mt[u] >= 0) hi[u] = w.n2i[mt[u]];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int i = i0 + LPT * u + gl;
                 if (i < nn) {
+                    const int np = nr[u].x;
                     int off = p1[u];
-                    if (np[u] > 2) { // predecessor rows beyond the second go to a list; the lists' order among rows does not matter
-                        off = atomicAdd(&sm.plist_n, np[u]);
-                        int k = 0; for (int e = w.in_head[v[u]]; e >= 0; e = w.e_ni[e]) plist_g[off + k++] = w.n2i[w.e_from[e]];
+                    if (np > 2) { // predecessor rows beyond the second go to a list; the lists' order among rows does not matter
+                        off = atomicAdd(&sm.plist_n, np);
+                        plist_g[off] = p0[u]; plist_g[off + 1] = p1[u]; plist_g[off + 2] = p2[u];
+                        if (np > 3) { int k = 0; for (int e = w.in_head[v[u]]; e >= 0; e = w.e_ni[e], ++k) if (k >= 3) plist_g[off + k] = w.n2i[w.e_from[e]]; }
                     }
                     w.hi_idx[i] = hi[u];
-                    bad |= np[u] > 1023 || (i > 0 && i < nn - 1 && (unsigned)(np[u] - 1) >= (unsigned)min(LPT, POA_MAXPRE)); // the row loop relies on 1 <= np <= LPT
-                    rdesc_g[i] = make_int4(p0[u], min(np[u], 1023) | (min(b[u], 7) << 10) | (v[u] << 13), 0, off);
+                    bad |= np > 1023 || (i > 0 && i < nn - 1 && (unsigned)(np - 1) >= (unsigned)min(LPT, POA_MAXPRE)); // the row loop relies on 1 <= np <= LPT
+                    rdesc_g[i] = make_int4(p0[u], min(np, 1023) | (min(b[u], 7) << 10) | (v[u] << 13), 0, off);
                 }
             }
         }
@@ -774,7 +768,8 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
             int lerr = 0;
             if (isnew) {
                 if (tgt >= w.ncap) lerr = 1;
-                else { w.base[tgt] = qb; w.out_head[tgt] = w.out_tail[tgt] = w.in_head[tgt] = w.in_tail[tgt] = -1; w.aln_n[tgt] = 0; w.hs[tgt] = 0; w.ev_node[ev] = tgt; }
+                else { w.base[tgt] = qb; w.out_head[tgt] = w.out_tail[tgt] = w.in_head[tgt] = w.in_tail[tgt] = -1; w.aln_n[tgt] = 0; w.hs[tgt] = 0; w.ev_node[ev] = tgt;
+                       w.nrec[tgt] = make_int4(0, -1, -1, -1); w.brec[tgt] = make_int4(-1, 0, 0, 0); }
             }
             if (isnew && op == 0 && an >= 4) lerr = 1; // a column holds at most 5 distinct codes (ACGT + N): 4 aligned nodes per node
             if (g.any(lerr)) { err = TH_ERR_CAP; ok = false; }
@@ -806,13 +801,17 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
             __syncwarp();
             // edges (abpoa_add_graph_edge :1063-1106): weight + 1 on an existing edge, else append to both lists
             int found = -1;
-            if (go && prod && !from_new && !isnew)
-                for (int e = w.out_head[from]; e >= 0; e = w.e_no[e]) if (w.e_to[e] == tgt) { found = e; break; }
+            if (go && prod && !from_new && !isnew) { // most steps follow the heaviest edge: look there before walking the list
+                const int4 br = w.brec[from];
+                if (br.x == tgt) found = br.z;
+                else for (int e = w.out_head[from]; e >= 0; e = w.e_no[e]) if (w.e_to[e] == tgt) { found = e; break; }
+            }
             const bool mk = go && prod && found < 0;
             const unsigned mkm = g.ballot(mk);
-            if (found >= 0) w.e_w[found] += 1;
+            if (found >= 0) { const int wt = w.e_w[found] + 1; w.e_w[found] = wt; g_note_out(w, from, tgt, found, wt); }
             if (mk) {
                 const int e = edge_n + __popc(mkm & below);
+                g_note_in(w, tgt, from); g_note_out(w, from, tgt, e, 1);
                 w.e_to[e] = tgt; w.e_from[e] = from; w.e_w[e] = 1; w.e_no[e] = -1; w.e_ni[e] = -1;
                 const int ot = w.out_tail[from];
                 if (ot < 0) w.out_head[from] = e; else w.e_no[ot] = e;
@@ -1047,9 +1046,10 @@ poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const in
                 const int from = i == 0 ? 0 : 1 + i, to = i == l0 ? 1 : 2 + i;
                 w.e_to[i] = to; w.e_from[i] = from; w.e_w[i] = 1; w.e_no[i] = -1; w.e_ni[i] = -1;
                 w.out_head[from] = w.out_tail[from] = i; w.in_head[to] = w.in_tail[to] = i;
+                w.nrec[to] = make_int4(1, from, -1, -1); w.brec[from] = make_int4(to, 1, i, 0);
                 if (i < l0) { w.base[2 + i] = s0[i]; w.ord[1 + i] = 2 + i; w.hs[2 + i] = 1; }
             }
-            if (gl == 0) { w.ord[0] = 0; w.ord[l0 + 1] = 1; w.base[0] = w.base[1] = 4; }
+            if (gl == 0) { w.ord[0] = 0; w.ord[l0 + 1] = 1; w.base[0] = w.base[1] = 4; w.nrec[0] = make_int4(0, -1, -1, -1); w.brec[1] = make_int4(-1, 0, 0, 0); }
             node_n = l0 + 2; edge_n = l0 + 1;
         }
         __syncwarp();
