@@ -433,16 +433,16 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         for (int i = 0; i < nt; ++i) order[i] = i;
         std::sort(order.begin(), order.end(), [&](int a, int b) { return (int64_t)tasks[a].ncap * tasks[a].n_seqs > (int64_t)tasks[b].ncap * tasks[b].n_seqs; });
         // Slabs: graph arrays + the DP arena of ONE alignment (recycled for every unit): rows <= nodes, three int16 planes
-        // (H, E1, E2) per banded cell.  Typical: the graph holds <= ~2.5 units worth of nodes; the adaptive band is 2w+1
+        // (H, E1, E2) and a code byte per banded cell.  Typical: the graph holds <= ~2.5 units worth of nodes; the adaptive band is 2w+1
         // columns around the predecessors' row maxima, rounded to whole vectors (measured mean ~61 columns on 1 kb units)
         auto slab_need = [](const PoaTask &T, bool full) -> size_t {
             const size_t fixed = poa_fixed_bytes(T.ncap, T.qmax, T.n_seqs);
-            const size_t fullb = (size_t)T.ncap * ((size_t)T.qmax + 64) * 6;
+            const size_t fullb = (size_t)T.ncap * (((size_t)T.qmax + 64) * 7 + 16);
             if (full) return fixed + fullb + 4096;
             const int wband = 10 + T.qmax / 100;
             const size_t rows_typ = std::min<size_t>((size_t)T.ncap, (size_t)T.qmax * 5 / 2 + 64);
             const size_t width_typ = std::min<size_t>((size_t)T.qmax + 64, (size_t)2 * wband + 64);
-            const size_t typ = std::max<size_t>(rows_typ * width_typ * 6, (size_t)1 << 20);
+            const size_t typ = std::max<size_t>(rows_typ * (width_typ * 7 + 16), (size_t)1 << 20);
             return fixed + std::min(typ, fullb) + 4096;
         };
         size_t slab_typ = 0;

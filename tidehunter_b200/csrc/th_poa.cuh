@@ -28,12 +28,15 @@
 //  * read-id bitsets are not stored: popcount(read_ids) of a node equals the sum of its out-edge weights.
 //  * The consensus DFS (msa rank) and column vote are literal.
 //
-// DP storage: 6 bytes per banded cell.  A row of W columns owns three int16 planes H | E1 | E2 (what successor rows and
-// the backtrack's match / deletion tests read).  F1 / F2 are NOT stored: the backtrack only needs them at the few
-// cells where an insertion is taken, and recomputes that row chunk from the predecessors' planes (same code as the
-// forward pass).  The last POA_NRING rows (when they fit one chunk) also stay in shared memory, where the next rows
-// read them; the backtrack stages the metadata of a 64-row window plus a 16-column H segment around each row's
-// arg-max (where the path crosses the row) in shared memory, so a match step touches no global memory.
+// DP storage: 7 bytes per banded cell.  A row of W columns owns three int16 planes H | E1 | E2 (what successor rows and
+// the backtrack's deletion tests read) and one byte per cell that says whether the cell's value is a match / mismatch
+// step and from which predecessor (bit 0: H == max_p H[p][j-1] + s; bits 1..4: the first predecessor reaching that
+// maximum, which is the first one the reference's value comparison accepts).  F1 / F2 are NOT stored: the backtrack only
+// needs them at the few cells where an insertion is taken, and recomputes that row chunk from the predecessors' planes
+// (same code as the forward pass).  The last POA_NRING rows (when they fit one chunk) also stay in shared memory, where
+// the next rows read them.  The backtrack stages, for a 64-row window, each row's predecessors and the codes of 32
+// columns around its arg-max (where the path crosses the row) in shared memory: a match step (85 % of the path) is two
+// shared-memory loads and no cross-lane operation; everything else takes the general value-comparison step.
 #pragma once
 #include "th_common.cuh"
 
@@ -53,14 +56,15 @@ struct PoaTask {
 
 // Row descriptor (static per alignment, by row index):  x = first predecessor row (-1: none),
 //   y = np | base << 10 | node << 13,  z = qlen - max_remain term of the band centre,
-//   w = second predecessor row (np == 2) or offset into plist (np > 2).
+//   w = second predecessor row.  rdesc2 holds predecessor rows 2..5; rows with more keep all of them in plist at rdesc2.x
+//   (then rdesc2.y = predecessor 2 ... is not used: np > 6 reads plist[rdesc2.x + p]).
 // Row metadata (written when the row is computed):  x = arena offset (int16 units), y = first column, z = last column,
 //   w = max_i + 1 of the row (what the reference scatters into max_pos_left/right of the successors).
 // Node records (kept up to date by the merge, so that the per-alignment setup walks no adjacency list):
 //   nrec[v] = in-degree, then the first three in-neighbours in in_id order;
 //   brec[v] = heaviest out-edge (the first one of maximum weight, abpoa_graph.c:216-226): target node, weight, edge id.
 struct PoaWs {
-    int4 *rdesc, *rmeta, *nrec, *brec;
+    int4 *rdesc, *rdesc2, *rmeta, *nrec, *brec;
     int32_t *out_head, *out_tail, *in_head, *in_tail, *aln_n, *aln, *n2i, *ri, *hs;
     int32_t *e_to, *e_from, *e_w, *e_no, *e_ni, *plist;
     int32_t *ord, *ord2, *ev_anchor, *ev_node, *hi_idx;
@@ -72,7 +76,7 @@ struct PoaWs {
 __host__ __device__ inline size_t poa_fixed_bytes(int ncap, int qmax, int nseq) {
     size_t ecap = (size_t)ncap + nseq + 2;
     size_t b = 0;
-    b += (size_t)ncap * 16 * 4;                        // rdesc, rmeta, nrec, brec
+    b += (size_t)ncap * 16 * 5;                        // rdesc, rdesc2, rmeta, nrec, brec
     b += (size_t)ncap * 4 * (9 + 3);                   // 9 node arrays (aln counts as 4) = 12 x int32
     b += ecap * 4 * 6;                                 // 5 edge arrays + plist
     b += (size_t)ncap * 4 * 3;                         // ord, ord2, hi_idx
@@ -86,7 +90,7 @@ __host__ __device__ inline size_t poa_fixed_bytes(int ncap, int qmax, int nseq) 
 __device__ inline void poa_carve(PoaWs &w, uint8_t *slab, size_t slab_bytes, int ncap, int qmax, int nseq) {
     size_t ecap = (size_t)ncap + nseq + 2;
     w.ncap = ncap;
-    w.rdesc = reinterpret_cast<int4 *>(slab); w.rmeta = w.rdesc + ncap; w.nrec = w.rmeta + ncap; w.brec = w.nrec + ncap;
+    w.rdesc = reinterpret_cast<int4 *>(slab); w.rdesc2 = w.rdesc + ncap; w.rmeta = w.rdesc2 + ncap; w.nrec = w.rmeta + ncap; w.brec = w.nrec + ncap;
     int32_t *p = reinterpret_cast<int32_t *>(w.brec + ncap);
     w.out_head = p; p += ncap; w.out_tail = p; p += ncap; w.in_head = p; p += ncap; w.in_tail = p; p += ncap;
     w.aln_n = p; p += ncap; w.aln = p; p += 4 * (size_t)ncap; w.n2i = p; p += ncap; w.ri = p; p += ncap; w.hs = p; p += ncap;
@@ -104,7 +108,15 @@ __device__ inline void poa_carve(PoaWs &w, uint8_t *slab, size_t slab_bytes, int
     w.arena_cap = (uint32_t)ne;
 }
 
+// int16 units a row of `width` columns takes in the arena: three planes and the byte codes, rounded to 16 bytes
+__host__ __device__ __forceinline__ uint32_t poa_row_size(int width) { return ((uint32_t)(3 * width + (width >> 1)) + 7u) & ~7u; }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+// asynchronous 16-byte copy global -> shared (LDGSTS): in flight while the warp goes on
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ int s16_at(uint32_t word, int odd) { return odd ? hi16(word) : lo16(word); }
 
 // a new edge `from -> to` with id e enters the node records (one lane per `to` and per `from` at a time)
@@ -120,6 +132,11 @@ __device__ __forceinline__ void g_note_out(PoaWs &w, int from, int to, int e, in
     int32_t *r = reinterpret_cast<int32_t *>(w.brec + from);
     const int bw = r[1], be = r[2];
     if (wt > bw || (wt == bw && e <= be)) { r[0] = to; r[1] = wt; r[2] = e; }
+}
+// row of predecessor p of a row with descriptors d, d2 (np > 6: all of them are in plist)
+__device__ __forceinline__ int poa_pred_row(const int4 d, const int4 d2, const int32_t *plist, const int np, const int p) {
+    if (np > 6) return plist[d2.x + p];
+    return p == 0 ? d.x : p == 1 ? d.w : p == 2 ? d2.x : p == 3 ? d2.y : p == 4 ? d2.z : d2.w;
 }
 // graph edit used for the final edge into the sink (one lane of the group)
 __device__ inline void g_add_edge(PoaWs &w, int &edge_n, int from, int to, bool check) {
@@ -157,15 +174,20 @@ template <int LPT> struct PoaG {
     }
 };
 
+// One row of the backtrack window: hdr = {first predecessor row, second predecessor row or offset into plist,
+// np | base << 10 | node << 13 (the row descriptor's y), first staged column}, code = the M-codes of 32 columns from there.
+struct PoaBt { int4 hdr; uint4 code[2]; };
 template <int LPT> struct PoaSmem {
     static constexpr int CW = LPT * 4;               // columns per chunk
-    static constexpr int RINGW = 3 * CW / 2;         // words per ring slot (three planes of CW int16)
-    static constexpr int Q8W = LPT == 16 ? 320 : 1536; // words of query bytes kept in shared memory
-    int4 meta[POA_WIN];
-    int4 desc[POA_WIN];                               // backtrack window only
-    union { uint32_t ring[POA_NRING * RINGW]; uint4 seg[POA_WIN * 2]; } u; // forward: recent rows; backtrack: 16 H columns per window row
-    int4 pre[POA_MAXPRE];                             // metadata of predecessors 1.. of the row being computed
-    uint32_t q8[Q8W];
+    static constexpr int RINGC = CW + 16;            // widest row a ring slot holds (columns)
+    static constexpr int RINGW = 3 * RINGC / 2;      // words per ring slot (three planes)
+    static constexpr int Q4N = LPT == 16 ? 320 : 1536; // 4-column groups of query codes kept in shared memory (16 bits each)
+    union {
+        struct { int4 meta[POA_WIN]; uint32_t ring[POA_NRING * RINGW]; } f; // forward pass: row metadata, recent rows
+        PoaBt bt[POA_WIN];                                                   // backtrack: window of rows
+    } u;
+    int4 pre[LPT];                                    // metadata of predecessors 1.. of the row being computed (np <= LPT)
+    uint16_t q4[Q4N];
     int plist_n;
     PoaWs ws;
 };
@@ -229,25 +251,33 @@ __device__ __forceinline__ void poa_pred(const uint32_t *A32, const uint32_t *ri
 template <int LPT, bool AFFINE>
 __device__ __forceinline__ void poa_chunk(const PoaG<LPT> &g, const DevParams &P, const uint32_t lk, const uint32_t *A32, const uint32_t *ring, const int4 *pre,
                                           const int4 pm0, const int np, const bool act, const int j0, const bool ch0,
-                                          const uint32_t carryH, const uint32_t carryF, const uint32_t basew, const uint32_t *q8,
-                                          uint32_t (&Hn)[2], uint32_t (&E1o)[2], uint32_t (&E2o)[2], uint32_t (&Fa)[2], uint32_t (&Fb)[2], uint32_t (&Hf)[2]) {
+                                          const uint32_t carryH, const uint32_t carryF, const uint32_t basew, const uint16_t *q4,
+                                          uint32_t (&Hn)[2], uint32_t (&E1o)[2], uint32_t (&E2o)[2], uint32_t (&Fa)[2], uint32_t (&Fb)[2], uint32_t (&Hf)[2], uint32_t &mcode) {
     const uint32_t INFP = P.INFP;
     uint32_t Mx[2], E1x[2], E2x[2];
     poa_pred<LPT, AFFINE>(A32, ring, pm0, act, j0, INFP, Mx, E1x, E2x);
 #pragma unroll 1
+    uint32_t midx[2] = {0u, 0u};   // per column: the first predecessor whose H[p][j-1] is the maximum
     for (int p = 1; p < np; ++p) { // no warp-synchronous operation in here: groups may run different trip counts
         uint32_t m[2], x1[2], x2[2];
         poa_pred<LPT, AFFINE>(A32, ring, pre[p], act, j0, INFP, m, x1, x2);
+        const uint32_t pp = (uint32_t)p * 0x00020002u; // the index, already in its place in the code
 #pragma unroll
-        for (int r = 0; r < 2; ++r) { Mx[r] = __vmaxs2(Mx[r], m[r]); E1x[r] = __vmaxs2(E1x[r], x1[r]); if (!AFFINE) E2x[r] = __vmaxs2(E2x[r], x2[r]); }
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t gt = __vcmpgts2(m[r], Mx[r]);
+            midx[r] = (midx[r] & ~gt) | (pp & gt);
+            Mx[r] = __vmaxs2(Mx[r], m[r]); E1x[r] = __vmaxs2(E1x[r], x1[r]); if (!AFFINE) E2x[r] = __vmaxs2(E2x[r], x2[r]);
+        }
     }
-    // scores of the lane's four columns against the node base: query bytes q8[j] = query[j-1] (0..3) or 0x40 where the
-    // score is 0 (column 0, N in the query, columns past the query end); basew = the node base in every byte, 0x20 for an
-    // N node (scores 0 against everything).  x = q ^ base: 0 = match, 1..3 = mismatch, >= 0x20 = no score.
+    // scores of the lane's four columns against the node base: q4 holds four 4-bit query codes per 16-bit entry, code of
+    // column j = query[j-1] (0..3), or 8 where the score is 0 (column 0, N in the query, columns past the query end);
+    // basew = the node base in every byte, 4 for an N node (scores 0 against everything).  x = q ^ base: 0 = match,
+    // 1..3 = mismatch, >= 4 = no score.
     uint32_t S[2];
     {
-        const uint32_t x = (act ? q8[j0 >> 2] : 0x40404040u) ^ basew;
-        const uint32_t hb = 0x80808080u - x, vb = x + 0x60606060u; // sign bit of each byte: match / no score (bytes are <= 0x63: no borrows or carries)
+        const uint32_t w4 = act ? (uint32_t)q4[j0 >> 2] : 0x8888u;
+        const uint32_t x = prmt(w4 & 0x0f0fu, (w4 >> 4) & 0x0f0fu, 0x5140) ^ basew; // one code per byte
+        const uint32_t hb = 0x80808080u - x, vb = x + 0x7c7c7c7cu; // sign bit of each byte: match / no score (bytes are <= 15: no borrows or carries)
         const uint32_t m0 = prmt(hb, 0, 0x9988), m1 = prmt(hb, 0, 0xbbaa), v0 = prmt(vb, 0, 0x9988), v1 = prmt(vb, 0, 0xbbaa);
         S[0] = (P.NEGMIS2 ^ (m0 & P.XMM)) & ~v0; S[1] = (P.NEGMIS2 ^ (m1 & P.XMM)) & ~v1;
     }
@@ -294,7 +324,9 @@ __device__ __forceinline__ void poa_chunk(const PoaG<LPT> &g, const DevParams &P
         E1o[r] = __viaddmax_s16x2(E1x[r], P.NE1P, __vadd2(Hn[r], P.NOE1P));
         if (AFFINE) { const uint32_t keep = __vcmpeq2(Hn[r], Hme[r]); E1o[r] = (E1o[r] & keep) | (INFP & ~keep); E2o[r] = INFP; } // F won the cell: no deletion from it
         else E2o[r] = __viaddmax_s16x2(E2x[r], P.NE2P, __vadd2(Hn[r], P.NOE2P));
+        midx[r] |= __vcmpeq2(Ms[r], Hn[r]) & 0x00010001u;  // the cell is a match / mismatch step from that predecessor
     }
+    mcode = prmt(midx[0], midx[1], 0x6420);                // one byte per column
 }
 
 // carries from this chunk to the next one of the same row (all lanes call)
@@ -317,7 +349,7 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
 #else
 #define PH(k) do { } while (0)
 #endif
-    constexpr int CW = PoaSmem<LPT>::CW, RINGW = PoaSmem<LPT>::RINGW;
+    constexpr int CW = PoaSmem<LPT>::CW, RINGW = PoaSmem<LPT>::RINGW, RINGC = PoaSmem<LPT>::RINGC;
     const PoaG<LPT> g;
     const int gl = g.gl;
     PoaWs &w = sm.ws;
@@ -364,15 +396,19 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
                 const int i = i0 + LPT * u + gl;
                 if (i < nn) {
                     const int np = nr[u].x;
-                    int off = p1[u];
-                    if (np > 2) { // predecessor rows beyond the second go to a list; the lists' order among rows does not matter
-                        off = atomicAdd(&sm.plist_n, np);
-                        plist_g[off] = p0[u]; plist_g[off + 1] = p1[u]; plist_g[off + 2] = p2[u];
-                        if (np > 3) { int k = 0; for (int e = w.in_head[v[u]]; e >= 0; e = w.e_ni[e], ++k) if (k >= 3) plist_g[off + k] = w.n2i[w.e_from[e]]; }
+                    int4 d2 = make_int4(p2[u], -1, -1, -1);
+                    if (np > 3) { // rare: the record holds three in-neighbours, the rest come from the list
+                        int off = 0, k = 0;
+                        if (np > 6) { off = atomicAdd(&sm.plist_n, np); d2.x = off; } // the lists' order among rows does not matter
+                        for (int e = w.in_head[v[u]]; e >= 0; e = w.e_ni[e], ++k) {
+                            const int pi = w.n2i[w.e_from[e]];
+                            if (np > 6) plist_g[off + k] = pi; else if (k == 3) d2.y = pi; else if (k == 4) d2.z = pi; else if (k == 5) d2.w = pi;
+                        }
                     }
+                    w.rdesc2[i] = d2;
                     w.hi_idx[i] = hi[u];
                     bad |= np > 1023 || (i > 0 && i < nn - 1 && (unsigned)(np - 1) >= (unsigned)min(LPT, POA_MAXPRE)); // the row loop relies on 1 <= np <= LPT
-                    rdesc_g[i] = make_int4(p0[u], min(np, 1023) | (min(b[u], 7) << 10) | (v[u] << 13), 0, off);
+                    rdesc_g[i] = make_int4(p0[u], min(np, 1023) | (min(b[u], 7) << 10) | (v[u] << 13), 0, p1[u]);
                 }
             }
         }
@@ -405,33 +441,34 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
             if (a) cb -= LPT;
         }
     }
-    // ---- query bytes (the reference's 5 x qlen profile, simd_abpoa_align.c:438-446, reduced to what it encodes):
-    // q8[j] = query[j-1] for an A/C/G/T base, 0x40 (score 0 against every node) for column 0, N and columns past the end
-    const int q8n = (qlen + pn + CW + 8) >> 2;          // words: every column a lane of any chunk may look at
-    uint32_t *const q8 = q8n <= PoaSmem<LPT>::Q8W ? sm.q8 : w.q8g;
-    if (ok) for (int wi = gl; wi < q8n; wi += LPT) {
+    // ---- query codes (the reference's 5 x qlen profile, simd_abpoa_align.c:438-446, reduced to what it encodes): 4 bits per
+    // column, code of column j = query[j-1] for an A/C/G/T base, 8 (score 0 against every node) for column 0, N and
+    // columns past the end
+    const int q4n = (qlen + pn + CW + 8) >> 2;          // entries: every column a lane of any chunk may look at
+    uint16_t *const q4 = q4n <= PoaSmem<LPT>::Q4N ? sm.q4 : reinterpret_cast<uint16_t *>(w.q8g);
+    if (ok) for (int wi = gl; wi < q4n; wi += LPT) {
         uint32_t word = 0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int j = 4 * wi + b;
-            uint32_t qc = 0x40;
-            if (j >= 1 && j <= qlen) { qc = query[j - 1]; if (qc > 3) qc = 0x40; }
-            word |= qc << (8 * b);
+            uint32_t qc = 8;
+            if (j >= 1 && j <= qlen) { qc = query[j - 1]; if (qc > 3) qc = 8; }
+            word |= qc << (4 * b);
         }
-        q8[wi] = word;
+        q4[wi] = (uint16_t)word;
     }
     // ---- first row (simd_abpoa_align.c:538-555, 591-610) ------------------------------------
     uint32_t used = 0;
     uint32_t *const A32w = reinterpret_cast<uint32_t *>(w.arena);
     const uint32_t *const A32 = A32w;
     const uint32_t arena_cap = w.arena_cap;
-    uint32_t *const ring = sm.u.ring;
+    uint32_t *const ring = sm.u.f.ring;
     if (ok) {
         const int end = min(qlen, max(0, qlen - ri[0]) + wband);
         const int esn = end >> lp, width = (esn + 1) << lp;
-        if (3ull * width > arena_cap) { err = TH_ERR_ARENA; ok = false; }
+        if ((unsigned long long)poa_row_size(width) + 64 > arena_cap) { err = TH_ERR_ARENA; ok = false; }
         else {
-            if (gl == 0) { const int4 m = make_int4(0, 0, width - 1, 1); rmeta_g[0] = m; sm.meta[0] = m; } // the source hands 1 to its successors (:549-552)
+            if (gl == 0) { const int4 m = make_int4(0, 0, width - 1, 1); rmeta_g[0] = m; sm.u.f.meta[0] = m; } // the source hands 1 to its successors (:549-552)
             const int ps = width >> 1;
             for (int q = gl; q < ps; q += LPT) {
                 uint32_t hh = 0, ee1 = 0, ee2 = 0;
@@ -444,9 +481,9 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
                     hh |= (uint32_t)(uint16_t)vh << (16 * h); ee1 |= (uint32_t)(uint16_t)v1 << (16 * h); ee2 |= (uint32_t)(uint16_t)v2 << (16 * h);
                 }
                 A32w[q] = hh; A32w[ps + q] = ee1; if (!AFFINE) A32w[2 * ps + q] = ee2;
-                if (width <= CW) { ring[q] = hh; ring[ps + q] = ee1; if (!AFFINE) ring[2 * ps + q] = ee2; }
+                if (width <= RINGC) { ring[q] = hh; ring[ps + q] = ee1; if (!AFFINE) ring[2 * ps + q] = ee2; }
             }
-            used = 3u * width; cells += width; rows += 1;
+            used = poa_row_size(width); cells += width; rows += 1;
         }
     }
     __syncwarp();
@@ -455,33 +492,34 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
     const int lam_bits = pn - 1;
     const int lane_vec = (4 * gl) >> lp;
     const int qsn = qlen >> lp;
-    const uint32_t used_rows0 = used;
+    uint32_t ncell = 0;
     {
         int i = 1;
         bool ract = ok && n > 2;
-        int4 dn = ract ? rdesc_g[1] : make_int4(0, 0, 0, 0);
+        int4 dn = ract ? rdesc_g[1] : make_int4(0, 0, 0, 0), dn2 = ract ? w.rdesc2[1] : make_int4(0, 0, 0, 0);
+        const int4 *const rdesc2_g = w.rdesc2;
         while (__any_sync(TH_FULL, ract)) {
             // ---- band and predecessors of row i (no warp-synchronous operation before the chunk)
-            const int4 d = dn;
+            const int4 d = dn, d2 = dn2;
             int4 pm0 = make_int4(0, 0, -1, 0);
             int np = 0, beg = 0, dend = -1, esn = 0, width = 0;
             uint32_t row_off = 0;
             bool go = false;
             if (ract) {
-                if (i + 1 < n - 1) dn = rdesc_g[i + 1];   // next row's descriptor: in flight while this row is computed
+                if (i + 1 < n - 1) { dn = rdesc_g[i + 1]; dn2 = rdesc2_g[i + 1]; } // next row's descriptors: in flight while this row is computed
                 np = d.y & 1023;                           // 1..LPT, checked when the descriptors were built
                 // band: what the predecessors' row maxima and max_remain say (abpoa_align.h:34-35, simd_abpoa_align.c:846-854)
-                int4 m = (i - d.x < POA_WIN) ? sm.meta[d.x & (POA_WIN - 1)] : rmeta_g[d.x];
+                int4 m = (i - d.x < POA_WIN) ? sm.u.f.meta[d.x & (POA_WIN - 1)] : rmeta_g[d.x];
                 int mpl = min(n, m.w), mpr = max(0, m.w), min_pre_beg = m.y;
-                if (i - d.x <= POA_NRING && m.z - m.y < CW) m.x = (int)(0x80000000u | (uint32_t)(d.x & (POA_NRING - 1)));
+                if (i - d.x < POA_NRING && m.z - m.y < RINGC) m.x = (int)(0x80000000u | (uint32_t)(d.x & (POA_NRING - 1)));
                 pm0 = m;
                 if (np > 1) {
 #pragma unroll 1
                     for (int p = 1; p < np; ++p) {
-                        const int pi = np == 2 ? d.w : plist_g[d.w + p];
-                        int4 q = (i - pi < POA_WIN) ? sm.meta[pi & (POA_WIN - 1)] : rmeta_g[pi];
+                        const int pi = poa_pred_row(d, d2, plist_g, np, p);
+                        int4 q = (i - pi < POA_WIN) ? sm.u.f.meta[pi & (POA_WIN - 1)] : rmeta_g[pi];
                         mpl = min(mpl, q.w); mpr = max(mpr, q.w); min_pre_beg = min(min_pre_beg, q.y);
-                        if (i - pi <= POA_NRING && q.z - q.y < CW) q.x = (int)(0x80000000u | (uint32_t)(pi & (POA_NRING - 1)));
+                        if (i - pi < POA_NRING && q.z - q.y < RINGC) q.x = (int)(0x80000000u | (uint32_t)(pi & (POA_NRING - 1)));
                         sm.pre[p] = q;                     // every lane of the group writes the same value and reads back its own write
                     }
                 }
@@ -489,14 +527,14 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
                 beg = max((beg0 >> lp) << lp, min_pre_beg); esn = end0 >> lp; dend = ((esn + 1) << lp) - 1;
                 width = dend - beg + 1;
                 if (beg > dend) err = TH_ERR_BAND;
-                else if (3ull * (uint32_t)width > (unsigned long long)(arena_cap - used)) err = TH_ERR_ARENA;
-                else { go = true; row_off = used; used += 3u * (uint32_t)width; } // cells and rows are derived from `used` after the loop
+                else if ((unsigned long long)poa_row_size(width) + 64 > (unsigned long long)(arena_cap - used)) err = TH_ERR_ARENA;
+                else { go = true; row_off = used; used += poa_row_size(width); ncell += (uint32_t)width; }
                 if (!go) { ract = false; ok = false; width = 0; }
             }
             const int ps = width >> 1, nchunk = (width + CW - 1) / CW;
-            const bool cache_row = width <= CW;
+            const bool cache_row = width <= RINGC;
             const int vb = (d.y >> 10) & 7;
-            const uint32_t basew = (uint32_t)(vb < 4 ? vb : 0x20) * 0x01010101u;
+            const uint32_t basew = (uint32_t)min(vb, 4) * 0x01010101u;
             const int jmax = esn == qsn ? qlen : dend;   // columns past the query end do not compete for the row maximum
             const int vlast = esn - (beg >> lp);          // the row's last vector is visited first by the reference's arg-max
             int best = INT_MIN;
@@ -505,15 +543,17 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
             auto chunk = [&](const int ch, const bool more) {
                 const bool a = go && ch < nchunk;
                 const int j0 = beg + ch * CW + 4 * gl;
-                uint32_t Hn[2], E1o[2], E2o[2], Fa[2], Fb[2], Hf[2];
-                poa_chunk<LPT, AFFINE>(g, P, lk, A32, ring, sm.pre, pm0, a ? np : 0, a, j0, ch == 0, carryH, carryF, basew, q8, Hn, E1o, E2o, Fa, Fb, Hf);
+                uint32_t Hn[2], E1o[2], E2o[2], Fa[2], Fb[2], Hf[2], mcode;
+                poa_chunk<LPT, AFFINE>(g, P, lk, A32, ring, sm.pre, pm0, a ? np : 0, a, j0, ch == 0, carryH, carryF, basew, q4, Hn, E1o, E2o, Fa, Fb, Hf, mcode);
                 if (a && j0 <= dend) {
                     const uint32_t wo = (row_off >> 1) + (uint32_t)((j0 - beg) >> 1);
+                    A32w[(row_off >> 1) + 3u * (uint32_t)ps + (uint32_t)((j0 - beg) >> 2)] = mcode;
                     *reinterpret_cast<uint2 *>(A32w + wo) = make_uint2(Hn[0], Hn[1]);
                     *reinterpret_cast<uint2 *>(A32w + wo + ps) = make_uint2(E1o[0], E1o[1]);
                     if (!AFFINE) *reinterpret_cast<uint2 *>(A32w + wo + 2 * ps) = make_uint2(E2o[0], E2o[1]);
-                    if (cache_row) { // every reader of the slot's old contents is past the scan's shuffles
-                        uint32_t *rs = ring + (i & (POA_NRING - 1)) * RINGW + 2 * gl;
+                    if (cache_row) { // the slot held row i - POA_NRING, which no row reads from the ring any more (a two-chunk row would
+                                     // otherwise overwrite it between its own chunks)
+                        uint32_t *rs = ring + (i & (POA_NRING - 1)) * RINGW + ((j0 - beg) >> 1);
                         *reinterpret_cast<uint2 *>(rs) = make_uint2(Hn[0], Hn[1]);
                         *reinterpret_cast<uint2 *>(rs + ps) = make_uint2(E1o[0], E1o[1]);
                         if (!AFFINE) *reinterpret_cast<uint2 *>(rs + 2 * ps) = make_uint2(E2o[0], E2o[1]);
@@ -541,26 +581,26 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
                 const int lam = lam_bits - (int)((rbest >> 12) & 0xf), vr = 0xfff - (int)(rbest & 0xfff);
                 const int vsn = vr == 0 ? esn : (beg >> lp) + vr - 1;
                 const int max_i = (rbest != INT_MIN && val > inf_min) ? vsn * pn + lam : -1;
-                if (gl == 0) { const int4 m = make_int4((int)row_off, beg, dend, max_i + 1); sm.meta[i & (POA_WIN - 1)] = m; rmeta_g[i] = m; }
+                if (gl == 0) { const int4 m = make_int4((int)row_off, beg, dend, max_i + 1); sm.u.f.meta[i & (POA_WIN - 1)] = m; rmeta_g[i] = m; }
                 ++i; ract = i < n - 1;
             }
             __syncwarp();
         }
     }
-    if (ok) { cells += (used - used_rows0) / 3u; rows += (unsigned long long)max(n - 2, 0); }
+    if (ok) { cells += ncell; rows += (unsigned long long)max(n - 2, 0); }
     PH(1);
     // ---- best end cell (simd_abpoa_align.c:976-989): sink's in-neighbours in in_id order, strict > ----
     const int16_t *const A16 = w.arena;
     int bi = 0, bj = 0;
     {
-        const int4 ds = ok ? rdesc_g[n - 1] : make_int4(0, 0, 0, 0);
+        const int4 ds = ok ? rdesc_g[n - 1] : make_int4(0, 0, 0, 0), ds2 = ok ? w.rdesc2[n - 1] : make_int4(0, 0, 0, 0);
         const int nps = ok ? (ds.y & 1023) : 0;
         int best_score = inf_min;
         for (int p0 = 0; __any_sync(TH_FULL, p0 < nps); p0 += LPT) {
             const int p = p0 + gl;
             int s = -0x7fffffff, pi = 0, end = 0;
             if (p < nps) {
-                pi = p == 0 ? ds.x : (nps == 2 ? ds.w : plist_g[ds.w + p]);
+                pi = poa_pred_row(ds, ds2, plist_g, nps, p);
                 const int4 m = rmeta_g[pi];
                 end = qlen > m.z ? m.z : qlen;
                 s = A16[(uint32_t)m.x + (uint32_t)(end - m.y)];
@@ -572,9 +612,11 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
             if (p0 < nps && mx > best_score) { best_score = mx; bi = fpi; bj = fend; }
         }
     }
-    // ---- backtrack by value comparison (simd_abpoa_align.c:248-377).  The walk is sequential; lane p of the group holds
-    // predecessor p.  Row metadata and descriptors come from a shared-memory window filled 32 rows at a time, and so do
-    // 16 columns of H around each window row's arg-max: a match step reads shared memory only.
+    // ---- backtrack (simd_abpoa_align.c:248-377).  The walk is sequential.  A window of 64 rows is staged in shared memory
+    // 32 rows at a time: each row's predecessors and the M-codes of 32 columns around its arg-max.  Where the code says
+    // "match / mismatch step from predecessor k" the step is taken from it (the code is exactly the outcome of the
+    // reference's first value test); every other step -- deletions, insertions, columns outside the staged ones -- is the
+    // reference's value comparison, lane p of the group holding predecessor p and reading the arena.
     int n_cig = 0;
     {
         enum { M_OP = 1, E1_OP = 2, E2_OP = 4, E_OP = 6, F1_OP = 8, F2_OP = 16, F_OP = 24, ALL_OP = 31 };
@@ -585,65 +627,81 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
             if (bj < qlen) n_cig = qlen - bj;
         }
         int wlo = n, whi = -1; // rows [wlo, whi] are in the window
-        const uint8_t *const q8b = reinterpret_cast<const uint8_t *>(q8);
-        const int16_t *const segs = reinterpret_cast<const int16_t *>(sm.u.seg);
+        const uint8_t *const A8 = reinterpret_cast<const uint8_t *>(w.arena);
         bool bact;
         while (__any_sync(TH_FULL, bact = (ok && i > 0 && j > 0))) {
             const bool need = bact && (i < wlo || (i < wlo + 32 && wlo > 0));
             if (__any_sync(TH_FULL, need)) {
+                // The walk is entering the 32 rows staged last time: their codes, copied asynchronously while the 32 rows before
+                // them were walked, have to be there now.  Then the next 32 rows are put in flight.
+                cp_async_wait_all();
+                __syncwarp();
+                bool jumped = false;
                 if (need) {
-                    const int top = i < wlo ? i + 1 : wlo; // load rows [top-32, top)
-                    if (i < wlo) whi = i;
+                    const int top = i < wlo ? i + 1 : wlo; // stage rows [top-32, top)
+                    jumped = i < wlo;
+                    if (jumped) whi = i;
                     for (int r = top - 32 + gl; r < top; r += LPT) if (r >= 0) {
-                        int4 m = rmeta_g[r];
-                        // the path crosses a row close to that row's maximum (the column that steered the band)
+                        const int4 m = rmeta_g[r], d = rdesc_g[r];
+                        // the path crosses a row close to that row's maximum (the column that steered the band): stage 32 columns
+                        // around it, from a multiple of 16 columns into the row
                         const int jp = m.w > 0 ? m.w - 1 : j - (i - r);
-                        int sb = (jp - 6) & ~7; sb = max(m.y, min(sb, m.z - 15));
-                        const uint4 *src = reinterpret_cast<const uint4 *>(A16 + (uint32_t)m.x + (uint32_t)(sb - m.y));
-                        const uint4 s0 = src[0], s1 = src[1]; // a row holds at least 24 int16, so this stays inside it
-                        sm.u.seg[2 * (r & (POA_WIN - 1))] = s0; sm.u.seg[2 * (r & (POA_WIN - 1)) + 1] = s1;
-                        sm.desc[r & (POA_WIN - 1)] = rdesc_g[r];
-                        m.w = sb; sm.meta[r & (POA_WIN - 1)] = m;
+                        const int wd = m.z - m.y + 1;
+                        int k16 = max(0, jp - m.y - 8) & ~15; k16 = min(k16, max(0, wd - 32) & ~15);
+                        const uint4 *src = reinterpret_cast<const uint4 *>(A8 + 2ull * ((uint32_t)m.x + 3u * (uint32_t)wd) + (uint32_t)k16);
+                        PoaBt &R = sm.u.bt[r & (POA_WIN - 1)];
+                        cp_async16(&R.code[0], src); cp_async16(&R.code[1], src + 1); // may run past a narrow row's codes: the arena keeps 128 bytes of slack
+                        R.hdr = make_int4(d.x, d.w, d.y, m.y + k16);
                     }
                     wlo = max(0, top - 32); whi = min(whi, wlo + POA_WIN - 1);
                 }
+                cp_async_commit();
+                if (__any_sync(TH_FULL, jumped)) cp_async_wait_all(); // a window started from scratch is walked at once
                 __syncwarp();
             }
-            const int4 d = sm.desc[i & (POA_WIN - 1)], mi = sm.meta[i & (POA_WIN - 1)];
-            const int np = d.y & 1023, vb = (d.y >> 10) & 7, v = d.y >> 13;
-            const int qb = bact ? q8b[j] : 0x40;
-            const int s = (qb < 4 && vb < 4) ? (qb == vb ? mat : -mis) : 0;
-            const int ib = mi.y, iw = mi.z - mi.y + 1;
-            int hij;
-            { const unsigned dj = (unsigned)(j - mi.w);
-              hij = !bact ? 0 : (dj < 16u ? segs[16 * (i & (POA_WIN - 1)) + dj] : A16[(uint32_t)mi.x + (uint32_t)(j - ib)]); }
-            // lane p holds predecessor p.  Most steps are matches: test those first.
-            int pi = 0; bool in1 = false, in0 = false; int4 pm = make_int4(0, 0, -1, 0); bool pwin = false;
-            if (bact && gl < np) {
-                pi = gl == 0 ? d.x : (np == 2 ? d.w : plist_g[d.w + gl]);
-                pwin = pi >= wlo;
-                pm = pwin ? sm.meta[pi & (POA_WIN - 1)] : rmeta_g[pi];
-                in1 = j - 1 >= pm.y && j - 1 <= pm.z; in0 = j >= pm.y && j <= pm.z;
-            }
+            const PoaBt &R = sm.u.bt[i & (POA_WIN - 1)];
+            const int4 h = R.hdr;
+            const int np = h.z & 1023, vb = (h.z >> 10) & 7, v = h.z >> 13;
+            const int cc = j - h.w;
+            const bool coded = bact && (cur_op & M_OP) && (unsigned)cc < 32u;
+            const int code = coded ? (int)reinterpret_cast<const uint8_t *>(R.code)[cc] : 0;
             bool stepped = false;
-            {
-                int a = 0;
-                if (in1 && (cur_op & M_OP)) {
-                    const unsigned dj = (unsigned)(j - 1 - pm.w);
-                    a = (pwin && dj < 16u) ? segs[16 * (pi & (POA_WIN - 1)) + dj] : A16[(uint32_t)pm.x + (uint32_t)(j - 1 - pm.y)];
-                }
-                const unsigned mm = g.ballot(in1 && (cur_op & M_OP) && a + s == hij);
-                const int f = mm ? __ffs(mm) - 1 : 0;
-                const int fpi = g.shfl(pi, f);
-                if (mm) {
-                    if (gl == 0) { cg[n_cig] = ((uint32_t)v << 2) | 0; cq[n_cig] = j - 1; }
-                    ++n_cig; cur_op = ALL_OP; i = fpi; --j; stepped = true;
-                }
+            if (coded && (code & 1)) { // a match / mismatch step from predecessor code >> 1
+                const int k = code >> 1;
+                int pi = k == 0 ? h.x : h.y;
+                if (k > 1) pi = poa_pred_row(make_int4(h.x, 0, 0, h.y), w.rdesc2[i], plist_g, np, k);
+                if (gl == 0) { cg[n_cig] = ((uint32_t)v << 2) | 0; cq[n_cig] = j - 1; }
+                ++n_cig; cur_op = ALL_OP; i = pi; --j; stepped = true;
             }
-            if (__any_sync(TH_FULL, bact && !stepped)) { // not a match (for some group)
+            if (__any_sync(TH_FULL, bact && !stepped)) { // the reference's step by value comparison (for some group)
                 const bool todo = bact && !stepped;
-                if (__any_sync(TH_FULL, todo && (cur_op & E_OP))) { // deletions: predecessors at column j
-                    const bool te = todo && (cur_op & E_OP);
+                const int qb = todo ? (q4[j >> 2] >> (4 * (j & 3))) & 0xf : 8;
+                const int s = (qb < 4 && vb < 4) ? (qb == vb ? mat : -mis) : 0;
+                int4 mi = make_int4(0, 0, -1, 0);
+                if (todo) mi = rmeta_g[i];
+                const int ib = mi.y, iw = mi.z - mi.y + 1;
+                const int hij = todo ? (int)A16[(uint32_t)mi.x + (uint32_t)(j - ib)] : 0;
+                // lane p holds predecessor p
+                int pi = 0; bool in1 = false, in0 = false; int4 pm = make_int4(0, 0, -1, 0);
+                if (todo && gl < np) {
+                    pi = gl < 2 ? (gl == 0 ? h.x : h.y) : poa_pred_row(make_int4(h.x, 0, 0, h.y), w.rdesc2[i], plist_g, np, gl);
+                    pm = rmeta_g[pi];
+                    in1 = j - 1 >= pm.y && j - 1 <= pm.z; in0 = j >= pm.y && j <= pm.z;
+                }
+                if (__any_sync(TH_FULL, todo && (cur_op & M_OP) && !coded)) { // match test where no code was staged
+                    const bool tm = todo && (cur_op & M_OP) && !coded;
+                    int a = 0;
+                    if (tm && in1) a = A16[(uint32_t)pm.x + (uint32_t)(j - 1 - pm.y)];
+                    const unsigned mm = g.ballot(tm && in1 && a + s == hij);
+                    const int f = mm ? __ffs(mm) - 1 : 0;
+                    const int fpi = g.shfl(pi, f);
+                    if (mm) {
+                        if (gl == 0) { cg[n_cig] = ((uint32_t)v << 2) | 0; cq[n_cig] = j - 1; }
+                        ++n_cig; cur_op = ALL_OP; i = fpi; --j; stepped = true;
+                    }
+                }
+                if (__any_sync(TH_FULL, todo && !stepped && (cur_op & E_OP))) { // deletions: predecessors at column j
+                    const bool te = todo && !stepped && (cur_op & E_OP);
                     int b = 0, x1 = 0, x2 = inf_min, e1ij = 0, e2ij = inf_min;
                     if (te && in0) {
                         const uint32_t pw = (uint32_t)(pm.z - pm.y + 1), po = (uint32_t)pm.x + (uint32_t)(j - pm.y);
@@ -664,24 +722,24 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
                         ++n_cig; i = fpi; stepped = true;
                     }
                 }
-                if (__any_sync(TH_FULL, bact && !stepped)) { // insertions: F1 / F2 of this row at columns j and j - 1, recomputed
-                    const bool tf = bact && !stepped && (cur_op & F_OP) && j > ib;
-                    if (bact && !stepped && !tf) { err = TH_ERR_BACKTRACK; ok = false; }
+                if (__any_sync(TH_FULL, todo && !stepped)) { // insertions: F1 / F2 of this row at columns j and j - 1, recomputed
+                    const bool tf = todo && !stepped && (cur_op & F_OP) && j > ib;
+                    if (todo && !stepped && !tf) { err = TH_ERR_BACKTRACK; ok = false; }
                     // predecessors' planes from the arena (the ring belongs to the forward pass)
                     int4 p0m = make_int4(0, 0, -1, 0);
                     if (tf) {
-                        p0m = d.x >= wlo ? sm.meta[d.x & (POA_WIN - 1)] : rmeta_g[d.x];
-                        for (int p = 1; p < np; ++p) { const int pp = np == 2 ? d.w : plist_g[d.w + p]; sm.pre[p] = pp >= wlo ? sm.meta[pp & (POA_WIN - 1)] : rmeta_g[pp]; }
+                        p0m = rmeta_g[h.x];
+                        for (int p = 1; p < np; ++p) { const int pp = p == 1 ? h.y : poa_pred_row(make_int4(h.x, 0, 0, h.y), w.rdesc2[i], plist_g, np, p); sm.pre[p] = rmeta_g[pp]; }
                     }
-                    const uint32_t basew = (uint32_t)(vb < 4 ? vb : 0x20) * 0x01010101u;
+                    const uint32_t basew = (uint32_t)min(vb, 4) * 0x01010101u;
                     const int cj = tf ? (j - ib) / CW : -1;
                     int f1 = 0, f2 = 0, f1m1 = 0, f2m1 = 0;
                     uint32_t carryH = 0, carryF = POA_NEGP;
                     for (int ch = 0; __any_sync(TH_FULL, ch <= cj); ++ch) {
                         const bool a = ch <= cj;
                         const int j0 = ib + ch * CW + 4 * gl;
-                        uint32_t Hn[2], E1o[2], E2o[2], Fa[2], Fb[2], Hf[2];
-                        poa_chunk<LPT, AFFINE>(g, P, lk, A32, ring, sm.pre, p0m, a ? np : 0, a, j0, ch == 0, carryH, carryF, basew, q8, Hn, E1o, E2o, Fa, Fb, Hf);
+                        uint32_t Hn[2], E1o[2], E2o[2], Fa[2], Fb[2], Hf[2], mcode;
+                        poa_chunk<LPT, AFFINE>(g, P, lk, A32, ring, sm.pre, p0m, a ? np : 0, a, j0, ch == 0, carryH, carryF, basew, q4, Hn, E1o, E2o, Fa, Fb, Hf, mcode);
 #pragma unroll
                         for (int x = 0; x < 2; ++x) { // x = 0: column j, x = 1: column j - 1
                             const int rel = j - x - ib - ch * CW;
@@ -694,9 +752,7 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
                         poa_chunk_carry<LPT>(g, P, Hf, Fa, Fb, carryH, carryF);
                     }
                     if (tf) {
-                        int hm1;
-                        { const unsigned dj = (unsigned)(j - 1 - mi.w);
-                          hm1 = dj < 16u ? segs[16 * (i & (POA_WIN - 1)) + dj] : A16[(uint32_t)mi.x + (uint32_t)(j - 1 - ib)]; }
+                        const int hm1 = A16[(uint32_t)mi.x + (uint32_t)(j - 1 - ib)];
                         bool hit = false, bad = false;
                         if (cur_op & F1_OP) {
                             if (!(cur_op & M_OP) || hij == f1) {
@@ -969,7 +1025,7 @@ __device__ int poa_consensus(PoaSmem<LPT> &sm, const bool act, int node_n, int n
 
 // persistent warps; every group pulls its tasks from an atomic counter
 #ifndef POA_MIN_BLOCKS16
-#define POA_MIN_BLOCKS16 4   // 16-lane groups: 16 warps = 32 tasks per SM, 128 registers
+#define POA_MIN_BLOCKS16 5   // 16-lane groups: 20 warps = 40 tasks per SM, 102 registers (6 blocks: +2 %, 7: spills; measured)
 #endif
 #ifndef POA_MIN_BLOCKS32
 #define POA_MIN_BLOCKS32 4

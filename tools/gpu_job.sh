@@ -5,6 +5,7 @@
 #   phases N [shape]         rebuild with -DPOA_PROFILE on the box and print the POA phase split
 #   ncu NAME N regex [count] ncu --set full capture of kernels matching regex -> gpurun_out/NAME.ncu-rep + summary
 #   launches NAME N          ncu launch list (gpu__time_duration) of one step -> gpurun_out/NAME.csv
+#   variants N [steps]       time one step with each build_variants/*.so in turn
 #   bench [args]             bench.py
 set -u
 mkdir -p gpurun_out
@@ -25,6 +26,10 @@ case $job in
     name=$1; n=$2
     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/$name.csv python tools/profile_step.py "$n" 2 > gpurun_out/$name.log 2>&1
     tail -2 gpurun_out/$name.log | cut -c1-300 ;;
+  variants) # build_variants/*.so (built here with different flags) take turns as libth_gpu.so: N [steps] [shape]
+    cp tidehunter_b200/libth_gpu.so /tmp/libth_gpu.so.keep
+    for f in build_variants/*.so; do cp $f tidehunter_b200/libth_gpu.so; echo "== $f"; timeout 600 python tools/profile_step.py "$@" 2>&1 | head -1 | tr "," "\n" | grep -E "ms_poa|ms_ksw|ms_chain|ms_total"; done
+    cp /tmp/libth_gpu.so.keep tidehunter_b200/libth_gpu.so ;;
   bench) timeout 1500 python bench.py "$@" ;;
   *) echo "unknown job $job"; exit 2 ;;
 esac
