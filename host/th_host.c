@@ -272,6 +272,10 @@ static void emit_read(th_host *h, str_t *out, long long *n_failed, const th_gpu_
     str_t cons_txt = {0, 0, 0};
     str_t *qs = &h->qual[global_index % TH_SLOTS];
     size_t qual_base = qs->l; (void)qual_base;
+    if (R->read_status && R->read_status[r] != 0 && R->read_task_off[r + 1] == R->read_task_off[r]) {
+        /* the read itself failed on the GPU (chain ranking or partition limits) before any task existed: say so, count it */
+        if ((*n_failed)++ < 20) fprintf(stderr, "[th_host] read %s: failed on the GPU before the consensus stage (code %d); its records are missing\n", name, R->read_status[r]);
+    }
     for (t = R->read_task_off[r]; t < R->read_task_off[r + 1]; ++t) {
         const int p0 = R->task_pos_off[t], pos_n = R->task_pos_off[t + 1] - p0;
         const int32_t *pos = R->pos + p0;

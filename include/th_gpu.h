@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TH_GPU_ABI_VERSION 1
+#define TH_GPU_ABI_VERSION 2
 
 /* Numeric fields of mini_tandem_para (src/tidehunter.h:47-61) that reach the hot path. */
 typedef struct {
@@ -66,6 +66,7 @@ typedef struct {
     const int32_t *iden_n;             /* ksw2_global identity count of unit u vs consensus: iden_n[task_pos_off[t]+u] */
     const int32_t *ext;                /* 4 per task: left max_q, left max_t, right max_q, right max_t (src/gen_cons.c:217-223) */
     const int32_t *task_status;        /* 0 ok; non-zero = th_gpu error code for that task */
+    const int32_t *read_status;        /* n_reads; non-zero = the read itself failed before any task existed (chain ranking / partition limits) */
     th_gpu_stats stats;
 } th_gpu_result;
 

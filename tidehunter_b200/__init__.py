@@ -39,7 +39,7 @@ class GpuResult(C.Structure):
         ("read_task_off", C.POINTER(C.c_int32)), ("task_pos_off", C.POINTER(C.c_int32)), ("pos", C.POINTER(C.c_int32)),
         ("task_n_seqs", C.POINTER(C.c_int32)), ("task_cons_off", C.POINTER(C.c_int32)), ("cons_base", C.POINTER(C.c_uint8)),
         ("cons_cov", C.POINTER(C.c_int32)), ("iden_n", C.POINTER(C.c_int32)), ("ext", C.POINTER(C.c_int32)),
-        ("task_status", C.POINTER(C.c_int32)), ("stats", GpuStats),
+        ("task_status", C.POINTER(C.c_int32)), ("read_status", C.POINTER(C.c_int32)), ("stats", GpuStats),
     ]
 
 

@@ -22,6 +22,7 @@
 #include "th_ksw.cuh"
 #include "th_partition.cuh"
 #include "th_poa.cuh"
+#include "th_tasks.cuh"
 
 static thread_local std::string g_err;
 static void set_err(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
@@ -82,12 +83,9 @@ struct th_gpu_ctx {
     DBuf d_parstream, d_parused, d_pardoff;
     DBuf d_tasks, d_torder, d_ustart, d_ulen, d_slabs, d_consb, d_consc, d_consl, d_tstatus, d_items, d_iden, d_ext;
     DBuf d_gsrc, d_gdst, d_glen, d_dense_b, d_dense_c, d_redo;
-    HBuf h_tmp, h_tmp2, h_consb, h_consc;
-    // host result storage
-    std::vector<int32_t> r_read_task_off, r_task_pos_off, r_pos, r_task_n_seqs, r_task_cons_off, r_cons_cov, r_iden, r_ext, r_task_status;
-    std::vector<uint8_t> r_cons_base;
-    // debug copies of the last chunk
-    std::vector<int32_t> dbg_par_stream; std::vector<int64_t> dbg_par_doff;
+    DBuf d_tcounts, d_totals, d_tkey, d_left, d_pos, d_rtoff, d_tposoff, d_tnseqs, d_tconsoff, d_retry;
+    // host result storage (pinned: the final copies are asynchronous and the host waits once)
+    HBuf h_totals, h_rtoff, h_tposoff, h_pos, h_tnseqs, h_tconsoff, h_tstatus, h_iden, h_ext, h_rstatus, h_counters, h_consb, h_consc;
     th_gpu_stats stats;
 };
 
@@ -168,9 +166,11 @@ extern "C" void th_gpu_destroy(th_gpu_ctx *c) {
                   &c->d_gflag, &c->d_rank, &c->d_nrank, &c->d_tracked, &c->d_choff, &c->d_chlen, &c->d_chscore, &c->d_chidx, &c->d_cells, &c->d_pchn, &c->d_pchoff,
                   &c->d_pchlen, &c->d_par, &c->d_paroff, &c->d_parn, &c->d_rstatus, &c->d_scratch, &c->d_scratch2, &c->d_bnd, &c->d_rev, &c->d_counters,
                   &c->d_parstream, &c->d_parused, &c->d_pardoff, &c->d_tasks, &c->d_torder, &c->d_ustart, &c->d_ulen, &c->d_slabs, &c->d_consb, &c->d_consc,
-                  &c->d_consl, &c->d_tstatus, &c->d_items, &c->d_iden, &c->d_ext, &c->d_gsrc, &c->d_gdst, &c->d_glen, &c->d_dense_b, &c->d_dense_c, &c->d_redo};
+                  &c->d_consl, &c->d_tstatus, &c->d_items, &c->d_iden, &c->d_ext, &c->d_gsrc, &c->d_gdst, &c->d_glen, &c->d_dense_b, &c->d_dense_c, &c->d_redo,
+                  &c->d_tcounts, &c->d_totals, &c->d_tkey, &c->d_left, &c->d_pos, &c->d_rtoff, &c->d_tposoff, &c->d_tnseqs, &c->d_tconsoff, &c->d_retry};
     for (DBuf *b : ds) b->release();
-    HBuf *hs[] = {&c->h_ascii, &c->h_tmp, &c->h_tmp2, &c->h_consb, &c->h_consc};
+    HBuf *hs[] = {&c->h_ascii, &c->h_totals, &c->h_rtoff, &c->h_tposoff, &c->h_pos, &c->h_tnseqs, &c->h_tconsoff, &c->h_tstatus, &c->h_iden, &c->h_ext, &c->h_rstatus,
+                  &c->h_counters, &c->h_consb, &c->h_consc};
     for (HBuf *b : hs) b->release();
     for (int i = 0; i < 16; ++i) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(c->mark[i]);
@@ -217,34 +217,6 @@ extern "C" int th_gpu_upload(th_gpu_ctx *c, int32_t n_reads, const char *const *
     return 0;
 }
 
-// generic range gather: one warp per range
-template <class T>
-__global__ void gather_kernel(int n, const int64_t *__restrict__ src_off, const int64_t *__restrict__ dst_off, const int32_t *__restrict__ len,
-                              const T *__restrict__ src, T *__restrict__ dst) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= n) return;
-    const T *s = src + src_off[w]; T *d = dst + dst_off[w]; const int l = len[w];
-    for (int i = lane; i < l; i += 32) d[i] = s[i];
-}
-
-// serialises every read's partition result as [n_chains, (par_n, values...)*] at the start of its par region
-__global__ void par_stream_kernel(int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ pch_n,
-                                  const int32_t *__restrict__ par, const int32_t *__restrict__ par_off, const int32_t *__restrict__ par_n,
-                                  int32_t *__restrict__ stream, int32_t *__restrict__ used) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    const int64_t off = roff[r], hoff = off / 2;
-    int32_t *o = stream + 2 * off; const int32_t *p = par + 2 * off;
-    const int nch = pch_n[r];
-    int u = 0; o[u++] = nch;
-    for (int c = 0; c < nch; ++c) {
-        const int n = par_n[hoff + c], po = par_off[hoff + c];
-        o[u++] = n;
-        for (int i = 0; i < n; ++i) o[u++] = p[po + i];
-    }
-    used[r] = u;
-}
-
 __global__ void ksw_test_kernel(int n, int mode, const uint8_t *__restrict__ buf, const int64_t *__restrict__ qoff, const int32_t *__restrict__ ql,
                                 const int64_t *__restrict__ toff, const int32_t *__restrict__ tl, const int32_t *__restrict__ arg,
                                 int4 *bnd_all, int64_t bnd_stride, int32_t *__restrict__ out2) {
@@ -268,10 +240,8 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     float keep_h2d = S.ms_h2d; int64_t keep_h2db = S.h2d_bytes;
     memset(&S, 0, sizeof(S)); S.ms_h2d = keep_h2d; S.h2d_bytes = keep_h2db;
     memset(out, 0, sizeof(*out));
-    c->r_read_task_off.assign(n + 1, 0);
-    c->r_task_pos_off.assign(1, 0); c->r_pos.clear(); c->r_task_n_seqs.clear(); c->r_task_cons_off.assign(1, 0);
-    c->r_cons_base.clear(); c->r_cons_cov.clear(); c->r_iden.clear(); c->r_ext.clear(); c->r_task_status.clear();
-    if (n == 0) { out->read_task_off = c->r_read_task_off.data(); out->task_pos_off = c->r_task_pos_off.data(); out->task_cons_off = c->r_task_cons_off.data(); return 0; }
+    static const int32_t zero2[2] = {0, 0};
+    if (n == 0) { out->read_task_off = zero2; out->task_pos_off = zero2; out->task_cons_off = zero2; return 0; }
     for (int i = 0; i < n; ++i) S.n_bases += c->h_rlen[i];
     const size_t B4 = (size_t)B * 4;
     if (c->d_bseq.ensure(B + 64) || c->d_pack.ensure(B / 4 + 64) || c->d_nmask.ensure(B / 8 + 64) ||
@@ -280,13 +250,17 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         c->d_choff.ensure(B4 / 2 + 256) || c->d_chlen.ensure(B4 / 2 + 256) || c->d_chscore.ensure(B4 / 2 + 256) || c->d_chidx.ensure(B4 / 2 + 256) ||
         c->d_cells.ensure(B4) || c->d_pchn.ensure(4 * (size_t)n) || c->d_pchoff.ensure(B4 / 2 + 256) || c->d_pchlen.ensure(B4 / 2 + 256) ||
         c->d_par.ensure(2 * B4) || c->d_paroff.ensure(B4 / 2 + 256) || c->d_parn.ensure(B4 / 2 + 256) || c->d_rstatus.ensure(4 * (size_t)n) ||
-        c->d_parstream.ensure(2 * B4) || c->d_parused.ensure(4 * (size_t)n) || c->d_pardoff.ensure(8 * (size_t)n) || c->d_counters.ensure(256))
+        c->d_counters.ensure(256) || c->d_tcounts.ensure(4 * (size_t)TC_N * n + 64) || c->d_totals.ensure(sizeof(TaskTotals)) ||
+        c->d_rtoff.ensure(4 * (size_t)(n + 1)) || c->h_totals.ensure(sizeof(TaskTotals)) || c->h_rtoff.ensure(4 * (size_t)(n + 1)) ||
+        c->h_rstatus.ensure(4 * (size_t)n) || c->h_counters.ensure(256))
         return -1;
     // counters: [0] chain evals (u64), [1] poa cells, [2] poa rows, [3] ksw cells, [8..] int work counters
     CK(cudaMemsetAsync(c->d_counters.p, 0, 256, st));
     CK(cudaMemsetAsync(c->d_rstatus.p, 0, 4 * (size_t)n, st));
+    CK(cudaMemsetAsync(c->d_totals.p, 0, sizeof(TaskTotals), st));
     unsigned long long *cnt64 = c->d_counters.as<unsigned long long>();
     int *cnt32 = c->d_counters.as<int>() + 16;
+    TaskTotals *d_tot = c->d_totals.as<TaskTotals>();
     const int64_t *roff = c->d_roff.as<int64_t>(); const int32_t *rlen = c->d_rlen.as<int32_t>();
     int ei = 2; // event index
     // ---- pack ----
@@ -334,134 +308,60 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         S.n_launches += 2;
     }
     CK(cudaEventRecord(c->ev[ei++], st)); // 6
-    // ---- partition ----
+    // ---- partition, then the tasks it implies are counted on the device ----
     const int n_pwarps = std::min(n, std::max(4, (int)(c->n_sm * PART_MIN_BLOCKS * PART_WARPS * c->share)));
     const int64_t bnd_stride = 2 * (int64_t)(c->max_len + 64);
     {
-        if (c->d_bnd.ensure((size_t)n_pwarps * bnd_stride * sizeof(int4))) return -1;
         const int grid = (n_pwarps + PART_WARPS - 1) / PART_WARPS;
         if (c->d_bnd.ensure((size_t)grid * PART_WARPS * bnd_stride * sizeof(int4))) return -1;
         partition_kernel<<<grid, PART_WARPS * 32, 0, st>>>(P, n, roff, rlen, c->d_bseq.as<uint8_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(), c->d_cells.as<int32_t>(),
                                                           c->d_pchn.as<int32_t>(), c->d_pchoff.as<int32_t>(), c->d_pchlen.as<int32_t>(), c->d_par.as<int32_t>(),
                                                           c->d_paroff.as<int32_t>(), c->d_parn.as<int32_t>(), c->d_bnd.as<int4>(), bnd_stride, cnt32 + 0,
                                                           c->d_rstatus.as<int32_t>(), cnt64 + 3);
-        par_stream_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, roff, c->d_pchn.as<int32_t>(), c->d_par.as<int32_t>(), c->d_paroff.as<int32_t>(), c->d_parn.as<int32_t>(),
-                                                       c->d_parstream.as<int32_t>(), c->d_parused.as<int32_t>());
-        S.n_launches += 2;
+        task_count_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, c->params.min_copy, roff, rlen, c->d_pchn.as<int32_t>(), c->d_par.as<int32_t>(), c->d_paroff.as<int32_t>(),
+                                                          c->d_parn.as<int32_t>(), c->d_nhits.as<int32_t>(), c->d_tcounts.as<int32_t>(), d_tot);
+        task_scan_kernel<<<1, 1024, 0, st>>>(n, c->d_tcounts.as<int32_t>(), d_tot);
+        S.n_launches += 3;
     }
     CK(cudaEventRecord(c->ev[ei++], st)); // 7
-    // ---- bring the partition streams to the host (dense) ----
-    std::vector<int32_t> used(n), nhits_h(n);
-    CK(cudaMemcpyAsync(used.data(), c->d_parused.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(nhits_h.data(), c->d_nhits.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    // ---- first (and only mid-chunk) wait: the totals that size everything downstream ----
+    TaskTotals *ht = c->h_totals.as<TaskTotals>();
+    CK(cudaMemcpyAsync(ht, d_tot, sizeof(TaskTotals), cudaMemcpyDeviceToHost, st));
     CK(th_wait(c));
-    std::vector<int64_t> doff(n + 1, 0), soff(n);
-    for (int i = 0; i < n; ++i) { doff[i + 1] = doff[i] + used[i]; soff[i] = 2 * c->h_roff[i]; S.n_hits += nhits_h[i]; }
-    const int64_t tot_stream = doff[n];
-    if (c->d_gsrc.ensure(8 * (size_t)n) || c->d_gdst.ensure(8 * (size_t)n) || c->d_dense_c.ensure(4 * (size_t)tot_stream + 64)) return -1;
-    CK(cudaMemcpyAsync(c->d_gsrc.p, soff.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(c->d_gdst.p, doff.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, st));
-    gather_kernel<int32_t><<<(n * 32 + 255) / 256, 256, 0, st>>>(n, c->d_gsrc.as<int64_t>(), c->d_gdst.as<int64_t>(), c->d_parused.as<int32_t>(), c->d_parstream.as<int32_t>(), c->d_dense_c.as<int32_t>());
+    const int nt = ht->n[TC_TASKS], n_units = ht->n[TC_UNITS], n_pos = ht->n[TC_POS];
+    const int n_pairs = ht->n[TC_PAIR3] + (ht->n[TC_LEFT] >> 1), n_singles = ht->n[TC_LEFT] & 1, n_exts = P.only_unit ? 0 : 2 * nt;
+    const int64_t cons_total = ht->n[TC_CONS];
+    S.n_hits = ht->n_hits; S.n_tasks = nt;
+    S.d2h_bytes += sizeof(TaskTotals);
+    if (c->d_tasks.ensure(sizeof(PoaTask) * (size_t)nt + 64) || c->d_torder.ensure(4 * (size_t)nt + 64) || c->d_tkey.ensure(4 * (size_t)nt + 64) ||
+        c->d_ustart.ensure(4 * (size_t)n_units + 64) || c->d_ulen.ensure(4 * (size_t)n_units + 64) || c->d_pos.ensure(4 * (size_t)n_pos + 64) ||
+        c->d_tposoff.ensure(4 * (size_t)(nt + 1)) || c->d_tnseqs.ensure(4 * (size_t)nt + 64) || c->d_tconsoff.ensure(4 * (size_t)(nt + 1)) ||
+        c->d_items.ensure(sizeof(KswItem) * ((size_t)n_pairs + n_singles + 2 * (size_t)nt) + 64) || c->d_left.ensure(sizeof(LeftUnit) * (size_t)ht->n[TC_LEFT] + 64) ||
+        c->d_consb.ensure((size_t)cons_total + 64) || c->d_consc.ensure(4 * (size_t)cons_total + 64) || c->d_consl.ensure(4 * (size_t)nt + 64) ||
+        c->d_tstatus.ensure(4 * (size_t)nt + 64) || c->d_iden.ensure(4 * (size_t)n_pos + 64) || c->d_ext.ensure(16 * (size_t)nt + 64) || c->d_retry.ensure(4 * (size_t)nt + 64) ||
+        c->h_tposoff.ensure(4 * (size_t)(nt + 1)) || c->h_pos.ensure(4 * (size_t)n_pos + 64) || c->h_tnseqs.ensure(4 * (size_t)nt + 64) || c->h_tconsoff.ensure(4 * (size_t)(nt + 1)) ||
+        c->h_tstatus.ensure(4 * (size_t)nt + 64) || c->h_iden.ensure(4 * (size_t)n_pos + 64) || c->h_ext.ensure(16 * (size_t)nt + 64)) return -1;
+    task_fill_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, c->params.min_copy, P.only_unit, roff, rlen, c->d_pchn.as<int32_t>(), c->d_par.as<int32_t>(), c->d_paroff.as<int32_t>(),
+                                                     c->d_parn.as<int32_t>(), c->d_tcounts.as<int32_t>(), d_tot, c->d_tasks.as<PoaTask>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(),
+                                                     c->d_pos.as<int32_t>(), c->d_rtoff.as<int32_t>(), c->d_tposoff.as<int32_t>(), c->d_tnseqs.as<int32_t>(), c->d_tkey.as<int32_t>(),
+                                                     c->d_items.as<KswItem>(), c->d_left.as<LeftUnit>());
     S.n_launches++;
-    c->dbg_par_stream.resize(tot_stream); c->dbg_par_doff = doff;
-    CK(cudaMemcpyAsync(c->dbg_par_stream.data(), c->d_dense_c.p, 4 * (size_t)tot_stream, cudaMemcpyDeviceToHost, st));
-    CK(th_wait(c));
-    S.d2h_bytes += 4 * tot_stream + 8 * (int64_t)n;
-    // ---- host: split runs into tasks exactly as seqs_msa (src/gen_cons.c:191-200) ----
-    std::vector<PoaTask> tasks; std::vector<int32_t> ustart, ulen; std::vector<KswItem> items;
-    int pending_single = -1; // index of an unpaired single-unit item
-    int64_t cons_total = 0;
-    const int min_copy = c->params.min_copy;
-    for (int r = 0; r < n; ++r) {
-        const int32_t *sp = c->dbg_par_stream.data() + doff[r];
-        const int L = c->h_rlen[r];
-        int u = 0; const int nch = sp[u++];
-        for (int ch = 0; ch < nch; ++ch) {
-            const int par_n = sp[u++]; const int32_t *par = sp + u; u += par_n;
-            if (par_n < min_copy + 1) continue; // src/tidehunter.c:42
-            int i = 0;
-            while (i < par_n - min_copy) {
-                if (par[i] < 0) { ++i; continue; }
-                int j;
-                for (j = i + 1; j < par_n; ++j) if (par[j] < 0) break;
-                if (j - i > min_copy) {
-                    PoaTask T; memset(&T, 0, sizeof(T));
-                    T.read = r; T.seq_off = c->h_roff[r]; T.unit_off = (int32_t)ustart.size();
-                    int nseq = 0, sum = 0, qmax = 0;
-                    for (int q = i; q < j - 1; ++q) { // src/abpoa_cons.c:40-50
-                        const int start = par[q], end = par[q + 1];
-                        if (start < 0 || end < 0 || start >= L - 1 || end + 1 > L) continue;
-                        ustart.push_back(start + 1); ulen.push_back(end - start); ++nseq; sum += end - start; qmax = std::max(qmax, end - start);
-                    }
-                    T.n_seqs = nseq; T.ncap = sum + 2; T.qmax = qmax; T.cons_off = (int32_t)cons_total;
-                    cons_total += sum + 4;
-                    const int t = (int)tasks.size();
-                    tasks.push_back(T);
-                    for (int q = i; q < j; ++q) c->r_pos.push_back(par[q]);
-                    c->r_task_pos_off.push_back((int32_t)c->r_pos.size());
-                    c->r_task_n_seqs.push_back(nseq);
-                    if (!P.only_unit) { // post-consensus alignments of seqs_msa (src/gen_cons.c:208-223); units go two per warp
-                        const int p0 = (int)c->r_pos.size() - (j - i);
-                        for (int q = i; q < j - 1; q += 2) {
-                            KswItem it; memset(&it, 0, sizeof(it));
-                            it.task = t; it.seq_off = c->h_roff[r]; it.out = p0 + (q - i);
-                            it.a = par[q] + 1; it.b = par[q + 1] - par[q];
-                            if (q + 1 < j - 1) { it.kind = 3; it.a2 = par[q + 1] + 1; it.b2 = par[q + 2] - par[q + 1]; items.push_back(it); }
-                            else if (pending_single >= 0) { // pair the left-over unit with the previous task's left-over
-                                KswItem &o = items[pending_single];
-                                o.kind = 4; o.task2 = t; o.a2 = it.a; o.b2 = it.b; o.out2 = it.out; o.seq_off2 = it.seq_off;
-                                pending_single = -1;
-                            } else { it.kind = 0; pending_single = (int)items.size(); items.push_back(it); }
-                        }
-                        KswItem le; memset(&le, 0, sizeof(le)); le.kind = 1; le.task = t; le.a = par[i] + 1; le.seq_off = c->h_roff[r]; le.out = 4 * t; items.push_back(le);
-                        KswItem re; memset(&re, 0, sizeof(re)); re.kind = 2; re.task = t; re.a = par[j - 1] + 1; re.b = L - par[j - 1] - 1; re.seq_off = c->h_roff[r]; re.out = 4 * t + 2; items.push_back(re);
-                    }
-                }
-                i = j + 1;
-            }
-        }
-        c->r_read_task_off[r + 1] = (int32_t)tasks.size();
-    }
-    const int nt = (int)tasks.size();
-    S.n_tasks = nt;
-    c->r_task_status.assign(nt, 0); c->r_task_cons_off.assign(nt + 1, 0);
-    c->r_iden.assign(c->r_pos.size(), 0); c->r_ext.assign((size_t)nt * 4, -1);
+    CK(cudaMemsetAsync(c->d_consl.p, 0, 4 * (size_t)nt + 64, st));
+    CK(cudaMemsetAsync(c->d_tstatus.p, 0, 4 * (size_t)nt + 64, st));
+    CK(cudaMemsetAsync(c->d_iden.p, 0, 4 * (size_t)n_pos + 64, st));
+    CK(cudaMemsetAsync(c->d_ext.p, 0xff, 16 * (size_t)nt + 64, st));
     CK(cudaEventRecord(c->ev[ei++], st)); // 8
+    long long dense_cap = 0;
     if (nt > 0 && !P.only_unit) {
-        // ---- POA ----
-        std::vector<int32_t> order(nt);
-        for (int i = 0; i < nt; ++i) order[i] = i;
-        std::sort(order.begin(), order.end(), [&](int a, int b) { return (int64_t)tasks[a].ncap * tasks[a].n_seqs > (int64_t)tasks[b].ncap * tasks[b].n_seqs; });
-        // Slabs: graph arrays + the DP arena of ONE alignment (recycled for every unit): rows <= nodes, three int16 planes
-        // (H, E1, E2) and a code byte per banded cell.  Typical: the graph holds <= ~2.5 units worth of nodes; the adaptive band is 2w+1
-        // columns around the predecessors' row maxima, rounded to whole vectors (measured mean ~61 columns on 1 kb units)
-        auto slab_need = [](const PoaTask &T, bool full) -> size_t {
-            const size_t fixed = poa_fixed_bytes(T.ncap, T.qmax, T.n_seqs);
-            const size_t fullb = (size_t)T.ncap * (((size_t)T.qmax + 64) * 7 + 16);
-            if (full) return fixed + fullb + 4096;
-            const int wband = 10 + T.qmax / 100;
-            const size_t rows_typ = std::min<size_t>((size_t)T.ncap, (size_t)T.qmax * 5 / 2 + 64);
-            const size_t width_typ = std::min<size_t>((size_t)T.qmax + 64, (size_t)2 * wband + 64);
-            const size_t typ = std::max<size_t>(rows_typ * (width_typ * 7 + 16), (size_t)1 << 20);
-            return fixed + std::min(typ, fullb) + 4096;
-        };
-        size_t slab_typ = 0;
-        for (const PoaTask &T : tasks) if (T.n_seqs > 2) slab_typ = std::max(slab_typ, slab_need(T, false));
-        slab_typ = (slab_typ + 255) & ~(size_t)255; // slabs hold 16-byte accesses
-        if (c->d_tasks.ensure(sizeof(PoaTask) * (size_t)nt) || c->d_torder.ensure(4 * (size_t)nt) || c->d_ustart.ensure(4 * ustart.size() + 64) ||
-            c->d_ulen.ensure(4 * ulen.size() + 64) || c->d_consb.ensure((size_t)cons_total + 64) || c->d_consc.ensure(4 * (size_t)cons_total + 64) ||
-            c->d_consl.ensure(4 * (size_t)nt) || c->d_tstatus.ensure(4 * (size_t)nt)) return -1;
-        CK(cudaMemcpyAsync(c->d_tasks.p, tasks.data(), sizeof(PoaTask) * (size_t)nt, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(c->d_torder.p, order.data(), 4 * (size_t)nt, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(c->d_ustart.p, ustart.data(), 4 * ustart.size(), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(c->d_ulen.p, ulen.data(), 4 * ulen.size(), cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(c->d_consl.p, 0, 4 * (size_t)nt, st));
-        CK(cudaMemsetAsync(c->d_tstatus.p, 0, 4 * (size_t)nt, st));
-        size_t free_b = 0, total_b = 0; CK(cudaMemGetInfo(&free_b, &total_b));
+        if (ht->n[TC_LEFT] > 0) { task_pair_left_kernel<<<(ht->n[TC_LEFT] / 2 + 128) / 128, 128, 0, st>>>(d_tot, c->d_left.as<LeftUnit>(), c->d_items.as<KswItem>()); S.n_launches++; }
+        task_order_kernel<<<1, 1024, 0, st>>>(d_tot, c->d_tkey.as<int32_t>(), c->d_torder.as<int32_t>());
+        S.n_launches++;
+        // ---- POA: 16-lane groups, two tasks per warp ----
+        size_t slab_typ = ((size_t)ht->slab_typ + 255) & ~(size_t)255; // slabs hold 16-byte accesses
         if (slab_typ == 0) slab_typ = 1 << 20;
+        size_t free_b = 0, total_b = 0; CK(cudaMemGetInfo(&free_b, &total_b));
         size_t budget = (size_t)((double)(free_b + c->d_slabs.cap) * 0.6);
         budget = std::min(budget, total_b / 5); // several contexts share the device (the host layer runs four): none may take it all
-        // first pass: 16-lane groups, two tasks per warp
         constexpr int GPB16 = POA_WARPS * 2, GPB32 = POA_WARPS;
         int ngroups = (int)std::min<size_t>((size_t)(c->n_sm * POA_MIN_BLOCKS16 * GPB16 * c->share), std::max<size_t>(1, budget / slab_typ));
         ngroups = std::min(ngroups, std::max(nt, 1));
@@ -473,69 +373,35 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
             if (grid <= 4) return -1;
             grid = (grid + 1) / 2;
         }
-        poa_kernel<16><<<grid, POA_WARPS * 32, sizeof(PoaSmem<16>) * GPB16 + sizeof(PoaLaneK) * 16, st>>>(P, nt, c->d_tasks.as<PoaTask>(), c->d_torder.as<int32_t>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(),
-                                                 c->d_bseq.as<uint8_t>(), c->d_slabs.as<uint8_t>(), slab_typ, cnt32 + 1, c->d_consb.as<uint8_t>(), c->d_consc.as<int32_t>(),
-                                                 c->d_consl.as<int32_t>(), c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2, cnt64 + 16, grid * GPB16);
-        S.n_launches++;
-        CK(cudaMemcpyAsync(c->r_task_status.data(), c->d_tstatus.p, 4 * (size_t)nt, cudaMemcpyDeviceToHost, st));
-        CK(th_wait(c));
-        // second pass, one task per warp with full-width slabs: tasks whose DP arena overflowed the typical slab, and rows
-        // with more than 16 predecessors.  The slab is sized for the retried tasks only; when memory is short the pass
-        // runs with fewer resident warps, and if even one slab cannot be had the tasks keep their error status (the host
-        // layer reports and drops those records) -- the chunk goes on.
-        std::vector<int32_t> retry;
-        for (int t = 0; t < nt; ++t) if (c->r_task_status[t] == TH_ERR_ARENA || c->r_task_status[t] == TH_ERR_CAP) retry.push_back(t);
-        if (!retry.empty()) {
-            size_t slab_full = 0;
-            for (int t : retry) slab_full = std::max(slab_full, slab_need(tasks[t], true));
-            slab_full = (slab_full + 255) & ~(size_t)255;
-            if (getenv("TH_GPU_DEBUG")) fprintf(stderr, "[th_gpu] %d of %d POA tasks are retried with %zu-byte slabs (first pass: %zu)\n", (int)retry.size(), nt, slab_full, slab_typ);
-            CK(cudaMemGetInfo(&free_b, &total_b));
-            budget = (size_t)((double)(free_b + c->d_slabs.cap) * 0.8);
-            int rg = (int)std::min<size_t>(retry.size(), std::max<size_t>(1, budget / slab_full));
-            rg = std::min(rg, (int)(c->n_sm * POA_MIN_BLOCKS32 * GPB32));
-            bool have = false;
-            while (true) {
-                const int rgrid = (rg + GPB32 - 1) / GPB32;
-                // fewer groups than a block holds: the extra groups of the last block find no task and never touch their slab
-                if (!c->d_slabs.ensure((size_t)std::min(rg, rgrid * GPB32) * slab_full)) { have = true; break; }
-                cudaGetLastError();
-                if (rg <= 1) break;
-                rg = (rg + 1) / 2;
-            }
-            if (have) {
-                const int rgrid = (rg + GPB32 - 1) / GPB32;
-                CK(cudaMemcpyAsync(c->d_torder.p, retry.data(), 4 * retry.size(), cudaMemcpyHostToDevice, st));
-                CK(cudaMemsetAsync(cnt32 + 1, 0, 4, st));
-                poa_kernel<32><<<rgrid, POA_WARPS * 32, sizeof(PoaSmem<32>) * GPB32 + sizeof(PoaLaneK) * 32, st>>>(P, std::min((int)retry.size(), INT_MAX), c->d_tasks.as<PoaTask>(), c->d_torder.as<int32_t>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(),
-                                                          c->d_bseq.as<uint8_t>(), c->d_slabs.as<uint8_t>(), slab_full, cnt32 + 1, c->d_consb.as<uint8_t>(), c->d_consc.as<int32_t>(),
-                                                          c->d_consl.as<int32_t>(), c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2, cnt64 + 16, rg);
-                S.n_launches++;
-            } else set_err("POA retry: no memory for one %zu-byte slab; %d tasks keep their error status", slab_full, (int)retry.size());
-        }
-        CK(cudaEventRecord(c->ev[ei++], st)); // 9
-        // ---- post-consensus ksw items ----
-        const int ni = (int)items.size();
+        poa_kernel<16><<<grid, POA_WARPS * 32, sizeof(PoaSmem<16>) * GPB16 + sizeof(PoaLaneK) * 16, st>>>(
+            P, nt, nullptr, c->d_tasks.as<PoaTask>(), c->d_torder.as<int32_t>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(), c->d_bseq.as<uint8_t>(),
+            c->d_slabs.as<uint8_t>(), slab_typ, nullptr, c->d_slabs.cap, cnt32 + 1, c->d_consb.as<uint8_t>(), c->d_consc.as<int32_t>(), c->d_consl.as<int32_t>(),
+            c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2, cnt64 + 16, grid * GPB16, c->d_retry.as<int32_t>(), d_tot);
+        // second pass, one task per warp with full-width slabs, driven from the device: tasks whose DP arena overflowed the
+        // typical slab and rows with more than 16 predecessors were put on a list by the first pass, together with the
+        // slab size they need.  It reuses the first pass's slabs, with as many resident warps as fit; when not even one
+        // slab fits, the tasks keep their error status (the host layer reports and drops those records).  With an empty
+        // list (the usual case) the launch ends at once.
         {
-            std::vector<int32_t> coff(nt);
-            for (int t = 0; t < nt; ++t) coff[t] = tasks[t].cons_off;
-            // pairs, singles, extensions: one kernel each (own register budgets)
-            std::stable_sort(items.begin(), items.end(), [](const KswItem &x, const KswItem &y) {
-                auto grp = [](int k) { return k >= 3 ? 0 : (k == 0 ? 1 : 2); };
-                return grp(x.kind) < grp(y.kind); });
-            int n_pairs = 0, n_singles = 0, n_exts = 0;
-            for (const KswItem &it : items) { if (it.kind >= 3) ++n_pairs; else if (it.kind == 0) ++n_singles; else ++n_exts; }
-            if (c->d_items.ensure(sizeof(KswItem) * (size_t)ni + 64) || c->d_iden.ensure(4 * c->r_pos.size() + 64) || c->d_ext.ensure(16 * (size_t)nt + 64) || c->d_glen.ensure(4 * (size_t)nt)) return -1;
-            CK(cudaMemcpyAsync(c->d_items.p, items.data(), sizeof(KswItem) * (size_t)ni, cudaMemcpyHostToDevice, st));
-            CK(cudaMemsetAsync(c->d_iden.p, 0, 4 * c->r_pos.size() + 64, st));
-            CK(cudaMemcpyAsync(c->d_glen.p, coff.data(), 4 * (size_t)nt, cudaMemcpyHostToDevice, st));
+            const int rgrid = std::min(c->n_sm * POA_MIN_BLOCKS32, std::max(1, (nt + GPB32 - 1) / GPB32));
+            poa_kernel<32><<<rgrid, POA_WARPS * 32, sizeof(PoaSmem<32>) * GPB32 + sizeof(PoaLaneK) * 32, st>>>(
+                P, 0, &d_tot->retry_n, c->d_tasks.as<PoaTask>(), c->d_retry.as<int32_t>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(), c->d_bseq.as<uint8_t>(),
+                c->d_slabs.as<uint8_t>(), 0, &d_tot->slab_full, c->d_slabs.cap, cnt32 + 6, c->d_consb.as<uint8_t>(), c->d_consc.as<int32_t>(), c->d_consl.as<int32_t>(),
+                c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2, cnt64 + 16, rgrid * GPB32, nullptr, d_tot);
+        }
+        S.n_launches += 2;
+        CK(cudaEventRecord(c->ev[ei++], st)); // 9
+        // ---- post-consensus ksw items: pairs, singles, extensions, one kernel each (own register budgets) ----
+        {
             const int64_t rev_stride = 2 * (int64_t)(c->max_len + 64);
             const KswItem *d_pairs = c->d_items.as<KswItem>(), *d_singles = d_pairs + n_pairs, *d_exts = d_singles + n_singles;
             auto grid_for = [&](int n_work, int min_blocks) { const int kw = std::min(std::max(n_work, 1), std::max(4, (int)(c->n_sm * min_blocks * KSW_WARPS * c->share))); return (kw + KSW_WARPS - 1) / KSW_WARPS; };
             const int g_pair = grid_for(n_pairs, KSW_PAIR_MIN_BLOCKS), g_single = grid_for(n_singles + 64, KSW_MIN_BLOCKS), g_ext = grid_for(n_exts, KSW_EXT_MIN_BLOCKS);
             const int g_max = std::max(g_pair, std::max(g_single, g_ext));
             if (c->d_bnd.ensure((size_t)g_max * KSW_WARPS * bnd_stride * sizeof(int4)) || c->d_rev.ensure((size_t)g_ext * KSW_WARPS * rev_stride) ||
-                c->d_redo.ensure(4 * (size_t)n_pairs + 64)) return -1;
+                c->d_redo.ensure(4 * (size_t)n_pairs + 64) || c->d_glen.ensure(4 * (size_t)nt + 64)) return -1;
+            task_cons_off_kernel<<<(nt + 255) / 256, 256, 0, st>>>(nt, c->d_tasks.as<PoaTask>(), c->d_glen.as<int32_t>());
+            S.n_launches++;
             if (n_pairs > 0) {
                 ksw_pair_kernel<<<g_pair, KSW_WARPS * 32, 0, st>>>(n_pairs, d_pairs, c->d_bseq.as<uint8_t>(), c->d_consb.as<uint8_t>(), c->d_glen.as<int32_t>(),
                                                                  c->d_consl.as<int32_t>(), c->d_bnd.as<int4>(), bnd_stride, cnt32 + 2, c->d_redo.as<int32_t>(), cnt32 + 5,
@@ -554,52 +420,66 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
             }
         }
         CK(cudaEventRecord(c->ev[ei++], st)); // 10
-        // ---- results to the host ----
-        std::vector<int32_t> cl(nt);
-        CK(cudaMemcpyAsync(cl.data(), c->d_consl.p, 4 * (size_t)nt, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(c->r_task_status.data(), c->d_tstatus.p, 4 * (size_t)nt, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(c->r_iden.data(), c->d_iden.p, 4 * c->r_pos.size(), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(c->r_ext.data(), c->d_ext.p, 16 * (size_t)nt, cudaMemcpyDeviceToHost, st));
-        CK(th_wait(c));
-        std::vector<int64_t> gs(nt), gd(nt);
-        int64_t tot = 0;
-        for (int t = 0; t < nt; ++t) { gs[t] = tasks[t].cons_off; gd[t] = tot; c->r_task_cons_off[t] = (int32_t)tot; tot += cl[t]; }
-        c->r_task_cons_off[nt] = (int32_t)tot;
-        c->r_cons_base.resize(tot); c->r_cons_cov.assign(tot, 0);
-        if (tot > 0) {
-            if (c->d_gsrc.ensure(8 * (size_t)nt) || c->d_gdst.ensure(8 * (size_t)nt) || c->d_dense_b.ensure(tot + 64) || c->d_dense_c.ensure(4 * (size_t)tot + 64)) return -1;
-            CK(cudaMemcpyAsync(c->d_gsrc.p, gs.data(), 8 * (size_t)nt, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(c->d_gdst.p, gd.data(), 8 * (size_t)nt, cudaMemcpyHostToDevice, st));
-            gather_kernel<uint8_t><<<(nt * 32 + 255) / 256, 256, 0, st>>>(nt, c->d_gsrc.as<int64_t>(), c->d_gdst.as<int64_t>(), c->d_consl.as<int32_t>(), c->d_consb.as<uint8_t>(), c->d_dense_b.as<uint8_t>());
-            S.n_launches++;
-            CK(cudaMemcpyAsync(c->r_cons_base.data(), c->d_dense_b.p, (size_t)tot, cudaMemcpyDeviceToHost, st));
-            if (c->params.need_cov) {
-                gather_kernel<int32_t><<<(nt * 32 + 255) / 256, 256, 0, st>>>(nt, c->d_gsrc.as<int64_t>(), c->d_gdst.as<int64_t>(), c->d_consl.as<int32_t>(), c->d_consc.as<int32_t>(), c->d_dense_c.as<int32_t>());
-                S.n_launches++;
-                CK(cudaMemcpyAsync(c->r_cons_cov.data(), c->d_dense_c.p, 4 * (size_t)tot, cudaMemcpyDeviceToHost, st));
-            }
-        }
-        CK(cudaEventRecord(c->ev[ei++], st)); // 11
-        CK(th_wait(c));
-        S.d2h_bytes += 4ll * nt * 2 + 4ll * (int64_t)c->r_pos.size() + 16ll * nt + tot * (c->params.need_cov ? 5 : 1);
-        S.ms_poa = ev_ms(c, 8, 9); S.ms_ksw = ev_ms(c, 9, 10); S.ms_d2h = ev_ms(c, 10, 11);
+        // ---- dense consensus: offsets by a scan over the tasks, one gather ----
+        dense_cap = std::min<long long>(ht->dense_bound, cons_total) + 64;
+        if (c->d_dense_b.ensure((size_t)dense_cap + 64) || c->h_consb.ensure((size_t)dense_cap + 64) ||
+            (c->params.need_cov && (c->d_dense_c.ensure(4 * (size_t)dense_cap + 64) || c->h_consc.ensure(4 * (size_t)dense_cap + 64)))) return -1;
+        cons_scan_kernel<<<1, 1024, 0, st>>>(d_tot, c->d_consl.as<int32_t>(), c->d_tconsoff.as<int32_t>());
+        cons_gather_kernel<<<(nt * 32 + 255) / 256, 256, 0, st>>>(d_tot, c->d_tasks.as<PoaTask>(), c->d_consl.as<int32_t>(), c->d_tconsoff.as<int32_t>(), c->d_consb.as<uint8_t>(),
+                                                                c->d_consc.as<int32_t>(), c->d_dense_b.as<uint8_t>(), c->params.need_cov ? c->d_dense_c.as<int32_t>() : nullptr, dense_cap);
+        S.n_launches += 2;
+        CK(cudaMemcpyAsync(c->h_consb.p, c->d_dense_b.p, (size_t)dense_cap, cudaMemcpyDeviceToHost, st));
+        if (c->params.need_cov) CK(cudaMemcpyAsync(c->h_consc.p, c->d_dense_c.p, 4 * (size_t)dense_cap, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_tconsoff.p, c->d_tconsoff.p, 4 * (size_t)(nt + 1), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_iden.p, c->d_iden.p, 4 * (size_t)n_pos, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_ext.p, c->d_ext.p, 16 * (size_t)nt, cudaMemcpyDeviceToHost, st));
     } else {
-        CK(cudaEventRecord(c->ev[ei++], st)); CK(cudaEventRecord(c->ev[ei++], st)); CK(cudaEventRecord(c->ev[ei++], st));
+        CK(cudaEventRecord(c->ev[ei++], st)); CK(cudaEventRecord(c->ev[ei++], st)); // 9, 10
+        CK(cudaMemsetAsync(c->d_tconsoff.p, 0, 4 * (size_t)(nt + 1), st));
+        CK(cudaMemcpyAsync(c->h_tconsoff.p, c->d_tconsoff.p, 4 * (size_t)(nt + 1), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_iden.p, c->d_iden.p, 4 * (size_t)n_pos, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_ext.p, c->d_ext.p, 16 * (size_t)nt, cudaMemcpyDeviceToHost, st));
+    }
+    // ---- everything else the host layer reads, then the second and last wait ----
+    CK(cudaMemcpyAsync(c->h_rtoff.p, c->d_rtoff.p, 4 * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c->h_tposoff.p, c->d_tposoff.p, 4 * (size_t)(nt + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c->h_pos.p, c->d_pos.p, 4 * (size_t)n_pos, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c->h_tnseqs.p, c->d_tnseqs.p, 4 * (size_t)nt, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c->h_tstatus.p, c->d_tstatus.p, 4 * (size_t)nt, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c->h_rstatus.p, c->d_rstatus.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 256, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ht, d_tot, sizeof(TaskTotals), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c->ev[ei++], st)); // 11
+    CK(th_wait(c));
+    int32_t *h_rtoff = c->h_rtoff.as<int32_t>(), *h_tstatus = c->h_tstatus.as<int32_t>();
+    if (nt > 0 && !P.only_unit && ht->cons_total + 64 > dense_cap) { // consensus longer than the units it came from: fetch the rest with an exact copy (never seen)
+        dense_cap = ht->cons_total + 64;
+        if (c->d_dense_b.ensure((size_t)dense_cap + 64) || c->h_consb.ensure((size_t)dense_cap + 64) ||
+            (c->params.need_cov && (c->d_dense_c.ensure(4 * (size_t)dense_cap + 64) || c->h_consc.ensure(4 * (size_t)dense_cap + 64)))) return -1;
+        cons_gather_kernel<<<(nt * 32 + 255) / 256, 256, 0, st>>>(d_tot, c->d_tasks.as<PoaTask>(), c->d_consl.as<int32_t>(), c->d_tconsoff.as<int32_t>(), c->d_consb.as<uint8_t>(),
+                                                                c->d_consc.as<int32_t>(), c->d_dense_b.as<uint8_t>(), c->params.need_cov ? c->d_dense_c.as<int32_t>() : nullptr, dense_cap);
+        CK(cudaMemcpyAsync(c->h_consb.p, c->d_dense_b.p, (size_t)dense_cap, cudaMemcpyDeviceToHost, st));
+        if (c->params.need_cov) CK(cudaMemcpyAsync(c->h_consc.p, c->d_dense_c.p, 4 * (size_t)dense_cap, cudaMemcpyDeviceToHost, st));
         CK(th_wait(c));
     }
-    // per-read status -> tasks of that read
-    { std::vector<int32_t> rs(n);
-      CK(cudaMemcpyAsync(rs.data(), c->d_rstatus.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st)); CK(th_wait(c));
-      for (int r = 0; r < n; ++r) if (rs[r]) for (int t = c->r_read_task_off[r]; t < c->r_read_task_off[r + 1]; ++t) if (!c->r_task_status[t]) c->r_task_status[t] = rs[r]; }
-    unsigned long long hc[4];
-    CK(cudaMemcpy(hc, c->d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost));
+    if (ht->retry_n > 0 && getenv("TH_GPU_DEBUG")) fprintf(stderr, "[th_gpu] %d of %d POA tasks went to the second pass (%llu-byte slabs)\n", ht->retry_n, nt, (unsigned long long)ht->slab_full);
+    // a read-level failure (chain ranking or partition limits) fails the read's tasks; th_gpu_result.read_status lets the
+    // caller see it even when the read ended up with no task at all
+    { const int32_t *rs = c->h_rstatus.as<int32_t>();
+      for (int r = 0; r < n; ++r) if (rs[r]) for (int t = h_rtoff[r]; t < h_rtoff[r + 1]; ++t) if (!h_tstatus[t]) h_tstatus[t] = rs[r]; }
+    S.d2h_bytes += 4ll * (n + 1) + 4ll * (nt + 1) * 2 + 8ll * n_pos + 4ll * nt * 2 + 16ll * nt + 4ll * n + 256 + sizeof(TaskTotals) +
+                   (nt > 0 && !P.only_unit ? dense_cap * (c->params.need_cov ? 5 : 1) : 0);
+    const unsigned long long *hc = c->h_counters.as<unsigned long long>();
     S.n_chain_evals = (int64_t)hc[0]; S.n_poa_cells = (int64_t)hc[1]; S.n_poa_rows = (int64_t)hc[2]; S.n_ksw_cells = (int64_t)hc[3];
     S.ms_pack = ev_ms(c, 2, 3); S.ms_seed = ev_ms(c, 3, 4); S.ms_chain = ev_ms(c, 4, 5); S.ms_select = ev_ms(c, 5, 6); S.ms_partition = ev_ms(c, 6, 7);
-    S.ms_total = ev_ms(c, 2, ei - 1);
+    S.ms_poa = ev_ms(c, 8, 9); S.ms_ksw = ev_ms(c, 9, 10); S.ms_d2h = ev_ms(c, 10, 11);
+    S.ms_total = ev_ms(c, 2, 11);
     out->n_reads = n; out->n_tasks = nt;
-    out->read_task_off = c->r_read_task_off.data(); out->task_pos_off = c->r_task_pos_off.data(); out->pos = c->r_pos.data();
-    out->task_n_seqs = c->r_task_n_seqs.data(); out->task_cons_off = c->r_task_cons_off.data(); out->cons_base = c->r_cons_base.data();
-    out->cons_cov = c->r_cons_cov.data(); out->iden_n = c->r_iden.data(); out->ext = c->r_ext.data(); out->task_status = c->r_task_status.data();
+    out->read_task_off = h_rtoff; out->task_pos_off = c->h_tposoff.as<int32_t>(); out->pos = c->h_pos.as<int32_t>();
+    out->task_n_seqs = c->h_tnseqs.as<int32_t>(); out->task_cons_off = c->h_tconsoff.as<int32_t>(); out->cons_base = c->h_consb.as<uint8_t>();
+    out->cons_cov = c->params.need_cov ? c->h_consc.as<int32_t>() : c->h_iden.as<int32_t>(); // only read when coverage was asked for
+    out->iden_n = c->h_iden.as<int32_t>(); out->ext = c->h_ext.as<int32_t>(); out->task_status = h_tstatus;
+    out->read_status = c->h_rstatus.as<int32_t>();
     out->stats = S;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_err("kernel failure: %s", cudaGetErrorString(e)); return -1; }
@@ -672,16 +552,17 @@ extern "C" int th_gpu_debug_chains(th_gpu_ctx *c, int32_t read, int32_t cap, int
     return tot;
 }
 extern "C" int th_gpu_debug_par_pos(th_gpu_ctx *c, int32_t read, int32_t chain, int32_t cap, int32_t *par_pos) {
-    if (read < 0 || read >= c->n_reads || c->dbg_par_doff.empty()) { set_err("read out of range"); return -1; }
-    const int32_t *sp = c->dbg_par_stream.data() + c->dbg_par_doff[read];
-    int u = 0; const int nch = sp[u++];
+    CK(cudaSetDevice(c->device));
+    if (read < 0 || read >= c->n_reads || !c->d_par.p) { set_err("read out of range"); return -1; }
+    int32_t nch = 0; CK(cudaMemcpy(&nch, c->d_pchn.as<int32_t>() + read, 4, cudaMemcpyDeviceToHost));
     if (chain < 0 || chain >= nch) return -1;
-    for (int ch = 0; ch < nch; ++ch) {
-        const int n = sp[u++];
-        if (ch == chain) { for (int i = 0; i < n && i < cap; ++i) par_pos[i] = sp[u + i]; return n; }
-        u += n;
-    }
-    return -1;
+    const int64_t off = c->h_roff[read], hoff = off / 2;
+    int32_t n = 0, po = 0;
+    CK(cudaMemcpy(&n, c->d_parn.as<int32_t>() + hoff + chain, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&po, c->d_paroff.as<int32_t>() + hoff + chain, 4, cudaMemcpyDeviceToHost));
+    const int m = std::min(n, cap);
+    if (m > 0) CK(cudaMemcpy(par_pos, c->d_par.as<int32_t>() + 2 * off + po, 4 * (size_t)m, cudaMemcpyDeviceToHost));
+    return n;
 }
 
 extern "C" int th_gpu_ksw_batch(th_gpu_ctx *c, int32_t n, int32_t mode, const uint8_t *const *q, const int32_t *ql,

@@ -25,6 +25,18 @@ struct DevParams {
     uint32_t INFP, NOE1P, NOE2P, NE1P, NE2P, PE12, NEGMIS2, XMM; // the same as s16x2 pairs: (inf, inf), (-oe1, -oe1), ..., (-e1, -e2), (-mis, -mis), mat ^ -mis
 };
 
+// per-read counters, one array each (index = TC_* x n_reads + read)
+enum { TC_TASKS = 0, TC_UNITS, TC_POS, TC_PAIR3, TC_LEFT, TC_CONS, TC_N };
+
+struct TaskTotals {
+    int32_t n[TC_N];            // sums of the per-read counters
+    int32_t max_key;            // largest task size key (ncap x n_seqs, saturated): scales the size buckets of the task order
+    int32_t retry_n;            // tasks the first POA pass handed to the second one
+    unsigned long long slab_typ, slab_full; // largest typical slab of all tasks; largest full-width slab of the retried ones
+    long long n_hits, dense_bound;          // hits of all reads; bound used for the dense consensus copy
+    long long cons_total;                   // dense consensus length (after the POA)
+};
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 // ---------------------------------------------------------------------------------------------

@@ -87,6 +87,20 @@ __host__ __device__ inline size_t poa_fixed_bytes(int ncap, int qmax, int nseq) 
     return (b + 4095) & ~(size_t)4095;
 }
 
+// slab sizes (bytes) of one task: graph arrays + the DP arena of ONE alignment (recycled for every unit): rows <= nodes, three
+// int16 planes and a code byte per banded cell.  Typical: the graph holds <= ~2.5 units worth of nodes; the adaptive band is
+// 2w+1 columns around the predecessors' row maxima, rounded to whole vectors (measured mean ~61 columns on 1 kb units).
+__host__ __device__ inline unsigned long long poa_slab_need(int ncap, int qmax, int n_seqs, bool full) {
+    const unsigned long long fixed = poa_fixed_bytes(ncap, qmax, n_seqs);
+    const unsigned long long fullb = (unsigned long long)ncap * (((unsigned long long)qmax + 64) * 7 + 16);
+    if (full) return fixed + fullb + 4096;
+    const int wband = 10 + qmax / 100;
+    unsigned long long rows_typ = (unsigned long long)qmax * 5 / 2 + 64; if (rows_typ > (unsigned long long)ncap) rows_typ = ncap;
+    unsigned long long width_typ = 2ull * wband + 64; if (width_typ > (unsigned long long)qmax + 64) width_typ = (unsigned long long)qmax + 64;
+    unsigned long long typ = rows_typ * (width_typ * 7 + 16); if (typ < (1ull << 20)) typ = 1ull << 20;
+    return fixed + (typ < fullb ? typ : fullb) + 4096;
+}
+
 __device__ inline void poa_carve(PoaWs &w, uint8_t *slab, size_t slab_bytes, int ncap, int qmax, int nseq) {
     size_t ecap = (size_t)ncap + nseq + 2;
     w.ncap = ncap;
@@ -573,8 +587,8 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
                 }
                 if (more) poa_chunk_carry<LPT>(g, P, Hf, Fa, Fb, carryH, carryF);
             };
-            chunk(0, multi);
-            if (multi) for (int ch = 1; __any_sync(TH_FULL, go && ch < nchunk); ++ch) chunk(ch, true); // rows wider than one chunk: the other group keeps the warp company
+            { int ch = 0; // rows wider than one chunk: the other group keeps the warp company
+              do { chunk(ch, multi); ++ch; } while (multi && __any_sync(TH_FULL, go && ch < nchunk)); }
             const int rbest = g.rmax(best);
             if (go) { // simd_abpoa_max_in_row + simd_abpoa_ada_max_i: successors pull max_i + 1 from this row's metadata
                 const int val = rbest >> 16;
@@ -1032,12 +1046,12 @@ __device__ int poa_consensus(PoaSmem<LPT> &sm, const bool act, int node_n, int n
 #endif
 template <int LPT>
 __global__ void __launch_bounds__(POA_WARPS * 32, LPT == 16 ? POA_MIN_BLOCKS16 : POA_MIN_BLOCKS32)
-poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const int32_t *__restrict__ task_order,
+poa_kernel(DevParams P, int n_tasks, const int *__restrict__ n_tasks_dev, const PoaTask *__restrict__ tasks, const int32_t *__restrict__ task_order,
            const int32_t *__restrict__ u_start, const int32_t *__restrict__ u_len, const uint8_t *__restrict__ bseq,
-           uint8_t *slabs, size_t slab_bytes, int *task_counter,
+           uint8_t *slabs, size_t slab_bytes, const unsigned long long *__restrict__ slab_bytes_dev, size_t slab_cap, int *task_counter,
            uint8_t *__restrict__ cons_base, int32_t *__restrict__ cons_cov, int32_t *__restrict__ cons_len,
            int32_t *__restrict__ task_status, unsigned long long *__restrict__ stat_cells, unsigned long long *__restrict__ stat_rows,
-           unsigned long long *__restrict__ stat_phase, int max_groups) {
+           unsigned long long *__restrict__ stat_phase, int max_groups, int32_t *__restrict__ retry_list, TaskTotals *tot) {
     constexpr int GPW = 32 / LPT;                      // groups per warp
     extern __shared__ __align__(16) unsigned char poa_smem_raw[];
     PoaSmem<LPT> *s_all = reinterpret_cast<PoaSmem<LPT> *>(poa_smem_raw);
@@ -1049,6 +1063,11 @@ poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const in
     PoaSmem<LPT> &sm = s_all[gib];
     const uint32_t lk = (uint32_t)__cvta_generic_to_shared(lk_tab + gl);
     const int gg = blockIdx.x * (POA_WARPS * GPW) + gib;
+    if (n_tasks_dev) { // second pass: the first one left the task count and the slab size these tasks need in device memory
+        n_tasks = *n_tasks_dev;
+        slab_bytes = ((size_t)*slab_bytes_dev + 255) & ~(size_t)255;
+        max_groups = (int)min((unsigned long long)max_groups, slab_bytes ? (unsigned long long)(slab_cap / slab_bytes) : 0ull); // no room for a single slab: the tasks keep their status
+    }
     uint8_t *slab = slabs + (size_t)gg * slab_bytes;
     unsigned long long cells = 0, rows = 0;
 #ifdef POA_PROFILE
@@ -1083,7 +1102,13 @@ poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const in
                 for (int i = gl; i < l0; i += LPT) { cons[i] = s0[i]; cov[i] = 0; }
                 if (gl == 0) { cons_len[t] = l0; task_status[t] = TH_OK; }
                 has = false;
-            } else if (poa_fixed_bytes(T.ncap, T.qmax, T.n_seqs) + 4096 > slab_bytes) { if (gl == 0) { cons_len[t] = 0; task_status[t] = TH_ERR_ARENA; } has = false; }
+            } else if (poa_fixed_bytes(T.ncap, T.qmax, T.n_seqs) + 4096 > slab_bytes) {
+                if (gl == 0) {
+                    cons_len[t] = 0; task_status[t] = TH_ERR_ARENA;
+                    if (retry_list) { retry_list[atomicAdd(&tot->retry_n, 1)] = t; atomicMax(&tot->slab_full, poa_slab_need(T.ncap, T.qmax, T.n_seqs, true)); }
+                }
+                has = false;
+            }
             if (!has) fresh = false;
         }
         __syncwarp();
@@ -1134,7 +1159,13 @@ poa_kernel(DevParams P, int n_tasks, const PoaTask *__restrict__ tasks, const in
             if (fin) {
                 if (err == TH_OK && cl < 0) err = TH_ERR_ARENA;
                 if (err != TH_OK) cl = 0;
-                if (gl == 0) { cons_len[t] = cl; task_status[t] = err; }
+                if (gl == 0) {
+                    cons_len[t] = cl; task_status[t] = err;
+                    if (retry_list && (err == TH_ERR_ARENA || err == TH_ERR_CAP)) { // a full-width slab and 32-lane groups take it in the second pass
+                        retry_list[atomicAdd(&tot->retry_n, 1)] = t;
+                        atomicMax(&tot->slab_full, poa_slab_need(T.ncap, T.qmax, T.n_seqs, true));
+                    }
+                }
                 has = false;
             }
 #ifdef POA_PROFILE
