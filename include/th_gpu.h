@@ -108,7 +108,8 @@ int th_gpu_debug_counters(th_gpu_ctx *ctx, int32_t cap, int64_t *out);          
 
 /* Stand-alone ksw2-style alignments on nt4-coded HOST sequences (tests of the alignment kernels).
  * mode 0: global -> out[0] = iden_n;  mode 1: global + left-end projection with q_left_ext = arg ->
- * out[0] = iden_n, out[1] = t_left_ext;  mode 2: extension -> out[0] = max_q, out[1] = max_t. */
+ * out[0] = iden_n, out[1] = t_left_ext;  mode 2: extension -> out[0] = max_q, out[1] = max_t;  mode 3: the same for
+ * entries 2k and 2k+1 together (no N), through the packed two-extensions-per-warp routine. */
 int th_gpu_ksw_batch(th_gpu_ctx *ctx, int32_t n, int32_t mode, const uint8_t *const *q, const int32_t *ql,
                      const uint8_t *const *t, const int32_t *tl, const int32_t *arg, int32_t *out2);
 

@@ -105,6 +105,24 @@ def test_ksw_global_and_extension(T, oracle):
     e2 = [H.ksw_ext(q, t) for q, t in pairs]
     bad = [(i, len(qs[i]), len(ts[i]), g2[i], e2[i]) for i in range(len(pairs)) if tuple(g2[i]) != e2[i]]
     assert not bad, ("extension", bad[:8])
+    # two extensions per warp (the kernel pairs extensions of similar target length): any two, no N
+    q3, t3 = [], []
+    for _ in range(80):
+        n = int(rng.integers(1, 1400)) if rng.random() < 0.8 else int(rng.integers(1, 12))
+        lowc = rng.random() < 0.3
+        def mk(l):
+            return (rng.integers(0, 2 if lowc else 4, l, dtype=np.uint8)).tobytes()
+        qa = mk(n); qb = bytes(reversed(qa)) if rng.random() < 0.4 else mk(n if rng.random() < 0.5 else int(rng.integers(1, 1400)))
+        def noisy(q, l):
+            a = np.frombuffer((q * (l // len(q) + 1))[:l], dtype=np.uint8).copy()
+            hit = rng.random(l) < 0.15
+            a[hit] = rng.integers(0, 4, int(hit.sum()), dtype=np.uint8)
+            return a.tobytes()
+        q3 += [qa, qb]; t3 += [noisy(qa, int(rng.integers(0, 1500))), noisy(qb, int(rng.integers(0, 1500)))]
+    g3 = ctx.ksw_batch(3, q3, t3)
+    e3 = [H.ksw_ext(q, t) if len(t) else (-1, -1) for q, t in zip(q3, t3)]
+    bad = [(i, len(q3[i]), len(t3[i]), g3[i], e3[i]) for i in range(len(q3)) if tuple(g3[i]) != e3[i]]
+    assert not bad, ("packed extension", bad[:8])
     ctx.close()
 
 

@@ -83,7 +83,7 @@ struct th_gpu_ctx {
     DBuf d_parstream, d_parused, d_pardoff;
     DBuf d_tasks, d_torder, d_ustart, d_ulen, d_slabs, d_consb, d_consc, d_consl, d_tstatus, d_items, d_iden, d_ext;
     DBuf d_gsrc, d_gdst, d_glen, d_dense_b, d_dense_c, d_redo;
-    DBuf d_tcounts, d_totals, d_tkey, d_left, d_pos, d_rtoff, d_tposoff, d_tnseqs, d_tconsoff, d_retry;
+    DBuf d_tcounts, d_totals, d_tkey, d_ekey, d_eorder, d_left, d_pos, d_rtoff, d_tposoff, d_tnseqs, d_tconsoff, d_retry;
     // host result storage (pinned: the final copies are asynchronous and the host waits once)
     HBuf h_totals, h_rtoff, h_tposoff, h_pos, h_tnseqs, h_tconsoff, h_tstatus, h_iden, h_ext, h_rstatus, h_counters, h_consb, h_consc;
     th_gpu_stats stats;
@@ -167,7 +167,7 @@ extern "C" void th_gpu_destroy(th_gpu_ctx *c) {
                   &c->d_pchlen, &c->d_par, &c->d_paroff, &c->d_parn, &c->d_rstatus, &c->d_scratch, &c->d_scratch2, &c->d_bnd, &c->d_rev, &c->d_counters,
                   &c->d_parstream, &c->d_parused, &c->d_pardoff, &c->d_tasks, &c->d_torder, &c->d_ustart, &c->d_ulen, &c->d_slabs, &c->d_consb, &c->d_consc,
                   &c->d_consl, &c->d_tstatus, &c->d_items, &c->d_iden, &c->d_ext, &c->d_gsrc, &c->d_gdst, &c->d_glen, &c->d_dense_b, &c->d_dense_c, &c->d_redo,
-                  &c->d_tcounts, &c->d_totals, &c->d_tkey, &c->d_left, &c->d_pos, &c->d_rtoff, &c->d_tposoff, &c->d_tnseqs, &c->d_tconsoff, &c->d_retry};
+                  &c->d_tcounts, &c->d_totals, &c->d_tkey, &c->d_ekey, &c->d_eorder, &c->d_left, &c->d_pos, &c->d_rtoff, &c->d_tposoff, &c->d_tnseqs, &c->d_tconsoff, &c->d_retry};
     for (DBuf *b : ds) b->release();
     HBuf *hs[] = {&c->h_ascii, &c->h_totals, &c->h_rtoff, &c->h_tposoff, &c->h_pos, &c->h_tnseqs, &c->h_tconsoff, &c->h_tstatus, &c->h_iden, &c->h_ext, &c->h_rstatus,
                   &c->h_counters, &c->h_consb, &c->h_consc};
@@ -226,7 +226,15 @@ __global__ void ksw_test_kernel(int n, int mode, const uint8_t *__restrict__ buf
     int o0 = 0, o1 = 0;
     if (mode == 0) ksw_warp<KSW_GLOBAL, 16>(buf + qoff[w], ql[w], buf + toff[w], tl[w], 0, bnd, o0, o1);
     else if (mode == 1) ksw_warp<KSW_GLOBAL_STOP, 4>(buf + qoff[w], ql[w], buf + toff[w], tl[w], ql[w] - arg[w], bnd, o0, o1);
-    else ksw_warp<KSW_EXT, 16>(buf + qoff[w], ql[w], buf + toff[w], tl[w], 0, bnd, o0, o1);
+    else if (mode == 2) ksw_warp<KSW_EXT, 16>(buf + qoff[w], ql[w], buf + toff[w], tl[w], 0, bnd, o0, o1);
+    else { // mode 3: entries 2k and 2k + 1 (queries of equal length) as the two halves of one packed extension
+        if (w & 1) return;
+        int a0 = -1, a1 = -1, b0 = -1, b1 = -1;
+        if (w + 1 < n) ksw_warp_ext2<16>(buf + qoff[w], ql[w], buf + toff[w], tl[w], buf + qoff[w + 1], ql[w + 1], buf + toff[w + 1], tl[w + 1], bnd, a0, a1, b0, b1);
+        else ksw_warp<KSW_EXT, 16>(buf + qoff[w], ql[w], buf + toff[w], tl[w], 0, bnd, a0, a1);
+        if (lane == 0) { out2[2 * w] = a0; out2[2 * w + 1] = a1; if (w + 1 < n) { out2[2 * w + 2] = b0; out2[2 * w + 3] = b1; } }
+        return;
+    }
     if (lane == 0) { out2[2 * w] = o0; out2[2 * w + 1] = o1; }
 }
 
@@ -333,7 +341,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     const int64_t cons_total = ht->n[TC_CONS];
     S.n_hits = ht->n_hits; S.n_tasks = nt;
     S.d2h_bytes += sizeof(TaskTotals);
-    if (c->d_tasks.ensure(sizeof(PoaTask) * (size_t)nt + 64) || c->d_torder.ensure(4 * (size_t)nt + 64) || c->d_tkey.ensure(4 * (size_t)nt + 64) ||
+    if (c->d_tasks.ensure(sizeof(PoaTask) * (size_t)nt + 64) || c->d_torder.ensure(4 * (size_t)nt + 64) || c->d_tkey.ensure(4 * (size_t)nt + 64) || c->d_ekey.ensure(8 * (size_t)nt + 64) || c->d_eorder.ensure(8 * (size_t)nt + 64) ||
         c->d_ustart.ensure(4 * (size_t)n_units + 64) || c->d_ulen.ensure(4 * (size_t)n_units + 64) || c->d_pos.ensure(4 * (size_t)n_pos + 64) ||
         c->d_tposoff.ensure(4 * (size_t)(nt + 1)) || c->d_tnseqs.ensure(4 * (size_t)nt + 64) || c->d_tconsoff.ensure(4 * (size_t)(nt + 1)) ||
         c->d_items.ensure(sizeof(KswItem) * ((size_t)n_pairs + n_singles + 2 * (size_t)nt) + 64) || c->d_left.ensure(sizeof(LeftUnit) * (size_t)ht->n[TC_LEFT] + 64) ||
@@ -344,7 +352,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     task_fill_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, c->params.min_copy, P.only_unit, roff, rlen, c->d_pchn.as<int32_t>(), c->d_par.as<int32_t>(), c->d_paroff.as<int32_t>(),
                                                      c->d_parn.as<int32_t>(), c->d_tcounts.as<int32_t>(), d_tot, c->d_tasks.as<PoaTask>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(),
                                                      c->d_pos.as<int32_t>(), c->d_rtoff.as<int32_t>(), c->d_tposoff.as<int32_t>(), c->d_tnseqs.as<int32_t>(), c->d_tkey.as<int32_t>(),
-                                                     c->d_items.as<KswItem>(), c->d_left.as<LeftUnit>());
+                                                     c->d_ekey.as<int32_t>(), c->d_items.as<KswItem>(), c->d_left.as<LeftUnit>());
     S.n_launches++;
     CK(cudaMemsetAsync(c->d_consl.p, 0, 4 * (size_t)nt + 64, st));
     CK(cudaMemsetAsync(c->d_tstatus.p, 0, 4 * (size_t)nt + 64, st));
@@ -354,8 +362,9 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     long long dense_cap = 0;
     if (nt > 0 && !P.only_unit) {
         if (ht->n[TC_LEFT] > 0) { task_pair_left_kernel<<<(ht->n[TC_LEFT] / 2 + 128) / 128, 128, 0, st>>>(d_tot, c->d_left.as<LeftUnit>(), c->d_items.as<KswItem>()); S.n_launches++; }
-        task_order_kernel<<<1, 1024, 0, st>>>(d_tot, c->d_tkey.as<int32_t>(), c->d_torder.as<int32_t>());
-        S.n_launches++;
+        bucket_order_kernel<<<1, 1024, 0, st>>>(d_tot, 1, &d_tot->max_key, c->d_tkey.as<int32_t>(), c->d_torder.as<int32_t>());
+        bucket_order_kernel<<<1, 1024, 0, st>>>(d_tot, 2, &d_tot->max_ext, c->d_ekey.as<int32_t>(), c->d_eorder.as<int32_t>());
+        S.n_launches += 2;
         // ---- POA: 16-lane groups, two tasks per warp ----
         size_t slab_typ = ((size_t)ht->slab_typ + 255) & ~(size_t)255; // slabs hold 16-byte accesses
         if (slab_typ == 0) slab_typ = 1 << 20;
@@ -393,10 +402,10 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         CK(cudaEventRecord(c->ev[ei++], st)); // 9
         // ---- post-consensus ksw items: pairs, singles, extensions, one kernel each (own register budgets) ----
         {
-            const int64_t rev_stride = 2 * (int64_t)(c->max_len + 64);
+            const int64_t rev_stride = 4 * (int64_t)(c->max_len + 64); // two (consensus + flank) pairs of reversed copies per warp
             const KswItem *d_pairs = c->d_items.as<KswItem>(), *d_singles = d_pairs + n_pairs, *d_exts = d_singles + n_singles;
             auto grid_for = [&](int n_work, int min_blocks) { const int kw = std::min(std::max(n_work, 1), std::max(4, (int)(c->n_sm * min_blocks * KSW_WARPS * c->share))); return (kw + KSW_WARPS - 1) / KSW_WARPS; };
-            const int g_pair = grid_for(n_pairs, KSW_PAIR_MIN_BLOCKS), g_single = grid_for(n_singles + 64, KSW_MIN_BLOCKS), g_ext = grid_for(n_exts, KSW_EXT_MIN_BLOCKS);
+            const int g_pair = grid_for(n_pairs, KSW_PAIR_MIN_BLOCKS), g_single = grid_for(n_singles + 64, KSW_MIN_BLOCKS), g_ext = grid_for((n_exts + 1) / 2, KSW_EXT_MIN_BLOCKS);
             const int g_max = std::max(g_pair, std::max(g_single, g_ext));
             if (c->d_bnd.ensure((size_t)g_max * KSW_WARPS * bnd_stride * sizeof(int4)) || c->d_rev.ensure((size_t)g_ext * KSW_WARPS * rev_stride) ||
                 c->d_redo.ensure(4 * (size_t)n_pairs + 64) || c->d_glen.ensure(4 * (size_t)nt + 64)) return -1;
@@ -413,7 +422,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
                                                                  cnt32 + 3, c->d_iden.as<int32_t>(), cnt64 + 3);
             S.n_launches++;
             if (n_exts > 0) {
-                ksw_ext_kernel<<<g_ext, KSW_WARPS * 32, 0, st>>>(n_exts, d_exts, c->d_bseq.as<uint8_t>(), c->d_consb.as<uint8_t>(), c->d_glen.as<int32_t>(),
+                ksw_ext_kernel<<<g_ext, KSW_WARPS * 32, 0, st>>>(n_exts, d_exts, c->d_eorder.as<int32_t>(), c->d_bseq.as<uint8_t>(), c->d_consb.as<uint8_t>(), c->d_glen.as<int32_t>(),
                                                                c->d_consl.as<int32_t>(), c->d_rev.as<uint8_t>(), rev_stride, c->d_bnd.as<int4>(), bnd_stride, cnt32 + 4,
                                                                c->d_ext.as<int32_t>(), cnt64 + 3);
                 S.n_launches++;

@@ -32,6 +32,7 @@ struct TaskTotals {
     int32_t n[TC_N];            // sums of the per-read counters
     int32_t max_key;            // largest task size key (ncap x n_seqs, saturated): scales the size buckets of the task order
     int32_t retry_n;            // tasks the first POA pass handed to the second one
+    int32_t max_ext, pad0;      // longest extension target (scales the length classes that pair extensions of similar size)
     unsigned long long slab_typ, slab_full; // largest typical slab of all tasks; largest full-width slab of the retried ones
     long long n_hits, dense_bound;          // hits of all reads; bound used for the dense consensus copy
     long long cons_total;                   // dense consensus length (after the POA)

@@ -246,3 +246,96 @@ __device__ void ksw_warp_global2(const uint8_t *qa, int qla, const uint8_t *ta, 
         __syncwarp();
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Two score-only extensions (boundary extensions of consensus sequences, src/gen_cons.c:217-223; any two, the caller pairs
+// extensions of similar target length) in one warp.  Extension A lives in the
+// low, B in the high 16 bits of every DP word, biased like ksw_warp_global2; the row maximum of a lane's columns is one
+// packed max per column, and candidates are ranked exactly as ksw_warp<KSW_EXT> ranks them (the reference's visiting order).  No N allowed
+// (the caller falls back to the single-alignment routine), lengths <= KSW2_MAXLEN.
+// ---------------------------------------------------------------------------------------------
+template <int C>
+__device__ void ksw_warp_ext2(const uint8_t *qa, int qla, const uint8_t *ta, int tla, const uint8_t *qb_, int qlb, const uint8_t *tb_, int tlb,
+                              int4 *bnd, int &mqA, int &mtA, int &mqB, int &mtB) {
+    const int lane = lane_id();
+    mqA = mtA = mqB = mtB = -1;
+    if (qla <= 0 || tla <= 0) { qla = 0; tla = 0; }
+    if (qlb <= 0 || tlb <= 0) { qlb = 0; tlb = 0; }
+    const int ql = max(qla, qlb), tl = max(tla, tlb);
+    if (ql <= 0 || tl <= 0) return;
+    const int BW = 32 * C;
+    const int nblk = (ql + BW - 1) / BW;
+    int bzA = 0, biA = -1, bjA = -1, bzB = 0, biB = -1, bjB = -1;
+    const uint32_t ONE2 = 0x00010001u, Q2 = (uint32_t)KSW_Q * 0x10001u, E2 = (uint32_t)KSW_E * 0x10001u;
+    int2 *bnd2 = reinterpret_cast<int2 *>(bnd);
+    for (int b = 0; b < nblk; ++b) {
+        const int jb = b * BW;
+        const int bw = min(ql - jb, BW), nl = (bw + C - 1) / C;
+        const int j0 = jb + lane * C;
+        const int2 *bin = bnd2 + (size_t)(b & 1) * tl;
+        int2 *bout = bnd2 + (size_t)((b + 1) & 1) * tl;
+        uint32_t Hp[C], Ea[C], qq[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = j0 + c;
+            const int h0 = KSW2_BIAS - (KSW_Q + KSW_E * (j + 1));
+            Hp[c] = pk2(h0); Ea[c] = pk2(h0 - KSW_Q - KSW_E);
+            const uint32_t a = j < qla ? qa[j] : 8u, bb = j < qlb ? qb_[j] : 8u; // 8 never equals a target code
+            qq[c] = a | bb << 16;
+        }
+        uint32_t hdiag = j0 == 0 ? pk2(KSW2_BIAS) : pk2(KSW2_BIAS - (KSW_Q + KSW_E * j0));
+        uint32_t oH = 0, oF = 0;
+        const int nstep = tl + nl - 1;
+        for (int s = 0; s < nstep; ++s) {
+            const int i = s - lane;
+            uint32_t iH = __shfl_up_sync(TH_FULL, oH, 1), iF = __shfl_up_sync(TH_FULL, oF, 1);
+            if (lane == 0) {
+                if (b == 0) { const int h0 = KSW2_BIAS - (KSW_Q + KSW_E * (s + 1)); iH = pk2(h0); iF = pk2(h0 - KSW_Q - KSW_E); }
+                else if (s < tl) { const int2 v = bin[s]; iH = (uint32_t)v.x; iF = (uint32_t)v.y; }
+            }
+            if (i >= 0 && i < tl && lane < nl) {
+                const uint32_t tb2 = (i < tla ? (uint32_t)ta[i] : 9u) | (i < tlb ? (uint32_t)tb_[i] : 9u) << 16; // 9: past the end, never equal
+                uint32_t hd = hdiag, F = iF;
+                hdiag = iH;
+                uint32_t rowm = 0; // biased scores are >= 1: 0 is below all of them
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const uint32_t mm = __vminu2(qq[c] ^ tb2, ONE2);           // 0 = equal, 1 = different, per half
+                    uint32_t z = hd + ONE2 - 3u * mm;                          // + (1 - 3 mm) per half
+                    const uint32_t e = Ea[c];
+                    z = __vmaxs2(__vmaxs2(z, e), F);
+                    const uint32_t t1 = z - Q2;
+                    Ea[c] = __vmaxs2(e, t1) - E2;
+                    F = __vmaxs2(F, t1) - E2;
+                    hd = Hp[c];
+                    Hp[c] = z;
+                    rowm = __vmaxs2(rowm, z);
+                }
+                // Row maximum of this lane's columns.  Columns past a query's end hold dead values, but a dead value is at least 2
+                // below a live one this lane has already seen (the cell diagonally above-left of the first dead column, or a
+                // live cell further left in the same row), so it never passes the test against the lane's best below; the column
+                // -- the first one on ties (smaller j = earlier anti-diagonal), hence a live one -- is only looked up then.
+                const int zrA = (int)(rowm & 0xffffu) - KSW2_BIAS, zrB = (int)(rowm >> 16) - KSW2_BIAS;
+                const bool ha = i < tla && zrA > 0 && zrA >= bzA, hb = i < tlb && zrB > 0 && zrB >= bzB;
+                if (ha || hb) {
+                    int ca = 0, cb = 0;
+#pragma unroll
+                    for (int c = C - 1; c >= 0; --c) { const uint32_t x = Hp[c] ^ rowm; if ((x & 0xffffu) == 0) ca = c; if ((x >> 16) == 0) cb = c; }
+                    if (ha && ksw_ext_better(zrA, i, j0 + ca, bzA, biA, bjA, qla, tla)) { bzA = zrA; biA = i; bjA = j0 + ca; }
+                    if (hb && ksw_ext_better(zrB, i, j0 + cb, bzB, biB, bjB, qlb, tlb)) { bzB = zrB; biB = i; bjB = j0 + cb; }
+                }
+                oH = Hp[C - 1]; oF = F;
+                if (lane == nl - 1 && b + 1 < nblk) bout[i] = make_int2((int)oH, (int)oF);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        int oz = __shfl_xor_sync(TH_FULL, bzA, d), oi = __shfl_xor_sync(TH_FULL, biA, d), oj = __shfl_xor_sync(TH_FULL, bjA, d);
+        if (oi >= 0 && (biA < 0 || ksw_ext_better(oz, oi, oj, bzA, biA, bjA, qla, tla))) { bzA = oz; biA = oi; bjA = oj; }
+        oz = __shfl_xor_sync(TH_FULL, bzB, d); oi = __shfl_xor_sync(TH_FULL, biB, d); oj = __shfl_xor_sync(TH_FULL, bjB, d);
+        if (oi >= 0 && (biB < 0 || ksw_ext_better(oz, oi, oj, bzB, biB, bjB, qlb, tlb))) { bzB = oz; biB = oi; bjB = oj; }
+    }
+    mqA = bjA; mtA = biA; mqB = bjB; mtB = biB;
+}

@@ -178,41 +178,54 @@ ksw_single_kernel(int n_single, const KswItem *__restrict__ singles, const KswIt
     if (lane == 0 && ncell) atomicAdd(stat_cells, ncell);
 }
 
+// Boundary extensions, two per warp (packed 16x2): `order` lists the items by target length, so entries 2k and 2k + 1 are
+// of similar size.  A pair with N in a sequence or one longer than KSW2_MAXLEN runs one after the other, 32-bit.
+__device__ __forceinline__ void ksw_ext_prepare(const KswItem &I, const uint8_t *bseq, const uint8_t *cons, int cl, uint8_t *rev,
+                                                const uint8_t *&q, const uint8_t *&t, int &tl) {
+    const int lane = lane_id();
+    if (I.kind == 1) { // ksw2_left_ext: both sequences reversed (src/ksw2_align.c:161-173)
+        tl = I.a; const uint8_t *rs = bseq + I.seq_off;
+        uint8_t *rq = rev, *rt = rev + ((cl + 15) & ~15);
+        for (int i = lane; i < cl; i += 32) rq[i] = cons[cl - 1 - i];
+        for (int i = lane; i < tl; i += 32) rt[i] = rs[tl - 1 - i];
+        q = rq; t = rt;
+    } else { q = cons; t = bseq + I.seq_off + I.a; tl = I.b; } // ksw2_right_ext (src/ksw2_align.c:153-159)
+}
 __global__ void __launch_bounds__(KSW_WARPS * 32, KSW_EXT_MIN_BLOCKS)
-ksw_ext_kernel(int n_items, const KswItem *__restrict__ items, const uint8_t *__restrict__ bseq,
+ksw_ext_kernel(int n_items, const KswItem *__restrict__ items, const int32_t *__restrict__ order, const uint8_t *__restrict__ bseq,
                const uint8_t *__restrict__ cons_base, const int32_t *__restrict__ cons_off, const int32_t *__restrict__ cons_len,
                uint8_t *rev_all, int64_t rev_stride, int4 *bnd_all, int64_t bnd_stride, int *counter,
                int32_t *__restrict__ out_ext, unsigned long long *__restrict__ stat_cells) {
     const int lane = lane_id();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int4 *bnd = bnd_all + (int64_t)gw * bnd_stride;
-    uint8_t *rev = rev_all + (int64_t)gw * rev_stride; // reversed copies for the left extension
+    uint8_t *rev = rev_all + (int64_t)gw * rev_stride; // reversed copies for left extensions: one half of it per item of the pair
     unsigned long long ncell = 0;
+    const int n_pairs = (n_items + 1) >> 1;
     while (true) {
         int it = 0;
         if (lane == 0) it = atomicAdd(counter, 1);
         it = __shfl_sync(TH_FULL, it, 0);
-        if (it >= n_items) break;
-        const KswItem I = items[it];
-        const int cl = cons_len[I.task];
-        const uint8_t *cons = cons_base + cons_off[I.task];
-        int o0 = -1, o1 = -1;
-        if (cl > 0) {
-            if (I.kind == 1) { // ksw2_left_ext: both sequences reversed (src/ksw2_align.c:161-173)
-                const int tl = I.a; const uint8_t *rs = bseq + I.seq_off;
-                uint8_t *rq = rev, *rt = rev + ((cl + 15) & ~15);
-                for (int i = lane; i < cl; i += 32) rq[i] = cons[cl - 1 - i];
-                for (int i = lane; i < tl; i += 32) rt[i] = rs[tl - 1 - i];
-                __syncwarp();
-                ksw_warp<KSW_EXT, 16>(rq, cl, rt, tl, 0, bnd, o0, o1);
-                ncell += (unsigned long long)cl * tl;
-                __syncwarp();
-            } else { // ksw2_right_ext (src/ksw2_align.c:153-159)
-                ksw_warp<KSW_EXT, 16>(cons, cl, bseq + I.seq_off + I.a, I.b, 0, bnd, o0, o1);
-                ncell += (unsigned long long)cl * I.b;
-            }
+        if (it >= n_pairs) break;
+        const bool hasb = 2 * it + 1 < n_items;
+        const KswItem A = items[order[2 * it]], B = items[order[hasb ? 2 * it + 1 : 2 * it]];
+        const int cla = cons_len[A.task], clb = hasb ? cons_len[B.task] : 0;
+        const uint8_t *qa = nullptr, *ta = nullptr, *qb = nullptr, *tb = nullptr; int tla = 0, tlb = 0;
+        if (cla > 0) ksw_ext_prepare(A, bseq, cons_base + cons_off[A.task], cla, rev, qa, ta, tla);
+        if (clb > 0) ksw_ext_prepare(B, bseq, cons_base + cons_off[B.task], clb, rev + rev_stride / 2, qb, tb, tlb);
+        __syncwarp();
+        int aq = -1, at = -1, bq = -1, bt = -1;
+        bool two = cla > 0 && clb > 0 && max(max(cla, clb), max(tla, tlb)) <= KSW2_MAXLEN;
+        if (two) two = !warp_has_n(qa, cla) && !warp_has_n(ta, max(tla, 0)) && !warp_has_n(qb, clb) && !warp_has_n(tb, max(tlb, 0));
+        if (two) ksw_warp_ext2<16>(qa, cla, ta, tla, qb, clb, tb, tlb, bnd, aq, at, bq, bt);
+        else {
+            if (cla > 0) ksw_warp<KSW_EXT, 16>(qa, cla, ta, tla, 0, bnd, aq, at);
+            if (clb > 0) ksw_warp<KSW_EXT, 16>(qb, clb, tb, tlb, 0, bnd, bq, bt);
         }
-        if (lane == 0) { out_ext[I.out] = o0; out_ext[I.out + 1] = o1; }
+        if (cla > 0) ncell += (unsigned long long)cla * max(tla, 0);
+        if (clb > 0) ncell += (unsigned long long)clb * max(tlb, 0);
+        __syncwarp();
+        if (lane == 0) { out_ext[A.out] = aq; out_ext[A.out + 1] = at; if (hasb) { out_ext[B.out] = bq; out_ext[B.out + 1] = bt; } }
     }
     if (lane == 0 && ncell) atomicAdd(stat_cells, ncell);
 }

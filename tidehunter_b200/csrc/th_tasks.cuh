@@ -100,10 +100,10 @@ struct LeftUnit { int32_t task, a, b, out; int64_t seq_off; };
 
 __global__ void task_fill_kernel(int n_reads, int min_copy, int only_unit, const int64_t *__restrict__ roff, const int32_t *__restrict__ rlen,
                                  const int32_t *__restrict__ pch_n, const int32_t *__restrict__ par, const int32_t *__restrict__ par_off,
-                                 const int32_t *__restrict__ par_n, const int32_t *__restrict__ offs, const TaskTotals *__restrict__ tot,
+                                 const int32_t *__restrict__ par_n, const int32_t *__restrict__ offs, TaskTotals *tot,
                                  PoaTask *__restrict__ tasks, int32_t *__restrict__ ustart, int32_t *__restrict__ ulen, int32_t *__restrict__ pos,
                                  int32_t *__restrict__ read_task_off, int32_t *__restrict__ task_pos_off, int32_t *__restrict__ task_n_seqs,
-                                 int32_t *__restrict__ task_key, KswItem *__restrict__ items, LeftUnit *__restrict__ left) {
+                                 int32_t *__restrict__ task_key, int32_t *__restrict__ ext_key, KswItem *__restrict__ items, LeftUnit *__restrict__ left) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     int t = offs[(size_t)TC_TASKS * n_reads + r], u = offs[(size_t)TC_UNITS * n_reads + r], ps = offs[(size_t)TC_POS * n_reads + r];
@@ -115,6 +115,7 @@ __global__ void task_fill_kernel(int n_reads, int min_copy, int only_unit, const
     if (r == n_reads - 1) read_task_off[n_reads] = nt;
     if (r == 0) task_pos_off[0] = 0;
     const int L = rlen[r]; const int64_t so = roff[r];
+    int max_ext = 0;
     th_for_each_task(r, min_copy, roff, pch_n, par, par_off, par_n, [&](const int32_t *pp, int i, int j) {
         PoaTask T; T.seq_off = so; T.read = r; T.unit_off = u;
         int nseq = 0, sum = 0, qmax = 0;
@@ -143,9 +144,11 @@ __global__ void task_fill_kernel(int n_reads, int min_copy, int only_unit, const
             KswItem le; le.kind = 1; le.task = t; le.a = pp[i] + 1; le.b = 0; le.a2 = le.b2 = 0; le.seq_off = so; le.out = 4 * t; le.task2 = le.out2 = le.pad = 0; le.seq_off2 = 0;
             KswItem re = le; re.kind = 2; re.a = pp[j - 1] + 1; re.b = L - pp[j - 1] - 1; re.out = 4 * t + 2;
             exts[2 * t] = le; exts[2 * t + 1] = re;
+            ext_key[2 * t] = max(le.a, 0); ext_key[2 * t + 1] = max(re.b, 0); max_ext = max(max_ext, max(le.a, re.b));
         }
         ++t;
     });
+    if (max_ext > 0) atomicMax(&tot->max_ext, max_ext);
 }
 
 // left-over units, two per item (kind 4); an odd last one is the single item
@@ -163,13 +166,15 @@ __global__ void task_pair_left_kernel(const TaskTotals *__restrict__ tot, const 
     } else { it.kind = 0; items[n3 + (n_left >> 1)] = it; }
 }
 
-// Task order for the persistent POA groups: largest first, by 1024 size classes (the order only balances the load: every
-// task's result is independent of it).  One block.
-__global__ void __launch_bounds__(1024) task_order_kernel(const TaskTotals *__restrict__ tot, const int32_t *__restrict__ key, int32_t *__restrict__ order) {
+// Order by decreasing key in 1024 size classes (a counting sort; the order inside a class is arbitrary).  Used for the task
+// order of the persistent POA groups (largest first: the order only balances the load, every task's result is independent
+// of it) and to pair boundary extensions of similar target length.  n = mult x tot->n[TC_TASKS].  One block.
+__global__ void __launch_bounds__(1024) bucket_order_kernel(const TaskTotals *__restrict__ tot, int mult, const int32_t *__restrict__ max_key,
+                                                            const int32_t *__restrict__ key, int32_t *__restrict__ order) {
     __shared__ int s_cnt[1024], s_part[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int nt = tot->n[TC_TASKS];
-    const unsigned long long mk = (unsigned long long)max(tot->max_key, 1);
+    const int nt = mult * tot->n[TC_TASKS];
+    const unsigned long long mk = (unsigned long long)max(*max_key, 1);
     s_cnt[tid] = 0;
     __syncthreads();
     for (int t = tid; t < nt; t += 1024) atomicAdd(&s_cnt[1023 - (int)((unsigned long long)key[t] * 1023ull / mk)], 1);
