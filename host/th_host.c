@@ -109,6 +109,19 @@ th_gpu_ctx *th_host_gpu(th_host *h) { return h->gpu; }
  * Case-insensitive equality.  infix_ed_plain is the column-by-column definition; infix_ed evaluates the same two
  * passes with Myers' bit-vector recurrences (Myers 1999, block form of Hyyro 2003: vertical deltas Pv/Mv per 64 rows,
  * horizontal delta carried from block to block), 64 DP cells per word operation. */
+/* character classes of the adapter search: edlib is given the five equalities a/A c/C g/G t/T n/N (src/edlib_align.c:21-27)
+ * and compares every other byte verbatim, so 'R' and 'r' (or '@' and '`') are different symbols */
+static unsigned char ed_class[256];
+static unsigned char nt4_class[256]; /* the read's nt4 code (src/seq.c:15-32): what abpoa_gen_cons compares */
+__attribute__((constructor)) static void init_classes(void) { /* filled when the library is loaded */
+    int c;
+    for (c = 0; c < 256; ++c) { ed_class[c] = (unsigned char)c; nt4_class[c] = 4; }
+    ed_class['a'] = 'A'; ed_class['c'] = 'C'; ed_class['g'] = 'G'; ed_class['t'] = 'T'; ed_class['n'] = 'N';
+    nt4_class[0] = 0; nt4_class[1] = 1; nt4_class[2] = 2; nt4_class[3] = 3; nt4_class['-'] = 5;
+    nt4_class['A'] = nt4_class['a'] = 0; nt4_class['C'] = nt4_class['c'] = 1; nt4_class['G'] = nt4_class['g'] = 2; nt4_class['T'] = nt4_class['t'] = 3;
+}
+#define ED_EQ(a, b) (ed_class[(unsigned char)(a)] == ed_class[(unsigned char)(b)])
+
 static int infix_ed_plain(const char *q, int ql, const char *t, int tl, int *start, int *end, int k) {
     int i, j, best = -1, best_end = -1, best_start = -1;
     int *col;
@@ -119,7 +132,7 @@ static int infix_ed_plain(const char *q, int ql, const char *t, int tl, int *sta
         int diag = col[0];
         col[0] = 0;
         for (i = 1; i <= ql; ++i) {
-            int up = col[i - 1] + 1, left = col[i] + 1, d = diag + (((q[i - 1] | 0x20) == (t[j] | 0x20)) ? 0 : 1);
+            int up = col[i - 1] + 1, left = col[i] + 1, d = diag + (ED_EQ(q[i - 1], t[j]) ? 0 : 1);
             int v = d < up ? d : up;
             if (left < v) v = left;
             diag = col[i]; col[i] = v;
@@ -133,7 +146,7 @@ static int infix_ed_plain(const char *q, int ql, const char *t, int tl, int *sta
         int diag = col[0];
         col[0] = j + 1;
         for (i = 1; i <= ql; ++i) {
-            int up = col[i - 1] + 1, left = col[i] + 1, d = diag + (((q[ql - i] | 0x20) == (t[best_end - j] | 0x20)) ? 0 : 1);
+            int up = col[i - 1] + 1, left = col[i] + 1, d = diag + (ED_EQ(q[ql - i], t[best_end - j]) ? 0 : 1);
             int v = d < up ? d : up;
             if (left < v) v = left;
             diag = col[i]; col[i] = v;
@@ -176,22 +189,22 @@ static int infix_ed(const char *q, int ql, const char *t, int tl, int *start, in
     if (ql > 64 * ED_MAXW) return infix_ed_plain(q, ql, t, tl, start, end, k);
     W = (ql + 63) / 64; last_bit = (uint64_t)1 << ((ql - 1) & 63);
     memset(peq, 0, sizeof(peq));
-    for (i = 0; i < ql; ++i) peq[(unsigned char)(q[i] | 0x20)][i >> 6] |= (uint64_t)1 << (i & 63);
+    for (i = 0; i < ql; ++i) peq[ed_class[(unsigned char)q[i]]][i >> 6] |= (uint64_t)1 << (i & 63);
     for (b = 0; b < W; ++b) { Pv[b] = ~(uint64_t)0; Mv[b] = 0; }
     score = ql;
     for (j = 0; j < tl; ++j) {
-        score += ed_column(W, last_bit, peq[(unsigned char)(t[j] | 0x20)], Pv, Mv, 0);
+        score += ed_column(W, last_bit, peq[ed_class[(unsigned char)t[j]]], Pv, Mv, 0);
         if (best < 0 || score < best) { best = score; best_end = j; }
     }
     if (best > ql) best = ql;
     if (k >= 0 && best > k) return -1;
     /* backwards from the end location: reversed adapter against the reversed text prefix, top row counting text */
     memset(peq, 0, sizeof(peq));
-    for (i = 0; i < ql; ++i) peq[(unsigned char)(q[ql - 1 - i] | 0x20)][i >> 6] |= (uint64_t)1 << (i & 63);
+    for (i = 0; i < ql; ++i) peq[ed_class[(unsigned char)q[ql - 1 - i]]][i >> 6] |= (uint64_t)1 << (i & 63);
     for (b = 0; b < W; ++b) { Pv[b] = ~(uint64_t)0; Mv[b] = 0; }
     score = ql;
     for (j = 0; j <= best_end; ++j) {
-        score += ed_column(W, last_bit, peq[(unsigned char)(t[best_end - j] | 0x20)], Pv, Mv, 1);
+        score += ed_column(W, last_bit, peq[ed_class[(unsigned char)t[best_end - j]]], Pv, Mv, 1);
         if (score == best) best_start = best_end - j;
     }
     *start = best_start; *end = best_end;
@@ -255,6 +268,55 @@ static int full_len_pair(int min_len, int left_n, const ed_res_t *left, int righ
     return tot_ed;
 }
 
+/* Adapter trimming of a consensus (src/gen_cons.c:224-291).  The consensus of a tandem repeat is circular -- a unit may
+ * start anywhere in it -- so both adapters are searched in two copies laid end to end, and the insert is what lies between
+ * the upstream adapter's end and the downstream adapter's start.  Two orientations are tried, in this order:
+ *   1: 5' adapter ... reverse complement of the 3' adapter      2: 3' adapter ... reverse complement of the 5' adapter
+ * The second one is only looked at when the first left a non-zero total distance, and only wins with a strictly smaller
+ * one (an orientation-1 hit pair that does not delimit an insert sets no distance to beat).  Returns the orientation
+ * taken (0: none; the consensus is left alone) and cuts cons_seq / cons_qual / *cons_len down to the insert. */
+typedef struct { int ed, start, end; } ada_hit_t;
+static int ada_find(const char *ada, int ada_len, float match_rat, const char *text, int text_len, ada_hit_t *hit) {
+    hit->start = hit->end = -1;
+    hit->ed = infix_ed(ada, ada_len, text, text_len, &hit->start, &hit->end, (int)(ada_len * (1 - match_rat)));
+    return hit->ed != -1;
+}
+static int trim_to_adapters(const th_host *h, char *cons_seq, uint8_t *cons_qual, int *cons_len_io) {
+    const th_host_para *p = &h->p;
+    const int cons_len = *cons_len_io, twice = cons_len << 1;
+    const struct { const char *up; int up_len; const char *down; int down_len; } ori[2] = {
+        {p->five_seq, h->five_len, h->three_rc, h->three_len},
+        {p->three_seq, h->three_len, h->five_rc, h->five_len}};
+    char *ring = (char *)malloc((size_t)twice + 1);
+    int o, taken = 0, to_beat = INT32_MAX, ins_start = -1, ins_end = -1;
+    memcpy(ring, cons_seq, cons_len); memcpy(ring + cons_len, cons_seq, cons_len); ring[twice] = 0;
+    for (o = 0; o < 2 && to_beat != 0; ++o) {
+        ada_hit_t up, down;
+        int s, e;
+        if (!ada_find(ori[o].up, ori[o].up_len, p->ada_match_rat, ring, twice, &up)) continue;
+        if (!ada_find(ori[o].down, ori[o].down_len, p->ada_match_rat, ring, twice, &down)) continue;
+        if (up.ed + down.ed >= to_beat) continue;
+        s = up.end + 1;
+        if (down.start > up.end) e = down.start - 1;                       /* downstream adapter in the same turn */
+        else if (down.end + cons_len < twice && down.start + cons_len > up.end) e = down.start + cons_len - 1; /* one turn later */
+        else continue;
+        ins_start = s; ins_end = e; taken = o + 1;
+        if (o == 0) to_beat = up.ed + down.ed;
+    }
+    if (ins_start > 0 && ins_end > ins_start) {
+        const int n = ins_end - ins_start + 1;
+        int k;
+        memcpy(cons_seq, ring + ins_start, n); cons_seq[n] = 0;
+        if (cons_qual) { /* same cut of the doubled quality string; cons_qual has room for two turns */
+            memcpy(cons_qual + cons_len, cons_qual, cons_len);
+            for (k = 0; k < n; ++k) cons_qual[k] = cons_qual[ins_start + k];
+        }
+        *cons_len_io = n;
+    }
+    free(ring);
+    return taken;
+}
+
 typedef struct { /* one record of tandem_seq_t */
     int cons_start, cons_end, cons_len, full_length, pos_n;
     double copy_num, ave_match;
@@ -300,7 +362,7 @@ static void emit_read(th_host *h, str_t *out, long long *n_failed, const th_gpu_
             if (min_cov > 0) {
                 if (n_seqs <= 2) {
                     int _min_cov = 2, l0 = pos[1] - pos[0], l1 = pos[2] - pos[1];
-                    if (l0 != l1) _min_cov = 1; else for (i = 0; i < l0; ++i) if ((seq[pos[0] + 1 + i] | 0x20) != (seq[pos[1] + 1 + i] | 0x20)) { _min_cov = 1; break; }
+                    if (l0 != l1) _min_cov = 1; else for (i = 0; i < l0; ++i) if (nt4_class[(unsigned char)seq[pos[0] + 1 + i]] != nt4_class[(unsigned char)seq[pos[1] + 1 + i]]) { _min_cov = 1; break; }
                     if (_min_cov < min_cov) skip = 1;
                 } else for (i = 0; i < cons_len; ++i) if (cov[i] < min_cov) { skip = 1; break; }
             }
@@ -328,39 +390,8 @@ static void emit_read(th_host *h, str_t *out, long long *n_failed, const th_gpu_
             copy_num += (R->ext[4 * t + 0] + 1.0) / cons_len;
             cons_end = pos[pos_n - 1] + R->ext[4 * t + 3] + 1;
             copy_num += (R->ext[4 * t + 2] + 1.0) / cons_len;
-            if (p->five_seq && p->three_seq && cons_len > h->five_len + h->three_len) { /* src/gen_cons.c:224-291 */
-                char *cons2 = (char *)malloc(((size_t)cons_len << 1) + 1); uint8_t *qual2 = NULL;
-                int tar_start = -1, tar_end = -1, tot_ed = INT32_MAX, _5_ed, _3_ed, _5_start = -1, _5_end = -1, _3_start = -1, _3_end = -1, k;
-                int k5 = (int)(h->five_len * (1 - p->ada_match_rat)), k3 = (int)(h->three_len * (1 - p->ada_match_rat));
-                memcpy(cons2, cons_seq, cons_len); memcpy(cons2 + cons_len, cons_seq, cons_len); cons2[cons_len << 1] = 0;
-                if (cons_qual) { qual2 = (uint8_t *)malloc((size_t)cons_len << 1); memcpy(qual2, cons_qual, cons_len); memcpy(qual2 + cons_len, cons_qual, cons_len); }
-                _5_ed = infix_ed(p->five_seq, h->five_len, cons2, cons_len << 1, &_5_start, &_5_end, k5);
-                if (_5_ed == -1) goto REV;
-                _3_ed = infix_ed(h->three_rc, h->three_len, cons2, cons_len << 1, &_3_start, &_3_end, k3);
-                if (_3_ed == -1) goto REV;
-                if (_3_start <= _5_end) {
-                    if (_3_end + cons_len < cons_len << 1 && _3_start + cons_len > _5_end) { tar_start = _5_end + 1; tar_end = _3_start + cons_len - 1; full_length = 1; tot_ed = _5_ed + _3_ed; }
-                } else { tar_start = _5_end + 1; tar_end = _3_start - 1; tot_ed = _5_ed + _3_ed; full_length = 1; }
-                if (tot_ed == 0) goto WRITE_CONS;
-REV:
-                _5_ed = infix_ed(h->five_rc, h->five_len, cons2, cons_len << 1, &_5_start, &_5_end, k5);
-                if (_5_ed == -1) goto WRITE_CONS;
-                _3_ed = infix_ed(p->three_seq, h->three_len, cons2, cons_len << 1, &_3_start, &_3_end, k3);
-                if (_3_ed == -1) goto WRITE_CONS;
-                if (_5_ed + _3_ed < tot_ed) {
-                    if (_5_start <= _3_end) {
-                        if (_5_end + cons_len < cons_len << 1 && _5_start + cons_len > _3_end) { tar_start = _3_end + 1; tar_end = _5_start + cons_len - 1; full_length = 2; }
-                    } else { tar_start = _3_end + 1; tar_end = _5_start - 1; full_length = 2; }
-                }
-WRITE_CONS:
-                if (tar_start > 0 && tar_end > tar_start) {
-                    memcpy(cons_seq, cons2 + tar_start, tar_end - tar_start + 1);
-                    cons_seq[tar_end - tar_start + 1] = 0;
-                    if (cons_qual) for (k = tar_start; k <= tar_end; ++k) cons_qual[k - tar_start] = qual2[k];
-                    cons_len = tar_end - tar_start + 1;
-                }
-                free(cons2); free(qual2);
-            }
+            if (p->five_seq && p->three_seq && cons_len > h->five_len + h->three_len) /* src/gen_cons.c:224-291 */
+                full_length = trim_to_adapters(h, cons_seq, cons_qual, &cons_len);
             if (!p->only_full_length || full_length > 0) { /* write_tandem_cons_seq, src/gen_cons.c:10-62 */
                 int keep = !(cons_len < p->min_len || cons_len > p->gpu.max_p);
                 if (keep && p->only_longest && n_rec == 1) {

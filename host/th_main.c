@@ -91,6 +91,7 @@ static void *reader_main(void *arg) {
 }
 
 int main(int argc, char *argv[]) {
+    long long n_failed = 0;
     th_host_para p; int c, device = 0, n_dev = 0, devs[16]; const char *out_fn = NULL, *five_fn = NULL, *three_fn = NULL; char *s;
     th_host_default_para(&p);
     if (argc < 2) return usage();
@@ -123,8 +124,8 @@ int main(int argc, char *argv[]) {
         case 't': break;
         case 'q': break;
         case 1001: device = atoi(optarg); break;
-        case 1002: p.chunk_reads = atoi(optarg); break;
-        case 1003: p.lanes = atoi(optarg); break;
+        case 1002: p.chunk_reads = atoi(optarg); if (p.chunk_reads <= 0) { fprintf(stderr, "[main] --chunk must be a positive number of reads\n"); return 1; } break;
+        case 1003: p.lanes = atoi(optarg); if (p.lanes <= 0) { fprintf(stderr, "[main] --lanes must be a positive number\n"); return 1; } break;
         case 1004: { char *q = optarg; n_dev = 0; while (*q && n_dev < 16) { devs[n_dev++] = (int)strtol(q, &q, 10); if (*q == ',') ++q; else break; } break; }
         case 'v': printf("%s (TideHunter v1.5.5 compatible)\n", PROG); return 0;
         case 'h': default: return usage();
@@ -173,7 +174,7 @@ int main(int argc, char *argv[]) {
             txt = th_host_run(h, b->n, (const char *const *)b->names, (const char *const *)b->seqs, b->lens, &ol);
             if (!txt) { fprintf(stderr, "[main] %s\n", th_host_last_error()); return 1; }
             clock_gettime(CLOCK_MONOTONIC, &ta); t_run += TSPAN(tb, ta);
-            fwrite(txt, 1, ol, out);
+            if (fwrite(txt, 1, ol, out) != ol) { fprintf(stderr, "[main] short write to the output (disk full or pipe closed)\n"); return 1; }
             clock_gettime(CLOCK_MONOTONIC, &tb); t_write += TSPAN(ta, tb);
             tot_reads += b->n;
             pthread_mutex_lock(&q.mu); q.state[k] = 0; pthread_cond_broadcast(&q.cv); pthread_mutex_unlock(&q.mu);
@@ -182,12 +183,13 @@ int main(int argc, char *argv[]) {
         pthread_join(rt, NULL);
         thr_batch_free(&q.slot[0]); thr_batch_free(&q.slot[1]); thr_close(q.r);
         pthread_mutex_destroy(&q.mu); pthread_cond_destroy(&q.cv);
-        if (th_host_failed_tasks(h) > 0) fprintf(stderr, "[main] WARNING: %lld consensus task(s) could not run on the GPU path; their records are missing from the output\n", th_host_failed_tasks(h));
+        n_failed = th_host_failed_tasks(h);
+        if (n_failed > 0) fprintf(stderr, "[main] ERROR: %lld read(s) / consensus task(s) could not run on the GPU path; their records are missing from the output\n", n_failed);
         th_host_destroy(h);
-        if (out != stdout) fclose(out);
+        if (fflush(out) != 0 || (out != stdout && fclose(out) != 0)) { fprintf(stderr, "[main] failed to flush the output\n"); return 1; }
         clock_gettime(CLOCK_MONOTONIC, &t1);
         fprintf(stderr, "[main] Real time: %.3f sec; reads: %lld\n", (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec), tot_reads);
         if (getenv("TH_HOST_TIMING")) fprintf(stderr, "[main] contexts %.2f s, waiting for the reader %.2f s, th_host_run %.2f s, writing %.2f s\n", t_create, t_wait, t_run, t_write);
     }
-    return 0;
+    return n_failed > 0 ? 2 : 0; /* message + non-zero exit, as the reference does for what it cannot process */
 }

@@ -377,7 +377,10 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         int grid = (ngroups + GPB16 - 1) / GPB16;
         // several contexts of one process (the host layer's lanes) size their slabs from the same free-memory reading:
         // if the allocation loses that race, run with fewer resident groups instead of failing the chunk
-        while (c->d_slabs.ensure((size_t)grid * GPB16 * slab_typ)) {
+        // the second pass reuses these slabs: room for at least one full-width slab of the chunk's largest task, so that no
+        // task is left without a pass that can hold it (when even that exceeds the budget the task keeps its error status)
+        const size_t wide_one = std::min<size_t>(((size_t)ht->slab_wide + 511) & ~(size_t)255, budget);
+        while (c->d_slabs.ensure(std::max((size_t)grid * GPB16 * slab_typ, wide_one))) {
             cudaGetLastError();
             if (grid <= 4) return -1;
             grid = (grid + 1) / 2;

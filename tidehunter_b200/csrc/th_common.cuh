@@ -36,6 +36,7 @@ struct TaskTotals {
     unsigned long long slab_typ, slab_full; // largest typical slab of all tasks; largest full-width slab of the retried ones
     long long n_hits, dense_bound;          // hits of all reads; bound used for the dense consensus copy
     long long cons_total;                   // dense consensus length (after the POA)
+    unsigned long long slab_wide;           // largest full-width slab any task of the chunk could ask of the second pass
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

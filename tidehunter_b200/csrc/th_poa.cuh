@@ -93,7 +93,11 @@ __host__ __device__ inline size_t poa_fixed_bytes(int ncap, int qmax, int nseq) 
 __host__ __device__ inline unsigned long long poa_slab_need(int ncap, int qmax, int n_seqs, bool full) {
     const unsigned long long fixed = poa_fixed_bytes(ncap, qmax, n_seqs);
     const unsigned long long fullb = (unsigned long long)ncap * (((unsigned long long)qmax + 64) * 7 + 16);
-    if (full) return fixed + fullb + 4096;
+    if (full) { // the wide pass: five int32 planes per cell; rows are banded (2 w + 1 columns around the predecessors' maxima, plus the
+        // spread of those maxima), so full width is only needed for short queries
+        const unsigned long long wd = (unsigned long long)qmax + 64, band = 4ull * (10 + qmax / 100) + 512;
+        return fixed + (unsigned long long)ncap * (wd < band ? wd : band) * 20 + 4096;
+    }
     const int wband = 10 + qmax / 100;
     unsigned long long rows_typ = (unsigned long long)qmax * 5 / 2 + 64; if (rows_typ > (unsigned long long)ncap) rows_typ = ncap;
     unsigned long long width_typ = 2ull * wband + 64; if (width_typ > (unsigned long long)qmax + 64) width_typ = (unsigned long long)qmax + 64;
@@ -352,6 +356,274 @@ __device__ __forceinline__ void poa_chunk_carry(const PoaG<LPT> &g, const DevPar
     carryF = __vadd2(prmt(fa, fb, 0x7632), P.PE12); // G of column j0 - 1 in the next chunk's frame
 }
 
+// ---- the wide path ------------------------------------------------------------------------------------------------
+// One alignment in plain 32-bit arithmetic, one task per warp (32-lane kernel only).  It serves what the packed 16-bit
+// path hands over: alignments the reference itself runs with 32-bit scores (simd_abpoa_align.c:1610-1621: more than about
+// 16.3 k graph rows or query bases; vectors of pn / 2 lanes, its own inf_min), alignments whose scores leave no headroom
+// for the packed scan, tasks that overflowed their arena, and rows with more than 16 predecessors.  For an alignment the
+// reference runs in 16 bits the band arithmetic keeps pn and the 16-bit inf_min: no value that survives a max ever wraps
+// or saturates there (every H is >= inf_min - mismatch, and the reference's saturating F shifts only clip losers), so
+// exact integers reproduce it bit for bit.  Simple by design: every row keeps all five planes H | E1 | E2 | F1 | F2 as
+// int32 in the arena (20 bytes per cell) and the backtrack is the reference's value comparison throughout.
+template <bool AFFINE>
+__device__ void poa_dp_wide(PoaSmem<32> &sm, const DevParams &P, bool &ok, int &err, const int n, const int qlen, const uint16_t *q4,
+                            int &n_cig, unsigned long long &cells, unsigned long long &rows) {
+    const int lane = lane_id();
+    PoaWs &w = sm.ws;
+    constexpr int CW = 128;
+    const int o1 = P.o1, e1 = P.e1, o2 = P.o2, e2 = P.e2, oe1 = P.oe1, oe2 = P.oe2, mis = P.mis_abs, mat = P.mat_abs;
+    int lp = P.lp, inf_min = P.inf_min;
+    { // score width as the reference picks it for THIS alignment
+        const int len = qlen > n ? qlen : n;
+        const long long max_score = max((long long)qlen * mat, (long long)len * e1 + o1);
+        if (max_score > 32767 - mis - oe1 - (P.o2_raw + P.e2_raw)) {
+            lp = P.lp - 1;
+            inf_min = max(max(INT_MIN + mis, INT_MIN + oe1), INT_MIN + P.o2_raw + P.e2_raw) + 31 * max(e1, P.e2_raw);
+        }
+    }
+    const int pn = 1 << lp, lam_bits = pn - 1;
+    const int wband = 10 + (int)(0.01f * (float)qlen); // wb + (int)(wf*qlen), float (simd_abpoa_align.c:393)
+    int4 *const rmeta_g = w.rmeta; const int4 *const rdesc_g = w.rdesc, *const rdesc2_g = w.rdesc2; const int32_t *const plist_g = w.plist;
+    int32_t *const A = reinterpret_cast<int32_t *>(w.arena);
+    const uint32_t cap = w.arena_cap / 2; // int32 units
+    uint32_t used = 0;
+    n_cig = 0;
+    // ---- first row (simd_abpoa_align.c:538-555, 591-610)
+    if (ok) {
+        const int end = min(qlen, max(0, qlen - w.ri[0]) + wband);
+        const int esn = end >> lp, width = (esn + 1) << lp;
+        if (5ull * width > cap) { err = TH_ERR_ARENA; ok = false; }
+        else {
+            if (lane == 0) rmeta_g[0] = make_int4(0, 0, width - 1, 1); // the source hands 1 to its successors (:549-552)
+            for (int j = lane; j < width; j += 32) {
+                const int f1 = -o1 - e1 * j, f2 = -o2 - e2 * j;
+                A[j] = j == 0 ? 0 : (AFFINE ? f1 : max(f1, f2));
+                A[width + j] = j == 0 ? -oe1 : inf_min; A[2 * width + j] = (j == 0 && !AFFINE) ? -oe2 : inf_min;
+                A[3 * width + j] = j == 0 ? inf_min : f1; A[4 * width + j] = (j == 0 || AFFINE) ? inf_min : f2;
+            }
+            used = 5u * width; cells += width; rows += 1;
+        }
+    }
+    __syncwarp();
+    // ---- rows in topological order
+    const int qsn = qlen >> lp;
+    for (int i = 1; ok && i < n - 1; ++i) {
+        const int4 d = rdesc_g[i], d2 = rdesc2_g[i];
+        const int np = d.y & 1023; // 1..32, checked when the descriptors were built
+        int mpl = n, mpr = 0, min_pre_beg = INT_MAX;
+        for (int p = 0; p < np; ++p) { // band: what the predecessors' row maxima and max_remain say (abpoa_align.h:34-35, simd_abpoa_align.c:846-854)
+            const int4 m = rmeta_g[poa_pred_row(d, d2, plist_g, np, p)];
+            mpl = min(mpl, m.w); mpr = max(mpr, m.w); min_pre_beg = min(min_pre_beg, m.y);
+            if (lane == 0) sm.pre[p] = m;
+        }
+        __syncwarp();
+        const int beg0 = max(0, min(mpl, d.z) - wband), end0 = min(qlen, max(mpr, d.z) + wband);
+        const int beg = max((beg0 >> lp) << lp, min_pre_beg), esn = end0 >> lp, dend = ((esn + 1) << lp) - 1, bsn = beg >> lp;
+        const int width = dend - beg + 1;
+        if (beg > dend) { err = TH_ERR_BAND; ok = false; break; }
+        if (5ull * (uint32_t)width > (unsigned long long)(cap - used)) { err = TH_ERR_ARENA; ok = false; break; }
+        const uint32_t row_off = used; used += 5u * (uint32_t)width; cells += width;
+        const int vb = (d.y >> 10) & 7;
+        const int jmax = esn == qsn ? qlen : dend, vlast = esn - bsn;
+        int32_t *R = A + row_off;
+        long long best = LLONG_MIN;
+        int carryH = 0, carryF1 = INT_MIN / 2, carryF2 = INT_MIN / 2; // carryF: F of the previous chunk's last column, one extension further
+        const int nchunk = (width + CW - 1) / CW;
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const int j0 = beg + ch * CW + 4 * lane;
+            int Mx[4], E1x[4], E2x[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { Mx[c] = inf_min; E1x[c] = inf_min; E2x[c] = inf_min; }
+            for (int p = 0; p < np; ++p) { // cells outside the predecessor's band count as inf_min (simd_abpoa_align.c:860-905)
+                const int4 pm = sm.pre[p];
+                const int pw = pm.z - pm.y + 1; const int32_t *Pp = A + (uint32_t)pm.x;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = j0 + c;
+                    if (j - 1 >= pm.y && j - 1 <= pm.z) Mx[c] = max(Mx[c], Pp[j - 1 - pm.y]);
+                    if (j >= pm.y && j <= pm.z) { E1x[c] = max(E1x[c], Pp[pw + j - pm.y]); if (!AFFINE) E2x[c] = max(E2x[c], Pp[2 * pw + j - pm.y]); }
+                }
+            }
+            const uint32_t w4 = q4[j0 >> 2];
+            int Ms[4], Hme[4], Hf[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int qc = (w4 >> (4 * c)) & 0xf;
+                const int sc = (qc < 4 && vb < 4) ? (qc == vb ? mat : -mis) : 0;
+                Ms[c] = Mx[c] + sc;
+                Hme[c] = AFFINE ? max(Ms[c], E1x[c]) : max(Ms[c], max(E1x[c], E2x[c]));
+                Hf[c] = AFFINE ? Ms[c] : Hme[c]; // what an insertion may open from
+            }
+            // F1[j] = max_k<=j (A1[k] - e1 (j-k)), A1[k] = Hf[k-1] - oe1, as a prefix max of G[k] = A1[k] + e1 (k - chunk start); the
+            // row's first cell feeds its own F (:924)
+            int hp = __shfl_up_sync(TH_FULL, Hf[3], 1);
+            if (lane == 0) hp = ch == 0 ? Ms[0] : carryH;
+            int G1[4], G2[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int prev = c == 0 ? hp : Hf[c - 1], k = 4 * lane + c;
+                G1[c] = prev - oe1 + e1 * k; G2[c] = prev - oe2 + e2 * k;
+            }
+            if (ch > 0 && lane == 0) { G1[0] = max(G1[0], carryF1); G2[0] = max(G2[0], carryF2); }
+#pragma unroll
+            for (int c = 1; c < 4; ++c) { G1[c] = max(G1[c], G1[c - 1]); G2[c] = max(G2[c], G2[c - 1]); }
+            int T1 = G1[3], T2 = G2[3];
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const int a = __shfl_up_sync(TH_FULL, T1, dd), b = __shfl_up_sync(TH_FULL, T2, dd);
+                if (lane >= dd) { T1 = max(T1, a); T2 = max(T2, b); }
+            }
+            int P1 = __shfl_up_sync(TH_FULL, T1, 1), P2 = __shfl_up_sync(TH_FULL, T2, 1);
+            if (lane == 0) { P1 = INT_MIN / 2; P2 = INT_MIN / 2; }
+            int Hn[4], E1o[4], E2o[4], Fa[4], Fb[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = 4 * lane + c;
+                Fa[c] = max(G1[c], P1) - e1 * k; Fb[c] = AFFINE ? inf_min : max(G2[c], P2) - e2 * k;
+                Hn[c] = AFFINE ? max(Hme[c], Fa[c]) : max(Hme[c], max(Fa[c], Fb[c]));
+                E1o[c] = max(E1x[c] - e1, Hn[c] - oe1);
+                if (AFFINE) { if (Hn[c] != Hme[c]) E1o[c] = inf_min; E2o[c] = inf_min; } // F won the cell: no deletion from it
+                else E2o[c] = max(E2x[c] - e2, Hn[c] - oe2);
+            }
+            if (ch + 1 < nchunk) { // (F - e) of the chunk's last column, in the next chunk's frame (k = 0)
+                carryH = __shfl_sync(TH_FULL, Hf[3], 31);
+                carryF1 = __shfl_sync(TH_FULL, Fa[3], 31) - e1; carryF2 = __shfl_sync(TH_FULL, Fb[3], 31) - e2;
+            }
+            const int rel = ((4 * lane) >> lp) + ch * (CW >> lp);
+            const int sub = rel == vlast ? 0 : rel + 1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = j0 + c;
+                if (j <= dend) {
+                    const int o = j - beg;
+                    R[o] = Hn[c]; R[width + o] = E1o[c]; R[2 * width + o] = E2o[c]; R[3 * width + o] = Fa[c]; R[4 * width + o] = Fb[c];
+                }
+                if (j <= jmax) { // row arg-max key: value, then lane (j mod pn) ascending, then vector order with end_sn first
+                    const long long key = ((long long)Hn[c] << 32) | (long long)(((unsigned)(lam_bits - (j & lam_bits)) << 12) | (unsigned)(0xfff - sub));
+                    best = max(best, key);
+                }
+            }
+        }
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) { const long long o = __shfl_xor_sync(TH_FULL, best, dd); best = max(best, o); }
+        { // simd_abpoa_max_in_row + simd_abpoa_ada_max_i: successors pull max_i + 1 from this row's metadata
+            const int val = (int)(best >> 32);
+            const int lam = lam_bits - (int)((best >> 12) & 0xf), vr = 0xfff - (int)(best & 0xfff);
+            const int vsn = vr == 0 ? esn : bsn + vr - 1;
+            const int max_i = (best != LLONG_MIN && val > inf_min) ? vsn * pn + lam : -1;
+            if (lane == 0) rmeta_g[i] = make_int4((int)row_off, beg, dend, max_i + 1);
+        }
+        __syncwarp();
+    }
+    if (ok) rows += (unsigned long long)max(n - 2, 0);
+    // ---- best end cell (simd_abpoa_align.c:976-989): sink's in-neighbours in in_id order, strict >
+    int bi = 0, bj = 0;
+    if (ok) {
+        const int4 ds = rdesc_g[n - 1], ds2 = rdesc2_g[n - 1];
+        const int nps = ds.y & 1023;
+        int best_score = inf_min;
+        for (int p0 = 0; p0 < nps; p0 += 32) {
+            const int p = p0 + lane;
+            long long s = LLONG_MIN; int pi = 0, end = 0;
+            if (p < nps) {
+                pi = poa_pred_row(ds, ds2, plist_g, nps, p);
+                const int4 m = rmeta_g[pi];
+                end = qlen > m.z ? m.z : qlen;
+                s = A[(uint32_t)m.x + (uint32_t)(end - m.y)];
+            }
+            long long mx = s;
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) mx = max(mx, __shfl_xor_sync(TH_FULL, mx, dd));
+            if (mx > (long long)best_score) {
+                const unsigned bm = __ballot_sync(TH_FULL, s == mx);
+                const int f = __ffs(bm) - 1;
+                best_score = (int)mx; bi = __shfl_sync(TH_FULL, pi, f); bj = __shfl_sync(TH_FULL, end, f);
+            }
+        }
+    }
+    // ---- backtrack by value comparison (simd_abpoa_align.c:248-377): lane p holds predecessor p
+    if (ok) {
+        enum { M_OP = 1, E1_OP = 2, E2_OP = 4, E_OP = 6, F1_OP = 8, F2_OP = 16, F_OP = 24, ALL_OP = 31 };
+        int i = bi, j = bj, cur_op = ALL_OP;
+        uint32_t *cg = w.cigar; int32_t *cq = w.cigq;
+        for (int t = lane; t < qlen - bj; t += 32) { cg[t] = 1; cq[t] = qlen - 1 - t; } // unaligned query tail
+        if (bj < qlen) n_cig = qlen - bj;
+        while (i > 0 && j > 0) {
+            const int4 d = rdesc_g[i], d2 = rdesc2_g[i], mi = rmeta_g[i];
+            const int np = d.y & 1023, vb = (d.y >> 10) & 7, v = d.y >> 13;
+            const int qc = (q4[j >> 2] >> (4 * (j & 3))) & 0xf;
+            const int s = (qc < 4 && vb < 4) ? (qc == vb ? mat : -mis) : 0;
+            const int ib = mi.y, iw = mi.z - mi.y + 1;
+            const int32_t *Ri = A + (uint32_t)mi.x;
+            const int hij = Ri[j - ib];
+            int pi = 0; bool in1 = false, in0 = false; int4 pm = make_int4(0, 0, -1, 0);
+            if (lane < np) {
+                pi = poa_pred_row(d, d2, plist_g, np, lane);
+                pm = rmeta_g[pi];
+                in1 = j - 1 >= pm.y && j - 1 <= pm.z; in0 = j >= pm.y && j <= pm.z;
+            }
+            const int pw = pm.z - pm.y + 1; const int32_t *Rp = A + (uint32_t)pm.x;
+            if (cur_op & M_OP) {
+                const long long a = in1 ? (long long)Rp[j - 1 - pm.y] : 0; // promoted arithmetic, as the reference compares
+                const unsigned mm = __ballot_sync(TH_FULL, in1 && a + s == (long long)hij);
+                if (mm) {
+                    const int f = __ffs(mm) - 1;
+                    if (lane == 0) { cg[n_cig] = ((uint32_t)v << 2) | 0; cq[n_cig] = j - 1; }
+                    ++n_cig; cur_op = ALL_OP; i = __shfl_sync(TH_FULL, pi, f); --j;
+                    continue;
+                }
+            }
+            if (cur_op & E_OP) {
+                long long b = 0, x1 = 0, x2 = inf_min, e1ij = Ri[iw + j - ib], e2ij = AFFINE ? inf_min : Ri[2 * iw + j - ib];
+                if (in0) { b = Rp[j - pm.y]; x1 = Rp[pw + j - pm.y]; if (!AFFINE) x2 = Rp[2 * pw + j - pm.y]; }
+                const bool ok1 = (cur_op & E1_OP) && in0 && ((cur_op & M_OP) ? (hij == x1) : (e1ij == x1 - e1));
+                const bool ok2 = (cur_op & E2_OP) && in0 && ((cur_op & M_OP) ? (hij == x2) : (e2ij == x2 - e2));
+                const unsigned em = __ballot_sync(TH_FULL, ok1 || ok2);
+                if (em) {
+                    const int f = __ffs(em) - 1;
+                    int nop;
+                    if (ok1) nop = (b - oe1 == x1) ? (M_OP | F_OP) : E1_OP;
+                    else nop = (b - oe2 == x2) ? (M_OP | F_OP) : E2_OP;
+                    cur_op = __shfl_sync(TH_FULL, nop, f);
+                    if (lane == 0) { cg[n_cig] = ((uint32_t)v << 2) | 2; cq[n_cig] = j - 1; }
+                    ++n_cig; i = __shfl_sync(TH_FULL, pi, f);
+                    continue;
+                }
+            }
+            if ((cur_op & F_OP) && j > ib) {
+                const long long f1 = Ri[3 * iw + j - ib], f2 = Ri[4 * iw + j - ib], hm1 = Ri[j - 1 - ib];
+                const long long f1m1 = Ri[3 * iw + j - 1 - ib], f2m1 = Ri[4 * iw + j - 1 - ib];
+                bool hit = false, bad = false;
+                if (cur_op & F1_OP) {
+                    if (!(cur_op & M_OP) || hij == f1) {
+                        if (hm1 - oe1 == f1) { cur_op = M_OP | E_OP; hit = true; }
+                        else if (f1m1 - e1 == f1) { cur_op = F1_OP; hit = true; }
+                        else bad = true;
+                    }
+                }
+                if (!hit && !bad && (cur_op & F2_OP)) {
+                    if (!(cur_op & M_OP) || hij == f2) {
+                        if (hm1 - oe2 == f2) { cur_op = M_OP | E_OP; hit = true; }
+                        else if (f2m1 - e2 == f2) { cur_op = F2_OP; hit = true; }
+                        else bad = true;
+                    }
+                }
+                if (bad) { err = TH_ERR_BACKTRACK; ok = false; break; }
+                if (lane == 0) { cg[n_cig] = 1; cq[n_cig] = j - 1; } // the insertion is taken whether or not a test above fired (:357-361)
+                ++n_cig; --j;
+                continue;
+            }
+            err = TH_ERR_BACKTRACK; ok = false; break;
+        }
+        if (ok) {
+            for (int t = lane; t < j; t += 32) { cg[n_cig + t] = 1; cq[n_cig + t] = j - 1 - t; } // unaligned query head
+            if (j > 0) n_cig += j;
+        }
+    }
+    if (!ok) n_cig = 0;
+    __syncwarp();
+}
+
 // Aligns sequence `query` of every active group to its graph and merges it in.  ALL lanes of the warp call; `act` says
 // whether this lane's group takes part.  err is the group's status (TH_OK going in).
 template <int LPT, bool AFFINE>
@@ -372,7 +644,8 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
     const int lp = P.lp, pn = P.pn;                   // log2 / width of the emulated vector (16: AVX2 int16, the reference build; 8: SSE)
     const int o1 = P.o1, e1 = P.e1, o2 = P.o2, e2 = P.e2, oe1 = P.oe1, oe2 = P.oe2;
     const int mis = P.mis_abs, mat = P.mat_abs;
-    if (ok) { // int16 path only (simd_abpoa_align.c:1610-1621); CW max(e) of headroom for the scan frame
+    if (LPT != 32 && ok) { // packed 16-bit scores only where the reference uses them (simd_abpoa_align.c:1610-1621) and with CW max(e) of
+        // headroom for the scan frame; the rest is the wide path's (second pass)
         const int len = qlen > n ? qlen : n;
         const int max_score = max(qlen * mat, len * e1 + o1);
         if (max_score > 32767 - mis - oe1 - max(oe2, P.o2_raw + P.e2_raw) - CW * max(max(e1, e2), P.e2_raw)) { err = TH_ERR_LEN; ok = false; }
@@ -471,6 +744,11 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
         }
         q4[wi] = (uint16_t)word;
     }
+    int n_cig = 0;
+    if constexpr (LPT == 32) { // the 32-lane kernel is the wide path: 32-bit arithmetic, see poa_dp_wide
+        poa_dp_wide<AFFINE>(sm, P, ok, err, n, qlen, q4, n_cig, cells, rows);
+        PH(1);
+    } else {
     // ---- first row (simd_abpoa_align.c:538-555, 591-610) ------------------------------------
     uint32_t used = 0;
     uint32_t *const A32w = reinterpret_cast<uint32_t *>(w.arena);
@@ -631,7 +909,6 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
     // "match / mismatch step from predecessor k" the step is taken from it (the code is exactly the outcome of the
     // reference's first value test); every other step -- deletions, insertions, columns outside the staged ones -- is the
     // reference's value comparison, lane p of the group holding predecessor p and reading the arena.
-    int n_cig = 0;
     {
         enum { M_OP = 1, E1_OP = 2, E2_OP = 4, E_OP = 6, F1_OP = 8, F2_OP = 16, F_OP = 24, ALL_OP = 31 };
         int i = ok ? bi : 0, j = ok ? bj : 0, cur_op = ALL_OP;
@@ -796,6 +1073,7 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
             if (j > 0) n_cig += j;
         }
         __syncwarp();
+    }
     }
     PH(2);
     // ---- merge the alignment into the graph (abpoa_graph.c:1218-1284), LPT path steps at a time ----------
@@ -1161,7 +1439,7 @@ poa_kernel(DevParams P, int n_tasks, const int *__restrict__ n_tasks_dev, const 
                 if (err != TH_OK) cl = 0;
                 if (gl == 0) {
                     cons_len[t] = cl; task_status[t] = err;
-                    if (retry_list && (err == TH_ERR_ARENA || err == TH_ERR_CAP)) { // a full-width slab and 32-lane groups take it in the second pass
+                    if (retry_list && (err == TH_ERR_ARENA || err == TH_ERR_CAP || err == TH_ERR_LEN)) { // a full-width slab, 32-lane groups and 32-bit scores take it in the second pass
                         retry_list[atomicAdd(&tot->retry_n, 1)] = t;
                         atomicMax(&tot->slab_full, poa_slab_need(T.ncap, T.qmax, T.n_seqs, true));
                     }

@@ -49,18 +49,23 @@ __global__ void task_count_kernel(int n_reads, int min_copy, const int64_t *__re
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     int c[TC_N] = {0, 0, 0, 0, 0, 0};
-    unsigned long long slab = 0; long long dense = 0; int max_key = 0;
+    unsigned long long slab = 0, wide = 0; long long dense = 0; int max_key = 0;
     const int L = rlen[r];
     th_for_each_task(r, min_copy, roff, pch_n, par, par_off, par_n, [&](const int32_t *pp, int i, int j) {
         int nseq, sum, qmax; th_run_units(pp, i, j, L, nseq, sum, qmax);
         c[TC_TASKS] += 1; c[TC_UNITS] += nseq; c[TC_POS] += j - i; c[TC_PAIR3] += (j - 1 - i) >> 1; c[TC_LEFT] += (j - 1 - i) & 1; c[TC_CONS] += sum + 4;
-        if (nseq > 2) { const unsigned long long s = poa_slab_need(sum + 2, qmax, nseq, false); if (s > slab) slab = s; }
+        if (nseq > 2) {
+            const unsigned long long s = poa_slab_need(sum + 2, qmax, nseq, false), sw = poa_slab_need(sum + 2, qmax, nseq, true);
+            if (s > slab) slab = s;
+            if (sw > wide) wide = sw;
+        }
         dense += qmax + 64;
         const long long key = (long long)(sum + 2) * nseq; max_key = max(max_key, (int)min(key, 0x7fffffffll));
     });
 #pragma unroll
     for (int k = 0; k < TC_N; ++k) counts[(size_t)k * n_reads + r] = c[k];
     if (slab) atomicMax(&tot->slab_typ, slab);
+    if (wide) atomicMax(&tot->slab_wide, wide);
     if (dense) atomicAdd((unsigned long long *)&tot->dense_bound, (unsigned long long)dense);
     if (max_key) atomicMax(&tot->max_key, max_key);
     atomicAdd((unsigned long long *)&tot->n_hits, (unsigned long long)nhits[r]);
