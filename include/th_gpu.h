@@ -102,7 +102,7 @@ int th_gpu_debug_par_pos(th_gpu_ctx *ctx, int32_t read, int32_t chain, int32_t c
 /* Raw device work / cycle counters of the last chunk (profiling aid): [0] chain evals, [1] POA cells, [2] POA rows,
  * [3] ksw cells, [16..22] POA warp-cycles per phase (setup, rows, backtrack, merge, reorder, consensus, total). */
 /* test hook without a device: how the options reach the kernels (k, w, hpc, min_copy, min_p, max_p, max_div * 1e6, match,
- * mismatch, o1, e1, o2, e2, affine, o2 and e2 as given, vector width, only_unit); returns the number of fields */
+ * mismatch, o1, e1, o2, e2, affine, o2 and e2 as given, vector width, only_unit, linear); returns the number of fields */
 int th_gpu_debug_dev_params(const th_gpu_params *p, int32_t cap, int32_t *out);
 int th_gpu_debug_counters(th_gpu_ctx *ctx, int32_t cap, int64_t *out);                                   /* returns entries written */
 

@@ -81,13 +81,13 @@ def test_adapter_search_bitvector_equals_definition():
 
 def test_options_reach_the_kernels():
     """th_gpu_debug_dev_params (no device needed): every option lands in the kernels' parameter block -- vector width and
-    only_unit included (an edit once dropped them; only the GPU run noticed) -- and the affine gap mode is flagged."""
+    only_unit included (an edit once dropped them; only the GPU run noticed) -- and the affine and linear gap modes are flagged."""
     import ctypes as C
     import tidehunter_b200 as T
     g = T.gpu_lib()
     g.th_gpu_debug_dev_params.argtypes = [C.POINTER(T.GpuParams), C.c_int32, C.POINTER(C.c_int32)]
     g.th_gpu_debug_dev_params.restype = C.c_int
-    names = ["k", "w", "hpc", "min_copy", "min_p", "max_p", "max_div_e6", "match", "mismatch", "o1", "e1", "o2", "e2", "affine", "o2_raw", "e2_raw", "pn", "only_unit"]
+    names = ["k", "w", "hpc", "min_copy", "min_p", "max_p", "max_div_e6", "match", "mismatch", "o1", "e1", "o2", "e2", "affine", "o2_raw", "e2_raw", "pn", "only_unit", "linear"]
 
     def dev(**kw):
         p = T.GpuParams()
@@ -100,9 +100,11 @@ def test_options_reach_the_kernels():
         return dict(zip(names, out[:n]))
     d = dev()
     assert d == dict(k=8, w=1, hpc=0, min_copy=2, min_p=30, max_p=10000, max_div_e6=250000, match=2, mismatch=4, o1=4, e1=2, o2=24, e2=1,
-                     affine=0, o2_raw=24, e2_raw=1, pn=16, only_unit=0)
+                     affine=0, o2_raw=24, e2_raw=1, pn=16, only_unit=0, linear=0)
     d = dev(k=12, w=5, hpc=1, min_copy=3, min_p=10, max_p=3000, max_div=0.1, simd_lanes16=8, only_unit=1, gap_open1=6, gap_ext1=3, gap_open2=40, gap_ext2=2)
     assert (d["k"], d["w"], d["hpc"], d["min_copy"], d["min_p"], d["max_p"], d["max_div_e6"], d["pn"], d["only_unit"]) == (12, 5, 1, 3, 10, 3000, 100000, 8, 1)
     assert (d["o1"], d["e1"], d["o2"], d["e2"], d["affine"]) == (6, 3, 40, 2, 0)
     d = dev(gap_open2=0)
-    assert d["affine"] == 1 and (d["o2_raw"], d["e2_raw"]) == (0, 1) and d["pn"] == 16
+    assert d["affine"] == 1 and d["linear"] == 0 and (d["o2_raw"], d["e2_raw"]) == (0, 1) and d["pn"] == 16
+    d = dev(gap_open1=0, gap_open2=0)   # abpoa_set_gap_mode: linear wins
+    assert d["linear"] == 1 and d["affine"] == 0 and d["o1"] == 0

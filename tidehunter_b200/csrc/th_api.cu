@@ -106,7 +106,8 @@ static DevParams dev_params_from(const th_gpu_params *p) {
     d.o2_raw = p->gap_open2; d.e2_raw = p->gap_ext2;
     // abPOA's affine mode (gap_open2 == 0, abpoa_align.c:85-88) has its own recurrences (template parameter AFFINE of
     // poa_add_sequence); the unused second gap function only has to stay inside the int16 headroom checks
-    d.affine = p->gap_open2 == 0;
+    d.linear = p->gap_open1 == 0;        // abpoa_set_gap_mode (abpoa_align.c:85-89): linear wins over affine
+    d.affine = !d.linear && p->gap_open2 == 0;
     if (d.affine) { d.o2 = d.o1 + 1; d.e2 = d.e1; }
     d.pn = p->simd_lanes16; d.only_unit = p->only_unit;
     d.lp = d.pn == 16 ? 4 : 3;
@@ -126,7 +127,7 @@ static DevParams dev_params_from(const th_gpu_params *p) {
 extern "C" int th_gpu_debug_dev_params(const th_gpu_params *p, int32_t cap, int32_t *out) {
     const DevParams d = dev_params_from(p);
     const int32_t v[] = {d.k, d.w, d.hpc, d.min_copy, (int32_t)d.min_p, (int32_t)d.max_p, (int32_t)(d.max_div * 1e6 + 0.5), d.match, d.mismatch,
-                         d.o1, d.e1, d.o2, d.e2, d.affine, d.o2_raw, d.e2_raw, d.pn, d.only_unit};
+                         d.o1, d.e1, d.o2, d.e2, d.affine, d.o2_raw, d.e2_raw, d.pn, d.only_unit, d.linear};
     const int n = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
     return n;
@@ -139,7 +140,7 @@ extern "C" th_gpu_ctx *th_gpu_create(const th_gpu_params *p, int device) {
     if (p->k < 2 || p->k > 16) { set_err("k must be in 2..16"); return nullptr; }
     if (p->w < 1 || p->w > 255) { set_err("w must be in 1..255"); return nullptr; }
     if (p->simd_lanes16 != 16 && p->simd_lanes16 != 8) { set_err("simd_lanes16 must be 8 or 16"); return nullptr; }
-    if (p->gap_open1 <= 0 || p->gap_open2 < 0 || p->gap_ext1 <= 0 || p->gap_ext2 < 0) { set_err("abPOA's linear gap mode (O1 = 0) is not implemented on the GPU path; convex (O1, O2 > 0) and affine (O2 = 0) are"); return nullptr; }
+    if (p->gap_open1 < 0 || p->gap_open2 < 0 || p->gap_ext1 <= 0 || p->gap_ext2 < 0) { set_err("gap penalties must not be negative (and the first extension penalty positive)"); return nullptr; }
     CKP(cudaSetDevice(device));
     th_gpu_ctx *c = new th_gpu_ctx();
     c->device = device; c->params = *p;

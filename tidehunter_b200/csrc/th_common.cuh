@@ -19,6 +19,7 @@ struct DevParams {
     int o2_raw, e2_raw;                  // the caller's values: abPOA derives inf_min and the int16 range check from them in every gap mode
     int pn;          // int16 lanes of the emulated abPOA vector (16)
     int only_unit;
+    int linear;                          // abPOA's linear gap mode (gap_open1 == 0): every consensus task runs on the wide path (poa_dp_linear)
     // derived once on the host (dev_params_from): the POA kernel reads them straight from the constant bank
     int lp;                              // log2(pn)
     int mat_abs, mis_abs, oe1, oe2, inf_min; // |match|, |mismatch|, o + e, abPOA's int16 "minus infinity" (simd_abpoa_align.c:1613-1614)

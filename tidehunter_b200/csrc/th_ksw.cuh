@@ -49,6 +49,11 @@ __device__ void ksw_warp(const uint8_t *q, int ql, const uint8_t *t, int tl, int
     const int lane = lane_id();
     out0 = MODE == KSW_EXT ? -1 : 0; out1 = MODE == KSW_EXT ? -1 : 0;
     if (ql <= 0 || tl <= 0) return;
+    // Extension: only cells with a positive score can become the maximum, and a cell (i, j) with i > j scores at most
+    // (j + 1) matches minus a gap of i - j bases = 2 j - 1 - i (likewise with i and j swapped), so rows from 2 ql on and
+    // columns from 2 tl on are never positive: they are not computed.  The visiting order still refers to the full matrix.
+    const int qlr = ql, tlr = tl;
+    if (MODE == KSW_EXT) { ql = min(qlr, 2 * tlr); tl = min(tlr, 2 * qlr); }
     const int BW = 32 * C;
     const int nblk = (ql + BW - 1) / BW;
     int bestz = 0, besti = -1, bestj = -1;
@@ -118,7 +123,7 @@ __device__ void ksw_warp(const uint8_t *q, int ql, const uint8_t *t, int tl, int
                     const int zr = rowk >> 5; // arithmetic shift: floor, exact because 0 <= 31 - c < 32
                     if (zr > 0 && zr >= bestz) {
                         const int jr = j0 + 31 - (rowk & 31);
-                        if (ksw_ext_better(zr, i, jr, bestz, besti, bestj, ql, tl)) { bestz = zr; besti = i; bestj = jr; }
+                        if (ksw_ext_better(zr, i, jr, bestz, besti, bestj, qlr, tlr)) { bestz = zr; besti = i; bestj = jr; }
                     }
                 }
                 oH = Hp[C - 1]; oF = F; oPH = pH[C - 1]; oPF = pF;
@@ -137,7 +142,7 @@ __device__ void ksw_warp(const uint8_t *q, int ql, const uint8_t *t, int tl, int
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             int oz = __shfl_xor_sync(TH_FULL, bestz, d), oi = __shfl_xor_sync(TH_FULL, besti, d), oj = __shfl_xor_sync(TH_FULL, bestj, d);
-            if (oi >= 0 && (besti < 0 || ksw_ext_better(oz, oi, oj, bestz, besti, bestj, ql, tl))) { bestz = oz; besti = oi; bestj = oj; }
+            if (oi >= 0 && (besti < 0 || ksw_ext_better(oz, oi, oj, bestz, besti, bestj, qlr, tlr))) { bestz = oz; besti = oi; bestj = oj; }
         }
         out0 = bestj; out1 = besti;
     } else {
@@ -261,6 +266,9 @@ __device__ void ksw_warp_ext2(const uint8_t *qa, int qla, const uint8_t *ta, int
     mqA = mtA = mqB = mtB = -1;
     if (qla <= 0 || tla <= 0) { qla = 0; tla = 0; }
     if (qlb <= 0 || tlb <= 0) { qlb = 0; tlb = 0; }
+    // rows from 2 ql on and columns from 2 tl on cannot hold a positive score (see ksw_warp): not computed
+    const int qlra = qla, tlra = tla, qlrb = qlb, tlrb = tlb;
+    qla = min(qlra, 2 * tlra); tla = min(tlra, 2 * qlra); qlb = min(qlrb, 2 * tlrb); tlb = min(tlrb, 2 * qlrb);
     const int ql = max(qla, qlb), tl = max(tla, tlb);
     if (ql <= 0 || tl <= 0) return;
     const int BW = 32 * C;
@@ -321,8 +329,8 @@ __device__ void ksw_warp_ext2(const uint8_t *qa, int qla, const uint8_t *ta, int
                     int ca = 0, cb = 0;
 #pragma unroll
                     for (int c = C - 1; c >= 0; --c) { const uint32_t x = Hp[c] ^ rowm; if ((x & 0xffffu) == 0) ca = c; if ((x >> 16) == 0) cb = c; }
-                    if (ha && ksw_ext_better(zrA, i, j0 + ca, bzA, biA, bjA, qla, tla)) { bzA = zrA; biA = i; bjA = j0 + ca; }
-                    if (hb && ksw_ext_better(zrB, i, j0 + cb, bzB, biB, bjB, qlb, tlb)) { bzB = zrB; biB = i; bjB = j0 + cb; }
+                    if (ha && ksw_ext_better(zrA, i, j0 + ca, bzA, biA, bjA, qlra, tlra)) { bzA = zrA; biA = i; bjA = j0 + ca; }
+                    if (hb && ksw_ext_better(zrB, i, j0 + cb, bzB, biB, bjB, qlrb, tlrb)) { bzB = zrB; biB = i; bjB = j0 + cb; }
                 }
                 oH = Hp[C - 1]; oF = F;
                 if (lane == nl - 1 && b + 1 < nblk) bout[i] = make_int2((int)oH, (int)oF);
@@ -333,9 +341,9 @@ __device__ void ksw_warp_ext2(const uint8_t *qa, int qla, const uint8_t *ta, int
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         int oz = __shfl_xor_sync(TH_FULL, bzA, d), oi = __shfl_xor_sync(TH_FULL, biA, d), oj = __shfl_xor_sync(TH_FULL, bjA, d);
-        if (oi >= 0 && (biA < 0 || ksw_ext_better(oz, oi, oj, bzA, biA, bjA, qla, tla))) { bzA = oz; biA = oi; bjA = oj; }
+        if (oi >= 0 && (biA < 0 || ksw_ext_better(oz, oi, oj, bzA, biA, bjA, qlra, tlra))) { bzA = oz; biA = oi; bjA = oj; }
         oz = __shfl_xor_sync(TH_FULL, bzB, d); oi = __shfl_xor_sync(TH_FULL, biB, d); oj = __shfl_xor_sync(TH_FULL, bjB, d);
-        if (oi >= 0 && (biB < 0 || ksw_ext_better(oz, oi, oj, bzB, biB, bjB, qlb, tlb))) { bzB = oz; biB = oi; bjB = oj; }
+        if (oi >= 0 && (biB < 0 || ksw_ext_better(oz, oi, oj, bzB, biB, bjB, qlrb, tlrb))) { bzB = oz; biB = oi; bjB = oj; }
     }
     mqA = bjA; mtA = biA; mqB = bjB; mtB = biB;
 }

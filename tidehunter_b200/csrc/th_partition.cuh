@@ -185,9 +185,10 @@ __device__ __forceinline__ void ksw_ext_prepare(const KswItem &I, const uint8_t 
     const int lane = lane_id();
     if (I.kind == 1) { // ksw2_left_ext: both sequences reversed (src/ksw2_align.c:161-173)
         tl = I.a; const uint8_t *rs = bseq + I.seq_off;
-        uint8_t *rq = rev, *rt = rev + ((cl + 15) & ~15);
-        for (int i = lane; i < cl; i += 32) rq[i] = cons[cl - 1 - i];
-        for (int i = lane; i < tl; i += 32) rt[i] = rs[tl - 1 - i];
+        const int cle = min(cl, 2 * max(tl, 0)), tle = min(tl, 2 * cl); // the part of each the extension looks at (ksw_warp)
+        uint8_t *rq = rev, *rt = rev + ((cle + 15) & ~15);
+        for (int i = lane; i < cle; i += 32) rq[i] = cons[cl - 1 - i];
+        for (int i = lane; i < tle; i += 32) rt[i] = rs[tl - 1 - i];
         q = rq; t = rt;
     } else { q = cons; t = bseq + I.seq_off + I.a; tl = I.b; } // ksw2_right_ext (src/ksw2_align.c:153-159)
 }
@@ -215,15 +216,16 @@ ksw_ext_kernel(int n_items, const KswItem *__restrict__ items, const int32_t *__
         if (clb > 0) ksw_ext_prepare(B, bseq, cons_base + cons_off[B.task], clb, rev + rev_stride / 2, qb, tb, tlb);
         __syncwarp();
         int aq = -1, at = -1, bq = -1, bt = -1;
-        bool two = cla > 0 && clb > 0 && max(max(cla, clb), max(tla, tlb)) <= KSW2_MAXLEN;
-        if (two) two = !warp_has_n(qa, cla) && !warp_has_n(ta, max(tla, 0)) && !warp_has_n(qb, clb) && !warp_has_n(tb, max(tlb, 0));
+        // effective sizes: rows from 2 cl on and columns from 2 tl on are never computed (ksw_warp)
+        const int cae = min(cla, 2 * max(tla, 0)), tae = min(max(tla, 0), 2 * cla), cbe = min(clb, 2 * max(tlb, 0)), tbe = min(max(tlb, 0), 2 * clb);
+        bool two = cae > 0 && cbe > 0 && tae > 0 && tbe > 0 && max(max(cae, cbe), max(tae, tbe)) <= KSW2_MAXLEN;
+        if (two) two = !warp_has_n(qa, cae) && !warp_has_n(ta, tae) && !warp_has_n(qb, cbe) && !warp_has_n(tb, tbe);
         if (two) ksw_warp_ext2<16>(qa, cla, ta, tla, qb, clb, tb, tlb, bnd, aq, at, bq, bt);
         else {
             if (cla > 0) ksw_warp<KSW_EXT, 16>(qa, cla, ta, tla, 0, bnd, aq, at);
             if (clb > 0) ksw_warp<KSW_EXT, 16>(qb, clb, tb, tlb, 0, bnd, bq, bt);
         }
-        if (cla > 0) ncell += (unsigned long long)cla * max(tla, 0);
-        if (clb > 0) ncell += (unsigned long long)clb * max(tlb, 0);
+        ncell += (unsigned long long)cae * tae + (unsigned long long)cbe * tbe; // cells computed
         __syncwarp();
         if (lane == 0) { out_ext[A.out] = aq; out_ext[A.out + 1] = at; if (hasb) { out_ext[B.out] = bq; out_ext[B.out + 1] = bt; } }
     }

@@ -624,6 +624,187 @@ __device__ void poa_dp_wide(PoaSmem<32> &sm, const DevParams &P, bool &ok, int &
     __syncwarp();
 }
 
+// abPOA's linear gap mode (gap_open1 == 0, abpoa_align.c:86) on the wide path: simd_abpoa_lg_first_dp / lg_dp / lg_backtrack
+// (simd_abpoa_align.c:557-570, 649-736, 108-158).  One matrix, H = max(M, max_pre H[pre][j] - e, H[j-1] - e), but the
+// reference's vector code is not that textbook recurrence at the band edges and it is reproduced as it is:
+//  * a row stores one vector more than its band (all inf_min) and successors read it;
+//  * predecessor p contributes to the vectors max(beg_sn, pre_beg_sn) .. min(pre_end_sn + 1, end_sn, dp_sn - 1) only; the
+//    first predecessor also writes inf_min to the row's other vectors;
+//  * the horizontal pass runs vector by vector with a carried `first`, and in vectors past the predecessors' last one the
+//    in-vector propagation is masked (set_num 1 or 0: SIMDShiftOneN with PRE_MASK / SUF_MIN, :613-647), which leaves
+//    lanes the textbook recurrence would fill untouched.
+// Values wrap to 16 bits where the reference runs the alignment with int16 vectors.  Lanes 0..pn-1 hold one vector in the
+// horizontal pass; everything else is column parallel.  The backtrack is match, then deletion, else insertion.
+__device__ void poa_dp_linear(PoaSmem<32> &sm, const DevParams &P, bool &ok, int &err, const int n, const int qlen, const uint16_t *q4,
+                              int &n_cig, unsigned long long &cells, unsigned long long &rows) {
+    const int lane = lane_id();
+    PoaWs &w = sm.ws;
+    const int e1 = P.e1, oe1 = P.oe1, mis = P.mis_abs, mat = P.mat_abs;
+    int lp = P.lp, inf_min = P.inf_min;
+    bool b16 = true;
+    { // score width as the reference picks it for THIS alignment (simd_abpoa_align.c:1610-1621)
+        const int len = qlen > n ? qlen : n;
+        const long long max_score = max((long long)qlen * mat, (long long)len * e1 + P.o1);
+        if (max_score > 32767 - mis - oe1 - (P.o2_raw + P.e2_raw)) {
+            lp = P.lp - 1; b16 = false;
+            inf_min = max(max(INT_MIN + mis, INT_MIN + oe1), INT_MIN + P.o2_raw + P.e2_raw) + 31 * max(e1, P.e2_raw);
+        }
+    }
+    auto Wv = [&](int x) { return b16 ? (int)(int16_t)x : x; };
+    const int pn = 1 << lp, lam_bits = pn - 1;
+    const int dp_sn = (qlen + pn) >> lp;
+    const int wband = 10 + (int)(0.01f * (float)qlen);
+    int4 *const rmeta_g = w.rmeta; const int4 *const rdesc_g = w.rdesc, *const rdesc2_g = w.rdesc2; const int32_t *const plist_g = w.plist;
+    int32_t *const A = reinterpret_cast<int32_t *>(w.arena);
+    const uint32_t cap = w.arena_cap / 2;
+    uint32_t used = 0;
+    n_cig = 0;
+    auto score = [&](int j, int vb) { const int qc = (q4[j >> 2] >> (4 * (j & 3))) & 0xf; return (qc < 4 && vb < 4) ? (qc == vb ? mat : -mis) : 0; };
+    // ---- first row: H[0][j] = -e j inside the band, the extra vector inf_min
+    if (ok) {
+        const int end = min(qlen, max(0, qlen - w.ri[0]) + wband);
+        const int esn = end >> lp, width = (esn + 1) << lp;
+        if ((unsigned long long)width + pn > cap) { err = TH_ERR_ARENA; ok = false; }
+        else {
+            if (lane == 0) rmeta_g[0] = make_int4(0, 0, width - 1, 1);
+            for (int j = lane; j < width + pn; j += 32) A[j] = j < width ? Wv(-e1 * j) : inf_min;
+            used = (uint32_t)(width + pn); cells += width; rows += 1;
+        }
+    }
+    __syncwarp();
+    const int qsn = qlen >> lp;
+    for (int i = 1; ok && i < n - 1; ++i) {
+        const int4 d = rdesc_g[i], d2 = rdesc2_g[i];
+        const int np = d.y & 1023, vb = (d.y >> 10) & 7;
+        int mpl = n, mpr = 0, min_pre_beg = INT_MAX, max_pre_end = -1;
+        for (int p = 0; p < np; ++p) {
+            const int4 m = rmeta_g[poa_pred_row(d, d2, plist_g, np, p)];
+            mpl = min(mpl, m.w); mpr = max(mpr, m.w); min_pre_beg = min(min_pre_beg, m.y); max_pre_end = max(max_pre_end, m.z);
+            if (lane == 0) sm.pre[p] = m;
+        }
+        __syncwarp();
+        const int beg0 = max(0, min(mpl, d.z) - wband), end0 = min(qlen, max(mpr, d.z) + wband);
+        const int bsn = max(beg0 >> lp, min_pre_beg >> lp), esn = end0 >> lp, max_pre_end_sn = max_pre_end >> lp;
+        const int beg = bsn << lp, dend = ((esn + 1) << lp) - 1, width = dend - beg + 1;
+        if (bsn > esn) { err = TH_ERR_BAND; ok = false; break; }
+        if ((unsigned long long)width + pn > (unsigned long long)(cap - used)) { err = TH_ERR_ARENA; ok = false; break; }
+        const uint32_t row_off = used; used += (uint32_t)(width + pn); cells += width;
+        int32_t *R = A + row_off;
+        // ---- match and deletion candidates, one predecessor after the other (:662-711)
+        for (int p = 0; p < np; ++p) {
+            const int4 pm = sm.pre[p];
+            const int32_t *Hp = A + (uint32_t)pm.x;
+            const int pbsn = pm.y >> lp, pesn = pm.z >> lp;
+            int fb_sn, first;
+            if (pbsn < bsn) { fb_sn = bsn; first = (bsn - 1 <= pesn + 1) ? Hp[(bsn << lp) - 1 - pm.y] : inf_min; }
+            else { fb_sn = pbsn; first = inf_min; }
+            const int fe_sn = min(min(pesn + 1, esn), dp_sn - 1);
+            for (int j = beg + lane; j <= dend + pn; j += 32) {
+                const int sn = j >> lp;
+                if (sn >= fb_sn && sn <= fe_sn) {
+                    const int left = j == (fb_sn << lp) ? first : Hp[j - 1 - pm.y];
+                    const int v = max(Wv(left + score(j, vb)), Wv(Hp[j - pm.y] - e1));
+                    if (p == 0 || v > R[j - beg]) R[j - beg] = v;
+                } else if (p == 0) R[j - beg] = inf_min;
+            }
+            __syncwarp();
+        }
+        // ---- horizontal pass, vector by vector (:713-733)
+        {
+            int first = R[0];
+            for (int sn = bsn; sn <= esn; ++sn) {
+                const int set_num = sn > max_pre_end_sn ? (sn == max_pre_end_sn + 1 ? 1 : 0) : pn;
+                int h = lane < pn ? R[((sn - bsn) << lp) + lane] : inf_min;
+                if (lane == 0) h = max(h, first);
+                int cov = set_num;
+                for (int k = 0; (1 << k) < pn; ++k) {
+                    const int sh = 1 << k;
+                    int t = __shfl_up_sync(TH_FULL, h, sh);
+                    bool take = lane >= sh && lane < pn;
+                    if (set_num != pn) { if (k > 0) cov += sh; take = take && lane <= min(cov, pn); }
+                    t = take ? Wv(t - e1 * sh) : inf_min;
+                    h = max(h, t);
+                }
+                if (lane < pn) R[((sn - bsn) << lp) + lane] = h;
+                first = Wv(__shfl_sync(TH_FULL, h, pn - 1) - e1);
+            }
+        }
+        __syncwarp();
+        // ---- row arg-max (:991-1005) as on the convex path
+        const int jmax = esn == qsn ? qlen : dend, vlast = esn - bsn;
+        long long best = LLONG_MIN;
+        for (int j = beg + lane; j <= jmax; j += 32) {
+            const int rel = (j - beg) >> lp, sub = rel == vlast ? 0 : rel + 1;
+            const long long key = ((long long)R[j - beg] << 32) | (long long)(((unsigned)(lam_bits - (j & lam_bits)) << 12) | (unsigned)(0xfff - sub));
+            best = max(best, key);
+        }
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) { const long long o = __shfl_xor_sync(TH_FULL, best, dd); best = max(best, o); }
+        {
+            const int val = (int)(best >> 32);
+            const int lam = lam_bits - (int)((best >> 12) & 0xf), vr = 0xfff - (int)(best & 0xfff);
+            const int vsn = vr == 0 ? esn : bsn + vr - 1;
+            const int max_i = (best != LLONG_MIN && val > inf_min) ? vsn * pn + lam : -1;
+            if (lane == 0) rmeta_g[i] = make_int4((int)row_off, beg, dend, max_i + 1);
+        }
+        __syncwarp();
+    }
+    if (ok) rows += (unsigned long long)max(n - 2, 0);
+    // ---- best end cell (:976-989)
+    int bi = 0, bj = 0;
+    if (ok) {
+        const int4 ds = rdesc_g[n - 1], ds2 = rdesc2_g[n - 1];
+        const int nps = ds.y & 1023;
+        int best_score = inf_min;
+        for (int p = 0; p < nps; ++p) { // every lane walks the list: the sink has few in-neighbours
+            const int pi = poa_pred_row(ds, ds2, plist_g, nps, p);
+            const int4 m = rmeta_g[pi];
+            const int end = qlen > m.z ? m.z : qlen;
+            const int s = A[(uint32_t)m.x + (uint32_t)(end - m.y)];
+            if (s > best_score) { best_score = s; bi = pi; bj = end; }
+        }
+    }
+    // ---- backtrack (:108-158): lane p holds predecessor p
+    if (ok) {
+        int i = bi, j = bj;
+        uint32_t *cg = w.cigar; int32_t *cq = w.cigq;
+        for (int t = lane; t < qlen - bj; t += 32) { cg[t] = 1; cq[t] = qlen - 1 - t; }
+        if (bj < qlen) n_cig = qlen - bj;
+        while (i > 0 && j > 0) {
+            const int4 d = rdesc_g[i], d2 = rdesc2_g[i], mi = rmeta_g[i];
+            const int np = d.y & 1023, vb = (d.y >> 10) & 7, v = d.y >> 13;
+            const long long hij = A[(uint32_t)mi.x + (uint32_t)(j - mi.y)];
+            const int s = score(j, vb);
+            int pi = 0; long long hm = 0, hd = 0; bool in1 = false, in0 = false;
+            if (lane < np) {
+                pi = poa_pred_row(d, d2, plist_g, np, lane);
+                const int4 pm = rmeta_g[pi];
+                in1 = j - 1 >= pm.y && j - 1 <= pm.z; in0 = j >= pm.y && j <= pm.z;
+                if (in1) hm = A[(uint32_t)pm.x + (uint32_t)(j - 1 - pm.y)];
+                if (in0) hd = A[(uint32_t)pm.x + (uint32_t)(j - pm.y)];
+            }
+            const unsigned mm = __ballot_sync(TH_FULL, in1 && hm + s == hij);
+            if (mm) {
+                if (lane == 0) { cg[n_cig] = ((uint32_t)v << 2) | 0; cq[n_cig] = j - 1; }
+                ++n_cig; i = __shfl_sync(TH_FULL, pi, __ffs(mm) - 1); --j;
+                continue;
+            }
+            const unsigned dm = __ballot_sync(TH_FULL, in0 && hd - e1 == hij);
+            if (dm) {
+                if (lane == 0) { cg[n_cig] = ((uint32_t)v << 2) | 2; cq[n_cig] = j - 1; }
+                ++n_cig; i = __shfl_sync(TH_FULL, pi, __ffs(dm) - 1);
+                continue;
+            }
+            if (lane == 0) { cg[n_cig] = 1; cq[n_cig] = j - 1; }
+            ++n_cig; --j;
+        }
+        for (int t = lane; t < j; t += 32) { cg[n_cig + t] = 1; cq[n_cig + t] = j - 1 - t; }
+        if (j > 0) n_cig += j;
+    }
+    if (!ok) n_cig = 0;
+    __syncwarp();
+}
+
 // Aligns sequence `query` of every active group to its graph and merges it in.  ALL lanes of the warp call; `act` says
 // whether this lane's group takes part.  err is the group's status (TH_OK going in).
 template <int LPT, bool AFFINE>
@@ -648,7 +829,7 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
         // headroom for the scan frame; the rest is the wide path's (second pass)
         const int len = qlen > n ? qlen : n;
         const int max_score = max(qlen * mat, len * e1 + o1);
-        if (max_score > 32767 - mis - oe1 - max(oe2, P.o2_raw + P.e2_raw) - CW * max(max(e1, e2), P.e2_raw)) { err = TH_ERR_LEN; ok = false; }
+        if (P.linear || max_score > 32767 - mis - oe1 - max(oe2, P.o2_raw + P.e2_raw) - CW * max(max(e1, e2), P.e2_raw)) { err = TH_ERR_LEN; ok = false; }
     }
     const int inf_min = P.inf_min;
     const int wband = 10 + (int)(0.01f * (float)qlen); // wb + (int)(wf*qlen), float (simd_abpoa_align.c:393)
@@ -746,7 +927,8 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
     }
     int n_cig = 0;
     if constexpr (LPT == 32) { // the 32-lane kernel is the wide path: 32-bit arithmetic, see poa_dp_wide
-        poa_dp_wide<AFFINE>(sm, P, ok, err, n, qlen, q4, n_cig, cells, rows);
+        if (P.linear) poa_dp_linear(sm, P, ok, err, n, qlen, q4, n_cig, cells, rows);
+        else poa_dp_wide<AFFINE>(sm, P, ok, err, n, qlen, q4, n_cig, cells, rows);
         PH(1);
     } else {
     // ---- first row (simd_abpoa_align.c:538-555, 591-610) ------------------------------------

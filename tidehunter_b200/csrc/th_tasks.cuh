@@ -149,7 +149,8 @@ __global__ void task_fill_kernel(int n_reads, int min_copy, int only_unit, const
             KswItem le; le.kind = 1; le.task = t; le.a = pp[i] + 1; le.b = 0; le.a2 = le.b2 = 0; le.seq_off = so; le.out = 4 * t; le.task2 = le.out2 = le.pad = 0; le.seq_off2 = 0;
             KswItem re = le; re.kind = 2; re.a = pp[j - 1] + 1; re.b = L - pp[j - 1] - 1; re.out = 4 * t + 2;
             exts[2 * t] = le; exts[2 * t + 1] = re;
-            ext_key[2 * t] = max(le.a, 0); ext_key[2 * t + 1] = max(re.b, 0); max_ext = max(max_ext, max(le.a, re.b));
+            { const int ka = min(max(le.a, 0), 2 * qmax), kb = min(max(re.b, 0), 2 * qmax); // rows the extension computes: at most twice the consensus length
+              ext_key[2 * t] = ka; ext_key[2 * t + 1] = kb; max_ext = max(max_ext, max(ka, kb)); }
         }
         ++t;
     });
