@@ -152,7 +152,7 @@ extern "C" th_gpu_ctx *th_gpu_create(const th_gpu_params *p, int device) {
     for (int i = 0; i < 16; ++i) CKP(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 4; ++i) CKP(cudaEventCreate(&c->mark[i]));
     CKP(cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
-    CKP(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_CAP * 8));
+    CKP(cudaFuncSetAttribute(seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEED_SMEM_BYTES));
     CKP(cudaFuncSetAttribute(poa_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PoaSmem<16>) * POA_WARPS * 2 + sizeof(PoaLaneK) * 16)));
     CKP(cudaFuncSetAttribute(poa_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PoaSmem<32>) * POA_WARPS + sizeof(PoaLaneK) * 32)));
     memset(&c->stats, 0, sizeof(c->stats));
@@ -281,7 +281,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         int gcap = 1; while (gcap < c->max_len) gcap <<= 1;
         const int grid = std::min(n, c->n_sm);
         if (c->d_scratch.ensure((size_t)grid * 2 * gcap * 8)) return -1;
-        seed_kernel<<<grid, SEED_THREADS, SEED_SMEM_CAP * 8, st>>>(P, n, roff, rlen, c->d_bseq.as<uint8_t>(), c->d_pack.as<uint64_t>(), c->d_nmask.as<uint32_t>(),
+        seed_kernel<<<grid, SEED_THREADS, SEED_SMEM_BYTES, st>>>(P, n, roff, rlen, c->d_bseq.as<uint8_t>(), c->d_pack.as<uint64_t>(), c->d_nmask.as<uint32_t>(),
                                                                   c->d_scratch.as<uint64_t>(), gcap, c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(), c->d_nhits.as<int32_t>());
         S.n_launches++;
     }
