@@ -32,12 +32,48 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# DRAM bytes per banded POA cell from the ncu --set full capture in profiles/ (dram__bytes_read.sum + dram__bytes_write.sum
-# of poa_kernel over its cell count): r1 final capture at 8192 reads = (55.58 + 67.88) GB / 5.693 G cells
-# (profiles/r1_ncu_full_summary_8192reads_final.txt)
-NCU_POA_TRAFFIC_PER_CELL = 21.69
+# Per-kernel constants taken from the ncu --set full captures under profiles/ (tools/ncu_constants.py writes the file):
+# warp-instructions, ALU-pipe warp-instructions and DRAM bytes per algorithmic unit (POA / ksw cell, chain pair evaluation).
+# bench.py times the kernels live (CUDA events); these constants turn that time into pipe utilisation and DRAM traffic.
+def load_ncu_constants():
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_constants.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
-WORKLOAD = "synthetic ONT R2C2-style reads: 10 kb, 1 kb unit x 10 copies, 15% error (BASELINE.json configs[1])"
+
+WORKLOADS = {
+    "r2c2": "synthetic ONT R2C2-style reads: 10 kb, 1 kb unit x 10 copies, 15% error (BASELINE.json configs[1])",
+    "mixed": "synthetic reads with the length mix of test_data/test.fq (1.8-23.6 kb, unit 200-1200 bp, 12% error), input order random",
+    "mixed_sorted": "synthetic reads with the length mix of test_data/test.fq (1.8-23.6 kb, unit 200-1200 bp, 12% error), input sorted by length",
+}
+WORKLOAD = WORKLOADS["r2c2"]
+
+
+def make_config(args, world):
+    """The `config` object of the JSON line -- the same for both arms (the reference arm times a bounded sample of it)."""
+    return {"workload": WORKLOADS[args.workload], "reads_per_gpu_per_step": args.reads, "options": "defaults, -f 1",
+            "l2": "per-step working set (reads + DP arenas, > 1 GB) exceeds the 126 MB L2",
+            "parallelism": "read-sharded x%d by bases, no collective" % world, "lanes_per_gpu": max(1, args.lanes), "e2e_chunk_reads": args.chunk}
+
+
+def rank_reads(workload, n_per_gpu, rank, world):
+    """(names, seqs, first_index) of this rank's part of the step's batch of world x n_per_gpu reads.  r2c2: reads
+    [rank n, (rank + 1) n) of the generator.  mixed / mixed_sorted: the batch (sorted by nominal length for the latter) is
+    cut into contiguous parts of equal nominal bases (tidehunter_b200.shard.shard_range_by_work), as the sharded front end does."""
+    from tidehunter_b200 import synth
+    from tidehunter_b200.shard import shard_range_by_work
+    if workload == "r2c2":
+        names, seqs = synth.gen_reads("r2c2", n_per_gpu, start=rank * n_per_gpu)
+        return names, seqs, rank * n_per_gpu
+    import numpy as np
+    tot = n_per_gpu * world
+    nominal = synth.nominal_lengths("mixed", tot)
+    order = np.argsort(nominal, kind="stable") if workload == "mixed_sorted" else np.arange(tot)
+    lo, hi = shard_range_by_work(nominal[order], rank, world)
+    names, seqs = synth.gen_reads_at("mixed", order[lo:hi])
+    return names, seqs, lo
 
 
 def load_peaks():
@@ -106,7 +142,12 @@ def reference_arm(args):
     cores = os.cpu_count() or 1
     kind, run = _ref_runner()
     n = cpu_sample_size(run, cores, 4.0)
-    names, seqs = synth.gen_reads("r2c2", n, start=0)
+    if args.workload == "r2c2":
+        names, seqs = synth.gen_reads("r2c2", n, start=0)
+    else:
+        names, seqs, _ = rank_reads(args.workload, args.reads, 0, max(1, args.gpus))
+        names, seqs = names[:n], seqs[:n]
+        n = len(seqs)
     bases = synth.total_bases(seqs)
     for _ in range(args.warmup):
         run(names[: max(n // 4, 1)], seqs[: max(n // 4, 1)], cores)
@@ -117,15 +158,74 @@ def reference_arm(args):
         "impl": "reference", "metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int16/int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reads_per_step": n, "bases_per_step": bases, "options": "defaults, -f 1"},
+        "config": make_config(args, max(1, args.gpus)),
+        "sample_reads_per_step": n, "sample_bases_per_step": bases,
         "gbp_per_s": bases * args.steps / tot / 1e9,
         "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": kind,
-                         "sample": "%d reads (%d bases) per step, TideHunter -t %d" % (n, bases, cores)},
+                         "sample": "first %d reads (%d bases) of the workload per step, TideHunter -t %d -f 1" % (n, bases, cores)},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+def config_legs(device):
+    """Short end-to-end legs over the other BASELINE.json config shapes (configs[2..4]): host buffers in, records out
+    through th_host_run; next to the unmodified reference (all host cores) on a sample of the same reads, with the outputs
+    of that sample compared byte for byte.  Rank 0 at N = 1 only; a few seconds per shape."""
+    import gzip
+    import hashlib
+    import tidehunter_b200 as T
+    from tidehunter_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    if not os.path.exists(O.REF_BIN):
+        return {"unavailable": "oracle/_ref/TideHunter is not built"}
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "golden.json.gz"), "rt") as f:
+        ad = json.load(f)["adapters"]
+    five, three = ad["five"], ad["three"]
+    cores = os.cpu_count() or 1
+    legs = [
+        ("configs[2] short units 50-200 bp x 20-50 copies, 10% error, -f 2", lambda n: synth.gen_reads("short", n, start=700000), 16384, 1024, ["-f", "2"], dict(out_fmt=2)),
+        ("configs[3] long units 4-5 kb x 2-4 copies, 20% error, -f 2", lambda n: synth.gen_reads("long", n, start=700000), 3072, 320, ["-f", "2"], dict(out_fmt=2)),
+        ("configs[4] adapters -5 -3 -u -f 2 (unit output)", lambda n: synth.gen_reads("r2c2", n, start=700000, adapters=(five, three)), 8192, 768, ["ADAPTERS", "-u", "-f", "2"],
+         dict(out_fmt=2, five_seq=five, three_seq=three, only_unit=1)),
+        ("configs[4] adapters -5 -3 -F -f 2 (full-length consensus)", lambda n: synth.gen_reads("r2c2", n, start=700000, adapters=(five, three), three_rc=True), 8192, 512,
+         ["ADAPTERS", "-F", "-f", "2"], dict(out_fmt=2, five_seq=five, three_seq=three, only_full_length=1)),
+    ]
+    rows = []
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+        p5, p3 = os.path.join(td, "5.fa"), os.path.join(td, "3.fa")
+        with open(p5, "w") as f:
+            f.write(">5\n%s\n" % five)
+        with open(p3, "w") as f:
+            f.write(">3\n%s\n" % three)
+        for tag, gen, n, ns, argv, kw in legs:
+            names, seqs = gen(n)
+            bases = synth.total_bases(seqs)
+            th = T.TideHunter(device=device, **kw)
+            th.run(names, seqs)                         # warm-up (buffers, slabs)
+            ts = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                out = th.run(names, seqs)
+                ts.append(time.perf_counter() - t0)
+            ours_s = th.run(names[:ns], seqs[:ns])
+            failed = th.failed_tasks()
+            th.close()
+            dt = min(ts)
+            path = os.path.join(td, "s.fa")
+            O.write_fasta(path, names[:ns], seqs[:ns])
+            argv2 = sum((["-5", p5, "-3", p3] if a == "ADAPTERS" else [a] for a in argv), [])
+            t0 = time.perf_counter()
+            ref = subprocess.run([O.REF_BIN, "-t", str(cores)] + argv2 + [path], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+            t_ref = time.perf_counter() - t0
+            rows.append({"config": tag, "reads_per_step": n, "bases_per_step": bases, "e2e": {"value": round(n / dt, 1), "unit": "reads/s", "gbp_per_s": round(bases / dt / 1e9, 4), "ms_per_step": round(1e3 * dt, 1)},
+                         "output_bytes": len(out), "failed_tasks": failed,
+                         "cpu_baseline": {"value": round(ns / t_ref, 1), "unit": "reads/s", "cores": cores, "kind": "reference", "sample": "first %d reads, TideHunter -t %d %s" % (ns, cores, " ".join(argv).replace("ADAPTERS", "-5 .. -3 .."))},
+                         "parity": {"reads": ns, "identical": bool(ours_s == ref), "md5_reference": hashlib.md5(ref).hexdigest()}})
+    return rows
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -189,6 +289,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=4, help="GPU contexts (streams) the step's reads are dealt to")
     ap.add_argument("--chunk", type=int, default=4096, help="reads per chunk of the end-to-end leg (th_host_run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="r2c2", choices=sorted(WORKLOADS), help="r2c2 = BASELINE configs[1] (the contract's line); mixed* = mixed read lengths, dealt by bases")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short legs over BASELINE configs[2..4]")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -233,7 +335,8 @@ def main():
     # this rank's batch: read indices [rank*reads, (rank+1)*reads) of the seeded generator
     n = args.reads
     L = max(1, args.lanes)
-    names, seqs = synth.gen_reads("r2c2", n, start=rank * n)
+    names, seqs, first_index = rank_reads(args.workload, n, rank, world)
+    n = len(seqs)                                      # mixed workloads: equal bases per rank, not equal read counts
     bases = synth.total_bases(seqs)
 
     # ---------------- device-resident leg (value) ----------------
@@ -304,7 +407,7 @@ def main():
     h2d = d2h = 0
     out_bytes = 0
     for _ in range(args.steps):
-        text = th.run(names, seqs)
+        text = th.run(names, seqs, first_index=first_index)
         parts = ordered_gather(text, rank, world, gloo)
         if parts is not None:
             out_bytes = sum(len(p) for p in parts)
@@ -346,28 +449,59 @@ def main():
     else:
         kernels, ser_ms, ser_cnt = kernels_over, over_ms, over_cnt
     dom = max(("poa", "ksw", "chain", "seed", "pack"), key=lambda k: ser_ms[k])
-    # algorithmic HBM bytes per unit (DESIGN.md section "kernels"): POA stores 5 int16 states per banded cell and
-    # re-reads them once as a predecessor row (20 B/cell); ksw keeps rows in registers (boundary hand-off only:
-    # 16 B per target row per 512-column block, ~0.03 B/cell); chain reads 12 B per evaluated predecessor (L1/L2 hits);
-    # seeding reads L/4 + L/8 bytes and writes 8 B per hit.
-    bytes_per_unit = {"poa": 20.0, "ksw": 16.0 / 512, "chain": 12.0, "seed": None, "pack": 1.0 + 1.0 + 0.25 + 0.125}
+    # Algorithmic HBM bytes per unit: POA stores 7 B per banded cell (H, E1, E2 as int16 + one code
+    # byte) and reads the three planes once more as a predecessor row or in the backtrack (13 B/cell); ksw keeps its rows in
+    # registers (boundary hand-off only: 16 B per target row per 512-column block, ~0.03 B/cell); chaining reads 12 B per
+    # evaluated predecessor (L1/L2 hits); seeding reads L/4 + L/8 bytes and writes 8 B per hit; packing 1 B in, 1.375 B out.
+    bytes_per_unit = {"poa": 13.0, "ksw": 16.0 / 512, "chain": 12.0, "seed": None, "pack": 1.0 + 1.0 + 0.25 + 0.125}
+    bound_of = {"pack": "hbm", "seed": "hbm", "chain": "int", "poa": "int", "ksw": "int"}
+    ncu = load_ncu_constants()
+    n_sm = 148
+    # integer roof: the ALU pipe issues 2 warp-instructions per clock per SM for the packed 16x2 DP operations
+    # (VIADD.16x2, VIMNMX.S16x2, VIMNMX3, PRMT, IMAD: tools/microbench/alu_peak.cu, profiles/r1_alu_peak.json)
+    int_peak = n_sm * sm_max * 1e6 * 2.0          # ALU-pipe warp-instructions per second
+    issue_peak = n_sm * sm_max * 1e6 * 4.0        # issue slots per second
 
-    def alg_bytes_of(counts):
-        if dom == "seed":
+    def alg_bytes_k(k, counts):
+        if k == "seed":
             return counts["n_bases"] * (0.25 + 0.125) + 8.0 * counts["n_hits"]
-        return counts[key_of[dom]] * bytes_per_unit[dom]
+        return counts[key_of[k]] * bytes_per_unit[k]
 
-    alg_bytes = alg_bytes_of(ser_cnt)
+    def annotate(tab, ms, counts):
+        """hbm_frac for every kernel; int_frac / issue_frac where the ncu constants know the instruction mix."""
+        for k in key_of:
+            if ms[k] <= 0:
+                continue
+            e = tab[k]
+            e["bound"] = bound_of[k]
+            e["hbm_frac"] = round(alg_bytes_k(k, counts) / (ms[k] * 1e-3) / 1e9 / hbm_peak, 5)
+            c = ncu.get(k)
+            if c and bound_of[k] == "int":
+                units = counts[key_of[k]]
+                e["int_frac"] = round(c["alu_inst_per_unit"] * units / (ms[k] * 1e-3) / int_peak, 4)
+                e["issue_frac"] = round(c["warp_inst_per_unit"] * units / (ms[k] * 1e-3) / issue_peak, 4)
+                e["warp_inst_per_unit"] = c["warp_inst_per_unit"]
+
+    annotate(kernels, ser_ms, ser_cnt)
+    annotate(kernels_over, over_ms, over_cnt)
+    alg_bytes = alg_bytes_k(dom, ser_cnt)
     achieved = alg_bytes / (ser_ms[dom] * 1e-3) / 1e9 if ser_ms[dom] > 0 else 0.0
-    achieved_over = alg_bytes_of(over_cnt) / (over_ms[dom] * 1e-3) / 1e9 if over_ms[dom] > 0 else 0.0
-    traffic = {"poa": NCU_POA_TRAFFIC_PER_CELL}.get(dom)
+    achieved_over = alg_bytes_k(dom, over_cnt) / (over_ms[dom] * 1e-3) / 1e9 if over_ms[dom] > 0 else 0.0
+    cdom = ncu.get(dom, {})
+    traffic = cdom.get("dram_bytes_per_unit")
     roofline = {"kernel": {"poa": "poa_kernel", "ksw": "ksw_pair_kernel+ksw_ext_kernel", "chain": "chain_dp_kernel", "seed": "seed_kernel", "pack": "pack_kernel"}[dom],
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": (traffic * ser_cnt[key_of[dom]] / 1e9) if traffic else None, "traffic_unit": "GB per launch (ncu dram bytes per cell x cells of this launch)",
+                "traffic": (traffic * ser_cnt[key_of[dom]] / 1e9) if traffic else None, "traffic_unit": "GB per launch (ncu dram bytes per unit x units of this launch)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ser_ms[dom],
                 "measured": "CUDA events on the library's stream around the kernel, one lane alone (after the timed region)" if L > 1 else "CUDA events on the library's stream inside the timed region",
                 "in_timed_region": {"ms_per_launch": over_ms[dom], "achieved": achieved_over, "frac": achieved_over / hbm_peak, "lanes_co_running": L},
-                "note": "integer DP kernel, latency/issue bound: see `kernels` for cell-update rates (GCUPS); the HBM fraction shows it is not bandwidth-bound"}
+                "binding": bound_of[dom],
+                "int_frac": kernels[dom].get("int_frac"), "issue_frac": kernels[dom].get("issue_frac"),
+                "int_peak": {"value": int_peak / 1e9, "unit": "G ALU-pipe warp-instructions/s (2 per clock per SM, profiles/r1_alu_peak.json)"},
+                "ncu_constants": "profiles/r2_ncu_constants.json" if ncu else None,
+                "note": "integer DP kernel: `frac` is the HBM fraction the contract asks for and shows the kernel is not bandwidth-bound; "
+                        "`int_frac` = ALU-pipe warp-instructions per unit (ncu) x units / live kernel time / the measured 2-per-clock pipe rate is the roof that "
+                        "applies; `kernels` carries both fractions for every kernel"}
 
     line = {
         "metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -375,9 +509,8 @@ def main():
         "timing": "CUDA events on the lanes' own streams (latest end - earliest start), max over ranks; host clock between synchronised barriers alongside",
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int16/int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reads_per_gpu_per_step": n, "bases_per_gpu_per_step": bases, "options": "defaults, -f 1",
-                   "l2": "per-step working set (reads + DP arenas, > 1 GB) exceeds the 126 MB L2", "parallelism": "read-sharded x%d, no collective" % world,
-                   "lanes_per_gpu": L, "e2e_chunk_reads": args.chunk},
+        "config": make_config(args, world),
+        "reads_this_rank_per_step": n, "bases_this_rank_per_step": bases,
         "gbp_per_s": tot_bases / dt / 1e9,
         "poa_gcups": kernels["poa"].get("g_units_per_s"), "ksw_gcups": kernels["ksw"].get("g_units_per_s"),
         "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
@@ -400,6 +533,8 @@ def main():
         line["cpu_baseline"] = {"value": ns / t, "unit": "reads/s", "cores": cores, "kind": kind,
                                 "sample": "first %d reads of the step's batch (%d bases), TideHunter -t %d -f 1, %.1f s" % (ns, synth.total_bases(seqs[:ns]), cores, t)}
     th.close()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_configs and args.workload == "r2c2":
+        line["configs"] = config_legs(local)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -102,6 +102,7 @@ void th_host_destroy(th_host *h) {
 }
 void th_host_stats(const th_host *h, th_gpu_stats *s) { *s = h->stats; }
 long long th_host_failed_tasks(const th_host *h) { return h->n_failed; }
+void th_host_set_read_index(th_host *h, long long first) { h->read_counter = first; }
 th_gpu_ctx *th_host_gpu(th_host *h) { return h->gpu; }
 
 /* Infix edit distance with threshold (edlib_align_HW, src/edlib_align.c:73-85): edit distance,
@@ -497,13 +498,31 @@ static void add_stats(th_gpu_stats *a, const th_gpu_stats *b) {
     a->n_ksw_cells += b->n_ksw_cells; a->n_tasks += b->n_tasks; a->n_launches += b->n_launches; a->h2d_bytes += b->h2d_bytes; a->d2h_bytes += b->d2h_bytes;
 }
 
-/* One th_host_run in flight: chunk c belongs to lane c % n_lanes.  A lane thread runs its chunks through the GPU one
- * after the other; the caller's thread formats the chunks strictly in input order (the FASTQ slot quirk and the output
- * order are sequential), and a lane only starts its next chunk once its previous result has been formatted, because
- * the result arrays belong to the context. */
+/* One th_host_run in flight.  Chunks are cut by work, not only by count: a chunk ends after chunk_reads reads or once it
+ * holds TH_CHUNK_BASES_PER_READ x chunk_reads bases (the reference balances reads over its threads dynamically,
+ * src/main.c:273-291; with mixed read lengths equal read counts are unequal work).  Lanes TAKE chunks -- a free lane takes
+ * the first chunk nobody has yet -- so a lane that drew long reads does not hold up the others.  The caller's thread formats
+ * the chunks strictly in input order (the FASTQ slot quirk and the output order are sequential), and a lane only takes its
+ * next chunk once its previous result has been formatted, because the result arrays belong to the context; every chunk
+ * before a taken one is taken too, so the formatter never waits on an untaken chunk. */
+#define TH_CHUNK_BASES_PER_READ 12288
+static int *cut_chunks(const th_host *h, int n, const int32_t *lens, int *n_chunks) {
+    const long long cap_b = (long long)h->p.chunk_reads * TH_CHUNK_BASES_PER_READ;
+    int *start = (int *)malloc(sizeof(int) * ((size_t)n + 2)), nc = 0, r = 0;
+    while (r < n) {
+        long long b = 0; int m = 0;
+        start[nc++] = r;
+        while (r < n && m < h->p.chunk_reads && (m == 0 || b + lens[r] <= cap_b)) { b += lens[r]; ++r; ++m; }
+    }
+    start[nc] = n;
+    *n_chunks = nc;
+    return start;
+}
 enum { CH_PENDING = 0, CH_READY = 1, CH_EMITTED = 2, CH_FAILED = 3 };
 typedef struct {
     th_host *h; int n, n_chunks; const char *const *seqs; const int32_t *lens;
+    const int *start;      /* chunk c = reads [start[c], start[c + 1]) */
+    int next;              /* first chunk no lane has taken yet */
     pthread_mutex_t mu; pthread_cond_t cv;
     int *state; th_gpu_result *res; int abort; char err[512];
 } run_job;
@@ -511,12 +530,12 @@ typedef struct { run_job *job; int lane; double t_gpu, t_wait; } lane_arg;
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 static void *lane_main(void *arg_) {
-    lane_arg *a = (lane_arg *)arg_; run_job *J = a->job; th_host *h = J->h; int c;
-    for (c = a->lane; c < J->n_chunks; c += h->n_lanes) {
-        const int c0 = c * h->p.chunk_reads, m = J->n - c0 < h->p.chunk_reads ? J->n - c0 : h->p.chunk_reads;
-        int rc, stop;
-        pthread_mutex_lock(&J->mu); stop = J->abort; pthread_mutex_unlock(&J->mu);
-        if (stop) break;
+    lane_arg *a = (lane_arg *)arg_; run_job *J = a->job; th_host *h = J->h;
+    for (;;) {
+        int c, c0, m, rc, stop;
+        pthread_mutex_lock(&J->mu); stop = J->abort; c = J->next; if (!stop && c < J->n_chunks) J->next = c + 1; pthread_mutex_unlock(&J->mu);
+        if (stop || c >= J->n_chunks) break;
+        c0 = J->start[c]; m = J->start[c + 1] - c0;
         { const double t0 = now_s();
           rc = th_gpu_process_chunk(h->lane[a->lane], m, J->seqs + c0, J->lens + c0, &J->res[c]);
           a->t_gpu += now_s() - t0; }
@@ -575,14 +594,15 @@ static void emit_chunk(th_host *h, const th_gpu_result *R, int m, const char *co
 }
 
 const char *th_host_run(th_host *h, int n, const char *const *names, const char *const *seqs, const int32_t *lens, size_t *out_len) {
-    int c, n_chunks = (n + h->p.chunk_reads - 1) / h->p.chunk_reads;
+    int c, n_chunks = 0;
+    int *start = cut_chunks(h, n, lens, &n_chunks);
     h->out.l = 0; str_reserve(&h->out, 16); h->out.s[0] = 0;
     memset(&h->stats, 0, sizeof(h->stats));
     if (n_chunks <= 1 || h->n_lanes == 1) {
         for (c = 0; c < n_chunks; ++c) {
-            const int c0 = c * h->p.chunk_reads, m = n - c0 < h->p.chunk_reads ? n - c0 : h->p.chunk_reads;
+            const int c0 = start[c], m = start[c + 1] - c0;
             th_gpu_result R;
-            if (th_gpu_process_chunk(h->gpu, m, seqs + c0, lens + c0, &R)) { set_err("%s", th_gpu_last_error()); *out_len = 0; return NULL; }
+            if (th_gpu_process_chunk(h->gpu, m, seqs + c0, lens + c0, &R)) { set_err("%s", th_gpu_last_error()); free(start); *out_len = 0; return NULL; }
             emit_chunk(h, &R, m, names + c0, seqs + c0, lens + c0);
             h->read_counter += m;
             add_stats(&h->stats, &R.stats);
@@ -590,13 +610,13 @@ const char *th_host_run(th_host *h, int n, const char *const *names, const char 
     } else {
         run_job J; pthread_t th[TH_MAX_LANES]; lane_arg la[TH_MAX_LANES]; int n_thr = h->n_lanes < n_chunks ? h->n_lanes : n_chunks, failed = 0;
         memset(&J, 0, sizeof(J));
-        J.h = h; J.n = n; J.n_chunks = n_chunks; J.seqs = seqs; J.lens = lens;
+        J.h = h; J.n = n; J.n_chunks = n_chunks; J.seqs = seqs; J.lens = lens; J.start = start; J.next = 0;
         J.state = (int *)calloc(n_chunks, sizeof(int)); J.res = (th_gpu_result *)calloc(n_chunks, sizeof(th_gpu_result));
         pthread_mutex_init(&J.mu, NULL); pthread_cond_init(&J.cv, NULL);
         const double t_run0 = now_s(); double t_emit = 0, t_mwait = 0;
         for (c = 0; c < n_thr; ++c) { la[c].job = &J; la[c].lane = c; la[c].t_gpu = la[c].t_wait = 0; pthread_create(&th[c], NULL, lane_main, &la[c]); }
         for (c = 0; c < n_chunks && !failed; ++c) {
-            const int c0 = c * h->p.chunk_reads, m = n - c0 < h->p.chunk_reads ? n - c0 : h->p.chunk_reads;
+            const int c0 = start[c], m = start[c + 1] - c0;
             double t0 = now_s();
             pthread_mutex_lock(&J.mu);
             while (J.state[c] == CH_PENDING && !J.abort) pthread_cond_wait(&J.cv, &J.mu);
@@ -619,9 +639,10 @@ const char *th_host_run(th_host *h, int n, const char *const *names, const char 
             fprintf(stderr, "\n");
         }
         pthread_mutex_destroy(&J.mu); pthread_cond_destroy(&J.cv);
-        if (failed) { set_err("%s", J.err[0] ? J.err : "a GPU lane failed"); free(J.state); free(J.res); *out_len = 0; return NULL; }
+        if (failed) { set_err("%s", J.err[0] ? J.err : "a GPU lane failed"); free(J.state); free(J.res); free(start); *out_len = 0; return NULL; }
         free(J.state); free(J.res);
     }
+    free(start);
     *out_len = h->out.l;
     return h->out.s;
 }

@@ -49,6 +49,9 @@ void th_host_destroy(th_host *h);
  * calls so that the FASTQ quality slot-reuse quirk of the reference (src/main.c:266-267) is kept. */
 const char *th_host_run(th_host *h, int n, const char *const *names, const char *const *seqs, const int32_t *lens, size_t *out_len);
 
+/* Index, in the whole input, of the first read of the NEXT th_host_run.  Only a process that handles part of an input (one
+ * rank of a sharded run) needs it: the reference's FASTQ quality slot is read_index % 4096 of the whole input (src/main.c:266-267). */
+void th_host_set_read_index(th_host *h, long long first);
 /* stats of the last th_host_run (summed over its chunks) */
 void th_host_stats(const th_host *h, th_gpu_stats *s);
 /* consensus tasks that failed on the GPU since th_host_create (status != 0, e.g. a unit beyond the int16 score range);

@@ -21,6 +21,30 @@ def test_shard_ranges_tile_in_order():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_work_balanced_ranges_tile_in_order_and_balance_bases():
+    """shard_range_by_work: contiguous, in order, and no rank's bases exceed the ideal share by more than one read --
+    also for length-sorted input, where equal read counts would give the last rank several times the work."""
+    import numpy as np
+    from tidehunter_b200.shard import shard_range, shard_range_by_work
+    rng = np.random.default_rng(7)
+    for n in (0, 1, 3, 100, 5000):
+        for w in (1, 2, 3, 8):
+            for order in ("random", "sorted"):
+                lens = rng.integers(1800, 23700, n)
+                if order == "sorted":
+                    lens = np.sort(lens)
+                blocks = [shard_range_by_work(lens, r, w) for r in range(w)]
+                assert blocks[0][0] == 0 and blocks[-1][1] == n
+                assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+                if n >= 100:
+                    share = [int(lens[a:b].sum()) for a, b in blocks]
+                    assert max(share) <= lens.sum() / w + lens.max()
+    lens = np.sort(rng.integers(1800, 23700, 5000))
+    by_count = max(int(lens[a:b].sum()) for a, b in (shard_range(5000, r, 8) for r in range(8)))
+    by_work = max(int(lens[a:b].sum()) for a, b in (shard_range_by_work(lens, r, 8) for r in range(8)))
+    assert by_count > 1.5 * by_work
+
+
 def _worker(rank, world, port, q, shm=False):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
     if shm:  # what torchrun exports on a single node: the gather then goes through /dev/shm files
@@ -34,7 +58,7 @@ def _worker(rank, world, port, q, shm=False):
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
 
     class Engine:  # same .run(names, seqs) -> bytes interface as tidehunter_b200.TideHunter
-        def run(self, names, seqs):
+        def run(self, names, seqs, first_index=None):
             return O.run_batch(names, seqs, O.default_para(out_fmt=2))[0]
     names, seqs = synth.gen_reads("short", 9)
     out = run_sharded(Engine(), names, seqs, rank, world)

@@ -141,8 +141,14 @@ class TideHunter:
         if not self._h:
             raise RuntimeError("th_host_create failed: %s" % h.th_host_last_error().decode())
 
-    def run(self, names, seqs):
+    def run(self, names, seqs, first_index=None):
+        """Records of these reads as the reference prints them.  `first_index`: index of names[0] in the whole input when this
+        object only sees part of it (a rank of a sharded run): the reference's FASTQ quality slot is index % 4096."""
         _, h = _load()
+        if first_index is not None:
+            h.th_host_set_read_index.argtypes = [C.c_void_p, C.c_longlong]
+            h.th_host_set_read_index.restype = None
+            h.th_host_set_read_index(self._h, int(first_index))
         bn = [x if isinstance(x, bytes) else x.encode() for x in names]
         bs, seqs_a, lens_a = _arrays(seqs)
         names_a = (C.c_char_p * len(bn))(*bn)

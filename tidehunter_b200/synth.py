@@ -10,6 +10,7 @@ Shapes (BASELINE.json `configs`):
   r2c2   : unit 1000, 10 copies, err 0.15            (config 2, the bench workload)
   short  : unit U{50..200}, copies U{20..50}, err 0.10  (config 3)
   long   : unit U{4000..5000}, copies U{2..4}, err 0.20  (config 4)
+  mixed  : read length drawn from test_data/test.fq's 100 lengths (1.8 - 23.6 kb), unit U{200..1200}, err 0.12
 """
 import numpy as np
 
@@ -19,7 +20,39 @@ SHAPES = {
     "short": dict(unit=(50, 200), copies=(20, 50), err=0.10, sid=1),
     "long": dict(unit=(4000, 5000), copies=(2, 4), err=0.20, sid=2),
 }
+# read lengths of the reference's test_data/test.fq (100 ONT reads, 1.8 - 23.6 kb): the "mixed" shape draws its read lengths
+# from this list, so a batch has the length mix of real data -- the case where dealing equal read counts is unequal work
+TESTFQ_LENGTHS = [1813, 1885, 1894, 2012, 2028, 2031, 2080, 2092, 2104, 2114, 2140, 2162, 2181, 2209, 2249, 2258, 2264, 2313, 2337, 2341,
+                  2368, 2373, 2503, 2508, 2509, 2539, 2556, 2607, 2618, 2638, 2697, 2714, 2747, 2783, 2798, 2805, 2890, 2904, 2921, 3011,
+                  3023, 3026, 3029, 3116, 3127, 3134, 3136, 3161, 3182, 3191, 3192, 3194, 3221, 3238, 3254, 3278, 3311, 3317, 3348, 3390,
+                  3411, 3465, 3478, 3538, 3560, 3607, 3745, 3805, 4131, 4183, 4464, 4597, 4640, 4717, 4745, 4868, 5197, 5208, 5211, 5231,
+                  5269, 5326, 5572, 5696, 6042, 6044, 6089, 6269, 6463, 6807, 6943, 7152, 7461, 7535, 7604, 7861, 8471, 9390, 14329, 23611]
+SHAPES["mixed"] = dict(unit=(200, 1200), lengths=TESTFQ_LENGTHS, err=0.12, sid=3)
 FLANK = 50
+
+
+def _unit_and_copies(cfg, rng):
+    """The first draws of a read: unit length and copy number (the "mixed" shape: a read length from the list, a unit
+    length, and as many copies as fill the read)."""
+    if "lengths" in cfg:
+        length = int(cfg["lengths"][int(rng.integers(0, len(cfg["lengths"])))])
+        ulen = int(rng.integers(cfg["unit"][0], cfg["unit"][1] + 1))
+        return ulen, max(2, int(round((length - 2 * FLANK) / ulen)))
+    ulen = int(rng.integers(cfg["unit"][0], cfg["unit"][1] + 1))
+    copies = int(rng.integers(cfg["copies"][0], cfg["copies"][1] + 1))
+    return ulen, copies
+
+
+def nominal_lengths(shape, n, start=0, seed=SEED):
+    """Template lengths (before the error channel) of reads start..start+n-1 without generating them: what a sharded run
+    deals its reads by."""
+    cfg = SHAPES[shape]
+    out = np.empty(n, dtype=np.int64)
+    for k, i in enumerate(range(start, start + n)):
+        rng = np.random.Generator(np.random.Philox(key=[seed + cfg["sid"], i]))
+        ulen, copies = _unit_and_copies(cfg, rng)
+        out[k] = 2 * FLANK + ulen * copies
+    return out
 _ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
@@ -30,12 +63,17 @@ def gen_reads(shape, n, start=0, seed=SEED, adapters=None, three_rc=False):
     five + unit + revcomp(three)-style R2C2 structure: the unit itself becomes
     three_rc... kept simple: unit' = five + unit + three (both as given), so -5/-3 searches succeed.
     """
+    return gen_reads_at(shape, range(start, start + n), seed=seed, adapters=adapters, three_rc=three_rc)
+
+
+def gen_reads_at(shape, indices, seed=SEED, adapters=None, three_rc=False):
+    """gen_reads for an arbitrary list of read indices (a rank's part of a length-sorted batch)."""
     cfg = SHAPES[shape]
     names, seqs = [], []
-    for i in range(start, start + n):
+    for i in indices:
+        i = int(i)
         rng = np.random.Generator(np.random.Philox(key=[seed + cfg["sid"], i]))
-        ulen = int(rng.integers(cfg["unit"][0], cfg["unit"][1] + 1))
-        copies = int(rng.integers(cfg["copies"][0], cfg["copies"][1] + 1))
+        ulen, copies = _unit_and_copies(cfg, rng)
         unit = rng.integers(0, 4, ulen, dtype=np.uint8)
         if adapters is not None:
             five, three = adapters
