@@ -565,7 +565,14 @@ static void *fmt_main(void *a_) {
 }
 static int fmt_threads(void) {
     static int n = 0;
-    if (n == 0) { const char *e = getenv("TH_HOST_FMT_THREADS"); long c = sysconf(_SC_NPROCESSORS_ONLN); n = e ? atoi(e) : (int)(c >= 16 ? 8 : c >= 4 ? c / 2 : 1); if (n < 1) n = 1; if (n > 32) n = 32; }
+    if (n == 0) {
+        const char *e = getenv("TH_HOST_FMT_THREADS"), *lw = getenv("LOCAL_WORLD_SIZE"); /* set by torchrun: processes sharing this host's cores */
+        long c = sysconf(_SC_NPROCESSORS_ONLN);
+        if (lw && atoi(lw) > 1) c /= atoi(lw);           /* one process per GPU: each takes its share of the cores, not all of them */
+        n = e ? atoi(e) : (int)(c >= 16 ? 8 : c >= 4 ? c / 2 : c >= 2 ? 2 : 1);
+        if (lw && atoi(lw) > 1 && !e && c >= 2 && c < 16) n = (int)c; /* lane threads sleep in blocking waits: formatting may use the whole share */
+        if (n < 1) n = 1; if (n > 32) n = 32;
+    }
     return n;
 }
 static void emit_chunk(th_host *h, const th_gpu_result *R, int m, const char *const *names, const char *const *seqs, const int32_t *lens) {

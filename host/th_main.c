@@ -136,6 +136,7 @@ int main(int argc, char *argv[]) {
     if (p.gpu.min_copy < 2) { fprintf(stderr, "[main] min copy number must be >= 2\n"); return 1; }
     if (p.gpu.min_p < 2) { fprintf(stderr, "[main] min period must be >= 2\n"); return 1; }
     if (p.gpu.max_p > 4294967295LL) { fprintf(stderr, "[main] max period must be <= 4294967295\n"); return 1; } /* MAX_PERIOD, src/tidehunter.h:23 */
+    if (p.gpu.max_p >= 65536) fprintf(stderr, "[main] note: with -P >= 65536 a read whose partition window reaches 65,536 bases is reported as failed on the GPU path (message, non-zero exit) instead of being processed\n");
     if (p.out_fmt < 1 || p.out_fmt > 4) { fprintf(stderr, "[main] unknown output format %d\n", p.out_fmt); return 1; }
     if (p.gpu.only_unit && p.out_fmt > 2) { fprintf(stderr, "[main] -u only works with -f 1/2\n"); return 1; }
     if (p.only_full_length && !(five_fn && three_fn)) { fprintf(stderr, "[main] -F needs -5 and -3\n"); return 1; }

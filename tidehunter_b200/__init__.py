@@ -129,6 +129,18 @@ def _arrays(seqs):
     return bs, (C.c_char_p * n)(*bs), (C.c_int32 * n)(*[len(s) for s in bs])
 
 
+class Batch:
+    """Reads held the way the C entry point takes them (th_host_run: arrays of name / sequence pointers and lengths), built
+    once from Python lists.  The command line front end gets these arrays straight from its reader; a Python caller that
+    processes the same lists more than once (bench.py) builds them once instead of on every call."""
+
+    def __init__(self, names, seqs):
+        self.names = [x if isinstance(x, bytes) else x.encode() for x in names]
+        self.seqs, self.seqs_a, self.lens_a = _arrays(seqs)
+        self.names_a = (C.c_char_p * len(self.names))(*self.names)
+        self.n = len(self.seqs)
+
+
 class TideHunter:
     """Drop-in for the reference's per-chunk loop (src/main.c:402-425): reads in, output text out."""
 
@@ -141,22 +153,24 @@ class TideHunter:
         if not self._h:
             raise RuntimeError("th_host_create failed: %s" % h.th_host_last_error().decode())
 
-    def run(self, names, seqs, first_index=None):
-        """Records of these reads as the reference prints them.  `first_index`: index of names[0] in the whole input when this
-        object only sees part of it (a rank of a sharded run): the reference's FASTQ quality slot is index % 4096."""
+    def run(self, names, seqs=None, first_index=None, copy=True):
+        """Records of these reads as the reference prints them.  `names` may be a Batch (then `seqs` is not given).
+        `first_index`: index of the first read in the whole input when this object only sees part of it (a rank of a sharded
+        run): the reference's FASTQ quality slot is index % 4096.  copy=False returns a memoryview of the library's own
+        output buffer (valid until the next call) instead of a bytes copy."""
         _, h = _load()
         if first_index is not None:
             h.th_host_set_read_index.argtypes = [C.c_void_p, C.c_longlong]
             h.th_host_set_read_index.restype = None
             h.th_host_set_read_index(self._h, int(first_index))
-        bn = [x if isinstance(x, bytes) else x.encode() for x in names]
-        bs, seqs_a, lens_a = _arrays(seqs)
-        names_a = (C.c_char_p * len(bn))(*bn)
+        b = names if isinstance(names, Batch) else Batch(names, seqs)
         out_len = C.c_size_t(0)
-        ptr = h.th_host_run(self._h, len(bs), names_a, seqs_a, lens_a, C.byref(out_len))
+        ptr = h.th_host_run(self._h, b.n, b.names_a, b.seqs_a, b.lens_a, C.byref(out_len))
         if not ptr:
             raise RuntimeError("th_host_run failed: %s" % h.th_host_last_error().decode())
-        return C.string_at(ptr, out_len.value)
+        if copy:
+            return C.string_at(ptr, out_len.value)
+        return memoryview((C.c_char * out_len.value).from_address(ptr)).cast("B") if out_len.value else memoryview(b"")
 
     def stats(self):
         s = GpuStats()

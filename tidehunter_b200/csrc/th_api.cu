@@ -279,10 +279,17 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     // ---- seed ----
     {
         int gcap = 1; while (gcap < c->max_len) gcap <<= 1;
-        const int grid = std::min(n, c->n_sm);
+        // shared memory per block: the default path needs two 32-bit buffers of the longest read plus the radix counters;
+        // up to ~113 KB two blocks share an SM (reads up to ~12 k bases), beyond that one block with the full 144 KB
+        int smem = SEED_SMEM_BYTES, per_sm = 1;
+        if (P.w <= 1 && !P.hpc) {
+            const int need = 8 * ((c->max_len + 31) & ~31) + SEED_HIST_BYTES;
+            if (need <= 113 * 1024) { smem = need; per_sm = 2; }
+        }
+        const int grid = std::min(n, c->n_sm * per_sm);
         if (c->d_scratch.ensure((size_t)grid * 2 * gcap * 8)) return -1;
-        seed_kernel<<<grid, SEED_THREADS, SEED_SMEM_BYTES, st>>>(P, n, roff, rlen, c->d_bseq.as<uint8_t>(), c->d_pack.as<uint64_t>(), c->d_nmask.as<uint32_t>(),
-                                                                  c->d_scratch.as<uint64_t>(), gcap, c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(), c->d_nhits.as<int32_t>());
+        seed_kernel<<<grid, SEED_THREADS, smem, st>>>(P, n, smem, roff, rlen, c->d_bseq.as<uint8_t>(), c->d_pack.as<uint64_t>(), c->d_nmask.as<uint32_t>(),
+                                                      c->d_scratch.as<uint64_t>(), gcap, c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(), c->d_nhits.as<int32_t>());
         S.n_launches++;
     }
     CK(cudaEventRecord(c->ev[ei++], st)); // 4

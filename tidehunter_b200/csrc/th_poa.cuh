@@ -1254,6 +1254,9 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
             for (int t = gl; t < j; t += LPT) { cg[n_cig + t] = 1; cq[n_cig + t] = j - 1 - t; } // unaligned query head
             if (j > 0) n_cig += j;
         }
+        // the walk usually ends with the next 32 rows' codes still in flight: they land in the window, which shares its
+        // shared memory with the next alignment's row metadata and ring (found by compute-sanitizer racecheck)
+        cp_async_wait_all();
         __syncwarp();
     }
     }

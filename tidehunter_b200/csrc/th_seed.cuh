@@ -13,8 +13,10 @@
 #include "th_common.cuh"
 
 #define SEED_SMEM_CAP 16384           // 128 KB of 64-bit seeds
-#define SEED_THREADS 1024
-#define SEED_SMEM_BYTES (SEED_SMEM_CAP * 8 + 32 * 256 * 4) // seed / hit buffers + the digit counters of the radix passes
+#define SEED_THREADS 512
+#define SEED_WARPS (SEED_THREADS / 32)
+#define SEED_HIST_BYTES (SEED_WARPS * 256 * 4)                 // digit counters of the radix passes
+#define SEED_SMEM_BYTES (SEED_SMEM_CAP * 8 + SEED_HIST_BYTES)  // largest launch: seed / hit buffers of a 16 k read + the counters
 #define SEED_INVALID 0xffffffffffffffffull
 
 // ASCII -> nt4 (src/seq.c:15-32): ACGT/acgt and raw 0..3 -> 0..3, '-' -> 5, everything else 4
@@ -143,7 +145,7 @@ __device__ void seeds_parallel(const uint8_t *bseq, int len, int k, int w, int h
 }
 
 // ---- block-wide helpers of the default path ----------------------------------------------------------------------------
-// exclusive prefix sum of one int per thread (1024 threads); returns the thread's offset, total in `total`
+// exclusive prefix sum of one int per thread (SEED_THREADS threads); returns the thread's offset, total in `total`
 __device__ __forceinline__ int seed_block_scan(int v, int *s_part, int &total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int x = v;
@@ -152,21 +154,21 @@ __device__ __forceinline__ int seed_block_scan(int v, int *s_part, int &total) {
     __syncthreads();                                   // s_part may still be read from the previous call
     if (lane == 31) s_part[wid] = x;
     __syncthreads();
-    int p = s_part[lane];
+    int p = lane < SEED_WARPS ? s_part[lane] : 0;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(TH_FULL, p, d); if (lane >= d) p += y; }
     total = __shfl_sync(TH_FULL, p, 31);
     const int wbase = __shfl_sync(TH_FULL, p, max(wid - 1, 0));
     return x - v + (wid > 0 ? wbase : 0);
 }
-// One stable counting pass of an LSD radix sort over an 8-bit digit: src[0..n) -> dst, hist = 32 x 256 ints.  Warp w owns
-// the w-th contiguous 1/32 of the input, so "stable" is (warp, position inside the warp's part); inside a chunk of 32 the
+// One stable counting pass of an LSD radix sort over an 8-bit digit: src[0..n) -> dst, hist = SEED_WARPS x 256 ints (8 per
+// thread in the scan: SEED_WARPS x 256 = 8 SEED_THREADS).  Warp w owns the w-th contiguous part of the input, so "stable" is (warp, position inside the warp's part); inside a chunk of 32 the
 // rank among equal digits comes from __match_any_sync.
 __device__ void seed_radix_pass(const uint32_t *src, uint32_t *dst, int n, int shift, uint32_t dmask, int *hist, int *s_part) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int per = ((n + 31) / 32 + 31) & ~31;          // elements per warp, a multiple of 32
-    const int lo = wid * per, hi = min(lo + per, n);
-    for (int j = threadIdx.x; j < 32 * 256; j += blockDim.x) hist[j] = 0;
+    const int per = ((n + SEED_WARPS - 1) / SEED_WARPS + 31) & ~31; // elements per warp, a multiple of 32
+    const int lo = min(wid * per, n), hi = min(lo + per, n);
+    for (int j = threadIdx.x; j < SEED_WARPS * 256; j += blockDim.x) hist[j] = 0;
     __syncthreads();
     int *my = hist + wid * 256;
     for (int j0 = lo; j0 < hi; j0 += 32) {
@@ -181,10 +183,10 @@ __device__ void seed_radix_pass(const uint32_t *src, uint32_t *dst, int n, int s
     { // exclusive scan in (digit, warp) order: thread t takes the 8 consecutive entries 8t .. 8t+7 of that order
         int v[8], sum = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { const int e = threadIdx.x * 8 + q; v[q] = hist[(e & 31) * 256 + (e >> 5)]; sum += v[q]; }
+        for (int q = 0; q < 8; ++q) { const int e = threadIdx.x * 8 + q; v[q] = hist[(e % SEED_WARPS) * 256 + e / SEED_WARPS]; sum += v[q]; }
         int total; int base = seed_block_scan(sum, s_part, total);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { const int e = threadIdx.x * 8 + q; hist[(e & 31) * 256 + (e >> 5)] = base; base += v[q]; }
+        for (int q = 0; q < 8; ++q) { const int e = threadIdx.x * 8 + q; hist[(e % SEED_WARPS) * 256 + e / SEED_WARPS] = base; base += v[q]; }
     }
     __syncthreads();
     for (int j0 = lo; j0 < hi; j0 += 32) {
@@ -207,8 +209,8 @@ __device__ void seed_radix_pass(const uint32_t *src, uint32_t *dst, int n, int s
 // Fast path (default options, reads up to 32 k bases): seeds are 32-bit words (key << bits(L) | pos), hits are
 // (end << bits(L) | period); both sorts and the hit staging stay in shared memory.  Same total order as the
 // reference's 64-bit words (key major, position minor / end major, period minor), so any correct sort is exact.
-__global__ void __launch_bounds__(SEED_THREADS, 1)
-seed_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ rlen,
+__global__ void __launch_bounds__(SEED_THREADS, 2)
+seed_kernel(DevParams P, int n_reads, int smem_bytes, const int64_t *__restrict__ roff, const int32_t *__restrict__ rlen,
             const uint8_t *__restrict__ bseq, const uint64_t *__restrict__ pack2, const uint32_t *__restrict__ nmask,
             uint64_t *__restrict__ gscratch, int64_t gcap,
             int32_t *__restrict__ hend, int32_t *__restrict__ hper, int32_t *__restrict__ nhits) {
@@ -224,11 +226,12 @@ seed_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const in
         const int npow = next_pow2(L);
         const int bitsL = 32 - __clz(npow - 1 > 0 ? npow - 1 : 1);
         const uint64_t *pw = pack2 + off / 32; const uint32_t *nm = nmask + off / 32;
-        if (P.w <= 1 && !P.hpc && 2 * P.k + bitsL < 32 && P.min_p >= 1 && npow <= SEED_SMEM_CAP) {
-            uint32_t *buf = reinterpret_cast<uint32_t *>(sbuf), *hbuf = buf + npow; // 2 x npow x 4 B <= 128 KB
-            int *hist = reinterpret_cast<int *>(hbuf + npow);                          // 32 x 256 digit counters
+        const int cap = (L + 31) & ~31;                  // buffer entries of the default path: a tile of 32 positions per thread
+        if (P.w <= 1 && !P.hpc && 2 * P.k + bitsL < 32 && P.min_p >= 1 && cap <= SEED_THREADS * 32 && 8 * cap + SEED_HIST_BYTES <= smem_bytes) {
+            uint32_t *buf = reinterpret_cast<uint32_t *>(sbuf), *hbuf = buf + cap;  // 2 x cap x 4 B
+            int *hist = reinterpret_cast<int *>(hbuf + cap);                          // SEED_WARPS x 256 digit counters
             const uint32_t posmask = (1u << bitsL) - 1;
-            // rolling 2-bit k-mer, one tile of 32 positions per thread (npow <= 16384: at most 512 tiles), k-1 bases of warm-up
+            // rolling 2-bit k-mer, one tile of 32 positions per thread (cap <= 16384: at most 512 tiles), k-1 bases of warm-up
             // (tandem_hit.c:37-56); the tile's seeds stay in registers until their place in the compacted list is known
             const int base0 = threadIdx.x * 32;
             uint32_t valid = 0;
@@ -268,7 +271,7 @@ seed_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const in
             // nearest earlier occurrence of the same key at distance >= min_p (tandem_hit.c:186-214).  A position yields at most
             // one hit, so the (end, period) order of the hit list is the position order: periods are scattered by position and
             // compacted in order -- no second sort
-            for (int j = threadIdx.x; j < npow; j += blockDim.x) other[j] = 0;
+            for (int j = threadIdx.x; j < cap; j += blockDim.x) other[j] = 0;
             __syncthreads();
             for (int j = threadIdx.x; j < n_seed; j += blockDim.x) {
                 const uint32_t cur = sorted[j], key = cur >> bitsL, pos = cur & posmask; uint32_t d = 0; bool found = false;
@@ -292,7 +295,8 @@ seed_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const in
             continue;
         }
         // ---- general path: 64-bit words, any option ----
-        uint64_t *buf = npow <= SEED_SMEM_CAP ? sbuf : gbuf;
+        const int smem_words = smem_bytes / 8;
+        uint64_t *buf = npow <= smem_words ? sbuf : gbuf;
         if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
         if (P.w <= 1 && !P.hpc) {
@@ -355,7 +359,7 @@ seed_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const in
         __syncthreads();
         const int n_hit = s_cnt;
         const int hpow = next_pow2(n_hit);
-        uint64_t *hb = hpow <= SEED_SMEM_CAP ? sbuf : gtmp; // the seeds are no longer needed
+        uint64_t *hb = hpow <= smem_words ? sbuf : gtmp; // the seeds are no longer needed
         if (hb != gtmp) for (int j = threadIdx.x; j < n_hit; j += blockDim.x) hb[j] = gtmp[j];
         for (int j = n_hit + threadIdx.x; j < hpow; j += blockDim.x) hb[j] = SEED_INVALID;
         __syncthreads();

@@ -59,7 +59,7 @@ def ordered_gather(payload, rank, world, group=None, dst=0):
     import torch.distributed as dist
     if not _same_node(world):
         out = [None] * world if rank == dst else None
-        dist.gather_object(payload, out, dst=dst, group=group)
+        dist.gather_object(bytes(payload), out, dst=dst, group=group)
         return out
     _gather_seq += 1
     tag = "th_b200_%s_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "run"), _gather_seq)

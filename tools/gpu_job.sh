@@ -7,6 +7,7 @@
 #   launches NAME N          ncu launch list (gpu__time_duration) of one step -> gpurun_out/NAME.csv
 #   variants N [steps]       time one step with each build_variants/*.so in turn
 #   bench [args]             bench.py
+#   sanitize TOOL [pytest args]  GPU parity tests under compute-sanitizer (memcheck | racecheck | synccheck | initcheck) -> gpurun_out/r2_sanitizer_TOOL.log
 set -u
 mkdir -p gpurun_out
 job=$1; shift
@@ -31,5 +32,9 @@ case $job in
     for f in build_variants/*.so; do cp $f tidehunter_b200/libth_gpu.so; echo "== $f"; timeout 600 python tools/profile_step.py "$@" 2>&1 | head -1 | tr "," "\n" | grep -E "ms_poa|ms_ksw|ms_chain|ms_total"; done
     cp /tmp/libth_gpu.so.keep tidehunter_b200/libth_gpu.so ;;
   bench) timeout 1500 python bench.py "$@" ;;
+  sanitize)
+    tool=$1; shift
+    timeout 1700 compute-sanitizer --tool "$tool" --target-processes all --print-limit 30 --log-file gpurun_out/r2_sanitizer_$tool.log python -m pytest tests/test_gpu_parity.py -m gpu -x -q "$@" 2>&1 | tail -4
+    echo "== $tool: $(grep -c 'ERROR SUMMARY' gpurun_out/r2_sanitizer_$tool.log) process(es)"; grep -h "ERROR SUMMARY\|RACECHECK SUMMARY" gpurun_out/r2_sanitizer_$tool.log | sort | uniq -c ;;
   *) echo "unknown job $job"; exit 2 ;;
 esac
