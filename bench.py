@@ -308,8 +308,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL prints (its version line at WARN / INFO) stays off stdout: one JSON line
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
         gloo = dist.new_group(backend="gloo")  # host-side ordered gather only; no data-path collective
 
@@ -410,15 +409,21 @@ def main():
     t0 = time.perf_counter()
     h2d = d2h = 0
     out_bytes = 0
+    t_run = t_gather = 0.0
     for _ in range(args.steps):
+        ta = time.perf_counter()
         text = th.run(batch, first_index=first_index, copy=False)
+        tb = time.perf_counter()
         parts = ordered_gather(text, rank, world, gloo)
         if parts is not None:
             out_bytes = sum(len(p) for p in parts)
+        del parts
+        t_gather += time.perf_counter() - tb; t_run += tb - ta
         s = th.stats()
         h2d += s["h2d_bytes"]; d2h += s["d2h_bytes"]
     barrier()
     dt_e2e = max_over_ranks(time.perf_counter() - t0)
+    t_run = max_over_ranks(t_run); t_gather = max_over_ranks(t_gather)
 
     tot_reads = sum_over_ranks(n) * args.steps
     tot_bases = sum_over_ranks(bases) * args.steps
@@ -518,7 +523,8 @@ def main():
         "gbp_per_s": tot_bases / dt / 1e9,
         "poa_gcups": kernels["poa"].get("g_units_per_s"), "ksw_gcups": kernels["ksw"].get("g_units_per_s"),
         "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
-                "ms_per_step": 1e3 * dt_e2e / args.steps, "output_bytes_per_step": out_bytes, "gbp_per_s": tot_bases / dt_e2e / 1e9},
+                "ms_per_step": 1e3 * dt_e2e / args.steps, "output_bytes_per_step": out_bytes, "gbp_per_s": tot_bases / dt_e2e / 1e9,
+                "th_host_run_ms_per_step_max_rank": round(1e3 * t_run / args.steps, 1), "ordered_gather_ms_per_step_max_rank": round(1e3 * t_gather / args.steps, 1)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "kernels_overlapped": kernels_over,
         "lane_ms_per_step": round(acc["total"] / (args.steps * L), 3), "poa_tasks_per_step": n_tasks,
     }

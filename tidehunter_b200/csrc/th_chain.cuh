@@ -65,11 +65,15 @@ chain_dp_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, cons
             const int init = P.k + min(P.k, cp);
             int max_score = init, best_pre = -1, iter_in = 0;
             const int max_h = cp;
+            // the next batch of predecessors is loaded while the current one is evaluated (its scores are final: they lie at
+            // least 32 cells behind the current one); a batch is ~100 instructions, about one L2 round trip
+            int n_pe = 0, n_pp = 1, n_psc = 0;
+            { const int pre = cur - 1 - lane; if (pre >= 0) { n_pe = en[pre]; n_pp = pr[pre]; n_psc = sc[pre]; } }
             for (int base = cur - 1; base >= 0; base -= 32) {
                 const int pre = base - lane;
                 const bool valid = pre >= 0;
-                int pe = 0, pp = 1, psc = 0;
-                if (valid) { pe = en[pre]; pp = pr[pre]; psc = sc[pre]; }
+                const int pe = n_pe, pp = n_pp, psc = n_psc;
+                { const int nx = pre - 32; n_pe = 0; n_pp = 1; n_psc = 0; if (nx >= 0) { n_pe = en[nx]; n_pp = pr[nx]; n_psc = sc[nx]; } }
                 const bool cstop = !valid || pe < cs;           // stop BEFORE this predecessor
                 int con = 0, cls = CON_NO;
                 if (!cstop) cls = con_score<SMALL>(cs, ce, pe - pp, pe, P.k, con);

@@ -1202,8 +1202,9 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
                     int4 p0m = make_int4(0, 0, -1, 0);
                     if (tf) {
                         p0m = rmeta_g[h.x];
-                        for (int p = 1; p < np; ++p) { const int pp = p == 1 ? h.y : poa_pred_row(make_int4(h.x, 0, 0, h.y), w.rdesc2[i], plist_g, np, p); sm.pre[p] = rmeta_g[pp]; }
+                        if (gl >= 1 && gl < np) sm.pre[gl] = rmeta_g[pi]; // lane p holds predecessor p (np <= LPT)
                     }
+                    __syncwarp();
                     const uint32_t basew = (uint32_t)min(vb, 4) * 0x01010101u;
                     const int cj = tf ? (j - ib) / CW : -1;
                     int f1 = 0, f2 = 0, f1m1 = 0, f2m1 = 0;
