@@ -45,8 +45,8 @@ def load_ncu_constants():
 
 WORKLOADS = {
     "r2c2": "synthetic ONT R2C2-style reads: 10 kb, 1 kb unit x 10 copies, 15% error (BASELINE.json configs[1])",
-    "mixed": "synthetic reads with the length mix of test_data/test.fq (1.8-23.6 kb, unit 200-1200 bp, 12% error), input order random",
-    "mixed_sorted": "synthetic reads with the length mix of test_data/test.fq (1.8-23.6 kb, unit 200-1200 bp, 12% error), input sorted by length",
+    "mixed": "synthetic reads with the length mix of test_data/test.fq (1.8-23.6 kb, unit 800-2400 bp, 12% error), input order random",
+    "mixed_sorted": "synthetic reads with the length mix of test_data/test.fq (1.8-23.6 kb, unit 800-2400 bp, 12% error), input sorted by length",
 }
 WORKLOAD = WORKLOADS["r2c2"]
 
@@ -55,34 +55,33 @@ def make_config(args, world):
     """The `config` object of the JSON line -- the same for both arms (the reference arm times a bounded sample of it)."""
     return {"workload": WORKLOADS[args.workload], "reads_per_gpu_per_step": args.reads, "options": "defaults, -f 1",
             "l2": "per-step working set (reads + DP arenas, > 1 GB) exceeds the 126 MB L2",
-            "parallelism": "read-sharded x%d by bases, no collective" % world, "lanes_per_gpu": max(1, args.lanes), "e2e_chunk_reads": args.chunk}
+            "parallelism": "read-sharded x%d, no collective%s" % (world, "" if args.workload == "r2c2" else "; %d units of equal predicted work per rank, dealt in snake order" % UNITS_PER_RANK), "lanes_per_gpu": max(1, args.lanes), "e2e_chunk_reads": args.chunk}
 
 
-def rank_reads(workload, n_per_gpu, rank, world):
-    """(names, seqs, first_index) of this rank's part of the step's batch of world x n_per_gpu reads.  r2c2: reads
-    [rank n, (rank + 1) n) of the generator.  mixed / mixed_sorted: the batch (sorted by nominal length for the latter) is
-    cut into contiguous parts of equal nominal bases (tidehunter_b200.shard.shard_range_by_work), as the sharded front end does."""
+UNITS_PER_RANK = 4
+
+
+def rank_units(workload, n_per_gpu, rank, world):
+    """This rank's share of the step's batch of world x n_per_gpu reads: a list of units (unit id, names, seqs, first_index).
+    r2c2 (uniform reads): one unit, reads [rank n, (rank + 1) n) of the generator.  mixed / mixed_sorted: the batch (sorted by
+    nominal length for the latter) is cut into world x UNITS_PER_RANK contiguous units of equal predicted work that are dealt
+    in snake order (tidehunter_b200.shard.cut_units / unit_owner), as the sharded front end does."""
     from tidehunter_b200 import synth
-    from tidehunter_b200.shard import shard_range_by_work
+    from tidehunter_b200.shard import cut_units, unit_owner, predicted_work
     if workload == "r2c2":
         names, seqs = synth.gen_reads("r2c2", n_per_gpu, start=rank * n_per_gpu)
-        return names, seqs, rank * n_per_gpu
+        return [(rank, names, seqs, rank * n_per_gpu)]
     import numpy as np
     tot = n_per_gpu * world
     nominal = synth.nominal_lengths("mixed", tot)
     order = np.argsort(nominal, kind="stable") if workload == "mixed_sorted" else np.arange(tot)
-    lo, hi = shard_range_by_work(nominal[order], rank, world)
-    names, seqs = synth.gen_reads_at("mixed", order[lo:hi])
-    return names, seqs, lo
-
-
-def load_peaks():
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(p.get("sm_max_mhz", 1965.0))
-    except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+    units = cut_units(predicted_work(nominal[order]), world * UNITS_PER_RANK)
+    out = []
+    for u, (lo, hi) in enumerate(units):
+        if unit_owner(u, world) == rank:
+            names, seqs = synth.gen_reads_at("mixed", order[lo:hi])
+            out.append((u, names, seqs, lo))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -145,8 +144,8 @@ def reference_arm(args):
     if args.workload == "r2c2":
         names, seqs = synth.gen_reads("r2c2", n, start=0)
     else:
-        names, seqs, _ = rank_reads(args.workload, args.reads, 0, max(1, args.gpus))
-        names, seqs = names[:n], seqs[:n]
+        units = rank_units(args.workload, args.reads, 0, max(1, args.gpus))   # rank 0's units: a cross-section of the batch
+        names = sum((u[1] for u in units), [])[:n]; seqs = sum((u[2] for u in units), [])[:n]
         n = len(seqs)
     bases = synth.total_bases(seqs)
     for _ in range(args.warmup):
@@ -295,6 +294,10 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly one line, the JSON: whatever libraries print to file descriptor 1 (NCCL's version line) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     import torch
@@ -308,7 +311,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL prints (its version line at WARN / INFO) stays off stdout: one JSON line
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
         gloo = dist.new_group(backend="gloo")  # host-side ordered gather only; no data-path collective
 
@@ -334,8 +336,9 @@ def main():
     # this rank's batch: read indices [rank*reads, (rank+1)*reads) of the seeded generator
     n = args.reads
     L = max(1, args.lanes)
-    names, seqs, first_index = rank_reads(args.workload, n, rank, world)
-    n = len(seqs)                                      # mixed workloads: equal bases per rank, not equal read counts
+    units = rank_units(args.workload, n, rank, world)
+    names = sum((u[1] for u in units), []); seqs = sum((u[2] for u in units), [])
+    n = len(seqs)                                      # mixed workloads: equal predicted work per rank, not equal read counts
     bases = synth.total_bases(seqs)
 
     # ---------------- device-resident leg (value) ----------------
@@ -402,9 +405,16 @@ def main():
     # once: tidehunter_b200.Batch); every step then runs th_host_run on those HOST buffers -- staging into pinned memory,
     # H2D, all kernels, D2H, record formatting -- and reads the output text where the library leaves it.
     th = T.TideHunter(device=local, out_fmt=1, chunk_reads=args.chunk, lanes=L)
-    batch = T.Batch(names, seqs)
+    from tidehunter_b200.shard import ordered_gather_units
+    batches = [(u[0], T.Batch(u[1], u[2]), u[3]) for u in units]
+    single = len(batches) == 1
+
+    def run_units():
+        if single:   # the library's own output buffer, no copy
+            return [th.run(batches[0][1], first_index=batches[0][2], copy=False)]
+        return [th.run(b, first_index=lo) for _, b, lo in batches]   # one th_host_run per unit, in input order
     for _ in range(2):
-        th.run(batch, first_index=first_index, copy=False)
+        run_units()
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
@@ -412,9 +422,9 @@ def main():
     t_run = t_gather = 0.0
     for _ in range(args.steps):
         ta = time.perf_counter()
-        text = th.run(batch, first_index=first_index, copy=False)
+        texts = run_units()
         tb = time.perf_counter()
-        parts = ordered_gather(text, rank, world, gloo)
+        parts = ordered_gather(texts[0], rank, world, gloo) if single else ordered_gather_units(texts, [b[0] for b in batches], rank, world, gloo)
         if parts is not None:
             out_bytes = sum(len(p) for p in parts)
         del parts
@@ -546,7 +556,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_configs and args.workload == "r2c2":
         line["configs"] = config_legs(local)
     if rank == 0:
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier(group=gloo)
         dist.destroy_process_group()

@@ -45,6 +45,35 @@ def test_work_balanced_ranges_tile_in_order_and_balance_bases():
     assert by_count > 1.5 * by_work
 
 
+def test_snake_dealt_units_balance_a_sorted_batch():
+    """cut_units + unit_owner: the units tile the input in order, every rank gets units_per_rank of them, and on a
+    length-sorted batch whose cost per base grows with the read length the busiest rank is close to the mean -- contiguous
+    parts of equal bases leave the last rank with several times the work."""
+    import numpy as np
+    from tidehunter_b200.shard import cut_units, unit_owner, predicted_work, shard_range_by_work
+    rng = np.random.default_rng(11)
+    lens = np.sort(rng.choice([1813, 2104, 2509, 3026, 3254, 3805, 5211, 6463, 9390, 23611], 40000))
+    cost = lens.astype(np.float64) * np.maximum(lens - 2500, 0)       # nothing below ~2 units, superlinear above
+    world, upr = 8, 4
+    units = cut_units(predicted_work(lens), world * upr)
+    assert units[0][0] == 0 and units[-1][1] == len(lens) and all(units[i][1] == units[i + 1][0] for i in range(len(units) - 1))
+    owners = [unit_owner(u, world) for u in range(len(units))]
+    assert owners[:world] == list(range(world)) and owners[world:2 * world] == list(range(world - 1, -1, -1))
+    assert all(owners.count(r) == upr for r in range(world))
+    load = np.zeros(world)
+    for u, (lo, hi) in enumerate(units):
+        load[owners[u]] += cost[lo:hi].sum()
+    contiguous = np.array([cost[slice(*shard_range_by_work(predicted_work(lens), r, world))].sum() for r in range(world)])
+    assert load.max() < 0.6 * contiguous.max()
+    assert load.max() / load.mean() < 1.6 < contiguous.max() / contiguous.mean()
+
+
+def test_unit_gather_orders_by_unit_id():
+    from tidehunter_b200.shard import ordered_gather_units
+    out = ordered_gather_units([b"bb", b"", b"dddd"], [1, 2, 3], 0, 1)
+    assert [bytes(x) for x in out] == [b"bb", b"", b"dddd"]
+
+
 def _worker(rank, world, port, q, shm=False):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
     if shm:  # what torchrun exports on a single node: the gather then goes through /dev/shm files

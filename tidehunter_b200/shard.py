@@ -1,10 +1,10 @@
 """Read-batch sharding across ranks and the host-side ordered gather.
 
 Reads are independent (the reference's only parallelism is a thread pool over reads, src/main.c:273-291),
-so rank r of W processes a contiguous block of every batch on its own GPU (shard_range_by_work: equal bases, not equal
-read counts) and
-there is no data-path collective.  Output order = input order: rank 0 concatenates the ranks' output
-texts in rank order, exactly what mini_tandem_output (src/main.c:214-271) prints for the whole batch.
+so a batch is cut into contiguous units of equal predicted work that are dealt to the ranks in snake order (cut_units,
+unit_owner), every rank processes its units on its own GPU, and
+there is no data-path collective.  Output order = input order: rank 0 concatenates the units' output
+texts in unit order, exactly what mini_tandem_output (src/main.c:214-271) prints for the whole batch.
 The gather runs over a gloo (host) group; NCCL / NVLink are not on the data path.
 """
 import os
@@ -17,9 +17,20 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+READ_OVERHEAD_BASES = 3000
+
+
+def predicted_work(lengths):
+    """Work of a read, in bases: its length plus a per-read cost.  Calibrated on one B200 from two workloads of different mean
+    read length (32,768 reads of 10.1 kb: 534 ms per step; 65,536 reads of 4.1 kb mean: 588 ms): time = 1.2 ns per base
+    + 4.0 us per read, i.e. a read costs as much as ~3,300 bases (block-per-read and thread-per-read kernels, launch tails)."""
+    import numpy as np
+    return np.asarray(lengths, dtype=np.int64) + READ_OVERHEAD_BASES
+
+
 def shard_range_by_work(work, rank, world):
     """Contiguous block of [0, len(work)) for `rank` such that the blocks of consecutive ranks tile the input in order and
-    carry about equal total `work` (per read: its length in bases -- seeding, chaining and consensus all grow with it).
+    carry about equal total `work` (per read: predicted_work of its length -- seeding, chaining and consensus all grow with it).
     The reference balances reads over its threads dynamically (src/main.c:273-291); with mixed read lengths equal read
     counts would be unequal work.  Block r ends at the first read where the running total reaches (r + 1) / world of the
     sum, so every rank derives the same cuts from the lengths alone."""
@@ -36,6 +47,22 @@ def shard_range_by_work(work, rank, world):
     cuts.append(n)
     cuts = [min(c, n) for c in cuts]
     return cuts[rank], cuts[rank + 1]
+
+
+def cut_units(work, n_units):
+    """Cuts [0, len(work)) into at most n_units contiguous units of about equal total work; returns [(lo, hi), ...]."""
+    n_units = max(1, int(n_units))
+    cuts = [shard_range_by_work(work, u, n_units) for u in range(n_units)]
+    return [(lo, hi) for lo, hi in cuts if hi > lo]
+
+
+def unit_owner(u, world):
+    """Rank that processes unit u: units are dealt in snake order (0 1 .. W-1, W-1 .. 1 0, 0 1 ..), so that a cost gradient
+    along the input -- reads sorted by length, where equal predicted work is not equal time because the cost per base grows
+    with the number of copies -- ends up spread over all ranks instead of on the last one ("length-sorted
+    bins dealt round-robin"; the reference's threads pull reads dynamically, src/main.c:273-291)."""
+    k, r = divmod(u, world)
+    return r if k % 2 == 0 else world - 1 - r
 
 
 _gather_seq = 0
@@ -86,10 +113,37 @@ def ordered_gather(payload, rank, world, group=None, dst=0):
     return out
 
 
-def run_sharded(th, names, seqs, rank, world, group=None):
-    """Process this rank's block of (names, seqs) with `th` (a tidehunter_b200.TideHunter) and gather the
-    text on rank 0 in input order.  Returns bytes on rank 0, None elsewhere."""
-    lo, hi = shard_range_by_work([len(x) for x in seqs], rank, world)
-    text = th.run(names[lo:hi], seqs[lo:hi], first_index=lo)   # global read index: the FASTQ quality slot follows it
-    parts = ordered_gather(text, rank, world, group)
+def ordered_gather_units(texts, unit_ids, rank, world, group=None, dst=0):
+    """Gather of per-unit output texts: every rank hands in the texts of the units it processed (`unit_ids`, ascending) and
+    `dst` gets all texts ordered by unit id (a list of bytes-like objects), None elsewhere.  One payload per rank travels
+    through ordered_gather (the texts back to back behind a small index), so the transport is the same."""
+    import json
+    import struct
+    index = json.dumps([[int(u), len(t)] for u, t in zip(unit_ids, texts)]).encode()
+    payload = b"".join([struct.pack("<q", len(index)), index] + [bytes(t) if not isinstance(t, (bytes, bytearray, memoryview)) else t for t in texts])
+    parts = ordered_gather(payload, rank, world, group, dst)
+    if parts is None:
+        return None
+    by_unit = {}
+    for p in parts:
+        mv = memoryview(p)
+        (il,) = struct.unpack("<q", bytes(mv[:8]))
+        off = 8 + il
+        for u, ln in json.loads(bytes(mv[8:8 + il])):
+            by_unit[u] = mv[off:off + ln]
+            off += ln
+    return [by_unit[u] for u in sorted(by_unit)]
+
+
+def run_sharded(th, names, seqs, rank, world, group=None, units_per_rank=4):
+    """Process this rank's share of (names, seqs) with `th` (a tidehunter_b200.TideHunter) and gather the text on rank 0 in
+    input order.  The input is cut into world x units_per_rank contiguous units of equal predicted work, dealt in snake
+    order (unit_owner); a unit is one th.run call, told the global index of its first read (FASTQ quality slots follow
+    it).  Returns bytes on rank 0, None elsewhere."""
+    if world == 1:
+        return th.run(names, seqs)
+    units = cut_units(predicted_work([len(x) for x in seqs]), world * units_per_rank)
+    mine = [u for u in range(len(units)) if unit_owner(u, world) == rank]
+    texts = [th.run(names[units[u][0]:units[u][1]], seqs[units[u][0]:units[u][1]], first_index=units[u][0]) for u in mine]
+    parts = ordered_gather_units(texts, mine, rank, world, group)
     return b"".join(bytes(p) for p in parts) if parts is not None else None

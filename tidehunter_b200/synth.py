@@ -10,7 +10,7 @@ Shapes (BASELINE.json `configs`):
   r2c2   : unit 1000, 10 copies, err 0.15            (config 2, the bench workload)
   short  : unit U{50..200}, copies U{20..50}, err 0.10  (config 3)
   long   : unit U{4000..5000}, copies U{2..4}, err 0.20  (config 4)
-  mixed  : read length drawn from test_data/test.fq's 100 lengths (1.8 - 23.6 kb), unit U{200..1200}, err 0.12
+  mixed  : read length drawn from test_data/test.fq's 100 lengths (1.8 - 23.6 kb), unit U{800..2400} (test.fq's consensus lengths), err 0.12
 """
 import numpy as np
 
@@ -27,7 +27,9 @@ TESTFQ_LENGTHS = [1813, 1885, 1894, 2012, 2028, 2031, 2080, 2092, 2104, 2114, 21
                   3023, 3026, 3029, 3116, 3127, 3134, 3136, 3161, 3182, 3191, 3192, 3194, 3221, 3238, 3254, 3278, 3311, 3317, 3348, 3390,
                   3411, 3465, 3478, 3538, 3560, 3607, 3745, 3805, 4131, 4183, 4464, 4597, 4640, 4717, 4745, 4868, 5197, 5208, 5211, 5231,
                   5269, 5326, 5572, 5696, 6042, 6044, 6089, 6269, 6463, 6807, 6943, 7152, 7461, 7535, 7604, 7861, 8471, 9390, 14329, 23611]
-SHAPES["mixed"] = dict(unit=(200, 1200), lengths=TESTFQ_LENGTHS, err=0.12, sid=3)
+SHAPES["mixed"] = dict(unit=(800, 2400), lengths=TESTFQ_LENGTHS, err=0.12, sid=3)   # units: the range of test.fq's consensus lengths (880 - 2416)
+SHAPES["mixed23k"] = dict(unit=(800, 2400), lengths=[23611], err=0.12, sid=4)    # the two ends of the mix, for per-stage profiles
+SHAPES["mixed2k"] = dict(unit=(800, 2400), lengths=TESTFQ_LENGTHS[:10], err=0.12, sid=5)
 FLANK = 50
 
 
