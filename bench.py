@@ -58,6 +58,15 @@ def make_config(args, world):
             "parallelism": "read-sharded x%d, no collective%s" % (world, "" if args.workload == "r2c2" else "; %d units of equal predicted work per rank, dealt in snake order" % UNITS_PER_RANK), "lanes_per_gpu": max(1, args.lanes), "e2e_chunk_reads": args.chunk}
 
 
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(p.get("sm_max_mhz", 1965.0))
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
 UNITS_PER_RANK = 4
 
 
