@@ -84,7 +84,7 @@ def rank_units(workload, n_per_gpu, rank, world):
     tot = n_per_gpu * world
     nominal = synth.nominal_lengths("mixed", tot)
     order = np.argsort(nominal, kind="stable") if workload == "mixed_sorted" else np.arange(tot)
-    units = cut_units(predicted_work(nominal[order]), world * UNITS_PER_RANK)
+    units = cut_units(predicted_work(nominal[order]), world * UNITS_PER_RANK if world > 1 else 1)   # one process: one th_host_run over everything
     out = []
     for u, (lo, hi) in enumerate(units):
         if unit_owner(u, world) == rank:
