@@ -380,7 +380,9 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         size_t budget = (size_t)((double)(free_b + c->d_slabs.cap) * 0.6);
         budget = std::min(budget, total_b / 5); // several contexts share the device (the host layer runs four): none may take it all
         constexpr int GPB16 = POA_WARPS * 2, GPB32 = POA_WARPS;
-        int ngroups = (int)std::min<size_t>((size_t)(c->n_sm * POA_MIN_BLOCKS16 * GPB16 * c->share), std::max<size_t>(1, budget / slab_typ));
+        double poa_blocks = POA_MIN_BLOCKS16;            // resident POA blocks per SM this context asks for (tuning: TH_POA_BLOCKS)
+        if (const char *e = getenv("TH_POA_BLOCKS")) { const double v = atof(e); if (v >= 0.5 && v <= POA_MIN_BLOCKS16) poa_blocks = v; }
+        int ngroups = (int)std::min<size_t>((size_t)(c->n_sm * poa_blocks * GPB16 * c->share), std::max<size_t>(1, budget / slab_typ));
         ngroups = std::min(ngroups, std::max(nt, 1));
         int grid = (ngroups + GPB16 - 1) / GPB16;
         // several contexts of one process (the host layer's lanes) size their slabs from the same free-memory reading:
