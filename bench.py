@@ -196,7 +196,7 @@ def config_legs(device):
     cores = os.cpu_count() or 1
     legs = [
         ("configs[2] short units 50-200 bp x 20-50 copies, 10% error, -f 2", lambda n: synth.gen_reads("short", n, start=700000), 16384, 1024, ["-f", "2"], dict(out_fmt=2)),
-        ("configs[3] long units 4-5 kb x 2-4 copies, 20% error, -f 2", lambda n: synth.gen_reads("long", n, start=700000), 3072, 320, ["-f", "2"], dict(out_fmt=2)),
+        ("configs[3] long units 4-5 kb x 2-4 copies, 20% error, -f 2", lambda n: synth.gen_reads("long", n, start=700000), 8192, 320, ["-f", "2"], dict(out_fmt=2)),
         ("configs[4] adapters -5 -3 -u -f 2 (unit output)", lambda n: synth.gen_reads("r2c2", n, start=700000, adapters=(five, three)), 8192, 768, ["ADAPTERS", "-u", "-f", "2"],
          dict(out_fmt=2, five_seq=five, three_seq=three, only_unit=1)),
         ("configs[4] adapters -5 -3 -F -f 2 (full-length consensus)", lambda n: synth.gen_reads("r2c2", n, start=700000, adapters=(five, three), three_rc=True), 8192, 512,

@@ -67,7 +67,7 @@ def main():
                 opt("-m", "min_len", rnd.choice([5, 30, 100, 500]))
             if rnd.random() < 0.2:
                 argv.append("-l"); kw["only_longest"] = 1
-            if os.environ.get("TH_FUZZ_LINEAR") and engine != "gpu":      # abPOA's linear gap mode: the oracle restates it, the GPU path rejects it
+            if os.environ.get("TH_FUZZ_LINEAR") or (engine == "gpu" and rnd.random() < 0.1):  # abPOA's linear gap mode (oracle restatement; GPU: wide pass)
                 o2 = rnd.choice([0, 24]); argv.extend(["-O", "0,%d" % o2]); kw["gap_open1"] = 0; kw["gap_open2"] = o2
             elif rnd.random() < 0.25 or os.environ.get("TH_FUZZ_AFFINE"):
                 o1 = rnd.choice([2, 4, 6]); o2 = 0 if os.environ.get("TH_FUZZ_AFFINE") else rnd.choice([0, 12, 24, 40])
