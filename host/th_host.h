@@ -49,8 +49,11 @@ void th_host_destroy(th_host *h);
  * calls so that the FASTQ quality slot-reuse quirk of the reference (src/main.c:266-267) is kept. */
 const char *th_host_run(th_host *h, int n, const char *const *names, const char *const *seqs, const int32_t *lens, size_t *out_len);
 
-/* Index, in the whole input, of the first read of the NEXT th_host_run.  Only a process that handles part of an input (one
- * rank of a sharded run) needs it: the reference's FASTQ quality slot is read_index % 4096 of the whole input (src/main.c:266-267). */
+/* Index, in the whole input, of the first read of the NEXT th_host_run, for a process that handles part of an input (one
+ * rank of a sharded run): quality slots are then numbered as in the whole input.  That alone does not make a part's FASTQ
+ * output (-f 3/4) equal to the reference's beyond 4,096 reads: the reference never rewinds a slot's quality buffer
+ * (src/main.c:262-266), so from read 4,096 on it prints the qualities of the FIRST record ever written to the slot, which may
+ * belong to another process's part.  Sharded FASTA / tabular output is exact; sharded FASTQ is exact up to 4,096 reads. */
 void th_host_set_read_index(th_host *h, long long first);
 /* stats of the last th_host_run (summed over its chunks) */
 void th_host_stats(const th_host *h, th_gpu_stats *s);

@@ -372,3 +372,23 @@ def test_option_sets_found_by_fuzzing(T):
         out = th.run(names, seqs)
         th.close()
         assert hashlib.md5(out).hexdigest() == c["md5"], c["args"]
+
+
+def test_sharded_parts_concatenate_to_the_whole(T):
+    """Two processes' parts of one input, each through its own object (different chunking and lanes, one through a Batch and
+    the zero-copy view): the outputs concatenate to the single-process output -- for FASTQ as long as the input has at most
+    4,096 reads (beyond that the reference prints stale quality bytes of the read 4,096 positions earlier from a buffer it
+    never rewinds, src/main.c:262-266, which a part that starts elsewhere cannot know), for the tabular format always."""
+    from tidehunter_b200 import synth
+    for fmt, n, cut in ((3, 3000, 1700), (2, 4600, 4300)):
+        names, seqs = synth.gen_reads("short", n, start=31000)
+        th = T.TideHunter(out_fmt=fmt, chunk_reads=1024, lanes=2)
+        whole = th.run(names, seqs)
+        th.close()
+        a = T.TideHunter(out_fmt=fmt, chunk_reads=1024, lanes=2)
+        b = T.TideHunter(out_fmt=fmt, chunk_reads=700, lanes=3)
+        pa = a.run(names[:cut], seqs[:cut])
+        pb = bytes(b.run(T.Batch(names[cut:], seqs[cut:]), first_index=cut, copy=False))
+        a.close(); b.close()
+        assert pa + pb == whole, fmt
+        assert whole.count(b"\n") > n

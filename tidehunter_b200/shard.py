@@ -138,8 +138,8 @@ def ordered_gather_units(texts, unit_ids, rank, world, group=None, dst=0):
 def run_sharded(th, names, seqs, rank, world, group=None, units_per_rank=4):
     """Process this rank's share of (names, seqs) with `th` (a tidehunter_b200.TideHunter) and gather the text on rank 0 in
     input order.  The input is cut into world x units_per_rank contiguous units of equal predicted work, dealt in snake
-    order (unit_owner); a unit is one th.run call, told the global index of its first read (FASTQ quality slots follow
-    it).  Returns bytes on rank 0, None elsewhere."""
+    order (unit_owner); a unit is one th.run call, told the global index of its first read.  Exact for FASTA / tabular
+    output; FASTQ (-f 3/4) is exact up to 4,096 reads (host/th_host.h: the reference's never-rewound quality buffers).  Returns bytes on rank 0, None elsewhere."""
     if world == 1:
         return th.run(names, seqs)
     units = cut_units(predicted_work([len(x) for x in seqs]), world * units_per_rank)
