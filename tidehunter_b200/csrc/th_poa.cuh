@@ -1225,6 +1225,7 @@ __device__ void poa_add_sequence(PoaSmem<LPT> &sm, const DevParams &P, const uin
                         }
                         poa_chunk_carry<LPT>(g, P, Hf, Fa, Fb, carryH, carryF);
                     }
+                    __syncwarp();                       // the staged predecessor metadata has been read: a later step may overwrite it
                     if (tf) {
                         const int hm1 = A16[(uint32_t)mi.x + (uint32_t)(j - 1 - ib)];
                         bool hit = false, bad = false;
