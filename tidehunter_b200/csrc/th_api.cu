@@ -83,7 +83,7 @@ struct th_gpu_ctx {
     DBuf d_parstream, d_parused, d_pardoff;
     DBuf d_tasks, d_torder, d_ustart, d_ulen, d_slabs, d_consb, d_consc, d_consl, d_tstatus, d_items, d_iden, d_ext;
     DBuf d_gsrc, d_gdst, d_glen, d_dense_b, d_dense_c, d_redo;
-    DBuf d_tcounts, d_totals, d_tkey, d_ekey, d_eorder, d_left, d_pos, d_rtoff, d_tposoff, d_tnseqs, d_tconsoff, d_retry;
+    DBuf d_tcounts, d_totals, d_tkey, d_ekey, d_eorder, d_left, d_pos, d_rtoff, d_tposoff, d_tnseqs, d_tconsoff, d_retry, d_rorder;
     // host result storage (pinned: the final copies are asynchronous and the host waits once)
     HBuf h_totals, h_rtoff, h_tposoff, h_pos, h_tnseqs, h_tconsoff, h_tstatus, h_iden, h_ext, h_rstatus, h_counters, h_consb, h_consc;
     th_gpu_stats stats;
@@ -168,7 +168,7 @@ extern "C" void th_gpu_destroy(th_gpu_ctx *c) {
                   &c->d_pchlen, &c->d_par, &c->d_paroff, &c->d_parn, &c->d_rstatus, &c->d_scratch, &c->d_scratch2, &c->d_bnd, &c->d_rev, &c->d_counters,
                   &c->d_parstream, &c->d_parused, &c->d_pardoff, &c->d_tasks, &c->d_torder, &c->d_ustart, &c->d_ulen, &c->d_slabs, &c->d_consb, &c->d_consc,
                   &c->d_consl, &c->d_tstatus, &c->d_items, &c->d_iden, &c->d_ext, &c->d_gsrc, &c->d_gdst, &c->d_glen, &c->d_dense_b, &c->d_dense_c, &c->d_redo,
-                  &c->d_tcounts, &c->d_totals, &c->d_tkey, &c->d_ekey, &c->d_eorder, &c->d_left, &c->d_pos, &c->d_rtoff, &c->d_tposoff, &c->d_tnseqs, &c->d_tconsoff, &c->d_retry};
+                  &c->d_tcounts, &c->d_totals, &c->d_tkey, &c->d_ekey, &c->d_eorder, &c->d_left, &c->d_pos, &c->d_rtoff, &c->d_tposoff, &c->d_tnseqs, &c->d_tconsoff, &c->d_retry, &c->d_rorder};
     for (DBuf *b : ds) b->release();
     HBuf *hs[] = {&c->h_ascii, &c->h_totals, &c->h_rtoff, &c->h_tposoff, &c->h_pos, &c->h_tnseqs, &c->h_tconsoff, &c->h_tstatus, &c->h_iden, &c->h_ext, &c->h_rstatus,
                   &c->h_counters, &c->h_consb, &c->h_consc};
@@ -296,13 +296,17 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     // ---- chain DP ----
     {
         const int grid = std::min((n + CHAIN_WARPS - 1) / CHAIN_WARPS, std::max(1, (int)(c->n_sm * CHAIN_BLOCKS_PER_SM * c->share)));
+        if (c->d_rorder.ensure(4 * (size_t)n + 64)) return -1;
+        bucket_order_kernel<<<1, 1024, 0, st>>>(nullptr, 0, nullptr, c->d_nhits.as<int32_t>(), c->d_rorder.as<int32_t>(), n, c->max_len); // reads by hit count, most first
         if (P.max_p < (1u << 27)) // hit periods are <= max_p (src/tandem_hit.c:204): the 1.8x gate fits 32-bit products
             chain_dp_kernel<true><<<grid, CHAIN_WARPS * 32, 0, st>>>(P, n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(),
-                                                                  c->d_score.as<int32_t>(), c->d_from.as<int32_t>(), c->d_gflag.as<int32_t>(), cnt64 + 0);
+                                                                  c->d_score.as<int32_t>(), c->d_from.as<int32_t>(), c->d_gflag.as<int32_t>(), cnt64 + 0,
+                                                                  c->d_rorder.as<int32_t>(), cnt32 + 7);
         else
             chain_dp_kernel<false><<<grid, CHAIN_WARPS * 32, 0, st>>>(P, n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(),
-                                                                   c->d_score.as<int32_t>(), c->d_from.as<int32_t>(), c->d_gflag.as<int32_t>(), cnt64 + 0);
-        S.n_launches++;
+                                                                   c->d_score.as<int32_t>(), c->d_from.as<int32_t>(), c->d_gflag.as<int32_t>(), cnt64 + 0,
+                                                                   c->d_rorder.as<int32_t>(), cnt32 + 7);
+        S.n_launches += 2;
         if (P.w > 1) { // repeated ends can only come from minimizer seeds
             chain_dp_generic_kernel<<<(n + 63) / 64, 64, 0, st>>>(P, n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(),
                                                                 c->d_score.as<int32_t>(), c->d_from.as<int32_t>(), c->d_gflag.as<int32_t>(), c->d_rank.as<int32_t>());

@@ -42,11 +42,17 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32)
 chain_dp_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ nhits,
                 const int32_t *__restrict__ hend, const int32_t *__restrict__ hper,
                 int32_t *score, int32_t *from, int32_t *__restrict__ generic_flag,
-                unsigned long long *__restrict__ eval_count) {
+                unsigned long long *__restrict__ eval_count, const int32_t *__restrict__ order, int *__restrict__ next_read) {
     const int lane = lane_id();
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     unsigned long long evals = 0;
-    for (int r = wid; r < n_reads; r += nw) {
+    // a read is one warp from start to end, and its time grows with hits x hits per period: warps take the reads from a
+    // queue ordered by hit count, most hits first, so that the longest reads do not start last
+    while (true) {
+        int qi = 0;
+        if (lane == 0) qi = atomicAdd(next_read, 1);
+        qi = __shfl_sync(TH_FULL, qi, 0);
+        if (qi >= n_reads) break;
+        const int r = order[qi];
         const int n = nhits[r];
         const int64_t off = roff[r];
         const int32_t *en = hend + off, *pr = hper + off;

@@ -175,15 +175,16 @@ __global__ void task_pair_left_kernel(const TaskTotals *__restrict__ tot, const 
 // Order by decreasing key in 1024 size classes (a counting sort; the order inside a class is arbitrary).  Used for the task
 // order of the persistent POA groups (largest first: the order only balances the load, every task's result is independent
 // of it) and to pair boundary extensions of similar target length.  n = mult x tot->n[TC_TASKS].  One block.
+// n_direct >= 0: n and the largest key are given by the caller instead (the chaining DP's read order by hit count).
 __global__ void __launch_bounds__(1024) bucket_order_kernel(const TaskTotals *__restrict__ tot, int mult, const int32_t *__restrict__ max_key,
-                                                            const int32_t *__restrict__ key, int32_t *__restrict__ order) {
+                                                            const int32_t *__restrict__ key, int32_t *__restrict__ order, int n_direct = -1, int max_key_direct = 1) {
     __shared__ int s_cnt[1024], s_part[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int nt = mult * tot->n[TC_TASKS];
-    const unsigned long long mk = (unsigned long long)max(*max_key, 1);
+    const int nt = n_direct >= 0 ? n_direct : mult * tot->n[TC_TASKS];
+    const unsigned long long mk = (unsigned long long)max(n_direct >= 0 ? max_key_direct : *max_key, 1);
     s_cnt[tid] = 0;
     __syncthreads();
-    for (int t = tid; t < nt; t += 1024) atomicAdd(&s_cnt[1023 - (int)((unsigned long long)key[t] * 1023ull / mk)], 1);
+    for (int t = tid; t < nt; t += 1024) atomicAdd(&s_cnt[1023 - (int)min((unsigned long long)key[t] * 1023ull / mk, 1023ull)], 1);
     __syncthreads();
     { // exclusive scan of the 1024 counts
         const int v = s_cnt[tid]; int inc = v;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(1024) bucket_order_kernel(const TaskTotals *__
         s_cnt[tid] = s_part[wid] + inc - v;
     }
     __syncthreads();
-    for (int t = tid; t < nt; t += 1024) order[atomicAdd(&s_cnt[1023 - (int)((unsigned long long)key[t] * 1023ull / mk)], 1)] = t;
+    for (int t = tid; t < nt; t += 1024) order[atomicAdd(&s_cnt[1023 - (int)min((unsigned long long)key[t] * 1023ull / mk, 1023ull)], 1)] = t;
 }
 
 // dense consensus offsets: exclusive prefix sum of cons_len over the tasks (one block), total to tot->cons_total
