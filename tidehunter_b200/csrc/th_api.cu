@@ -337,7 +337,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         partition_kernel<<<grid, PART_WARPS * 32, 0, st>>>(P, n, roff, rlen, c->d_bseq.as<uint8_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(), c->d_cells.as<int32_t>(),
                                                           c->d_pchn.as<int32_t>(), c->d_pchoff.as<int32_t>(), c->d_pchlen.as<int32_t>(), c->d_par.as<int32_t>(),
                                                           c->d_paroff.as<int32_t>(), c->d_parn.as<int32_t>(), c->d_bnd.as<int4>(), bnd_stride, cnt32 + 0,
-                                                          c->d_rstatus.as<int32_t>(), cnt64 + 3);
+                                                          c->d_rstatus.as<int32_t>(), cnt64 + 3, c->d_rorder.as<int32_t>());
         task_count_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, c->params.min_copy, roff, rlen, c->d_pchn.as<int32_t>(), c->d_par.as<int32_t>(), c->d_paroff.as<int32_t>(),
                                                           c->d_parn.as<int32_t>(), c->d_nhits.as<int32_t>(), c->d_tcounts.as<int32_t>(), d_tot);
         task_scan_kernel<<<1, 1024, 0, st>>>(n, c->d_tcounts.as<int32_t>(), d_tot);

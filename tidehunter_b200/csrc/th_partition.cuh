@@ -24,7 +24,7 @@ partition_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, con
                  const int32_t *__restrict__ cells, const int32_t *__restrict__ pch_n, const int32_t *__restrict__ pch_off,
                  const int32_t *__restrict__ pch_len, int32_t *__restrict__ par, int32_t *__restrict__ par_off, int32_t *__restrict__ par_n,
                  int4 *bnd_all, int64_t bnd_stride, int *read_counter, int32_t *__restrict__ read_status,
-                 unsigned long long *__restrict__ stat_cells) {
+                 unsigned long long *__restrict__ stat_cells, const int32_t *__restrict__ order) {
     const int lane = lane_id();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int4 *bnd = bnd_all + (int64_t)gw * bnd_stride;
@@ -35,6 +35,7 @@ partition_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, con
         if (lane == 0) r = atomicAdd(read_counter, 1);
         r = __shfl_sync(TH_FULL, r, 0);
         if (r >= n_reads) break;
+        r = order[r];                                  // reads with the most hits first (the chaining DP's queue order)
         const int nch = pch_n[r];
         if (nch == 0) continue;
         const int64_t off = roff[r], hoff = off / 2; const int L = rlen[r];
