@@ -395,7 +395,7 @@ def main():
             for st in STAGES + ("total",):
                 acc[st] += s["ms_" + st]
             launches += s["n_launches"]
-    for key in ("n_bases", "n_hits", "n_chain_evals", "n_poa_cells", "n_poa_rows", "n_ksw_cells", "n_tasks"):
+    for key in ("n_bases", "n_hits", "n_chain_evals", "n_poa_cells", "n_poa_rows", "n_ksw_cells", "n_ksw_cells_full", "n_tasks"):
         cnt[key] = sum(lane_stats[k][-1][key] for k in range(L))   # per step, all lanes
     n_tasks = cnt["n_tasks"]
     # one lane alone (serial stages, nothing co-running): the per-kernel times comparable with the ncu launch list
@@ -465,11 +465,16 @@ def main():
             if k in key_of and ms_per_launch[k] > 0:
                 e["unit"] = unit_name[k]
                 e["g_units_per_s"] = round(counts[key_of[k]] / (ms_per_launch[k] * 1e-3) / 1e9, 3)
+                if k == "ksw" and counts.get("n_ksw_cells_full"):
+                    # `cells` = cells computed (certified bands of the identity alignments, cut extension matrices); the
+                    # reference computes the full matrices: their cells per second is the rate comparable with a CPU's GCUPS
+                    e["computed_share_of_full_matrices"] = round(counts["n_ksw_cells"] / counts["n_ksw_cells_full"], 4)
+                    e["g_full_matrix_cells_per_s"] = round(counts["n_ksw_cells_full"] / (ms_per_launch[k] * 1e-3) / 1e9, 3)
             out[k] = e
         return out
 
     over_ms = {k: acc[k] / (args.steps * L) for k in STAGES}
-    over_cnt = {key: cnt[key] / L for key in key_of.values()}
+    over_cnt = {key: cnt[key] / L for key in list(key_of.values()) + ["n_ksw_cells_full"]}
     kernels_over = table(over_ms, over_cnt)
     if L > 1:
         kernels = table(serial, serial_cnt)
@@ -479,9 +484,9 @@ def main():
     dom = max(("poa", "ksw", "chain", "seed", "pack"), key=lambda k: ser_ms[k])
     # Algorithmic HBM bytes per unit: POA stores 7 B per banded cell (H, E1, E2 as int16 + one code
     # byte) and reads the three planes once more as a predecessor row or in the backtrack (13 B/cell); ksw keeps its rows in
-    # registers (boundary hand-off only: 16 B per target row per 512-column block, ~0.03 B/cell); chaining reads 12 B per
+    # registers (boundary hand-off only: 16 B per target row per 256-column block, ~0.06 B/cell); chaining reads 12 B per
     # evaluated predecessor (L1/L2 hits); seeding reads L/4 + L/8 bytes and writes 8 B per hit; packing 1 B in, 1.375 B out.
-    bytes_per_unit = {"poa": 13.0, "ksw": 16.0 / 512, "chain": 12.0, "seed": None, "pack": 1.0 + 1.0 + 0.25 + 0.125}
+    bytes_per_unit = {"poa": 13.0, "ksw": 16.0 / 256, "chain": 12.0, "seed": None, "pack": 1.0 + 1.0 + 0.25 + 0.125}
     bound_of = {"pack": "hbm", "seed": "hbm", "chain": "int", "poa": "int", "ksw": "int"}
     ncu = load_ncu_constants()
     n_sm = 148

@@ -495,7 +495,7 @@ static void add_stats(th_gpu_stats *a, const th_gpu_stats *b) {
     a->ms_h2d += b->ms_h2d; a->ms_pack += b->ms_pack; a->ms_seed += b->ms_seed; a->ms_chain += b->ms_chain; a->ms_select += b->ms_select;
     a->ms_partition += b->ms_partition; a->ms_poa += b->ms_poa; a->ms_ksw += b->ms_ksw; a->ms_d2h += b->ms_d2h; a->ms_total += b->ms_total;
     a->n_bases += b->n_bases; a->n_hits += b->n_hits; a->n_chain_evals += b->n_chain_evals; a->n_poa_cells += b->n_poa_cells; a->n_poa_rows += b->n_poa_rows;
-    a->n_ksw_cells += b->n_ksw_cells; a->n_tasks += b->n_tasks; a->n_launches += b->n_launches; a->h2d_bytes += b->h2d_bytes; a->d2h_bytes += b->d2h_bytes;
+    a->n_ksw_cells += b->n_ksw_cells; a->n_tasks += b->n_tasks; a->n_launches += b->n_launches; a->h2d_bytes += b->h2d_bytes; a->d2h_bytes += b->d2h_bytes; a->n_ksw_cells_full += b->n_ksw_cells_full;
 }
 
 /* One th_host_run in flight.  Chunks are cut by work, not only by count: a chunk ends after chunk_reads reads or once it

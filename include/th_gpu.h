@@ -48,6 +48,8 @@ typedef struct {
     int64_t n_bases, n_hits, n_chain_evals, n_poa_cells, n_poa_rows, n_ksw_cells, n_tasks;
     int64_t n_launches;                /* kernels launched for the chunk */
     int64_t h2d_bytes, d2h_bytes;
+    int64_t n_ksw_cells_full;          /* n_ksw_cells counts the cells computed (certified bands, cut extension matrices);
+                                          this is the full matrices' count, i.e. what the reference computes */
 } th_gpu_stats;
 
 /* Result of one chunk: structure of arrays, owned by the context, valid until the next call on it.

@@ -35,7 +35,7 @@ def test_abi_structs_match_header_sizes():
     import tidehunter_b200 as T
     # th_gpu_params: 4 x i32, f64, 2 x i64, 6 x i32, 3 x i32 -> 16 + 8 + 16 + 36 (+4 pad) = 80
     assert C.sizeof(T.GpuParams) == 80
-    assert C.sizeof(T.GpuStats) == 10 * 4 + 10 * 8
+    assert C.sizeof(T.GpuStats) == 10 * 4 + 11 * 8
     p = T.GpuParams()
     T.gpu_lib().th_gpu_default_params(C.byref(p))
     assert (p.k, p.w, p.min_copy, p.min_p, p.max_p, p.simd_lanes16) == (8, 1, 2, 30, 10000, 16)

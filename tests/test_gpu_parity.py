@@ -128,6 +128,41 @@ def test_ksw_global_and_extension(T, oracle):
     ctx.close()
 
 
+def test_ksw_banded_pair_identity(T, oracle):
+    """The packed identity alignments as ksw_pair_kernel runs them (two per warp, certified band first, th_ksw.cuh): the
+    identity counts equal the oracle's full-matrix ksw2 whatever the first band width, and every path through the retry
+    logic (certified at the first width, at the second, full matrix at once, full matrix after failed bands) is taken."""
+    rng = np.random.default_rng(11)
+    pairs = []
+    for div, lo, hi, n in ((0.10, 600, 1500, 16), (0.15, 900, 1100, 24), (0.15, 1500, 2600, 8), (0.25, 700, 1400, 16), (0.20, 3000, 4500, 4),
+                           (0.15, 1, 300, 24), (0.45, 600, 1200, 8)):
+        pairs += H.random_pairs(rng, n, lo, hi, div=div)
+    for _ in range(12):  # low complexity and internal repeats (many co-optimal paths), unrelated pairs, one long indel
+        m = int(rng.integers(1, 6))
+        u = np.tile(rng.integers(0, 4, m, dtype=np.uint8), 900 // m)
+        pairs.append((H.random_pairs(rng, 1, 1, 1)[0][0] + u.tobytes(), u[: int(rng.integers(500, 880))].tobytes()))
+        v = np.tile(rng.integers(0, 4, 97, dtype=np.uint8), 9).tobytes()
+        pairs.append((v, v[int(rng.integers(0, 300)):]))
+        pairs.append((rng.integers(0, 4, int(rng.integers(600, 1200)), dtype=np.uint8).tobytes(), rng.integers(0, 4, int(rng.integers(600, 1200)), dtype=np.uint8).tobytes()))
+        w = rng.integers(0, 4, 1200, dtype=np.uint8)
+        k = int(rng.integers(40, 400))
+        pairs.append((np.concatenate([w[:500], w[500 + k:]]).tobytes(), w.tobytes()))
+        pairs.append((w.tobytes(), np.concatenate([w[:300], w[300 + k:]]).tobytes()))
+    order = rng.permutation(len(pairs))  # neighbours in the list are packed together: mix lengths and kinds
+    pairs = [pairs[i] for i in order] + pairs[:1]  # odd count: the last entry runs packed with itself
+    qs = [p[0] for p in pairs]; ts = [p[1] for p in pairs]
+    exp = [H.ksw_global(q, t)[0] for q, t in pairs]
+    ctx = T.GpuContext()
+    paths = set()
+    for alpha in (0, 20, 60, 120, 250, 400):
+        g = ctx.ksw_batch(4, qs, ts, [alpha] * len(pairs))
+        bad = [(alpha, i, len(qs[i]), len(ts[i]), g[i], exp[i]) for i in range(len(pairs)) if g[i][0] != exp[i]]
+        assert not bad, ("packed banded identity", bad[:8])
+        paths |= {x[1] for x in g}
+    ctx.close()
+    assert {0, 1, 2}.issubset(paths) and (3 in paths or 4 in paths), paths
+
+
 def _run_case(T, golden_inputs, c, **extra):
     names, seqs = golden_inputs(c["input"])
     th = T.TideHunter(**dict(c["para"], **extra))

@@ -27,7 +27,7 @@ class GpuStats(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("ms_h2d", "ms_pack", "ms_seed", "ms_chain", "ms_select", "ms_partition",
                                          "ms_poa", "ms_ksw", "ms_d2h", "ms_total")] + \
                [(n, C.c_int64) for n in ("n_bases", "n_hits", "n_chain_evals", "n_poa_cells", "n_poa_rows",
-                                         "n_ksw_cells", "n_tasks", "n_launches", "h2d_bytes", "d2h_bytes")]
+                                         "n_ksw_cells", "n_tasks", "n_launches", "h2d_bytes", "d2h_bytes", "n_ksw_cells_full")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

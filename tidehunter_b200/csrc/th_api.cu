@@ -228,6 +228,16 @@ __global__ void ksw_test_kernel(int n, int mode, const uint8_t *__restrict__ buf
     if (mode == 0) ksw_warp<KSW_GLOBAL, 16>(buf + qoff[w], ql[w], buf + toff[w], tl[w], 0, bnd, o0, o1);
     else if (mode == 1) ksw_warp<KSW_GLOBAL_STOP, 4>(buf + qoff[w], ql[w], buf + toff[w], tl[w], ql[w] - arg[w], bnd, o0, o1);
     else if (mode == 2) ksw_warp<KSW_EXT, 16>(buf + qoff[w], ql[w], buf + toff[w], tl[w], 0, bnd, o0, o1);
+    else if (mode == 4) { // entries 2k and 2k + 1 as the two halves of one packed identity alignment, exactly as ksw_pair_kernel runs it;
+        // arg = first band half-width in thousandths of the length (0: the kernel's default); out = (identity, path taken)
+        if (w & 1) return;
+        const int v = w + 1 < n ? w + 1 : w;
+        float alpha = arg[w] > 0 ? 0.001f * (float)arg[w] : KSW_BAND_ALPHA0;
+        int a = 0, b = 0, path = 0; unsigned long long nc = 0;
+        ksw_pair_identity<KSW2_C>(buf + qoff[w], ql[w], buf + toff[w], tl[w], buf + qoff[v], ql[v], buf + toff[v], tl[v], bnd, alpha, a, b, nc, &path);
+        if (lane == 0) { out2[2 * w] = a; out2[2 * w + 1] = path; if (v != w) { out2[2 * v] = b; out2[2 * v + 1] = path; } }
+        return;
+    }
     else { // mode 3: entries 2k and 2k + 1 (queries of equal length) as the two halves of one packed extension
         if (w & 1) return;
         int a0 = -1, a1 = -1, b0 = -1, b1 = -1;
@@ -496,7 +506,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     S.d2h_bytes += 4ll * (n + 1) + 4ll * (nt + 1) * 2 + 8ll * n_pos + 4ll * nt * 2 + 16ll * nt + 4ll * n + 256 + sizeof(TaskTotals) +
                    (nt > 0 && !P.only_unit ? dense_cap * (c->params.need_cov ? 5 : 1) : 0);
     const unsigned long long *hc = c->h_counters.as<unsigned long long>();
-    S.n_chain_evals = (int64_t)hc[0]; S.n_poa_cells = (int64_t)hc[1]; S.n_poa_rows = (int64_t)hc[2]; S.n_ksw_cells = (int64_t)hc[3];
+    S.n_chain_evals = (int64_t)hc[0]; S.n_poa_cells = (int64_t)hc[1]; S.n_poa_rows = (int64_t)hc[2]; S.n_ksw_cells = (int64_t)hc[3]; S.n_ksw_cells_full = (int64_t)hc[4];
     S.ms_pack = ev_ms(c, 2, 3); S.ms_seed = ev_ms(c, 3, 4); S.ms_chain = ev_ms(c, 4, 5); S.ms_select = ev_ms(c, 5, 6); S.ms_partition = ev_ms(c, 6, 7);
     S.ms_poa = ev_ms(c, 8, 9); S.ms_ksw = ev_ms(c, 9, 10); S.ms_d2h = ev_ms(c, 10, 11);
     S.ms_total = ev_ms(c, 2, 11);

@@ -169,51 +169,74 @@ __device__ __forceinline__ uint32_t ksw_sel2(uint32_t a, uint32_t b, bool ph, bo
 }
 __device__ __forceinline__ uint32_t pk2(int v) { return ((uint32_t)(uint16_t)v) * 0x10001u; }
 
+// Banded mode (Bu >= 0): column block b (columns jb .. jb + 32 C - 1) only computes the target rows jb - Bu .. jb + 32 C + Bl - 1,
+// a staircase of rectangles around the diagonals -Bl .. Bu (d = column - row).  The cells left out are replaced by values
+// that are lower bounds of the true ones (the score of "gap along the first row, then gap down the column",
+// -(i + j + 6) in ksw2's scoring), so every banded value is at most the full matrix's and at least the best path that stays
+// inside the band.  A path that touches a diagonal d > max(0, n - m) has at least d inserted query bases, as many target
+// bases deleted again minus (n - m), and two gap openings: it scores at most 2 n - m - 4 - 3 d (n = query, m = target
+// length); likewise 2 m - n - 4 - 3 |d| below the band.  CERTIFICATE: if the banded score is strictly above both bounds
+// for d = Bu + 1 and d = -(Bl + 1), no optimal or co-optimal path leaves the band, so the score, every traceback decision
+// on the optimal path (a competing candidate that reached the cell through a left-out cell would complete to a path
+// above the bound) and with them the identity payload equal the full matrix's.  The caller checks it (ksw_band_certified)
+// and widens the band or runs the full matrix when it fails.  scA / scB = score of the final cell (INT_MIN when the
+// final cell was not computed).  Checked on the CPU against the oracle by tools/ksw_band_check.py (tools/sim/ksw_band_sim.c
+// is the scalar model of this routine).  Requires, for both alignments, Bu >= max(0, ql - tl) and Bl >= max(0, tl - ql).
 template <int C>
 __device__ void ksw_warp_global2(const uint8_t *qa, int qla, const uint8_t *ta, int tla, const uint8_t *qb_, int qlb, const uint8_t *tb_, int tlb,
-                                 int4 *bnd, int &idenA, int &idenB) {
+                                 int4 *bnd, const int Bu, const int Bl, int &idenA, int &idenB, int &scA, int &scB) {
     const int lane = lane_id();
-    idenA = 0; idenB = 0;
+    idenA = 0; idenB = 0; scA = INT_MIN; scB = INT_MIN;
     if (qla <= 0 || tla <= 0) { qla = 0; tla = 0; }
     if (qlb <= 0 || tlb <= 0) { qlb = 0; tlb = 0; }
     const int ql = max(qla, qlb), tl = max(tla, tlb);
     if (ql <= 0 || tl <= 0) return;
-    uint32_t capA = 0, capB = 0; // payload of cell (tl_x - 1, ql_x - 1), captured when its row is computed
+    const bool full = Bu < 0;
+    uint32_t capA = 0, capB = 0;   // payload of cell (tl_x - 1, ql_x - 1), captured when its row is computed
+    uint32_t capHA = 0, capHB = 0; // its (biased) score; 0 = not computed (biased scores are >= 1)
     const int BW = 32 * C;
     const int nblk = (ql + BW - 1) / BW;
     const int blkA = qla > 0 ? (qla - 1) / BW : -1, blkB = qlb > 0 ? (qlb - 1) / BW : -1;
     // Scores are kept biased by +KSW2_BIAS per half, so every half stays in [1, 32767]: adding small per-half
     // deltas with ordinary 32-bit integer arithmetic can then neither borrow nor carry across the halves, and the
     // compiler is free to put those adds on the FMA pipe (IMAD) while the 16x2 max ops take the ALU pipe.
+    // (Banded mode keeps the range: every computed cell's E is >= -(i + j + 8), by induction down its column.)
     const uint32_t ONE2 = 0x00010001u, Q2 = (uint32_t)KSW_Q * 0x10001u, E2 = (uint32_t)KSW_E * 0x10001u;
+    int p_hi = 0;                  // rows [.., p_hi) of the previous column block were computed
     for (int b = 0; b < nblk; ++b) {
         const int jb = b * BW;
         const int bw = min(ql - jb, BW), nl = (bw + C - 1) / C;
         const int j0 = jb + lane * C;
+        const int r_lo = full ? 0 : max(0, jb - Bu), r_hi = full ? tl : min(tl, jb + BW + Bl);
+        if (r_lo >= r_hi) break;   // the caller's band always reaches the last block; kept as a guard (no certificate then)
         const int4 *bin = bnd + (size_t)(b & 1) * tl;
         int4 *bout = bnd + (size_t)((b + 1) & 1) * tl;
         uint32_t Hp[C], Ea[C], pH[C], pE[C], qq[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = j0 + c;
-            const int h0 = KSW2_BIAS - (KSW_Q + KSW_E * (j + 1));
+            const int h0 = KSW2_BIAS - (r_lo == 0 ? KSW_Q + KSW_E * (j + 1) : r_lo + j + 5); // row r_lo - 1: the matrix's first row, or the lower bound
             Hp[c] = pk2(h0); Ea[c] = pk2(h0 - KSW_Q - KSW_E);
             pH[c] = 0; pE[c] = 0;
             const uint32_t a = j < qla ? qa[j] : 8u, bb = j < qlb ? qb_[j] : 8u; // 8 never equals a target code
             qq[c] = a | bb << 16;
         }
-        uint32_t hdiag = j0 == 0 ? pk2(KSW2_BIAS) : pk2(KSW2_BIAS - (KSW_Q + KSW_E * j0)), phdiag = 0;
+        uint32_t hdiag, phdiag = 0;    // cell (r_lo - 1, j0 - 1)
+        if (r_lo == 0) hdiag = j0 == 0 ? pk2(KSW2_BIAS) : pk2(KSW2_BIAS - (KSW_Q + KSW_E * j0));
+        else if (lane == 0) { const int4 v = bin[r_lo - 1]; hdiag = (uint32_t)v.x; phdiag = (uint32_t)v.z; } // computed by the previous block
+        else hdiag = pk2(KSW2_BIAS - (r_lo + j0 + 4));
         uint32_t oH = 0, oF = 0, oPH = 0, oPF = 0;
-        const int nstep = tl + nl - 1;
+        const int nstep = (r_hi - r_lo) + nl - 1;
         for (int s = 0; s < nstep; ++s) {
-            const int i = s - lane;
+            const int i = r_lo + s - lane;
             uint32_t iH = __shfl_up_sync(TH_FULL, oH, 1), iF = __shfl_up_sync(TH_FULL, oF, 1);
             uint32_t iPH = __shfl_up_sync(TH_FULL, oPH, 1), iPF = __shfl_up_sync(TH_FULL, oPF, 1);
             if (lane == 0) {
-                if (b == 0) { const int h0 = KSW2_BIAS - (KSW_Q + KSW_E * (s + 1)); iH = pk2(h0); iF = pk2(h0 - KSW_Q - KSW_E); iPH = 0; iPF = 0; }
-                else if (s < tl) { const int4 v = bin[s]; iH = (uint32_t)v.x; iF = (uint32_t)v.y; iPH = (uint32_t)v.z; iPF = (uint32_t)v.w; }
+                if (b == 0) { const int h0 = KSW2_BIAS - (KSW_Q + KSW_E * (i + 1)); iH = pk2(h0); iF = pk2(h0 - KSW_Q - KSW_E); iPH = 0; iPF = 0; }
+                else if (i < p_hi) { const int4 v = bin[i]; iH = (uint32_t)v.x; iF = (uint32_t)v.y; iPH = (uint32_t)v.z; iPF = (uint32_t)v.w; }
+                else if (i < r_hi) { const int h0 = KSW2_BIAS - (i + jb + 5); iH = pk2(h0); iF = pk2(h0 - KSW_Q - KSW_E); iPH = 0; iPF = 0; } // below the previous block's rows
             }
-            if (i >= 0 && i < tl && lane < nl) {
+            if (i >= r_lo && i < r_hi && lane < nl) {
                 const uint32_t tb2 = (i < tla ? (uint32_t)ta[i] : 9u) | (i < tlb ? (uint32_t)tb_[i] : 9u) << 16; // 9: past the end, never equal
                 uint32_t hd = hdiag, phd = phdiag, F = iF, pF = iPF;
                 hdiag = iH; phdiag = iPH;
@@ -237,19 +260,98 @@ __device__ void ksw_warp_global2(const uint8_t *qa, int qla, const uint8_t *ta, 
                 if (i == tla - 1 && b == blkA) {
                     const int cc = (qla - 1 - jb) - lane * C;
 #pragma unroll
-                    for (int c = 0; c < C; ++c) if (c == cc) capA = pH[c];
+                    for (int c = 0; c < C; ++c) if (c == cc) { capA = pH[c]; capHA = Hp[c]; }
                 }
                 if (i == tlb - 1 && b == blkB) {
                     const int cc = (qlb - 1 - jb) - lane * C;
 #pragma unroll
-                    for (int c = 0; c < C; ++c) if (c == cc) capB = pH[c];
+                    for (int c = 0; c < C; ++c) if (c == cc) { capB = pH[c]; capHB = Hp[c]; }
                 }
             }
         }
-        if (b == blkA) idenA = (int)(__shfl_sync(TH_FULL, capA, (qla - 1 - jb) / C) & 0xffffu);
-        if (b == blkB) idenB = (int)(__shfl_sync(TH_FULL, capB, (qlb - 1 - jb) / C) >> 16);
+        if (b == blkA) {
+            idenA = (int)(__shfl_sync(TH_FULL, capA, (qla - 1 - jb) / C) & 0xffffu);
+            const int h = (int)(__shfl_sync(TH_FULL, capHA, (qla - 1 - jb) / C) & 0xffffu);
+            if (h) scA = h - KSW2_BIAS;
+        }
+        if (b == blkB) {
+            idenB = (int)(__shfl_sync(TH_FULL, capB, (qlb - 1 - jb) / C) >> 16);
+            const int h = (int)(__shfl_sync(TH_FULL, capHB, (qlb - 1 - jb) / C) >> 16);
+            if (h) scB = h - KSW2_BIAS;
+        }
+        p_hi = r_hi;
         __syncwarp();
     }
+}
+
+// The band's certificate for one alignment (query length n, target length m, banded score sc): see ksw_warp_global2.
+__device__ __forceinline__ bool ksw_band_certified(int n, int m, int sc, int Bu, int Bl) {
+    if (n <= 0 || m <= 0) return true;
+    if (sc == INT_MIN) return false;
+    return sc > max(2 * n - m - 4 - 3 * (Bu + 1), 2 * m - n - 4 - 3 * (Bl + 1));
+}
+// Smallest half-widths (above max(0, n - m), below max(0, m - n)) whose certificate a score >= sc passes.
+__device__ __forceinline__ void ksw_band_needed(int n, int m, int sc, int &bu, int &bl) {
+    bu = 0; bl = 0;
+    if (n <= 0 || m <= 0) return;
+    const int nu = 2 * n - m - 4 - sc, nl = 2 * m - n - 4 - sc;   // 3 (B + 1) must exceed these
+    bu = max(0, nu >= 0 ? nu / 3 : 0); bl = max(0, nl >= 0 ? nl / 3 : 0);
+}
+// target rows the banded routine walks, summed over the column blocks (full matrix: blocks x tl)
+__device__ __forceinline__ int ksw_band_rows(int ql, int tl, int BW, int Bu, int Bl) {
+    int rows = 0;
+    for (int jb = 0; jb < ql; jb += BW) rows += max(0, min(tl, jb + BW + Bl) - max(0, jb - Bu));
+    return rows;
+}
+// cells of an n x m matrix inside those row ranges
+__device__ __forceinline__ unsigned long long ksw_band_cells(int n, int m, int BW, int Bu, int Bl) {
+    unsigned long long cells = 0;
+    for (int jb = 0; jb < n; jb += BW) cells += (unsigned long long)max(0, min(m, jb + BW + Bl) - min(m, max(0, jb - Bu))) * (unsigned)min(BW, n - jb);
+    return cells;
+}
+
+#ifndef KSW_BANDED
+#define KSW_BANDED 1          // identity alignments try a certified band before the full matrix (0: always the full matrix)
+#endif
+#ifndef KSW_BAND_MARGIN
+#define KSW_BAND_MARGIN 0.04f // added to what the last certified pair needed (a failed band costs a second pass, a wide one a few rows)
+#endif
+#ifndef KSW_BAND_ALPHA0
+#define KSW_BAND_ALPHA0 0.19f // first band half-width / length: what 15 % divergence needs (tools/ksw_band_check.py)
+#endif
+// Identity counts of two global alignments (unit vs consensus, src/gen_cons.c:208-216): banded first, as wide as the warp's
+// recent alignments needed plus a margin (`alpha` = half-width / length, carried from pair to pair by the caller); a failed
+// certificate tells the width that is enough, because the banded score is a lower bound of the true one; the full matrix is
+// the last resort, and the first choice where the band would leave out less than an eighth of the rows.  The results never
+// depend on `alpha`.  `path` (optional): 1 = certified at the first width, 2 = at the second, 0 = full matrix only, 3 / 4 =
+// full matrix after one / two failed bands.  ncell counts the cells computed, failed attempts included.
+template <int C>
+__device__ void ksw_pair_identity(const uint8_t *qa, int qla, const uint8_t *ta, int tla, const uint8_t *qb, int qlb, const uint8_t *tb, int tlb,
+                                  int4 *bnd, float &alpha, int &idenA, int &idenB, unsigned long long &ncell, int *path = nullptr) {
+    int s0 = 0, s1 = 0, tried = 0;
+    const int BW = 32 * C, ql = max(qla, qlb), tl = max(tla, tlb), rows_full = ((ql + BW - 1) / BW) * tl;
+    const int dq = max(0, max(qla - tla, qlb - tlb)), dt = max(0, max(tla - qla, tlb - qlb));
+    int Bu = dq + 16 + (int)(alpha * (float)max(ql, tl)), Bl = dt + 16 + (int)(alpha * (float)max(ql, tl));
+    bool banded = KSW_BANDED && qla > 0 && qlb > 0 && tla > 0 && tlb > 0, done = false;
+    while (true) { // one call site: the routine is inlined once
+        banded = banded && tried < 2 && ksw_band_rows(ql, tl, BW, Bu, Bl) * 8 <= rows_full * 7; // else not worth it: the full matrix
+        ksw_warp_global2<C>(qa, qla, ta, tla, qb, qlb, tb, tlb, bnd, banded ? Bu : -1, banded ? Bl : -1, idenA, idenB, s0, s1);
+        if (!banded) { ncell += (unsigned long long)max(qla, 0) * max(tla, 0) + (unsigned long long)max(qlb, 0) * max(tlb, 0); break; }
+        ncell += ksw_band_cells(qla, tla, BW, Bu, Bl) + ksw_band_cells(qlb, tlb, BW, Bu, Bl);
+        ++tried;
+        if (s0 == INT_MIN || s1 == INT_MIN) { banded = false; continue; }
+        done = ksw_band_certified(qla, tla, s0, Bu, Bl) && ksw_band_certified(qlb, tlb, s1, Bu, Bl);
+        int ua, la, ub, lb;
+        ksw_band_needed(qla, tla, s0, ua, la); ksw_band_needed(qlb, tlb, s1, ub, lb);
+        const int nu = max(ua, ub), nl = max(la, lb);
+        if (done) { // what this pair needed, relative to its length, steers the next one
+            const float need = (float)max(max(nu - dq, nl - dt), 0) / (float)max(ql, tl);
+            alpha = 0.5f * alpha + 0.5f * fminf(fmaxf(need + KSW_BAND_MARGIN, 0.05f), 0.5f);
+            break;
+        }
+        Bu = max(Bu, nu) + 8; Bl = max(Bl, nl) + 8; alpha = fminf(alpha + 0.03f, 0.5f);
+    }
+    if (path) *path = done ? tried : (tried ? 2 + tried : 0);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -78,7 +78,7 @@ partition_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, con
             if (lane == 0) { par_off[hoff + c] = p0; par_n[hoff + c] = overflow ? 0 : pn_; }
         }
     }
-    if (lane == 0 && ncell) atomicAdd(stat_cells, ncell);
+    if (lane == 0 && ncell) { atomicAdd(stat_cells, ncell); atomicAdd(stat_cells + 1, ncell); }
 }
 
 // item kinds: 0: global identity of unit (offset a, length b) vs consensus -> out_iden[out];
@@ -100,7 +100,7 @@ __device__ __forceinline__ bool warp_has_n(const uint8_t *s, int l) {
 #define KSW_PAIR_MIN_BLOCKS 4
 #endif
 #ifndef KSW2_C
-#define KSW2_C 16
+#define KSW2_C 8     // columns per lane of the packed identity alignments: 256-column blocks follow the band closely (16: 42.5 ms, 8: 38.3 ms per 8,192 R2C2 reads for the ksw stage)
 #endif
 #define KSW_MIN_BLOCKS 4
 #ifndef KSW_EXT_MIN_BLOCKS
@@ -121,7 +121,8 @@ ksw_pair_kernel(int n_items, const KswItem *__restrict__ items, const uint8_t *_
     const int lane = lane_id();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int4 *bnd = bnd_all + (int64_t)gw * bnd_stride;
-    unsigned long long ncell = 0;
+    unsigned long long ncell = 0, nfull = 0; // cells computed / cells of the full matrices (what the reference computes)
+    float alpha = KSW_BAND_ALPHA0; // band half-width as a fraction of the alignment's length (adapts to the data, per warp)
     while (true) {
         int it = 0;
         if (lane == 0) it = atomicAdd(counter, 1);
@@ -138,11 +139,11 @@ ksw_pair_kernel(int n_items, const KswItem *__restrict__ items, const uint8_t *_
         ok = ok && !warp_has_n(qa, I.b) && !warp_has_n(qb, I.b2) && !warp_has_n(cons, cl) && (cons2 == cons || !warp_has_n(cons2, cl2));
         if (!ok) { if (lane == 0) redo_list[atomicAdd(redo_count, 1)] = it; continue; }
         int o0 = 0, o1 = 0;
-        ksw_warp_global2<KSW2_C>(qa, I.b, cons, cl, qb, I.b2, cons2, cl2, bnd, o0, o1);
-        ncell += (unsigned long long)I.b * cl + (unsigned long long)I.b2 * cl2;
+        ksw_pair_identity<KSW2_C>(qa, I.b, cons, cl, qb, I.b2, cons2, cl2, bnd, alpha, o0, o1, ncell);
+        nfull += (unsigned long long)I.b * cl + (unsigned long long)I.b2 * cl2;
         if (lane == 0) { out_iden[I.out] = o0; out_iden[out2] = o1; }
     }
-    if (lane == 0 && ncell) atomicAdd(stat_cells, ncell);
+    if (lane == 0 && ncell) { atomicAdd(stat_cells, ncell); atomicAdd(stat_cells + 1, nfull); }
 }
 
 __global__ void __launch_bounds__(KSW_WARPS * 32, KSW_MIN_BLOCKS)
@@ -176,7 +177,7 @@ ksw_single_kernel(int n_single, const KswItem *__restrict__ singles, const KswIt
         }
         if (lane == 0) out_iden[out] = o0;
     }
-    if (lane == 0 && ncell) atomicAdd(stat_cells, ncell);
+    if (lane == 0 && ncell) { atomicAdd(stat_cells, ncell); atomicAdd(stat_cells + 1, ncell); }
 }
 
 // Boundary extensions, two per warp (packed 16x2): `order` lists the items by target length, so entries 2k and 2k + 1 are
@@ -202,7 +203,7 @@ ksw_ext_kernel(int n_items, const KswItem *__restrict__ items, const int32_t *__
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int4 *bnd = bnd_all + (int64_t)gw * bnd_stride;
     uint8_t *rev = rev_all + (int64_t)gw * rev_stride; // reversed copies for left extensions: one half of it per item of the pair
-    unsigned long long ncell = 0;
+    unsigned long long ncell = 0, nfull = 0;
     const int n_pairs = (n_items + 1) >> 1;
     while (true) {
         int it = 0;
@@ -227,8 +228,9 @@ ksw_ext_kernel(int n_items, const KswItem *__restrict__ items, const int32_t *__
             if (clb > 0) ksw_warp<KSW_EXT, 16>(qb, clb, tb, tlb, 0, bnd, bq, bt);
         }
         ncell += (unsigned long long)cae * tae + (unsigned long long)cbe * tbe; // cells computed
+        nfull += (unsigned long long)max(cla, 0) * max(tla, 0) + (unsigned long long)max(clb, 0) * max(tlb, 0);
         __syncwarp();
         if (lane == 0) { out_ext[A.out] = aq; out_ext[A.out + 1] = at; if (hasb) { out_ext[B.out] = bq; out_ext[B.out + 1] = bt; } }
     }
-    if (lane == 0 && ncell) atomicAdd(stat_cells, ncell);
+    if (lane == 0 && ncell) { atomicAdd(stat_cells, ncell); atomicAdd(stat_cells + 1, nfull); }
 }

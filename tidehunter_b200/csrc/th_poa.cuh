@@ -274,8 +274,8 @@ __device__ __forceinline__ void poa_chunk(const PoaG<LPT> &g, const DevParams &P
     const uint32_t INFP = P.INFP;
     uint32_t Mx[2], E1x[2], E2x[2];
     poa_pred<LPT, AFFINE>(A32, ring, pm0, act, j0, INFP, Mx, E1x, E2x);
-#pragma unroll 1
     uint32_t midx[2] = {0u, 0u};   // per column: the first predecessor whose H[p][j-1] is the maximum
+#pragma unroll 1
     for (int p = 1; p < np; ++p) { // no warp-synchronous operation in here: groups may run different trip counts
         uint32_t m[2], x1[2], x2[2];
         poa_pred<LPT, AFFINE>(A32, ring, pre[p], act, j0, INFP, m, x1, x2);
