@@ -402,8 +402,8 @@ def main():
     serial = {k: 0.0 for k in STAGES}
     serial_cnt = {}
     if L > 1:
-        runs = [ctxs[0].process_resident().stats.as_dict() for _ in range(3)]
-        for st in STAGES:   # median of three launches: the per-launch time of the POA kernel varies by ~10 % between launches
+        runs = [ctxs[0].process_resident().stats.as_dict() for _ in range(5)]
+        for st in STAGES:   # median of five launches: the per-launch time of the POA kernel varies between launches (63 - 72 ms, once 122 ms, on the same batch)
             serial[st] = statistics.median(r["ms_" + st] for r in runs)
         serial_cnt = runs[-1]
     for c in ctxs:

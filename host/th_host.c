@@ -502,9 +502,10 @@ static void add_stats(th_gpu_stats *a, const th_gpu_stats *b) {
  * holds TH_CHUNK_BASES_PER_READ x chunk_reads bases (the reference balances reads over its threads dynamically,
  * src/main.c:273-291; with mixed read lengths equal read counts are unequal work).  Lanes TAKE chunks -- a free lane takes
  * the first chunk nobody has yet -- so a lane that drew long reads does not hold up the others.  The caller's thread formats
- * the chunks strictly in input order (the FASTQ slot quirk and the output order are sequential), and a lane only takes its
- * next chunk once its previous result has been formatted, because the result arrays belong to the context; every chunk
- * before a taken one is taken too, so the formatter never waits on an untaken chunk. */
+ * the chunks strictly in input order (the FASTQ slot quirk and the output order are sequential).  A lane copies its chunk's
+ * result out of the context's buffers (copy_result) and takes its next chunk at once; it only waits when the formatter is
+ * more than max_ahead chunks behind.  Every chunk before a taken one is taken too, so the formatter never waits on an
+ * untaken chunk. */
 #define TH_CHUNK_BASES_PER_READ 12288
 static int *cut_chunks(const th_host *h, int n, const int32_t *lens, int *n_chunks) {
     const long long cap_b = (long long)h->p.chunk_reads * TH_CHUNK_BASES_PER_READ;
@@ -523,31 +524,64 @@ typedef struct {
     th_host *h; int n, n_chunks; const char *const *seqs; const int32_t *lens;
     const int *start;      /* chunk c = reads [start[c], start[c + 1]) */
     int next;              /* first chunk no lane has taken yet */
+    int n_emitted;         /* chunks formatted so far (they are formatted in order) */
+    int max_ahead;         /* a lane takes chunk c only while c - n_emitted < max_ahead: bounds the copies waiting to be formatted */
     pthread_mutex_t mu; pthread_cond_t cv;
-    int *state; th_gpu_result *res; int abort; char err[512];
+    int *state; th_gpu_result *res; void **own; int abort; char err[512];
 } run_job;
 typedef struct { run_job *job; int lane; double t_gpu, t_wait; } lane_arg;
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+/* A chunk's result lives in buffers of the GPU context and is overwritten by the context's next chunk.  The lane copies
+ * it out (a few MB) so that it can start its next chunk at once instead of waiting until the formatter, which works in
+ * input order, has got to this one.  One allocation holds all arrays; *own is what the formatter frees. */
+static int copy_result(const th_gpu_result *s, th_gpu_result *d, void **own) {
+    const size_t n = (size_t)s->n_reads, nt = (size_t)s->n_tasks;
+    const size_t n_pos = nt && s->task_pos_off ? (size_t)s->task_pos_off[nt] : 0, n_cons = nt && s->task_cons_off ? (size_t)s->task_cons_off[nt] : 0;
+    const int cov_is_alias = (const void *)s->cons_cov == (const void *)s->iden_n;
+    const size_t sz[11] = { 4 * (n + 1), 4 * (nt + 1), 4 * n_pos, 4 * nt, 4 * (nt + 1), n_cons, cov_is_alias ? 0 : 4 * n_cons, 4 * n_pos, 16 * nt, 4 * nt, 4 * n };
+    const void *src[11] = { s->read_task_off, s->task_pos_off, s->pos, s->task_n_seqs, s->task_cons_off, s->cons_base, s->cons_cov, s->iden_n, s->ext, s->task_status, s->read_status };
+    void *dst[11]; size_t tot = 256, off = 0; int i; char *blk;
+    for (i = 0; i < 11; ++i) tot += (sz[i] + 15) & ~(size_t)15;
+    blk = (char *)malloc(tot);
+    if (!blk) return -1;
+    for (i = 0; i < 11; ++i) {
+        dst[i] = NULL;
+        if (src[i] && sz[i]) { dst[i] = blk + off; memcpy(dst[i], src[i], sz[i]); off += (sz[i] + 15) & ~(size_t)15; }
+        else if (src[i] && i != 6) { dst[i] = blk + off; off += 16; }   /* present but empty: keep a valid pointer */
+    }
+    *d = *s;
+    d->read_task_off = (const int32_t *)dst[0]; d->task_pos_off = (const int32_t *)dst[1]; d->pos = (const int32_t *)dst[2];
+    d->task_n_seqs = (const int32_t *)dst[3]; d->task_cons_off = (const int32_t *)dst[4]; d->cons_base = (const uint8_t *)dst[5];
+    d->iden_n = (const int32_t *)dst[7]; d->cons_cov = cov_is_alias ? d->iden_n : (const int32_t *)dst[6];
+    d->ext = (const int32_t *)dst[8]; d->task_status = (const int32_t *)dst[9]; d->read_status = (const int32_t *)dst[10];
+    *own = blk;
+    return 0;
+}
 
 static void *lane_main(void *arg_) {
     lane_arg *a = (lane_arg *)arg_; run_job *J = a->job; th_host *h = J->h;
     for (;;) {
         int c, c0, m, rc, stop;
-        pthread_mutex_lock(&J->mu); stop = J->abort; c = J->next; if (!stop && c < J->n_chunks) J->next = c + 1; pthread_mutex_unlock(&J->mu);
+        th_gpu_result R;
+        { const double t0 = now_s();
+          pthread_mutex_lock(&J->mu);
+          while (!J->abort && J->next < J->n_chunks && J->next - J->n_emitted >= J->max_ahead) pthread_cond_wait(&J->cv, &J->mu);
+          stop = J->abort; c = J->next; if (!stop && c < J->n_chunks) J->next = c + 1;
+          pthread_mutex_unlock(&J->mu);
+          a->t_wait += now_s() - t0; }
         if (stop || c >= J->n_chunks) break;
         c0 = J->start[c]; m = J->start[c + 1] - c0;
         { const double t0 = now_s();
-          rc = th_gpu_process_chunk(h->lane[a->lane], m, J->seqs + c0, J->lens + c0, &J->res[c]);
+          rc = th_gpu_process_chunk(h->lane[a->lane], m, J->seqs + c0, J->lens + c0, &R);
+          if (rc) { pthread_mutex_lock(&J->mu); if (!J->err[0]) snprintf(J->err, sizeof(J->err), "%s", th_gpu_last_error()); pthread_mutex_unlock(&J->mu); }
+          else if (copy_result(&R, &J->res[c], &J->own[c])) { rc = -1; pthread_mutex_lock(&J->mu); if (!J->err[0]) snprintf(J->err, sizeof(J->err), "out of memory copying a chunk's result"); pthread_mutex_unlock(&J->mu); }
           a->t_gpu += now_s() - t0; }
-        { const double t0 = now_s();
         pthread_mutex_lock(&J->mu);
-        if (rc) { J->state[c] = CH_FAILED; J->abort = 1; snprintf(J->err, sizeof(J->err), "%s", th_gpu_last_error()); }
-        else J->state[c] = CH_READY;
+        if (rc) { J->state[c] = CH_FAILED; J->abort = 1; } else J->state[c] = CH_READY;
         pthread_cond_broadcast(&J->cv);
-        while (J->state[c] == CH_READY && !J->abort) pthread_cond_wait(&J->cv, &J->mu);
         stop = J->abort;
         pthread_mutex_unlock(&J->mu);
-        a->t_wait += now_s() - t0; }
         if (stop) break;
     }
     return NULL;
@@ -618,7 +652,8 @@ const char *th_host_run(th_host *h, int n, const char *const *names, const char 
         run_job J; pthread_t th[TH_MAX_LANES]; lane_arg la[TH_MAX_LANES]; int n_thr = h->n_lanes < n_chunks ? h->n_lanes : n_chunks, failed = 0;
         memset(&J, 0, sizeof(J));
         J.h = h; J.n = n; J.n_chunks = n_chunks; J.seqs = seqs; J.lens = lens; J.start = start; J.next = 0;
-        J.state = (int *)calloc(n_chunks, sizeof(int)); J.res = (th_gpu_result *)calloc(n_chunks, sizeof(th_gpu_result));
+        J.state = (int *)calloc(n_chunks, sizeof(int)); J.res = (th_gpu_result *)calloc(n_chunks, sizeof(th_gpu_result)); J.own = (void **)calloc(n_chunks, sizeof(void *));
+        J.n_emitted = 0; J.max_ahead = 2 * n_thr + 2;
         pthread_mutex_init(&J.mu, NULL); pthread_cond_init(&J.cv, NULL);
         const double t_run0 = now_s(); double t_emit = 0, t_mwait = 0;
         for (c = 0; c < n_thr; ++c) { la[c].job = &J; la[c].lane = c; la[c].t_gpu = la[c].t_wait = 0; pthread_create(&th[c], NULL, lane_main, &la[c]); }
@@ -636,7 +671,8 @@ const char *th_host_run(th_host *h, int n, const char *const *names, const char 
             t_emit += now_s() - t0;
             h->read_counter += m;
             add_stats(&h->stats, &J.res[c].stats);
-            pthread_mutex_lock(&J.mu); J.state[c] = CH_EMITTED; pthread_cond_broadcast(&J.cv); pthread_mutex_unlock(&J.mu);
+            free(J.own[c]); J.own[c] = NULL;
+            pthread_mutex_lock(&J.mu); J.state[c] = CH_EMITTED; J.n_emitted = c + 1; pthread_cond_broadcast(&J.cv); pthread_mutex_unlock(&J.mu);
         }
         if (failed) { pthread_mutex_lock(&J.mu); J.abort = 1; pthread_cond_broadcast(&J.cv); pthread_mutex_unlock(&J.mu); }
         for (c = 0; c < n_thr; ++c) pthread_join(th[c], NULL);
@@ -646,6 +682,8 @@ const char *th_host_run(th_host *h, int n, const char *const *names, const char 
             fprintf(stderr, "\n");
         }
         pthread_mutex_destroy(&J.mu); pthread_cond_destroy(&J.cv);
+        for (c = 0; c < n_chunks; ++c) free(J.own[c]);
+        free(J.own);
         if (failed) { set_err("%s", J.err[0] ? J.err : "a GPU lane failed"); free(J.state); free(J.res); free(start); *out_len = 0; return NULL; }
         free(J.state); free(J.res);
     }

@@ -149,7 +149,12 @@ def test_ksw_banded_pair_identity(T, oracle):
         pairs.append((np.concatenate([w[:500], w[500 + k:]]).tobytes(), w.tobytes()))
         pairs.append((w.tobytes(), np.concatenate([w[:300], w[300 + k:]]).tobytes()))
     order = rng.permutation(len(pairs))  # neighbours in the list are packed together: mix lengths and kinds
-    pairs = [pairs[i] for i in order] + pairs[:1]  # odd count: the last entry runs packed with itself
+    pairs = [pairs[i] for i in order]
+    if len(pairs) & 1:
+        pairs.append(pairs[0])
+    # nothing in common (every column a mismatch or two gaps): the band the failed certificate asks for is the full matrix
+    pairs += [(bytes([0]) * 900, bytes([1]) * 880), (bytes([2]) * 900, bytes([3]) * 910)]
+    pairs.append(pairs[1])  # odd count: the last entry runs packed with itself
     qs = [p[0] for p in pairs]; ts = [p[1] for p in pairs]
     exp = [H.ksw_global(q, t)[0] for q, t in pairs]
     ctx = T.GpuContext()

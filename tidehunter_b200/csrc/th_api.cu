@@ -81,6 +81,7 @@ struct th_gpu_ctx {
     DBuf d_choff, d_chlen, d_chscore, d_chidx, d_cells, d_pchn, d_pchoff, d_pchlen;
     DBuf d_par, d_paroff, d_parn, d_rstatus, d_scratch, d_scratch2, d_bnd, d_rev, d_counters;
     DBuf d_parstream, d_parused, d_pardoff;
+    DBuf d_kswalpha; // ksw_pair_kernel's band-width estimate (one float), kept across chunks
     DBuf d_tasks, d_torder, d_ustart, d_ulen, d_slabs, d_consb, d_consc, d_consl, d_tstatus, d_items, d_iden, d_ext;
     DBuf d_gsrc, d_gdst, d_glen, d_dense_b, d_dense_c, d_redo;
     DBuf d_tcounts, d_totals, d_tkey, d_ekey, d_eorder, d_left, d_pos, d_rtoff, d_tposoff, d_tnseqs, d_tconsoff, d_retry, d_rorder;
@@ -156,6 +157,8 @@ extern "C" th_gpu_ctx *th_gpu_create(const th_gpu_params *p, int device) {
     CKP(cudaFuncSetAttribute(poa_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PoaSmem<16>) * POA_WARPS * 2 + sizeof(PoaLaneK) * 16)));
     CKP(cudaFuncSetAttribute(poa_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PoaSmem<32>) * POA_WARPS + sizeof(PoaLaneK) * 32)));
     memset(&c->stats, 0, sizeof(c->stats));
+    { const float a0 = KSW_BAND_ALPHA0;
+      if (c->d_kswalpha.ensure(sizeof(float)) || cudaMemcpy(c->d_kswalpha.p, &a0, sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { set_err("cannot allocate device memory"); th_gpu_destroy(c); return nullptr; } }
     return c;
 }
 
@@ -168,7 +171,7 @@ extern "C" void th_gpu_destroy(th_gpu_ctx *c) {
                   &c->d_pchlen, &c->d_par, &c->d_paroff, &c->d_parn, &c->d_rstatus, &c->d_scratch, &c->d_scratch2, &c->d_bnd, &c->d_rev, &c->d_counters,
                   &c->d_parstream, &c->d_parused, &c->d_pardoff, &c->d_tasks, &c->d_torder, &c->d_ustart, &c->d_ulen, &c->d_slabs, &c->d_consb, &c->d_consc,
                   &c->d_consl, &c->d_tstatus, &c->d_items, &c->d_iden, &c->d_ext, &c->d_gsrc, &c->d_gdst, &c->d_glen, &c->d_dense_b, &c->d_dense_c, &c->d_redo,
-                  &c->d_tcounts, &c->d_totals, &c->d_tkey, &c->d_ekey, &c->d_eorder, &c->d_left, &c->d_pos, &c->d_rtoff, &c->d_tposoff, &c->d_tnseqs, &c->d_tconsoff, &c->d_retry, &c->d_rorder};
+                  &c->d_tcounts, &c->d_totals, &c->d_tkey, &c->d_ekey, &c->d_eorder, &c->d_left, &c->d_pos, &c->d_rtoff, &c->d_tposoff, &c->d_tnseqs, &c->d_tconsoff, &c->d_retry, &c->d_rorder, &c->d_kswalpha};
     for (DBuf *b : ds) b->release();
     HBuf *hs[] = {&c->h_ascii, &c->h_totals, &c->h_rtoff, &c->h_tposoff, &c->h_pos, &c->h_tnseqs, &c->h_tconsoff, &c->h_tstatus, &c->h_iden, &c->h_ext, &c->h_rstatus,
                   &c->h_counters, &c->h_consb, &c->h_consc};
@@ -409,6 +412,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
             if (grid <= 4) return -1;
             grid = (grid + 1) / 2;
         }
+        if (getenv("TH_GPU_DEBUG")) fprintf(stderr, "[th_gpu] POA: %d tasks on %d blocks (%d groups), slabs of %zu bytes, %.1f GB free, budget %.1f GB\n", nt, grid, grid * GPB16, slab_typ, free_b / 1e9, budget / 1e9);
         poa_kernel<16><<<grid, POA_WARPS * 32, sizeof(PoaSmem<16>) * GPB16 + sizeof(PoaLaneK) * 16, st>>>(
             P, nt, nullptr, c->d_tasks.as<PoaTask>(), c->d_torder.as<int32_t>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(), c->d_bseq.as<uint8_t>(),
             c->d_slabs.as<uint8_t>(), slab_typ, nullptr, c->d_slabs.cap, cnt32 + 1, c->d_consb.as<uint8_t>(), c->d_consc.as<int32_t>(), c->d_consl.as<int32_t>(),
@@ -441,7 +445,7 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
             if (n_pairs > 0) {
                 ksw_pair_kernel<<<g_pair, KSW_WARPS * 32, 0, st>>>(n_pairs, d_pairs, c->d_bseq.as<uint8_t>(), c->d_consb.as<uint8_t>(), c->d_glen.as<int32_t>(),
                                                                  c->d_consl.as<int32_t>(), c->d_bnd.as<int4>(), bnd_stride, cnt32 + 2, c->d_redo.as<int32_t>(), cnt32 + 5,
-                                                                 c->d_iden.as<int32_t>(), cnt64 + 3);
+                                                                 c->d_iden.as<int32_t>(), cnt64 + 3, c->d_kswalpha.as<float>());
                 S.n_launches++;
             }
             ksw_single_kernel<<<g_single, KSW_WARPS * 32, 0, st>>>(n_singles, d_singles, d_pairs, c->d_redo.as<int32_t>(), cnt32 + 5, c->d_bseq.as<uint8_t>(),

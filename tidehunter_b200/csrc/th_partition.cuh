@@ -117,12 +117,19 @@ __global__ void __launch_bounds__(KSW_WARPS * 32, KSW_PAIR_MIN_BLOCKS)
 ksw_pair_kernel(int n_items, const KswItem *__restrict__ items, const uint8_t *__restrict__ bseq,
                 const uint8_t *__restrict__ cons_base, const int32_t *__restrict__ cons_off, const int32_t *__restrict__ cons_len,
                 int4 *bnd_all, int64_t bnd_stride, int *counter, int32_t *__restrict__ redo_list, int *redo_count,
-                int32_t *__restrict__ out_iden, unsigned long long *__restrict__ stat_cells) {
+                int32_t *__restrict__ out_iden, unsigned long long *__restrict__ stat_cells, float *band_alpha) {
     const int lane = lane_id();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int4 *bnd = bnd_all + (int64_t)gw * bnd_stride;
     unsigned long long ncell = 0, nfull = 0; // cells computed / cells of the full matrices (what the reference computes)
-    float alpha = KSW_BAND_ALPHA0; // band half-width as a fraction of the alignment's length (adapts to the data, per warp)
+    // Band half-width as a fraction of the alignment's length: every warp adapts its own from pair to pair
+    // (ksw_pair_identity); it starts from a running mean of what the warps of the context's earlier launches ended with (plain
+    // loads and stores of one float in device memory: lost updates do not matter, and a stale or odd value costs a few rows
+    // or one retry, never a result), so a launch with few pairs per warp already knows what the data needs.
+    float alpha = 0.f;
+    if (lane == 0) alpha = *(volatile float *)band_alpha;
+    alpha = fminf(fmaxf(__shfl_sync(TH_FULL, alpha, 0), 0.02f), 0.5f);
+    bool any_pair = false;
     while (true) {
         int it = 0;
         if (lane == 0) it = atomicAdd(counter, 1);
@@ -140,10 +147,12 @@ ksw_pair_kernel(int n_items, const KswItem *__restrict__ items, const uint8_t *_
         if (!ok) { if (lane == 0) redo_list[atomicAdd(redo_count, 1)] = it; continue; }
         int o0 = 0, o1 = 0;
         ksw_pair_identity<KSW2_C>(qa, I.b, cons, cl, qb, I.b2, cons2, cl2, bnd, alpha, o0, o1, ncell);
+        any_pair = true;
         nfull += (unsigned long long)I.b * cl + (unsigned long long)I.b2 * cl2;
         if (lane == 0) { out_iden[I.out] = o0; out_iden[out2] = o1; }
     }
     if (lane == 0 && ncell) { atomicAdd(stat_cells, ncell); atomicAdd(stat_cells + 1, nfull); }
+    if (lane == 0 && any_pair) { volatile float *g = band_alpha; *g = 0.75f * *g + 0.25f * alpha; } // damped: one odd pair does not steer the next launch
 }
 
 __global__ void __launch_bounds__(KSW_WARPS * 32, KSW_MIN_BLOCKS)
