@@ -400,11 +400,13 @@ def main():
     n_tasks = cnt["n_tasks"]
     # one lane alone (serial stages, nothing co-running): the per-kernel times comparable with the ncu launch list
     serial = {k: 0.0 for k in STAGES}
+    serial_range = {}
     serial_cnt = {}
     if L > 1:
         runs = [ctxs[0].process_resident().stats.as_dict() for _ in range(5)]
         for st in STAGES:   # median of five launches: the per-launch time of the POA kernel varies between launches (63 - 72 ms, once 122 ms, on the same batch)
             serial[st] = statistics.median(r["ms_" + st] for r in runs)
+            serial_range[st] = [round(min(r["ms_" + st] for r in runs), 3), round(max(r["ms_" + st] for r in runs), 3)]
         serial_cnt = runs[-1]
     for c in ctxs:
         c.close()
@@ -478,6 +480,8 @@ def main():
     kernels_over = table(over_ms, over_cnt)
     if L > 1:
         kernels = table(serial, serial_cnt)
+        for k, mm in serial_range.items():   # the median is what the fractions use; the spread of the five launches is shown beside it
+            kernels[k]["ms_per_launch_min_max"] = mm
         ser_ms, ser_cnt = serial, serial_cnt
     else:
         kernels, ser_ms, ser_cnt = kernels_over, over_ms, over_cnt

@@ -393,14 +393,21 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         // ---- POA: 16-lane groups, two tasks per warp ----
         size_t slab_typ = ((size_t)ht->slab_typ + 255) & ~(size_t)255; // slabs hold 16-byte accesses
         if (slab_typ == 0) slab_typ = 1 << 20;
-        size_t free_b = 0, total_b = 0; CK(cudaMemGetInfo(&free_b, &total_b));
-        size_t budget = (size_t)((double)(free_b + c->d_slabs.cap) * 0.6);
-        budget = std::min(budget, total_b / 5); // several contexts share the device (the host layer runs four): none may take it all
         constexpr int GPB16 = POA_WARPS * 2, GPB32 = POA_WARPS;
         double poa_blocks = POA_MIN_BLOCKS16;            // resident POA blocks per SM this context asks for (tuning: TH_POA_BLOCKS)
         if (const char *e = getenv("TH_POA_BLOCKS")) { const double v = atof(e); if (v >= 0.5 && v <= POA_MIN_BLOCKS16) poa_blocks = v; }
-        int ngroups = (int)std::min<size_t>((size_t)(c->n_sm * poa_blocks * GPB16 * c->share), std::max<size_t>(1, budget / slab_typ));
-        ngroups = std::min(ngroups, std::max(nt, 1));
+        const int want_groups = std::min((int)(c->n_sm * poa_blocks * GPB16 * c->share), std::max(nt, 1));
+        // The memory budget is only consulted when the slabs have to grow: cudaMemGetInfo is a driver call that takes from a
+        // fraction of a millisecond to 70 ms (measured: it added 13 ms per chunk on average, on the host, between the task
+        // kernels and the POA launch), and chunks of one run are alike, so the slabs of the previous chunk nearly always do.
+        size_t free_b = 0, total_b = 0, budget = c->d_slabs.cap;
+        const bool fits = (size_t)((want_groups + GPB16 - 1) / GPB16) * GPB16 * slab_typ <= c->d_slabs.cap && (((size_t)ht->slab_wide + 511) & ~(size_t)255) <= c->d_slabs.cap;
+        if (!fits) {
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            budget = (size_t)((double)(free_b + c->d_slabs.cap) * 0.6);
+            budget = std::min(budget, total_b / 5); // several contexts share the device (the host layer runs four): none may take it all
+        }
+        int ngroups = (int)std::min<size_t>((size_t)want_groups, std::max<size_t>(1, budget / slab_typ));
         int grid = (ngroups + GPB16 - 1) / GPB16;
         // several contexts of one process (the host layer's lanes) size their slabs from the same free-memory reading:
         // if the allocation loses that race, run with fewer resident groups instead of failing the chunk
@@ -412,11 +419,13 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
             if (grid <= 4) return -1;
             grid = (grid + 1) / 2;
         }
-        if (getenv("TH_GPU_DEBUG")) fprintf(stderr, "[th_gpu] POA: %d tasks on %d blocks (%d groups), slabs of %zu bytes, %.1f GB free, budget %.1f GB\n", nt, grid, grid * GPB16, slab_typ, free_b / 1e9, budget / 1e9);
+        if (getenv("TH_GPU_DEBUG")) fprintf(stderr, "[th_gpu] POA: %d tasks on %d blocks (%d groups), slabs of %zu bytes, budget %.1f GB%s\n", nt, grid, grid * GPB16, slab_typ, budget / 1e9, fits ? " (slabs of the previous chunk reused, memory not queried)" : "");
+        CK(cudaEventRecord(c->ev[12], st));   // 12, 13: the packed POA kernel alone (TH_GPU_DEBUG prints it beside the stage's bracket)
         poa_kernel<16><<<grid, POA_WARPS * 32, sizeof(PoaSmem<16>) * GPB16 + sizeof(PoaLaneK) * 16, st>>>(
             P, nt, nullptr, c->d_tasks.as<PoaTask>(), c->d_torder.as<int32_t>(), c->d_ustart.as<int32_t>(), c->d_ulen.as<int32_t>(), c->d_bseq.as<uint8_t>(),
             c->d_slabs.as<uint8_t>(), slab_typ, nullptr, c->d_slabs.cap, cnt32 + 1, c->d_consb.as<uint8_t>(), c->d_consc.as<int32_t>(), c->d_consl.as<int32_t>(),
             c->d_tstatus.as<int32_t>(), cnt64 + 1, cnt64 + 2, cnt64 + 16, grid * GPB16, c->d_retry.as<int32_t>(), d_tot);
+        CK(cudaEventRecord(c->ev[13], st));
         // second pass, one task per warp with full-width slabs, driven from the device: tasks whose DP arena overflowed the
         // typical slab and rows with more than 16 predecessors were put on a list by the first pass, together with the
         // slab size they need.  It reuses the first pass's slabs, with as many resident warps as fit; when not even one
@@ -514,6 +523,8 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
     S.ms_pack = ev_ms(c, 2, 3); S.ms_seed = ev_ms(c, 3, 4); S.ms_chain = ev_ms(c, 4, 5); S.ms_select = ev_ms(c, 5, 6); S.ms_partition = ev_ms(c, 6, 7);
     S.ms_poa = ev_ms(c, 8, 9); S.ms_ksw = ev_ms(c, 9, 10); S.ms_d2h = ev_ms(c, 10, 11);
     S.ms_total = ev_ms(c, 2, 11);
+    if (nt > 0 && !P.only_unit && getenv("TH_GPU_DEBUG"))
+        fprintf(stderr, "[th_gpu] POA stage %.2f ms: %.2f before the packed kernel (host + ordering kernels), %.2f packed kernel, %.2f wide pass\n", S.ms_poa, ev_ms(c, 8, 12), ev_ms(c, 12, 13), ev_ms(c, 13, 9));
     out->n_reads = n; out->n_tasks = nt;
     out->read_task_off = h_rtoff; out->task_pos_off = c->h_tposoff.as<int32_t>(); out->pos = c->h_pos.as<int32_t>();
     out->task_n_seqs = c->h_tnseqs.as<int32_t>(); out->task_cons_off = c->h_tconsoff.as<int32_t>(); out->cons_base = c->h_consb.as<uint8_t>();

@@ -29,7 +29,7 @@ case $job in
     tail -2 gpurun_out/$name.log | cut -c1-300 ;;
   variants) # build_variants/*.so (built here with different flags) take turns as libth_gpu.so: N [steps] [shape]
     cp tidehunter_b200/libth_gpu.so /tmp/libth_gpu.so.keep
-    for f in build_variants/*.so; do cp $f tidehunter_b200/libth_gpu.so; echo "== $f"; timeout 600 python tools/profile_step.py "$@" 2>&1 | head -1 | tr "," "\n" | grep -E "ms_poa|ms_ksw|ms_chain|ms_total|n_ksw_cells"; done
+    for f in build_variants/*.so; do cp $f tidehunter_b200/libth_gpu.so; echo "== $f"; timeout 600 python tools/profile_step.py "$@" 2>&1 | grep -E "per step"; done
     cp /tmp/libth_gpu.so.keep tidehunter_b200/libth_gpu.so ;;
   bench) timeout 1500 python bench.py "$@" ;;
   sanitize)

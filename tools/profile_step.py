@@ -13,9 +13,15 @@ shape = sys.argv[3] if len(sys.argv) > 3 else "r2c2"
 names, seqs = synth.gen_reads(shape, n)
 ctx = T.GpuContext()
 ctx.upload(seqs)
+hist = []
 for _ in range(steps):
     r = ctx.process_resident()
+    hist.append(r.stats.as_dict())
 print({k: v for k, v in r.stats.as_dict().items()})
+if steps > 2:  # the POA kernel's time varies from launch to launch: all steps but the first, sorted
+    for key in ("ms_poa", "ms_ksw", "ms_chain", "ms_total"):
+        print(key, "per step:", " ".join("%.1f" % h[key] for h in sorted(hist[1:], key=lambda h: h[key])))
+    print("ms_poa in launch order:", " ".join("%.1f" % h["ms_poa"] for h in hist))
 cn = ctx.counters()
 ph = cn[16:23]
 names = ["setup", "rows", "backtrack", "merge", "reorder", "consensus", "total"]
