@@ -311,14 +311,17 @@ extern "C" int th_gpu_process_resident(th_gpu_ctx *c, th_gpu_result *out) {
         const int grid = std::min((n + CHAIN_WARPS - 1) / CHAIN_WARPS, std::max(1, (int)(c->n_sm * CHAIN_BLOCKS_PER_SM * c->share)));
         if (c->d_rorder.ensure(4 * (size_t)n + 64)) return -1;
         bucket_order_kernel<<<1, 1024, 0, st>>>(nullptr, 0, nullptr, c->d_nhits.as<int32_t>(), c->d_rorder.as<int32_t>(), n, c->max_len); // reads by hit count, most first
+        // period buckets of the chaining DP: four chunk-wide int arrays that are only written later (chain cells, par_pos x 2, ranks)
         if (P.max_p < (1u << 27)) // hit periods are <= max_p (src/tandem_hit.c:204): the 1.8x gate fits 32-bit products
             chain_dp_kernel<true><<<grid, CHAIN_WARPS * 32, 0, st>>>(P, n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(),
                                                                   c->d_score.as<int32_t>(), c->d_from.as<int32_t>(), c->d_gflag.as<int32_t>(), cnt64 + 0,
-                                                                  c->d_rorder.as<int32_t>(), cnt32 + 7);
+                                                                  c->d_rorder.as<int32_t>(), cnt32 + 7,
+                                                                  c->d_cells.as<int32_t>(), c->d_par.as<int32_t>(), c->d_par.as<int32_t>() + B, c->d_rank.as<int32_t>());
         else
             chain_dp_kernel<false><<<grid, CHAIN_WARPS * 32, 0, st>>>(P, n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(),
                                                                    c->d_score.as<int32_t>(), c->d_from.as<int32_t>(), c->d_gflag.as<int32_t>(), cnt64 + 0,
-                                                                   c->d_rorder.as<int32_t>(), cnt32 + 7);
+                                                                   c->d_rorder.as<int32_t>(), cnt32 + 7,
+                                                                   c->d_cells.as<int32_t>(), c->d_par.as<int32_t>(), c->d_par.as<int32_t>() + B, c->d_rank.as<int32_t>());
         S.n_launches += 2;
         if (P.w > 1) { // repeated ends can only come from minimizer seeds
             chain_dp_generic_kernel<<<(n + 63) / 64, 64, 0, st>>>(P, n, roff, c->d_nhits.as<int32_t>(), c->d_hend.as<int32_t>(), c->d_hper.as<int32_t>(),

@@ -37,13 +37,38 @@ __device__ __forceinline__ int con_score(int cs, int ce, int ps, int pe, int k, 
 #ifndef CHAIN_BLOCKS_PER_SM
 #define CHAIN_BLOCKS_PER_SM 8   // persistent grid: blocks per SM (tuning knob)
 #endif
+#ifndef CHAIN_BUCKETS
+#define CHAIN_BUCKETS 1         // 0: always the plain window scan
+#endif
+#define CHAIN_BK_S 512          // period buckets [S j, S j + 2 S), stride S: every hit is in two of them
+#define CHAIN_BK_MAX 64         // most buckets kept in shared memory (max_p <= 31,744); more: plain scan
+
+// Period buckets (round 2).  The reference scans, for every cell, ALL earlier cells that end within one period -- ~300 of
+// them on 10 kb reads, most of them chance matches or harmonics with other periods.  A predecessor q can only raise the
+// running maximum when dpd^2 < 2 (gmax + 2k), dpd = |period(cur) - period(q)|, gmax = the largest score of the read so far:
+// otherwise con_score's penalty floor(dpd^2 / 2) alone exceeds every score, and the stop rules that need no improvement
+// (overlap, dpd == 0) cannot fire either.  Skipping such a predecessor changes nothing the reference computes.  So the hits
+// are kept a second time sorted into period buckets (stable: index order inside a bucket), with the scores written through,
+// and a cell scans only the one bucket that contains [period - D, period + D] (D = the bound above, <= S / 2), newest entry
+// first, with the same ordered stop rules as the plain scan.  The number of predecessors the reference evaluates (the work
+// counter) follows from indices: one hit per end position, so rows = index differences.  The plain scan remains for cells
+// whose window is as long as their period (the reference's "max_h rows without improvement" rule could fire; it cannot
+// otherwise), for D > S / 2 (scores beyond 32 k), more than CHAIN_BK_MAX buckets, or reads with more hits than half their
+// length (the bucket arrays reuse chunk-wide buffers that are free at this point).  Model and check against the oracle:
+// tools/sim/chain_bucket_sim.py.
 template <bool SMALL>
 __global__ void __launch_bounds__(CHAIN_WARPS * 32)
 chain_dp_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, const int32_t *__restrict__ nhits,
                 const int32_t *__restrict__ hend, const int32_t *__restrict__ hper,
                 int32_t *score, int32_t *from, int32_t *__restrict__ generic_flag,
-                unsigned long long *__restrict__ eval_count, const int32_t *__restrict__ order, int *__restrict__ next_read) {
+                unsigned long long *__restrict__ eval_count, const int32_t *__restrict__ order, int *__restrict__ next_read,
+                int32_t *bk_idx, int32_t *bk_en, int32_t *bk_pr, int32_t *bk_sc) {
+    __shared__ int s_off_all[CHAIN_WARPS][CHAIN_BK_MAX + 1], s_fill_all[CHAIN_WARPS][CHAIN_BK_MAX];
     const int lane = lane_id();
+    int *const s_off = s_off_all[threadIdx.x >> 5], *const s_fill = s_fill_all[threadIdx.x >> 5];
+    const int nbk = (int)min((unsigned)(P.max_p / CHAIN_BK_S) + 2u, 1u << 20);
+    const bool can_bucket = CHAIN_BUCKETS && bk_idx != nullptr && nbk <= CHAIN_BK_MAX;
+    const unsigned below = (1u << lane) - 1u;
     unsigned long long evals = 0;
     // a read is one warp from start to end, and its time grows with hits x hits per period: warps take the reads from a
     // queue ordered by hit count, most hits first, so that the longest reads do not start last
@@ -65,12 +90,103 @@ chain_dp_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, cons
         if (lane == 0) generic_flag[r] = dup;
         if (dup) continue;
         for (int i = lane; i < n; i += 32) { sc[i] = P.k + min(P.k, pr[i]); fr[i] = -1; } // init_dp
+        const bool bucketed = can_bucket && 2ll * n <= roff[r + 1] - off;
+        int32_t *const bi = bk_idx + off, *const be = bk_en + off, *const bp = bk_pr + off, *const bs = bk_sc + off;
+        if (bucketed) { // stable counting sort of the entries e = 2 i + t (hit i, bucket period / S - 1 + t) by bucket
+            for (int b = lane; b < nbk; b += 32) s_fill[b] = 0;
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                const int b = min(pr[i] / CHAIN_BK_S, nbk - 1);
+                atomicAdd(&s_fill[b], 1);
+                if (b >= 1) atomicAdd(&s_fill[b - 1], 1);
+            }
+            __syncwarp();
+            if (lane == 0) { int acc = 0; for (int b = 0; b < nbk; ++b) { const int c = s_fill[b]; s_off[b] = acc; s_fill[b] = acc; acc += c; } s_off[nbk] = acc; }
+            __syncwarp();
+            for (int base = 0; base < 2 * n; base += 32) {
+                const int e = base + lane, i = e >> 1;
+                int key = -1 - lane, pv = 0, ev = 0;   // entries without a bucket get keys of their own
+                if (e < 2 * n) { pv = pr[i]; ev = en[i]; const int b = min(pv / CHAIN_BK_S, nbk - 1) - 1 + (e & 1); if (b >= 0) key = b; }
+                const unsigned m = __match_any_sync(TH_FULL, key);
+                int pos = 0;
+                if (key >= 0) pos = s_fill[key] + __popc(m & below);
+                __syncwarp();
+                if (key >= 0 && (m & below) == 0) s_fill[key] += __popc(m);
+                if (key >= 0) { bi[pos] = i; be[pos] = ev; bp[pos] = pv; bs[pos] = P.k + min(P.k, pv); }
+                __syncwarp();
+            }
+            for (int b = lane; b < nbk; b += 32) s_fill[b] = 0;   // from here on: entries of the bucket with index < cur
+            __syncwarp();
+            if (lane == 0) { const int b = min(pr[0] / CHAIN_BK_S, nbk - 1); s_fill[b] = 1; if (b >= 1) s_fill[b - 1] = 1; }
+        }
         __syncwarp();
+        int gmax = 2 * P.k;   // >= every score of the read so far
         for (int cur = 1; cur < n; ++cur) {
             const int ce = en[cur], cp = pr[cur], cs = ce - cp;
             const int init = P.k + min(P.k, cp);
             int max_score = init, best_pre = -1, iter_in = 0;
             const int max_h = cp;
+            bool fast = false;
+            int wlo = 0;
+            const int T2 = 2 * (min(gmax, 1 << 27) + 2 * P.k);   // (scores that large send the cell to the plain scan through Dc)
+            const int Dc = (int)sqrtf((float)T2) + 1;     // >= the largest dpd with dpd^2 < T2
+            if (bucketed && Dc <= CHAIN_BK_S / 2) {
+                // first index whose end is >= cs (the window's far end): 32-ary search over the ends before cur
+                int lo = 0, hi = cur;
+                while (hi - lo > 32) {
+                    const int step = (hi - lo + 31) >> 5, probe = lo + lane * step;
+                    const int v = probe < hi ? en[probe] : INT_MAX;
+                    const unsigned m = __ballot_sync(TH_FULL, v >= cs);
+                    if (m == 0) lo = lo + 31 * step + 1;    // every probed end is before cs
+                    else { const int f = __ffs(m) - 1; hi = min(hi, lo + f * step); if (f) lo = lo + (f - 1) * step + 1; }
+                }
+                { const int probe = lo + lane; const int v = probe < hi ? en[probe] : INT_MAX;
+                  const unsigned m = __ballot_sync(TH_FULL, v >= cs);
+                  wlo = m ? min(hi, lo + __ffs(m) - 1) : hi; }
+                fast = cur - wlo < max_h;
+            }
+            if (fast) {
+                const int j = max(cp - Dc, 0) / CHAIN_BK_S;
+                const int seg_lo = s_off[j];
+                int stop_idx = -1;
+                for (int base = seg_lo + s_fill[j] - 1; base >= seg_lo; base -= 32) {
+                    const int p = base - lane;
+                    const bool valid = p >= seg_lo;
+                    int pe = 0, pp = 1, psc = 0, pq = 0;
+                    if (valid) { pe = be[p]; pp = bp[p]; psc = bs[p]; pq = bi[p]; }
+                    const bool cstop = !valid || pe < cs;           // stop BEFORE this predecessor
+                    const int dpd = abs(cp - pp);                   // <= 2 S inside a bucket: the square fits
+                    int con = 0, cls = CON_NO;
+                    if (!cstop && dpd * dpd < T2) cls = con_score<SMALL>(cs, ce, pe - pp, pe, P.k, con);
+                    const int s = cls != CON_NO ? psc + con : INT_MIN;
+                    const unsigned cm = __ballot_sync(TH_FULL, cstop);
+                    const int first_c = cm ? __ffs(cm) - 1 : 32;
+                    int first_a;
+                    if (__reduce_max_sync(TH_FULL, s) <= max_score) {
+                        const unsigned am = __ballot_sync(TH_FULL, !cstop && cls == CON_OVL);
+                        first_a = am ? __ffs(am) - 1 : 32;
+                    } else {
+                        int inc = s;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) inc = max(inc, __shfl_up_sync(TH_FULL, inc, d)); // lanes < d get their own value
+                        int excl = __shfl_up_sync(TH_FULL, inc, 1);
+                        excl = lane == 0 ? max_score : max(max_score, excl);
+                        const bool imp = cls != CON_NO && s > excl;
+                        const bool stop_after = (imp && (cls == CON_SAME || cls == CON_OVL)) || (!imp && cls == CON_OVL);
+                        const unsigned am = __ballot_sync(TH_FULL, stop_after && !cstop);
+                        first_a = am ? __ffs(am) - 1 : 32;
+                        const bool processed = lane < first_c && lane <= first_a;
+                        const int bm = __reduce_max_sync(TH_FULL, processed ? s : INT_MIN);
+                        if (bm > max_score) {
+                            const unsigned wm = __ballot_sync(TH_FULL, processed && imp && s == bm);
+                            max_score = bm; best_pre = __shfl_sync(TH_FULL, pq, __ffs(wm) - 1);
+                        }
+                    }
+                    if (first_a < first_c) stop_idx = __shfl_sync(TH_FULL, pq, first_a);   // a stop rule fired at that predecessor
+                    if (first_c < 32 || first_a < 32) break;
+                }
+                evals += (unsigned long long)(cur - max(wlo, stop_idx));   // rows the reference walks: down to the stop or the window's end
+            } else {
             // the next batch of predecessors is loaded while the current one is evaluated (its scores are final: they lie at
             // least 32 cells behind the current one); a batch is ~100 instructions, about one L2 round trip
             int n_pe = 0, n_pp = 1, n_psc = 0;
@@ -104,8 +220,8 @@ chain_dp_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, cons
                     const bool imp = cls != CON_NO && s > excl;
                     const unsigned impm = __ballot_sync(TH_FULL, imp);
                     // rows without improvement so far (iter_n), as of this lane
-                    const unsigned below = impm & (0xffffffffu >> (31 - lane));
-                    cnt = below ? lane - (31 - __clz(below)) : iter_in + lane + 1;
+                    const unsigned blw = impm & (0xffffffffu >> (31 - lane));
+                    cnt = blw ? lane - (31 - __clz(blw)) : iter_in + lane + 1;
                     const bool stop_after = (imp && (cls == CON_SAME || cls == CON_OVL)) || (!imp && cls == CON_OVL) || (!imp && cnt >= max_h);
                     const unsigned am = __ballot_sync(TH_FULL, stop_after && !cstop);
                     first_a = am ? __ffs(am) - 1 : 32;
@@ -121,7 +237,17 @@ chain_dp_kernel(DevParams P, int n_reads, const int64_t *__restrict__ roff, cons
                 if (first_c < 32 || first_a < 32) break;
                 iter_in = __shfl_sync(TH_FULL, cnt, 31);
             }
+            }
+            __syncwarp();   // every lane has read the bucket fill counts (an empty bucket scan has no vote in it) before lane 0 moves them
             if (lane == 0 && max_score > init) { sc[cur] = max_score; fr[cur] = best_pre; }
+            if (bucketed) { // the cell becomes a predecessor: its entries are the next ones of its two buckets; the score is written through
+                gmax = max(gmax, max_score);
+                if (lane == 0) {
+                    const int b = min(cp / CHAIN_BK_S, nbk - 1);
+                    if (max_score > init) { bs[s_off[b] + s_fill[b]] = max_score; if (b >= 1) bs[s_off[b - 1] + s_fill[b - 1]] = max_score; }
+                    s_fill[b] += 1; if (b >= 1) s_fill[b - 1] += 1;
+                }
+            }
             __syncwarp();
         }
     }
